@@ -1,0 +1,341 @@
+/*
+ * optk.h -- C ABI of liboptk, the B200-native (sm_100a) engine for optika's
+ * sequential-raytrace hot path.
+ *
+ * The reference (sun-data/optika) is pure Python and has no FFI; the seam this
+ * library replaces is the set of Python calls listed beside each entry point
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add at each of them.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, POD structs.  No torch / CUDA types.
+ *   - `stream` is a CUDA stream handle (cudaStream_t / CUstream) passed as
+ *     void*; NULL is the legacy default stream.  Calls with device pointers are
+ *     asynchronous and stream ordered; calls taking host pointers return after
+ *     the results are in the host buffers.
+ *   - all lengths are millimetres, angles radians, attenuation 1/mm.
+ *   - every function returns 0 on success or a negative optk_status_t;
+ *     optk_last_error() returns a thread-local message.  There is NO CPU
+ *     fallback: without a CUDA device every compute entry point fails with
+ *     OPTK_ERR_CUDA.
+ *   - ownership: inputs are never written; outputs are caller-allocated.
+ */
+#ifndef OPTK_H
+#define OPTK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPTK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OPTK_API __attribute__((visibility("default")))
+#else
+#define OPTK_API
+#endif
+
+#define OPTK_MAX_SURFACES 24 /* surfaces per launch; longer systems are chained   */
+#define OPTK_MAX_VERTICES 16 /* polygon aperture vertices                          */
+#define OPTK_MAX_COEFF 8     /* terms of a Polynomial1dRulingSpacing               */
+#define OPTK_MAX_AXES 8      /* named axes of a ray grid                           */
+#define OPTK_NUM_FIELDS 10   /* fp64 fields of a ray                               */
+
+typedef enum optk_status {
+    OPTK_OK = 0,
+    OPTK_ERR_INVALID = -1,     /* bad argument                     -> ValueError          */
+    OPTK_ERR_UNSUPPORTED = -2, /* unsupported surface kind         -> NotImplementedError */
+    OPTK_ERR_CUDA = -3,        /* CUDA runtime error / no device   -> RuntimeError        */
+    OPTK_ERR_NOMEM = -4
+} optk_status_t;
+
+/* Order of the fp64 ray fields (optika/rays/_ray_vectors.py:256-278). */
+typedef enum optk_field {
+    OPTK_WAVELENGTH = 0,
+    OPTK_PX = 1, OPTK_PY = 2, OPTK_PZ = 3,
+    OPTK_DX = 4, OPTK_DY = 5, OPTK_DZ = 6,
+    OPTK_INTENSITY = 7,
+    OPTK_ATTENUATION = 8,
+    OPTK_INDEX_REFRACTION = 9
+} optk_field_t;
+
+typedef enum optk_sag_kind {
+    OPTK_SAG_FLAT = 0,        /* optika/sags/_flat.py:26-64          */
+    OPTK_SAG_SPHERICAL = 1,   /* optika/sags/_spherical.py:100-191   */
+    OPTK_SAG_CYLINDRICAL = 2, /* optika/sags/_cylindrical.py:75-160  */
+    OPTK_SAG_CONIC = 3,       /* optika/sags/_conic.py:31-170        */
+    OPTK_SAG_PARABOLIC = 4,   /* optika/sags/_parabolic.py:40-158    */
+    OPTK_SAG_TOROIDAL = 5     /* optika/sags/_toroidal.py:38-88 + _abc.py:76-107 */
+} optk_sag_kind_t;
+
+typedef enum optk_material_kind {
+    OPTK_MAT_VACUUM = 0, /* optika/materials/_materials.py:82-116  */
+    OPTK_MAT_MIRROR = 1, /* optika/materials/_materials.py:120-175 */
+    OPTK_MAT_GLASS = 2   /* optika/materials/_materials.py:428-455 */
+} optk_material_kind_t;
+
+typedef enum optk_ruling_kind {
+    OPTK_RULING_NONE = 0,
+    OPTK_RULING_CONSTANT = 1,    /* optika/rulings/_spacing.py:45-74   */
+    OPTK_RULING_POLYNOMIAL = 2,  /* optika/rulings/_spacing.py:78-128  */
+    OPTK_RULING_HOLOGRAPHIC = 3  /* optika/rulings/_spacing.py:295-328 */
+} optk_ruling_kind_t;
+
+typedef enum optk_aperture_kind {
+    OPTK_APERTURE_NONE = 0,
+    OPTK_APERTURE_CIRCULAR = 1,    /* optika/apertures/_apertures.py:292-314 */
+    OPTK_APERTURE_RECTANGULAR = 2, /* optika/apertures/_apertures.py:941-968 */
+    OPTK_APERTURE_POLYGON = 3,     /* optika/apertures/_apertures.py:739-778 */
+    OPTK_APERTURE_ELLIPTICAL = 4,  /* optika/apertures/_apertures.py:640-663 */
+    OPTK_APERTURE_SECTOR = 5       /* optika/apertures/_apertures.py:438-480 */
+} optk_aperture_kind_t;
+
+/* optk_surface_t.flags */
+#define OPTK_F_TRANSFORM 0x001          /* surface.transformation is not None      */
+#define OPTK_F_SAG_TRANSFORM 0x002      /* sag.transformation is not None          */
+#define OPTK_F_APERTURE_TRANSFORM 0x004 /* aperture.transformation is not None     */
+#define OPTK_F_RULING_TRANSFORM 0x008   /* Polynomial1dRulingSpacing.transformation */
+#define OPTK_F_APERTURE_INVERTED 0x010
+#define OPTK_F_APERTURE_ACTIVE 0x020
+#define OPTK_F_APERTURE_ANGULAR 0x040   /* clip on direction instead of position   */
+#define OPTK_F_HOLO_DIVERGING_1 0x080
+#define OPTK_F_HOLO_DIVERGING_2 0x100
+
+/*
+ * optk_surface_t.stages: which steps of AbstractSurface.propagate_rays
+ * (optika/surfaces.py:123-198) run.  OPTK_STAGE_ALL is the full operator; the
+ * partial masks implement the reference's unit operations (sag.intercept,
+ * aperture.clip_rays, ...) on the same kernel.
+ */
+#define OPTK_STAGE_INTERCEPT 0x01 /* sag.intercept           (sags/_abc.py:76-107)        */
+#define OPTK_STAGE_ATTENUATE 0x02 /* Beer-Lambert            (sags/_abc.py:109-122)       */
+#define OPTK_STAGE_RULINGS 0x04   /* incident_effective      (rulings/_rulings.py:170-204) */
+#define OPTK_STAGE_REFRACT 0x08   /* index, wavelength, Snell (surfaces.py:156-190)        */
+#define OPTK_STAGE_CLIP 0x10      /* aperture.clip_rays      (apertures/_apertures.py:82-102) */
+#define OPTK_STAGE_NORMAL_OUT 0x20 /* write sag.normal(position) into the direction fields */
+#define OPTK_STAGE_SAG_OUT 0x40    /* write sag(position) into the z position field        */
+#define OPTK_STAGE_KAPPA_OUT 0x80  /* write spacing_(position, normal) into direction      */
+#define OPTK_STAGE_ALL 0x1f
+
+/* x -> R x + t, row-major R.  The inverse is evaluated as R^T (x - t). */
+typedef struct optk_affine {
+    double r[9];
+    double t[3];
+} optk_affine_t;
+
+/*
+ * One optical surface, lowered from optika.surfaces.Surface
+ * (optika/surfaces.py:282-395) for ONE configuration: every parameter a scalar.
+ */
+typedef struct optk_surface {
+    int32_t sag_kind;
+    int32_t material_kind;
+    int32_t ruling_kind;
+    int32_t aperture_kind;
+    int32_t flags;
+    int32_t stages;
+    int32_t n_vertices;
+    int32_t n_coeff;
+
+    optk_affine_t transform;          /* surface-local -> global                        */
+    optk_affine_t sag_transform;      /* sag-local -> surface-local                     */
+    optk_affine_t aperture_transform; /* aperture-local -> surface-local                */
+    optk_affine_t ruling_transform;   /* applied FORWARDS to the position (spacing.py:118-119) */
+
+    /* sag: [0] radius (spherical/cylindrical/conic/toroidal minor) or focal length
+     * (parabolic); [1] conic constant; [2] radius of rotation (toroidal).        */
+    double sag[4];
+
+    /* Glass: Sellmeier b1 b2 b3 c1 c2 c3 (c in mm^2). */
+    double material[6];
+
+    double ruling_order;        /* diffraction order m                               */
+    double ruling_normal[3];    /* unit vector normal to the ruling planes           */
+    double ruling_coeff[OPTK_MAX_COEFF]; /* constant: [0] = spacing; polynomial: c_k  */
+    int32_t ruling_power[OPTK_MAX_COEFF];
+    double holo_x1[3];
+    double holo_x2[3];
+    double holo_wavelength;
+
+    /* aperture: circular [0]=radius; rectangular [0..1]=half widths; elliptical
+     * [0..1]=radii; sector [0]=radius [1]=angle_start [2]=angle_stop.              */
+    double aperture[4];
+    double vertices_x[OPTK_MAX_VERTICES];
+    double vertices_y[OPTK_MAX_VERTICES];
+} optk_surface_t;
+
+typedef struct optk_system optk_system_t;
+
+/*
+ * Rays as structure-of-arrays.  `field[f]` may be a broadcast view: element
+ * (i_0, ..., i_{n_axes-1}) of field f lives at
+ * field[f][sum_a i_a * stride[f][a]]  (strides in ELEMENTS, 0 = broadcast), and
+ * the mask likewise with mask_stride.  This is how a separable ray grid
+ * (wavelength x field x pupil, optika/systems/_sequential.py:791-828) is passed
+ * without being materialised.  Rays are enumerated in C order of `dims`.
+ */
+typedef struct optk_rays_in {
+    int32_t n_axes;
+    int64_t dims[OPTK_MAX_AXES];
+    const double* field[OPTK_NUM_FIELDS];
+    int64_t stride[OPTK_NUM_FIELDS][OPTK_MAX_AXES];
+    const uint8_t* unvignetted; /* NULL = all true */
+    int64_t mask_stride[OPTK_MAX_AXES];
+} optk_rays_in_t;
+
+/* Dense outputs, prod(dims) elements each (times the number of traced surfaces
+ * when accumulating).  A NULL field pointer skips that output. */
+typedef struct optk_rays_out {
+    double* field[OPTK_NUM_FIELDS];
+    uint8_t* unvignetted;
+} optk_rays_out_t;
+
+/* Detector binning target (optika/sensors/_sensors.py:139-161). Planes are
+ * [n_wavelength][n_x][n_y], C order, caller-zeroed; contributions are ADDED. */
+typedef struct optk_image {
+    int32_t n_wavelength, n_x, n_y;
+    const double* edges_wavelength; /* n_wavelength + 1, device or host like the rays */
+    const double* edges_x;          /* n_x + 1 */
+    const double* edges_y;          /* n_y + 1 */
+    double* flux;                   /* sum of intensity            (may be NULL) */
+    double* moment_real;            /* sum of intensity * Re cos   (may be NULL) */
+    double* moment_imag;            /* sum of intensity * Im cos   (may be NULL) */
+    unsigned long long* counts;     /* number of rays              (may be NULL) */
+} optk_image_t;
+
+/* Counters returned by the trace (device-side reductions, optional). */
+typedef struct optk_trace_stats {
+    unsigned long long n_rays;
+    unsigned long long n_unvignetted;
+    unsigned long long n_newton_iterations;
+    unsigned long long n_binned;
+} optk_trace_stats_t;
+
+/* ---- library --------------------------------------------------------------- */
+OPTK_API int optk_abi_version(void);
+OPTK_API const char* optk_last_error(void);
+/* Number of visible CUDA devices, or a negative status. */
+OPTK_API int optk_device_count(void);
+
+/* ---- system handle ---------------------------------------------------------
+ * Replaces the Python list `SequentialSystem.surfaces_all`
+ * (optika/systems/_sequential.py:93-108) as consumed by
+ * optika.propagators.propagate_rays / accumulate_rays (optika/propagators.py:19-73).
+ * `table` is [n_config][n_surface], copied.  Unsupported kinds are rejected here.
+ */
+OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, int32_t n_config,
+                       optk_system_t** out);
+OPTK_API int optk_system_destroy(optk_system_t* sys);
+OPTK_API int optk_system_size(const optk_system_t* sys, int32_t* n_surface, int32_t* n_config);
+
+/* ---- fused sequential trace (kernel 1) --------------------------------------
+ * Replaces optika.propagators.propagate_rays (optika/propagators.py:19-41) and,
+ * with accumulate != 0, accumulate_rays (:44-73): each ray walks surfaces
+ * surf_begin, surf_begin + surf_step, ... (surf_count of them) of configuration
+ * `config`, running AbstractSurface.propagate_rays (optika/surfaces.py:123-198)
+ * at each.  surf_step = -1 gives the backwards trace of the stop solver
+ * (optika/systems/_sequential.py:640-654).
+ * With accumulate, the state after the k-th traced surface is written at element
+ * offset k * accumulate_stride of every output array.
+ * `image` (may be NULL) additionally bins the FINAL rays, transformed by the
+ * inverse of `image_frame` (NULL = already local; this is the sensor's
+ * transformation, optika/systems/_sequential.py:983-986), as
+ * AbstractImagingSensor.collect does (optika/sensors/_sensors.py:92-171).
+ * `out` may be NULL when only the image is wanted.
+ * All pointers are DEVICE pointers.
+ */
+OPTK_API int optk_trace(const optk_system_t* sys, int32_t config,
+               const optk_rays_in_t* in, const optk_rays_out_t* out,
+               int32_t surf_begin, int32_t surf_count, int32_t surf_step,
+               int32_t accumulate, int64_t accumulate_stride,
+               const optk_image_t* image, const optk_affine_t* image_frame,
+               optk_trace_stats_t* stats_device, void* stream);
+
+/* Same operation with HOST pointers everywhere (rays, edges, image planes).
+ * The library streams the rays through the device in slabs of `slab_rays`
+ * (0 = default), overlapping H2D, kernel and D2H on three streams; `pinned`
+ * says the host buffers are page-locked.  Returns when outputs are complete. */
+OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config,
+                    const optk_rays_in_t* in, const optk_rays_out_t* out,
+                    int32_t surf_begin, int32_t surf_count, int32_t surf_step,
+                    int32_t accumulate, int64_t accumulate_stride,
+                    const optk_image_t* image, const optk_affine_t* image_frame,
+                    optk_trace_stats_t* stats_host, int64_t slab_rays, int32_t pinned);
+
+/* ---- detector binning (kernel 2) --------------------------------------------
+ * Replaces the three na.histogram calls of AbstractImagingSensor.collect
+ * (optika/sensors/_sensors.py:139-161) for rays already in sensor-local
+ * coordinates: sample (wavelength, x, y), weight intensity * unvignetted
+ * [* cos_real / cos_imag].  cos_* may be NULL (IdealSensorMaterial: cos = d_z,
+ * optika/sensors/materials/_materials.py:1603-1616 is then taken from `dz`).
+ * Device pointers; contributions are added to the planes of `image`.
+ */
+OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y,
+             const double* dz, const double* intensity, const uint8_t* unvignetted,
+             const optk_image_t* image, void* stream);
+
+/* ---- multilayer transfer-matrix efficiency (kernel 3) -----------------------
+ * Replaces optika.materials.multilayer_efficiency
+ * (optika/materials/_multilayers.py:240-532).  The evaluation grid has n_axes
+ * named axes of sizes dims[]; every input is a broadcast view with element
+ * strides per axis.  Layers are listed top (ambient side) to bottom; the LAST
+ * layer is the substrate (its thickness is ignored, _multilayers.py:190-193).
+ * Segments express PeriodicLayerSequence (optika/materials/_layers.py:611-645):
+ * layers [first, first + count) repeated `repeat` times.  Optical constants
+ * n_j(lambda) are interpolated by the caller (optika/chemicals/_chemicals.py:101-144).
+ * Outputs are dense, prod(dims) elements.  Device pointers.
+ */
+#define OPTK_ML_MAX_AXES 4
+#define OPTK_ML_MAX_LAYERS 256
+
+typedef struct optk_ml_layer {
+    const double* n_re;
+    const double* n_im;
+    int64_t n_stride[OPTK_ML_MAX_AXES];
+    const double* thickness; /* NULL = 0 */
+    int64_t thickness_stride[OPTK_ML_MAX_AXES];
+    const double* width; /* interface profile width, NULL = no profile */
+    int64_t width_stride[OPTK_ML_MAX_AXES];
+    int32_t profile_kind; /* 0 none, 1 erf, 2 exponential, 3 linear, 4 sinusoidal
+                             (optika/materials/profiles.py:221-222, 320-325, 424-431, 532-541) */
+    int32_t reserved;
+} optk_ml_layer_t;
+
+typedef struct optk_ml_segment {
+    int32_t first;
+    int32_t count;
+    int32_t repeat;
+    int32_t reserved;
+} optk_ml_segment_t;
+
+typedef struct optk_ml_input {
+    int32_t n_axes;
+    int64_t dims[OPTK_ML_MAX_AXES];
+    const double* wavelength;
+    int64_t wavelength_stride[OPTK_ML_MAX_AXES];
+    const double* direction_re; /* cosine of the incidence angle in the ambient medium */
+    const double* direction_im; /* NULL = real */
+    int64_t direction_stride[OPTK_ML_MAX_AXES];
+    const double* n_re; /* ambient index of refraction */
+    const double* n_im; /* NULL = real */
+    int64_t n_stride[OPTK_ML_MAX_AXES];
+} optk_ml_input_t;
+
+OPTK_API int optk_multilayer(const optk_ml_input_t* input,
+                    int32_t n_layers, const optk_ml_layer_t* layers,
+                    int32_t n_segments, const optk_ml_segment_t* segments,
+                    double* reflectivity_s, double* reflectivity_p,
+                    double* transmissivity_s, double* transmissivity_p,
+                    void* stream);
+
+/* ---- measurement helpers ----------------------------------------------------
+ * FP64 DFMA peak micro-benchmark (the roofline denominator that
+ * MEASURED_PEAKS.json does not record): returns achieved FLOP/s. */
+OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTK_H */

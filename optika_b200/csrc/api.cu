@@ -1,0 +1,623 @@
+// C ABI of liboptk (see include/optk.h).  Host-side glue only: argument
+// checking, parameter packing, launch, and the host-pointer streaming path.
+#include "common.cuh"
+#include "bin.cuh"
+#include "params.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace optk {
+
+// ---- errors -------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return OPTK_ERR_CUDA;
+}
+
+}  // namespace optk
+
+using namespace optk;
+
+struct optk_system {
+    int32_t n_surface;
+    int32_t n_config;
+    std::vector<optk_surface_t> table;
+};
+
+// ---- scratch cache for the host-pointer path ------------------------------------
+namespace {
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        if (n <= bytes) return OPTK_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, n);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+            return OPTK_ERR_NOMEM;
+        }
+        bytes = n;
+        return OPTK_OK;
+    }
+};
+
+const int kSlots = 3;
+
+struct HostPipeline {
+    std::mutex mutex;
+    cudaStream_t stream[kSlots] = {nullptr, nullptr, nullptr};
+    DeviceBuffer in[kSlots], out[kSlots];
+    DeviceBuffer small;  // broadcast (non-slabbed) inputs, edges, image planes, stats
+    bool init = false;
+    int ensure_streams() {
+        if (init) return OPTK_OK;
+        for (int k = 0; k < kSlots; ++k) OPTK_CUDA(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
+        init = true;
+        return OPTK_OK;
+    }
+};
+
+HostPipeline g_pipeline;
+
+int validate_surface(const optk_surface_t& s, int index) {
+    if (s.sag_kind < OPTK_SAG_FLAT || s.sag_kind > OPTK_SAG_TOROIDAL) {
+        set_error("surface %d: unsupported sag kind %d", index, s.sag_kind);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.material_kind < OPTK_MAT_VACUUM || s.material_kind > OPTK_MAT_GLASS) {
+        set_error("surface %d: unsupported material kind %d", index, s.material_kind);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.ruling_kind < OPTK_RULING_NONE || s.ruling_kind > OPTK_RULING_HOLOGRAPHIC) {
+        set_error("surface %d: unsupported ruling kind %d", index, s.ruling_kind);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.aperture_kind < OPTK_APERTURE_NONE || s.aperture_kind > OPTK_APERTURE_SECTOR) {
+        set_error("surface %d: unsupported aperture kind %d", index, s.aperture_kind);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.aperture_kind == OPTK_APERTURE_POLYGON && (s.n_vertices < 3 || s.n_vertices > OPTK_MAX_VERTICES)) {
+        set_error("surface %d: polygon aperture needs 3..%d vertices, got %d", index, OPTK_MAX_VERTICES,
+                  s.n_vertices);
+        return OPTK_ERR_INVALID;
+    }
+    if (s.ruling_kind == OPTK_RULING_POLYNOMIAL && (s.n_coeff < 1 || s.n_coeff > OPTK_MAX_COEFF)) {
+        set_error("surface %d: polynomial ruling needs 1..%d coefficients, got %d", index, OPTK_MAX_COEFF,
+                  s.n_coeff);
+        return OPTK_ERR_INVALID;
+    }
+    return OPTK_OK;
+}
+
+// Number of rays and a check of the grid description.
+int grid_size(const optk_rays_in_t* in, long long* n_out) {
+    if (!in) {
+        set_error("rays_in is NULL");
+        return OPTK_ERR_INVALID;
+    }
+    if (in->n_axes < 0 || in->n_axes > OPTK_MAX_AXES) {
+        set_error("n_axes must be in 0..%d, got %d", OPTK_MAX_AXES, in->n_axes);
+        return OPTK_ERR_INVALID;
+    }
+    long long n = 1;
+    for (int a = 0; a < in->n_axes; ++a) {
+        if (in->dims[a] < 0) {
+            set_error("dims[%d] is negative", a);
+            return OPTK_ERR_INVALID;
+        }
+        n *= in->dims[a];
+    }
+    for (int f = 0; f < OPTK_NUM_FIELDS; ++f) {
+        if (!in->field[f]) {
+            set_error("input field %d is NULL", f);
+            return OPTK_ERR_INVALID;
+        }
+    }
+    *n_out = n;
+    return OPTK_OK;
+}
+
+bool stride_is_dense(const int64_t* stride, const int64_t* dims, int n_axes) {
+    long long expect = 1;
+    for (int a = n_axes - 1; a >= 0; --a) {
+        if (dims[a] != 1 && stride[a] != expect) return false;
+        expect *= dims[a];
+    }
+    return true;
+}
+
+bool all_dense(const optk_rays_in_t& in) {
+    for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
+        if (!stride_is_dense(in.stride[f], in.dims, in.n_axes)) return false;
+    if (in.unvignetted && !stride_is_dense(in.mask_stride, in.dims, in.n_axes)) return false;
+    return true;
+}
+
+// 1 + the largest element offset a strided view touches
+long long view_extent(const int64_t* stride, const int64_t* dims, int n_axes) {
+    long long e = 0;
+    for (int a = 0; a < n_axes; ++a) {
+        if (dims[a] == 0) return 0;
+        e += (dims[a] - 1) * (stride[a] < 0 ? 0 : stride[a]);
+    }
+    return e + 1;
+}
+
+int fill_image(const optk_image_t* image, ImageDev* dev) {
+    if (image->n_wavelength < 1 || image->n_x < 1 || image->n_y < 1) {
+        set_error("image needs at least one bin along every axis");
+        return OPTK_ERR_INVALID;
+    }
+    if (!image->edges_wavelength || !image->edges_x || !image->edges_y) {
+        set_error("image bin edges are NULL");
+        return OPTK_ERR_INVALID;
+    }
+    dev->n_w = image->n_wavelength;
+    dev->n_x = image->n_x;
+    dev->n_y = image->n_y;
+    dev->pad = 0;
+    dev->e_w = image->edges_wavelength;
+    dev->e_x = image->edges_x;
+    dev->e_y = image->edges_y;
+    dev->flux = image->flux;
+    dev->moment_real = image->moment_real;
+    dev->moment_imag = image->moment_imag;
+    dev->counts = image->counts;
+    return OPTK_OK;
+}
+
+// Common packing of everything except ray pointers.
+int pack_trace(const optk_system_t* sys, int32_t config, int32_t surf_begin, int32_t surf_count, int32_t surf_step,
+               int32_t accumulate, TraceParams* P) {
+    if (!sys) {
+        set_error("system handle is NULL");
+        return OPTK_ERR_INVALID;
+    }
+    if (config < 0 || config >= sys->n_config) {
+        set_error("config %d out of range [0, %d)", config, sys->n_config);
+        return OPTK_ERR_INVALID;
+    }
+    if (surf_count < 0 || surf_count > OPTK_MAX_SURFACES) {
+        set_error("surf_count %d out of range [0, %d]; chain longer systems", surf_count, OPTK_MAX_SURFACES);
+        return OPTK_ERR_INVALID;
+    }
+    if (surf_step != 1 && surf_step != -1) {
+        set_error("surf_step must be +1 or -1");
+        return OPTK_ERR_INVALID;
+    }
+    const optk_surface_t* row = sys->table.data() + (size_t)config * sys->n_surface;
+    for (int k = 0; k < surf_count; ++k) {
+        const int s = surf_begin + k * surf_step;
+        if (s < 0 || s >= sys->n_surface) {
+            set_error("surface index %d out of range [0, %d)", s, sys->n_surface);
+            return OPTK_ERR_INVALID;
+        }
+        P->surf[k] = row[s];
+    }
+    P->n_surf = surf_count;
+    P->accumulate = accumulate ? 1 : 0;
+    return OPTK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+OPTK_API int optk_abi_version(void) { return OPTK_ABI_VERSION; }
+
+OPTK_API const char* optk_last_error(void) { return g_error; }
+
+OPTK_API int optk_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, int32_t n_config, optk_system_t** out) {
+    if (!table || !out || n_surface < 1 || n_config < 1) {
+        set_error("optk_system_create: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    for (int c = 0; c < n_config; ++c)
+        for (int s = 0; s < n_surface; ++s) {
+            int rc = validate_surface(table[(size_t)c * n_surface + s], s);
+            if (rc) return rc;
+        }
+    optk_system* sys = new (std::nothrow) optk_system;
+    if (!sys) return OPTK_ERR_NOMEM;
+    sys->n_surface = n_surface;
+    sys->n_config = n_config;
+    sys->table.assign(table, table + (size_t)n_surface * n_config);
+    *out = sys;
+    return OPTK_OK;
+}
+
+OPTK_API int optk_system_destroy(optk_system_t* sys) {
+    delete sys;
+    return OPTK_OK;
+}
+
+OPTK_API int optk_system_size(const optk_system_t* sys, int32_t* n_surface, int32_t* n_config) {
+    if (!sys) {
+        set_error("system handle is NULL");
+        return OPTK_ERR_INVALID;
+    }
+    if (n_surface) *n_surface = sys->n_surface;
+    if (n_config) *n_config = sys->n_config;
+    return OPTK_OK;
+}
+
+OPTK_API int optk_trace(const optk_system_t* sys, int32_t config, const optk_rays_in_t* in, const optk_rays_out_t* out,
+               int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
+               int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
+               optk_trace_stats_t* stats_device, void* stream) {
+    static thread_local TraceParams P;
+    long long n = 0;
+    int rc = grid_size(in, &n);
+    if (rc) return rc;
+    rc = pack_trace(sys, config, surf_begin, surf_count, surf_step, accumulate, &P);
+    if (rc) return rc;
+    if (n > 0x7fffffffLL) {
+        set_error("optk_trace: %lld rays exceed one launch (2^31 - 1); split the outermost axis", n);
+        return OPTK_ERR_INVALID;
+    }
+    P.in = *in;
+    if (out) P.out = *out; else memset(&P.out, 0, sizeof(P.out));
+    for (int a = 0; a < OPTK_MAX_AXES; ++a)
+        P.div[a] = make_fastdiv(a < in->n_axes ? (uint32_t)in->dims[a] : 1u);
+    P.n_rays = n;
+    P.index_offset = 0;
+    P.accumulate_stride = accumulate ? accumulate_stride : 0;
+    if (accumulate && accumulate_stride < n) {
+        set_error("accumulate_stride %lld is smaller than the number of rays %lld", (long long)accumulate_stride, n);
+        return OPTK_ERR_INVALID;
+    }
+    P.dense_in = all_dense(*in) ? 1 : 0;
+    P.has_image = image ? 1 : 0;
+    P.has_frame = image_frame ? 1 : 0;
+    if (image) {
+        rc = fill_image(image, &P.image);
+        if (rc) return rc;
+    }
+    if (image_frame) P.frame = *image_frame;
+    P.stats = stats_device;
+    return launch_trace(P, (cudaStream_t)stream);
+}
+
+OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
+             const double* intensity, const uint8_t* unvignetted, const optk_image_t* image, void* stream) {
+    if (!wavelength || !x || !y || !image) {
+        set_error("optk_bin: NULL argument");
+        return OPTK_ERR_INVALID;
+    }
+    ImageDev dev;
+    int rc = fill_image(image, &dev);
+    if (rc) return rc;
+    return launch_bin(n_rays, wavelength, x, y, dz, intensity, unvignetted, dev, (cudaStream_t)stream);
+}
+
+OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const optk_rays_in_t* in, const optk_rays_out_t* out,
+                    int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
+                    int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
+                    optk_trace_stats_t* stats_host, int64_t slab_rays, int32_t pinned) {
+    (void)pinned;
+    static thread_local TraceParams P;
+    long long n = 0;
+    int rc = grid_size(in, &n);
+    if (rc) return rc;
+    rc = pack_trace(sys, config, surf_begin, surf_count, surf_step, accumulate, &P);
+    if (rc) return rc;
+    if (n > 0xffffffffLL) {
+        set_error("optk_trace_host: %lld rays exceed 2^32 - 1; split the outermost axis", n);
+        return OPTK_ERR_INVALID;
+    }
+    if (accumulate && accumulate_stride < n) {
+        set_error("accumulate_stride %lld is smaller than the number of rays %lld", (long long)accumulate_stride, n);
+        return OPTK_ERR_INVALID;
+    }
+    if (n == 0) return OPTK_OK;
+
+    std::lock_guard<std::mutex> lock(g_pipeline.mutex);
+    HostPipeline& pl = g_pipeline;
+    rc = pl.ensure_streams();
+    if (rc) return rc;
+
+    if (slab_rays <= 0) slab_rays = 1 << 22;
+    if (slab_rays > n) slab_rays = n;
+    const int n_slabs = (int)((n + slab_rays - 1) / slab_rays);
+    const int n_out_states = accumulate ? surf_count : 1;
+
+    // --- classify inputs: dense fields are streamed in slabs, the rest are
+    //     broadcast views whose (small) backing arrays are uploaded once.
+    bool dense[OPTK_NUM_FIELDS + 1];
+    long long extent[OPTK_NUM_FIELDS + 1];
+    size_t small_bytes = 0;
+    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) {
+        const int64_t* st = f < OPTK_NUM_FIELDS ? in->stride[f] : in->mask_stride;
+        const bool present = f < OPTK_NUM_FIELDS ? true : in->unvignetted != nullptr;
+        dense[f] = present && stride_is_dense(st, in->dims, in->n_axes);
+        extent[f] = present ? view_extent(st, in->dims, in->n_axes) : 0;
+        if (present && !dense[f]) {
+            for (int a = 0; a < in->n_axes; ++a)
+                if (st[a] < 0) {
+                    set_error("negative strides are not supported");
+                    return OPTK_ERR_INVALID;
+                }
+            small_bytes += ((size_t)extent[f] * (f < OPTK_NUM_FIELDS ? 8 : 1) + 255) & ~(size_t)255;
+        }
+    }
+    size_t image_bytes = 0, plane_elems = 0;
+    if (image) {
+        plane_elems = (size_t)image->n_wavelength * image->n_x * image->n_y;
+        image_bytes += (((size_t)image->n_wavelength + 1) * 8 + 255) & ~(size_t)255;
+        image_bytes += (((size_t)image->n_x + 1) * 8 + 255) & ~(size_t)255;
+        image_bytes += (((size_t)image->n_y + 1) * 8 + 255) & ~(size_t)255;
+        image_bytes += 4 * ((plane_elems * 8 + 255) & ~(size_t)255);
+    }
+    const size_t stats_bytes = 256;
+    rc = pl.small.ensure(small_bytes + image_bytes + stats_bytes);
+    if (rc) return rc;
+
+    cudaStream_t s0 = pl.stream[0];
+    char* cursor = (char*)pl.small.ptr;
+    auto take = [&](size_t bytes) {
+        char* p = cursor;
+        cursor += (bytes + 255) & ~(size_t)255;
+        return (void*)p;
+    };
+
+    P.in = *in;
+    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) {
+        const bool present = f < OPTK_NUM_FIELDS ? true : in->unvignetted != nullptr;
+        if (!present || dense[f]) continue;
+        const size_t bytes = (size_t)extent[f] * (f < OPTK_NUM_FIELDS ? 8 : 1);
+        void* d = take(bytes);
+        const void* h = f < OPTK_NUM_FIELDS ? (const void*)in->field[f] : (const void*)in->unvignetted;
+        OPTK_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s0));
+        if (f < OPTK_NUM_FIELDS) P.in.field[f] = (const double*)d; else P.in.unvignetted = (const uint8_t*)d;
+    }
+    optk_image_t image_dev;
+    if (image) {
+        image_dev = *image;
+        double* ew = (double*)take(((size_t)image->n_wavelength + 1) * 8);
+        double* ex = (double*)take(((size_t)image->n_x + 1) * 8);
+        double* ey = (double*)take(((size_t)image->n_y + 1) * 8);
+        OPTK_CUDA(cudaMemcpyAsync(ew, image->edges_wavelength, ((size_t)image->n_wavelength + 1) * 8,
+                                  cudaMemcpyHostToDevice, s0));
+        OPTK_CUDA(cudaMemcpyAsync(ex, image->edges_x, ((size_t)image->n_x + 1) * 8, cudaMemcpyHostToDevice, s0));
+        OPTK_CUDA(cudaMemcpyAsync(ey, image->edges_y, ((size_t)image->n_y + 1) * 8, cudaMemcpyHostToDevice, s0));
+        image_dev.edges_wavelength = ew;
+        image_dev.edges_x = ex;
+        image_dev.edges_y = ey;
+        void* host_planes[4] = {image->flux, image->moment_real, image->moment_imag, image->counts};
+        void* dev_planes[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int k = 0; k < 4; ++k) {
+            if (!host_planes[k]) continue;
+            dev_planes[k] = take(plane_elems * 8);
+            OPTK_CUDA(cudaMemcpyAsync(dev_planes[k], host_planes[k], plane_elems * 8, cudaMemcpyHostToDevice, s0));
+        }
+        image_dev.flux = (double*)dev_planes[0];
+        image_dev.moment_real = (double*)dev_planes[1];
+        image_dev.moment_imag = (double*)dev_planes[2];
+        image_dev.counts = (unsigned long long*)dev_planes[3];
+        rc = fill_image(&image_dev, &P.image);
+        if (rc) return rc;
+    }
+    optk_trace_stats_t* stats_dev = nullptr;
+    if (stats_host) {
+        stats_dev = (optk_trace_stats_t*)take(sizeof(optk_trace_stats_t));
+        OPTK_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(optk_trace_stats_t), s0));
+    }
+    OPTK_CUDA(cudaStreamSynchronize(s0));
+
+    // --- per-slot slab buffers
+    size_t in_bytes = 0, out_bytes = 0;
+    for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
+        if (dense[f]) in_bytes += (size_t)slab_rays * 8;
+    if (dense[OPTK_NUM_FIELDS]) in_bytes += ((size_t)slab_rays + 255) & ~(size_t)255;
+    if (out) {
+        for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
+            if (out->field[f]) out_bytes += (size_t)slab_rays * 8 * n_out_states;
+        if (out->unvignetted) out_bytes += (((size_t)slab_rays + 255) & ~(size_t)255) * n_out_states;
+    }
+    const int slots = n_slabs < kSlots ? n_slabs : kSlots;
+    for (int k = 0; k < slots; ++k) {
+        rc = pl.in[k].ensure(in_bytes ? in_bytes : 256);
+        if (rc) return rc;
+        rc = pl.out[k].ensure(out_bytes ? out_bytes : 256);
+        if (rc) return rc;
+    }
+
+    for (int a = 0; a < OPTK_MAX_AXES; ++a)
+        P.div[a] = make_fastdiv(a < in->n_axes ? (uint32_t)in->dims[a] : 1u);
+    P.has_image = image ? 1 : 0;
+    P.has_frame = image_frame ? 1 : 0;
+    if (image_frame) P.frame = *image_frame;
+    P.stats = stats_dev;
+    bool every_dense = true;
+    for (int f = 0; f < OPTK_NUM_FIELDS; ++f) every_dense = every_dense && dense[f];
+    if (in->unvignetted) every_dense = every_dense && dense[OPTK_NUM_FIELDS];
+    P.dense_in = every_dense ? 1 : 0;
+
+    const optk_rays_in_t base_in = P.in;
+    for (int slab = 0; slab < n_slabs; ++slab) {
+        const int k = slab % kSlots;
+        cudaStream_t st = pl.stream[k];
+        const long long i0 = (long long)slab * slab_rays;
+        const long long m = (i0 + slab_rays <= n) ? slab_rays : n - i0;
+        // the stream is in order: reusing slot k waits for its previous D2H
+
+        // H2D of the dense inputs of this slab
+        char* cin = (char*)pl.in[k].ptr;
+        P.in = base_in;
+        for (int f = 0; f < OPTK_NUM_FIELDS; ++f) {
+            if (!dense[f]) continue;
+            OPTK_CUDA(cudaMemcpyAsync(cin, in->field[f] + i0, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+            // dense view: element offset == global ray index; bias so that offset i0 + j lands on cin[j]
+            P.in.field[f] = every_dense ? (const double*)cin : (const double*)cin - i0;
+            cin += (size_t)slab_rays * 8;
+        }
+        if (dense[OPTK_NUM_FIELDS]) {
+            OPTK_CUDA(cudaMemcpyAsync(cin, in->unvignetted + i0, (size_t)m, cudaMemcpyHostToDevice, st));
+            P.in.unvignetted = every_dense ? (const uint8_t*)cin : (const uint8_t*)cin - i0;
+        }
+        // outputs of this slab
+        char* cout = (char*)pl.out[k].ptr;
+        memset(&P.out, 0, sizeof(P.out));
+        if (out) {
+            for (int f = 0; f < OPTK_NUM_FIELDS; ++f) {
+                if (!out->field[f]) continue;
+                P.out.field[f] = (double*)cout;
+                cout += (size_t)slab_rays * 8 * n_out_states;
+            }
+            if (out->unvignetted) P.out.unvignetted = (uint8_t*)cout;
+        }
+        P.n_rays = m;
+        P.index_offset = every_dense ? 0 : i0;
+        P.accumulate_stride = accumulate ? slab_rays : 0;
+        rc = launch_trace(P, st);
+        if (rc) return rc;
+        // D2H
+        if (out) {
+            for (int f = 0; f < OPTK_NUM_FIELDS; ++f) {
+                if (!out->field[f]) continue;
+                for (int s = 0; s < n_out_states; ++s)
+                    OPTK_CUDA(cudaMemcpyAsync(out->field[f] + (long long)s * accumulate_stride + i0,
+                                              P.out.field[f] + (long long)s * slab_rays, (size_t)m * 8,
+                                              cudaMemcpyDeviceToHost, st));
+            }
+            if (out->unvignetted)
+                for (int s = 0; s < n_out_states; ++s)
+                    OPTK_CUDA(cudaMemcpyAsync(out->unvignetted + (long long)s * accumulate_stride + i0,
+                                              P.out.unvignetted + (long long)s * slab_rays, (size_t)m,
+                                              cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int k = 0; k < slots; ++k) OPTK_CUDA(cudaStreamSynchronize(pl.stream[k]));
+
+    if (image) {
+        void* host_planes[4] = {image->flux, image->moment_real, image->moment_imag, image->counts};
+        void* dev_planes[4] = {image_dev.flux, image_dev.moment_real, image_dev.moment_imag, image_dev.counts};
+        for (int k = 0; k < 4; ++k)
+            if (host_planes[k])
+                OPTK_CUDA(cudaMemcpyAsync(host_planes[k], dev_planes[k], plane_elems * 8, cudaMemcpyDeviceToHost, s0));
+    }
+    if (stats_host)
+        OPTK_CUDA(cudaMemcpyAsync(stats_host, stats_dev, sizeof(optk_trace_stats_t), cudaMemcpyDeviceToHost, s0));
+    OPTK_CUDA(cudaStreamSynchronize(s0));
+    return OPTK_OK;
+}
+
+OPTK_API int optk_multilayer(const optk_ml_input_t* input, int32_t n_layers, const optk_ml_layer_t* layers,
+                    int32_t n_segments, const optk_ml_segment_t* segments, double* reflectivity_s,
+                    double* reflectivity_p, double* transmissivity_s, double* transmissivity_p, void* stream) {
+    if (!input || !layers || n_layers < 1 || n_layers > OPTK_ML_MAX_LAYERS) {
+        set_error("optk_multilayer: need 1..%d layers (the last one is the substrate)", OPTK_ML_MAX_LAYERS);
+        return OPTK_ERR_INVALID;
+    }
+    if (n_segments < 0 || n_segments > 32 || (n_segments > 0 && !segments)) {
+        set_error("optk_multilayer: n_segments must be in 0..32");
+        return OPTK_ERR_INVALID;
+    }
+    if (input->n_axes < 0 || input->n_axes > OPTK_ML_MAX_AXES) {
+        set_error("optk_multilayer: n_axes must be in 0..%d", OPTK_ML_MAX_AXES);
+        return OPTK_ERR_INVALID;
+    }
+    if (!input->wavelength || !input->direction_re || !input->n_re) {
+        set_error("optk_multilayer: wavelength, direction_re and n_re are required");
+        return OPTK_ERR_INVALID;
+    }
+    static thread_local MultilayerParams P;
+    P.in = *input;
+    long long n = 1;
+    for (int a = 0; a < input->n_axes; ++a) n *= input->dims[a];
+    if (n > 0xffffffffLL) {
+        set_error("optk_multilayer: %lld evaluations exceed 2^32 - 1; split an axis", n);
+        return OPTK_ERR_INVALID;
+    }
+    for (int a = 0; a < OPTK_ML_MAX_AXES; ++a)
+        P.div[a] = make_fastdiv(a < input->n_axes ? (uint32_t)input->dims[a] : 1u);
+    P.n_eval = n;
+    P.n_layers = n_layers;
+    P.n_segments = n_segments;
+    for (int g = 0; g < n_segments; ++g) {
+        const optk_ml_segment_t& s = segments[g];
+        if (s.first < 0 || s.count < 0 || s.first + s.count > n_layers - 1 || s.repeat < 0) {
+            set_error("optk_multilayer: segment %d is out of range", g);
+            return OPTK_ERR_INVALID;
+        }
+        P.segments[g] = s;
+    }
+    for (int j = 0; j < n_layers; ++j)
+        if (!layers[j].n_re) {
+            set_error("optk_multilayer: layer %d has no index of refraction", j);
+            return OPTK_ERR_INVALID;
+        }
+
+    // layer table -> device (stream ordered; the staging buffer is kept per thread)
+    static thread_local DeviceBuffer table_dev;
+    static thread_local std::vector<LayerDev> table_host;
+    static thread_local LayerDev* table_pinned = nullptr;
+    static thread_local size_t table_pinned_count = 0;
+    if (table_pinned_count < (size_t)n_layers) {
+        if (table_pinned) cudaFreeHost(table_pinned);
+        OPTK_CUDA(cudaMallocHost((void**)&table_pinned, sizeof(LayerDev) * OPTK_ML_MAX_LAYERS));
+        table_pinned_count = OPTK_ML_MAX_LAYERS;
+    }
+    int rc = table_dev.ensure(sizeof(LayerDev) * OPTK_ML_MAX_LAYERS);
+    if (rc) return rc;
+    // the pinned staging table may still be in flight from a previous call on this stream
+    OPTK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int j = 0; j < n_layers; ++j) {
+        LayerDev& d = table_pinned[j];
+        const optk_ml_layer_t& l = layers[j];
+        d.n_re = l.n_re;
+        d.n_im = l.n_im;
+        d.thickness = l.thickness;
+        d.width = l.width;
+        for (int a = 0; a < OPTK_ML_MAX_AXES; ++a) {
+            d.n_stride[a] = l.n_stride[a];
+            d.t_stride[a] = l.thickness ? l.thickness_stride[a] : 0;
+            d.w_stride[a] = l.width ? l.width_stride[a] : 0;
+        }
+        d.profile_kind = l.width ? l.profile_kind : 0;
+        d.pad = 0;
+    }
+    OPTK_CUDA(cudaMemcpyAsync(table_dev.ptr, table_pinned, sizeof(LayerDev) * n_layers, cudaMemcpyHostToDevice,
+                              (cudaStream_t)stream));
+    P.layers = (const LayerDev*)table_dev.ptr;
+    P.r_s = reflectivity_s;
+    P.r_p = reflectivity_p;
+    P.t_s = transmissivity_s;
+    P.t_p = transmissivity_p;
+    return launch_multilayer(P, (cudaStream_t)stream);
+}
+
+OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream) {
+    if (!flops_per_second) {
+        set_error("optk_measure_fp64_peak: NULL argument");
+        return OPTK_ERR_INVALID;
+    }
+    return measure_fp64_peak(flops_per_second, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Shared device/host helpers for liboptk (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "optk.h"
+
+namespace optk {
+
+// ---------------------------------------------------------------------------
+// error handling (host)
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define OPTK_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return ::optk::cuda_fail(e__, #call); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// exact division of a 32-bit index by a runtime constant: q = umul64hi(n, M),
+// M = floor((2^64 - 1) / d) + 1, exact for all n < 2^32 and 2 <= d < 2^32.
+// ---------------------------------------------------------------------------
+struct FastDiv {
+    uint64_t magic;
+    uint32_t divisor;
+    uint32_t pad;
+};
+
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.divisor = d;
+    f.pad = 0;
+    f.magic = d > 1 ? (~0ull / d) + 1ull : 0ull;
+    return f;
+}
+
+__device__ __forceinline__ void divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+    q = (uint32_t)__umul64hi((uint64_t)n, f.magic);
+    r = n - q * f.divisor;
+}
+
+// ---------------------------------------------------------------------------
+// fp64 helpers.  "exact" variants use the _rn intrinsics, which nvcc never
+// contracts into FMAs: they reproduce NumPy's operation-by-operation rounding
+// for the edge-sensitive comparisons (aperture edges, bin edges).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// numpy.sign: -1, 0, +1 (NaN -> NaN)
+__device__ __forceinline__ double sign0(double x) {
+    return x != x ? x : (double)((x > 0.0) - (x < 0.0));
+}
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// x -> R x + t
+__device__ __forceinline__ void affine_forward(const optk_affine_t& a, double& x, double& y, double& z,
+                                               bool is_direction) {
+    double rx = a.r[0] * x + a.r[1] * y + a.r[2] * z;
+    double ry = a.r[3] * x + a.r[4] * y + a.r[5] * z;
+    double rz = a.r[6] * x + a.r[7] * y + a.r[8] * z;
+    if (!is_direction) {
+        rx += a.t[0];
+        ry += a.t[1];
+        rz += a.t[2];
+    }
+    x = rx; y = ry; z = rz;
+}
+
+// x -> R^T (x - t)
+__device__ __forceinline__ void affine_inverse(const optk_affine_t& a, double& x, double& y, double& z,
+                                               bool is_direction) {
+    if (!is_direction) {
+        x -= a.t[0];
+        y -= a.t[1];
+        z -= a.t[2];
+    }
+    double rx = a.r[0] * x + a.r[3] * y + a.r[6] * z;
+    double ry = a.r[1] * x + a.r[4] * y + a.r[7] * z;
+    double rz = a.r[2] * x + a.r[5] * y + a.r[8] * z;
+    x = rx; y = ry; z = rz;
+}
+
+}  // namespace optk

@@ -1,0 +1,62 @@
+// Kernel parameter blocks shared by the launchers (trace.cu, multilayer.cu) and
+// the C ABI glue (api.cu).  Passed by value as __grid_constant__ kernel
+// parameters: they live in the constant bank and are broadcast to the warp.
+#pragma once
+#include "common.cuh"
+#include "bin.cuh"
+
+namespace optk {
+
+struct TraceParams {
+    optk_rays_in_t in;
+    optk_rays_out_t out;
+    FastDiv div[OPTK_MAX_AXES];
+    long long n_rays;
+    long long index_offset;  // added to the thread index before decomposing it into grid indices
+    long long accumulate_stride;
+    int32_t n_surf;
+    int32_t accumulate;
+    int32_t dense_in;  // every input is a dense array indexed by the thread index
+    int32_t has_image;
+    int32_t has_frame;
+    int32_t pad;
+    ImageDev image;
+    optk_affine_t frame;
+    optk_trace_stats_t* stats;
+    optk_surface_t surf[OPTK_MAX_SURFACES];
+};
+
+int launch_trace(const TraceParams& P, cudaStream_t stream);
+int launch_bin(long long n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
+               const double* intensity, const uint8_t* unvignetted, const ImageDev& im, cudaStream_t stream);
+
+struct LayerDev {
+    const double* n_re;
+    const double* n_im;
+    const double* thickness;
+    const double* width;
+    long long n_stride[OPTK_ML_MAX_AXES];
+    long long t_stride[OPTK_ML_MAX_AXES];
+    long long w_stride[OPTK_ML_MAX_AXES];
+    int32_t profile_kind;
+    int32_t pad;
+};
+
+struct MultilayerParams {
+    optk_ml_input_t in;
+    FastDiv div[OPTK_ML_MAX_AXES];
+    long long n_eval;
+    const LayerDev* layers;  // device, n_layers entries; the last one is the substrate
+    int32_t n_layers;
+    int32_t n_segments;
+    optk_ml_segment_t segments[32];
+    double* r_s;
+    double* r_p;
+    double* t_s;
+    double* t_p;
+};
+
+int launch_multilayer(const MultilayerParams& P, cudaStream_t stream);
+int measure_fp64_peak(double* flops, cudaStream_t stream);
+
+}  // namespace optk

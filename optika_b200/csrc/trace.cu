@@ -1,0 +1,628 @@
+// Kernel 1: the fused sequential raytrace (sm_100a, fp64).
+//
+// One thread owns one ray and walks the whole surface list, which arrives as a
+// kernel parameter (constant bank, broadcast to the warp).  Ray state stays in
+// registers; per surface the thread runs AbstractSurface.propagate_rays
+// (optika/surfaces.py:123-198): global->local, sag intercept + Beer-Lambert,
+// sag normal, grating equation, index / wavelength rescale, vector Snell,
+// aperture clip, local->global.  Rays touch HBM on entry and exit only (plus one
+// store per surface when accumulating), and optionally never leave the chip:
+// the final rays can be binned straight into the detector image.
+#include "common.cuh"
+#include "bin.cuh"
+#include "params.cuh"
+
+namespace optk {
+
+struct Ray {
+    double w, px, py, pz, dx, dy, dz, intensity, att, n;
+    bool unv;
+};
+
+// ---------------------------------------------------------------------------
+// sag profiles, evaluated in the sag's own frame
+// ---------------------------------------------------------------------------
+
+// Path length t to the surface for a ray o + t u (closed forms), or NaN/inf on a miss.
+__device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, double ox, double oy, double oz,
+                                                       double ux, double uy, double uz) {
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            // optika/sags/_flat.py:58: d = -o.z / u.z
+            return -oz / uz;
+        case OPTK_SAG_SPHERICAL: {
+            // optika/sags/_spherical.py:176-184
+            const double r = S.sag[0];
+            const double pz = oz - r;
+            const double up = ux * ox + uy * oy + uz * pz;
+            const double disc = up * up - (ox * ox + oy * oy + pz * pz - r * r);
+            return -up - sign0(r * uz) * sqrt(disc);
+        }
+        case OPTK_SAG_PARABOLIC: {
+            // optika/sags/_parabolic.py:142-151
+            const double f = S.sag[0];
+            const double uxy2 = ux * ux + uy * uy;
+            if (uxy2 > 1e-10) {
+                const double oyux = oy * ux, oxuy = ox * uy;
+                const double disc = -(oyux * oyux) - oxuy * oxuy + 2 * oy * uy * (ox * ux - 2 * f * uz) +
+                                    4 * f * (oz * uxy2 - ox * ux * uz + f * uz * uz);
+                return (-ox * ux - oy * uy + 2 * f * uz - sign0(f * uz) * sqrt(disc)) / uxy2;
+            }
+            return (ox * ox + oy * oy - 4 * f * oz) / (4 * f * uz);
+        }
+        case OPTK_SAG_CONIC: {
+            // optika/sags/_conic.py:126-162
+            const double c = 1.0 / S.sag[0];
+            const double kp1 = 1.0 + S.sag[1];
+            const double a = c * (ux * ux + uy * uy + kp1 * uz * uz);
+            const double b = 2 * (c * (ox * ux + oy * uy + kp1 * oz * uz) - uz);
+            const double cc = c * (ox * ox + oy * oy + kp1 * oz * oz) - 2 * oz;
+            const double disc = b * b - 4 * a * cc;
+            const bool real = disc >= 0;
+            const double sq_disc = sqrt(real ? disc : 0.0);
+            const bool degenerate = fabs(a) < 1e-12;
+            const double denom = degenerate ? 1.0 : 2 * a;
+            const double t_linear = -cc / b;
+            double t_root[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const double sgn = k == 0 ? -1.0 : 1.0;
+                const double t = degenerate ? t_linear : (-b + sgn * sq_disc) / denom;
+                const double x = ox + ux * t, y = oy + uy * t, z = oz + uz * t;
+                const double r2 = x * x + y * y;
+                const bool on_vertex_sheet = (z * (c * r2 - z)) >= 0;
+                t_root[k] = (real && on_vertex_sheet) ? t : INFINITY;
+            }
+            return fabs(t_root[0]) <= fabs(t_root[1]) ? t_root[0] : t_root[1];
+        }
+        case OPTK_SAG_CYLINDRICAL: {
+            // optika/sags/_cylindrical.py:126-152, cross products with a = y-hat written out
+            const double r = S.sag[0];
+            const double bx = -ox, bz = r - oz;
+            const double ncx = -uz, ncz = ux;
+            const double nca2 = ncx * ncx + ncz * ncz;
+            const double negative_b = ncx * (-bz) + ncz * bx;
+            const double dot = bx * ncx + bz * ncz;
+            const double disc = nca2 * (r * r) - dot * dot;
+            if (disc > 0) return (negative_b - sign0(r * uz) * sqrt(disc)) / nca2;
+            return -oz / uz;
+        }
+    }
+    return NAN;
+}
+
+// Toroid: z and its gradient (optika/sags/_toroidal.py:38-88).
+__device__ __forceinline__ void toroid_eval(double c, double r, double x, double y, double& z, double& dzdx,
+                                            double& dzdy) {
+    const double y2 = y * y;
+    const double g = sqrt(1.0 - c * c * y2);
+    const double zy = c * y2 / (1.0 + g);
+    const double rz = r - zy;
+    const double f = sqrt(rz * rz - x * x);
+    z = r - f;
+    const double inv_f = 1.0 / f;
+    dzdx = x * inv_f;
+    dzdy = rz * (c * y / g) * inv_f;
+}
+
+// Unit normal at a point of the sag frame (not rotated back, as in the reference).
+__device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, double y, double& nx, double& ny,
+                                           double& nz) {
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            nx = 0.0; ny = 0.0; nz = -1.0;  // optika/sags/_flat.py:43-47
+            return;
+        case OPTK_SAG_SPHERICAL: {
+            // optika/sags/_spherical.py:141-146
+            const double c = 1.0 / S.sag[0];
+            nx = c * x;
+            ny = c * y;
+            nz = -sqrt(1.0 - nx * nx - ny * ny);
+            return;
+        }
+        case OPTK_SAG_CYLINDRICAL: {
+            // optika/sags/_cylindrical.py:107-113
+            nx = x / S.sag[0];
+            ny = 0.0;
+            nz = -sqrt(1.0 - nx * nx);
+            return;
+        }
+        case OPTK_SAG_PARABOLIC: {
+            // optika/sags/_parabolic.py:56-63: (x, y, -R) / sqrt((x/R)^2 + (y/R)^2 + 1) / R
+            const double r = 2.0 * S.sag[0];
+            const double xr = x / r, yr = y / r;
+            const double inv = 1.0 / sqrt(xr * xr + yr * yr + 1.0);
+            nx = xr * inv;
+            ny = yr * inv;
+            nz = -inv;
+            return;
+        }
+        case OPTK_SAG_CONIC: {
+            // optika/sags/_conic.py:69-81
+            const double c = 1.0 / S.sag[0];
+            const double g = sqrt(1.0 - (1.0 + S.sag[1]) * c * c * (x * x + y * y));
+            const double dzdx = c * x / g, dzdy = c * y / g;
+            const double inv = 1.0 / sqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+            nx = dzdx * inv;
+            ny = dzdy * inv;
+            nz = -inv;
+            return;
+        }
+        case OPTK_SAG_TOROIDAL: {
+            // optika/sags/_toroidal.py:71-88
+            double z, dzdx, dzdy;
+            toroid_eval(1.0 / S.sag[0], S.sag[2], x, y, z, dzdx, dzdy);
+            const double inv = 1.0 / sqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+            nx = dzdx * inv;
+            ny = dzdy * inv;
+            nz = -inv;
+            return;
+        }
+    }
+    nx = ny = nz = NAN;
+}
+
+// z(x, y) in the sag frame, for OPTK_STAGE_SAG_OUT.
+__device__ __forceinline__ double sag_value(const optk_surface_t& S, double x, double y) {
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            return 0.0;
+        case OPTK_SAG_SPHERICAL: {
+            const double c = 1.0 / S.sag[0];
+            const double r2 = x * x + y * y;
+            return c * r2 / (1.0 + sqrt(1.0 - c * c * r2));
+        }
+        case OPTK_SAG_CYLINDRICAL: {
+            const double c = 1.0 / S.sag[0];
+            const double r2 = x * x;
+            return c * r2 / (1.0 + sqrt(1.0 - c * c * r2));
+        }
+        case OPTK_SAG_PARABOLIC:
+        case OPTK_SAG_CONIC: {
+            const double radius = S.sag_kind == OPTK_SAG_PARABOLIC ? 2.0 * S.sag[0] : S.sag[0];
+            const double conic = S.sag_kind == OPTK_SAG_PARABOLIC ? -1.0 : S.sag[1];
+            const double c = 1.0 / radius;
+            const double r2 = x * x + y * y;
+            return c * r2 / (1.0 + sqrt(1.0 - (1.0 + conic) * c * c * r2));
+        }
+        case OPTK_SAG_TOROIDAL: {
+            double z, dzdx, dzdy;
+            toroid_eval(1.0 / S.sag[0], S.sag[2], x, y, z, dzdx, dzdy);
+            return z;
+        }
+    }
+    return NAN;
+}
+
+// ---------------------------------------------------------------------------
+// rulings: kappa = spacing_(position, normal)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ipow(double x, int p) {
+    bool neg = p < 0;
+    unsigned e = neg ? (unsigned)(-p) : (unsigned)p;
+    double r = 1.0, b = x;
+    while (e) {
+        if (e & 1u) r *= b;
+        b *= b;
+        e >>= 1;
+    }
+    return neg ? 1.0 / r : r;
+}
+
+__device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px, double py, double pz, double nx,
+                                              double ny, double nz, double& kx, double& ky, double& kz) {
+    switch (S.ruling_kind) {
+        case OPTK_RULING_CONSTANT: {
+            // optika/rulings/_spacing.py:69-74
+            const double c = S.ruling_coeff[0];
+            kx = c * S.ruling_normal[0];
+            ky = c * S.ruling_normal[1];
+            kz = c * S.ruling_normal[2];
+            return;
+        }
+        case OPTK_RULING_POLYNOMIAL: {
+            // optika/rulings/_spacing.py:109-128
+            if (S.flags & OPTK_F_RULING_TRANSFORM) affine_forward(S.ruling_transform, px, py, pz, false);
+            const double x = px * S.ruling_normal[0] + py * S.ruling_normal[1] + pz * S.ruling_normal[2];
+            double d = 0.0;
+            for (int k = 0; k < S.n_coeff; ++k) d += S.ruling_coeff[k] * ipow(x, S.ruling_power[k]);
+            kx = d * S.ruling_normal[0];
+            ky = d * S.ruling_normal[1];
+            kz = d * S.ruling_normal[2];
+            return;
+        }
+        case OPTK_RULING_HOLOGRAPHIC: {
+            // optika/rulings/_spacing.py:295-328
+            const double d1 = (S.flags & OPTK_F_HOLO_DIVERGING_1) ? 1.0 : -1.0;
+            const double d2 = (S.flags & OPTK_F_HOLO_DIVERGING_2) ? 1.0 : -1.0;
+            double ax = px - S.holo_x1[0], ay = py - S.holo_x1[1], az = pz - S.holo_x1[2];
+            double bx = px - S.holo_x2[0], by = py - S.holo_x2[1], bz = pz - S.holo_x2[2];
+            const double ia = d1 / sqrt(ax * ax + ay * ay + az * az);
+            const double ib = d2 / sqrt(bx * bx + by * by + bz * bz);
+            const double rx = ax * ia - bx * ib, ry = ay * ia - by * ib, rz = az * ia - bz * ib;
+            // aq = n x dr
+            const double qx = ny * rz - nz * ry, qy = nz * rx - nx * rz, qz = nx * ry - ny * rx;
+            // spacing * (q/a) x n  with spacing = w / a   =>  (w / a^2) (aq x n)
+            const double s = S.holo_wavelength / (qx * qx + qy * qy + qz * qz);
+            kx = s * (qy * nz - qz * ny);
+            ky = s * (qz * nx - qx * nz);
+            kz = s * (qx * ny - qy * nx);
+            return;
+        }
+    }
+    kx = ky = kz = NAN;
+}
+
+// ---------------------------------------------------------------------------
+// apertures (edge-sensitive: products and sums are not contracted)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double py_mod(double a, double b) {
+    // numpy's float remainder: result takes the sign of the divisor
+    double r = fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+
+__device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x, double y, double z) {
+    if (S.flags & OPTK_F_APERTURE_TRANSFORM) affine_inverse(S.aperture_transform, x, y, z, false);
+    bool mask = false;
+    switch (S.aperture_kind) {
+        case OPTK_APERTURE_CIRCULAR:
+            // optika/apertures/_apertures.py:309: position.xy.length <= radius
+            mask = sqrt(add_rn(mul_rn(x, x), mul_rn(y, y))) <= S.aperture[0];
+            break;
+        case OPTK_APERTURE_RECTANGULAR:
+            // optika/apertures/_apertures.py:962-963
+            mask = (-S.aperture[0] <= x) && (x <= S.aperture[0]) && (-S.aperture[1] <= y) && (y <= S.aperture[1]);
+            break;
+        case OPTK_APERTURE_ELLIPTICAL: {
+            // optika/apertures/_apertures.py:657
+            const double a = x / S.aperture[0], b = y / S.aperture[1];
+            mask = add_rn(mul_rn(a, a), mul_rn(b, b)) <= 1.0;
+            break;
+        }
+        case OPTK_APERTURE_SECTOR: {
+            // optika/apertures/_apertures.py:466-476
+            const bool mask_radius = sqrt(add_rn(mul_rn(x, x), mul_rn(y, y))) <= S.aperture[0];
+            const double a0 = S.aperture[1], a1 = S.aperture[2];
+            const double angle = atan2(y, x);
+            const double two_pi = 6.283185307179586;
+            const double ap = py_mod(angle, two_pi);
+            const double an = py_mod(angle, -two_pi);
+            mask = mask_radius && (((a0 < ap) && (ap < a1)) || ((a0 < an) && (an < a1)));
+            break;
+        }
+        case OPTK_APERTURE_POLYGON: {
+            // na.geometry.point_in_polygon (third party): even-odd crossing, boundary inside
+            if (!(S.flags & OPTK_F_APERTURE_ACTIVE)) return true;  // _apertures.py:751, 775-776
+            bool inside = false, on_edge = false;
+            const int nv = S.n_vertices;
+            double x0 = S.vertices_x[nv - 1], y0 = S.vertices_y[nv - 1];
+            for (int i = 0; i < nv; ++i) {
+                const double x1 = S.vertices_x[i], y1 = S.vertices_y[i];
+                const double ex = sub_rn(x1, x0), ey = sub_rn(y1, y0);
+                const double cross = sub_rn(mul_rn(ex, sub_rn(y, y0)), mul_rn(ey, sub_rn(x, x0)));
+                const bool within = (fmin(x0, x1) <= x) && (x <= fmax(x0, x1)) && (fmin(y0, y1) <= y) &&
+                                    (y <= fmax(y0, y1));
+                on_edge |= (cross == 0.0) && within;
+                const bool straddles = (y0 > y) != (y1 > y);
+                const double x_cross = add_rn(x0, mul_rn(sub_rn(y, y0), ex) / ey);
+                inside ^= straddles && (x < x_cross);
+                x0 = x1;
+                y0 = y1;
+            }
+            mask = inside || on_edge;
+            break;
+        }
+        default:
+            return true;
+    }
+    if (S.flags & OPTK_F_APERTURE_INVERTED) mask = !mask;
+    if (!(S.flags & OPTK_F_APERTURE_ACTIVE)) mask = true;
+    return mask;
+}
+
+// ---------------------------------------------------------------------------
+// one surface: AbstractSurface.propagate_rays, optika/surfaces.py:123-198
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& r, unsigned& newton_iterations) {
+    const int stages = S.stages;
+    const int flags = S.flags;
+
+    // 1. global -> surface-local (surfaces.py:141-142)
+    if (flags & OPTK_F_TRANSFORM) {
+        affine_inverse(S.transform, r.px, r.py, r.pz, false);
+        affine_inverse(S.transform, r.dx, r.dy, r.dz, true);
+    }
+
+    // sag frame copy of the ray (sag.transformation, e.g. optika/sags/_spherical.py:153-154)
+    double qx = r.px, qy = r.py, qz = r.pz;
+    double vx = r.dx, vy = r.dy, vz = r.dz;
+    const bool sag_t = flags & OPTK_F_SAG_TRANSFORM;
+    if (sag_t) {
+        affine_inverse(S.sag_transform, qx, qy, qz, false);
+        affine_inverse(S.sag_transform, vx, vy, vz, true);
+    }
+
+    // 2. sag.propagate_rays: intercept (+ Beer-Lambert)  (surfaces.py:144)
+    if (stages & OPTK_STAGE_INTERCEPT) {
+        double t;
+        if (S.sag_kind == OPTK_SAG_TOROIDAL) {
+            // AbstractSag.intercept, optika/sags/_abc.py:76-107: root of
+            // f(t) = (o + t u).z - sag(T^-1 (o + t u)) from t = 0.  Newton with the
+            // analytic gradient, iterated to convergence (the reference's secant
+            // stops at |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
+            const double c = 1.0 / S.sag[0], rr = S.sag[2];
+            t = 0.0;
+            for (int it = 0; it < 64; ++it) {
+                double z, dzdx, dzdy;
+                toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
+                const double f = (r.pz + r.dz * t) - z;
+                const double df = r.dz - (dzdx * vx + dzdy * vy);
+                const double step = f / df;
+                t -= step;
+                ++newton_iterations;
+                if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(t)))) break;
+            }
+        } else {
+            t = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
+        }
+        const double nx_ = r.px + r.dx * t, ny_ = r.py + r.dy * t, nz_ = r.pz + r.dz * t;
+        if (stages & OPTK_STAGE_ATTENUATE) {
+            // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|)
+            const double ex = nx_ - r.px, ey = ny_ - r.py, ez = nz_ - r.pz;
+            const double len2 = ex * ex + ey * ey + ez * ez;
+            if (r.att != 0.0) {
+                r.intensity = exp(-r.att * sqrt(len2)) * r.intensity;
+            } else if (!(len2 <= 1.7976931348623157e308)) {
+                r.intensity = NAN;  // exp(-0 * inf) = exp(-0 * nan) = nan in the reference
+            }
+        }
+        r.px = nx_; r.py = ny_; r.pz = nz_;
+        qx += vx * t; qy += vy * t; qz += vz * t;
+        if (sag_t) {  // keep the sag-frame position consistent with the surface-frame one
+            qx = r.px; qy = r.py; qz = r.pz;
+            affine_inverse(S.sag_transform, qx, qy, qz, false);
+        }
+    }
+
+    // 3. normal = sag.normal(position_1)  (surfaces.py:146-148)
+    double nx, ny, nz;
+    sag_normal(S, qx, qy, nx, ny, nz);
+
+    if (stages & OPTK_STAGE_SAG_OUT) {
+        double z = sag_value(S, qx, qy);
+        if (S.sag_kind == OPTK_SAG_FLAT && sag_t) {
+            // optika/sags/_flat.py:31-41: z of the transformed (x, y, 0)
+            double tx = qx, ty = qy, tz = 0.0;
+            affine_forward(S.sag_transform, tx, ty, tz, false);
+            z = tz;
+        }
+        r.pz = z;
+    }
+    if (stages & OPTK_STAGE_NORMAL_OUT) {
+        r.dx = nx; r.dy = ny; r.dz = nz;
+    }
+
+    // 4. rulings.incident_effective  (surfaces.py:150-154, rulings/_rulings.py:107-128, 187-204)
+    if ((stages & (OPTK_STAGE_RULINGS | OPTK_STAGE_KAPPA_OUT)) && S.ruling_kind != OPTK_RULING_NONE) {
+        double kx, ky, kz;
+        ruling_vector(S, r.px, r.py, r.pz, nx, ny, nz, kx, ky, kz);
+        if (stages & OPTK_STAGE_KAPPA_OUT) {
+            r.dx = kx; r.dy = ky; r.dz = kz;
+        } else {
+            // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
+            const double k2 = kx * kx + ky * ky + kz * kz;
+            const double s = sign0(r.dx * nx + r.dy * ny + r.dz * nz);
+            const double f = s * S.ruling_order * r.w / (r.n * k2);
+            r.dx += f * kx;
+            r.dy += f * ky;
+            r.dz += f * kz;
+        }
+    }
+
+    // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
+    if (stages & OPTK_STAGE_REFRACT) {
+        const double n1 = r.n;
+        double n2;
+        const bool mirror = S.material_kind == OPTK_MAT_MIRROR;
+        if (S.material_kind == OPTK_MAT_GLASS) {
+            // optika/materials/_materials.py:428-438
+            const double w2 = r.w * r.w;
+            n2 = sqrt(1.0 + (S.material[0] * w2 / (w2 - S.material[3]) + S.material[1] * w2 / (w2 - S.material[4]) +
+                             S.material[2] * w2 / (w2 - S.material[5])));
+        } else if (mirror) {
+            n2 = n1;  // _materials.py:135-139
+        } else {
+            n2 = 1.0;  // _materials.py:95-99
+        }
+        // optika/materials/_snells_law.py:341-366
+        const double a2 = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
+        const double au = r.dx * nx + r.dy * ny + r.dz * nz;
+        double ratio = 1.0, inv_r2 = 1.0;
+        if (n1 != n2) {  // n1 == n2: r = 1 and 1 / r^2 = 1 exactly, skip the divisions
+            ratio = n1 / n2;
+            inv_r2 = 1.0 / (ratio * ratio);
+            r.w = r.w / ratio;  // surfaces.py:165
+        }
+        const double sgn = -copysign(1.0, au);
+        const double d = -au + sgn * (mirror ? 1.0 : -1.0) * sqrt(inv_r2 + au * au - a2);
+        r.dx = ratio * (r.dx + d * nx);
+        r.dy = ratio * (r.dy + d * ny);
+        r.dz = ratio * (r.dz + d * nz);
+        // efficiency = 1 for Vacuum / Mirror / Glass and ideal Rulings (surfaces.py:175-179)
+        if (!mirror) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
+        r.n = n2;
+    }
+
+    // 9. aperture.clip_rays on the outgoing ray, local coordinates  (surfaces.py:192-193)
+    if ((stages & OPTK_STAGE_CLIP) && S.aperture_kind != OPTK_APERTURE_NONE) {
+        bool m;
+        if (flags & OPTK_F_APERTURE_ANGULAR)
+            m = aperture_test(S, r.dx, r.dy, r.dz);  // dimensionless aperture: test the direction
+        else
+            m = aperture_test(S, r.px, r.py, r.pz);
+        r.unv = r.unv && m;
+    }
+
+    // 10. local -> global  (surfaces.py:195-196)
+    if (flags & OPTK_F_TRANSFORM) {
+        affine_forward(S.transform, r.px, r.py, r.pz, false);
+        affine_forward(S.transform, r.dx, r.dy, r.dz, true);
+    }
+}
+
+__device__ __forceinline__ void store_ray(const optk_rays_out_t& out, long long o, const Ray& r) {
+    if (out.field[OPTK_WAVELENGTH]) out.field[OPTK_WAVELENGTH][o] = r.w;
+    if (out.field[OPTK_PX]) out.field[OPTK_PX][o] = r.px;
+    if (out.field[OPTK_PY]) out.field[OPTK_PY][o] = r.py;
+    if (out.field[OPTK_PZ]) out.field[OPTK_PZ][o] = r.pz;
+    if (out.field[OPTK_DX]) out.field[OPTK_DX][o] = r.dx;
+    if (out.field[OPTK_DY]) out.field[OPTK_DY][o] = r.dy;
+    if (out.field[OPTK_DZ]) out.field[OPTK_DZ][o] = r.dz;
+    if (out.field[OPTK_INTENSITY]) out.field[OPTK_INTENSITY][o] = r.intensity;
+    if (out.field[OPTK_ATTENUATION]) out.field[OPTK_ATTENUATION][o] = r.att;
+    if (out.field[OPTK_INDEX_REFRACTION]) out.field[OPTK_INDEX_REFRACTION][o] = r.n;
+    if (out.unvignetted) out.unvignetted[o] = r.unv ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams P) {
+    __shared__ ImageGuess guess;
+    if (P.has_image) image_guess_init(P.image, &guess);
+
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < P.n_rays;
+    unsigned newton_iterations = 0;
+    Ray r = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, false};
+
+    if (valid) {
+        if (P.dense_in) {
+            r.w = __ldg(P.in.field[OPTK_WAVELENGTH] + i);
+            r.px = __ldg(P.in.field[OPTK_PX] + i);
+            r.py = __ldg(P.in.field[OPTK_PY] + i);
+            r.pz = __ldg(P.in.field[OPTK_PZ] + i);
+            r.dx = __ldg(P.in.field[OPTK_DX] + i);
+            r.dy = __ldg(P.in.field[OPTK_DY] + i);
+            r.dz = __ldg(P.in.field[OPTK_DZ] + i);
+            r.intensity = __ldg(P.in.field[OPTK_INTENSITY] + i);
+            r.att = __ldg(P.in.field[OPTK_ATTENUATION] + i);
+            r.n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + i);
+            r.unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + i) != 0) : true;
+        } else {
+            // broadcast view: decompose the flat index in C order of dims
+            long long off[OPTK_NUM_FIELDS + 1];
+#pragma unroll
+            for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] = 0;
+            uint32_t rem = (uint32_t)(i + P.index_offset);
+            for (int a = P.in.n_axes - 1; a >= 0; --a) {
+                uint32_t q, idx;
+                if (a == 0) {
+                    idx = rem;
+                } else {
+                    divmod(rem, P.div[a], q, idx);
+                    rem = q;
+                }
+#pragma unroll
+                for (int f = 0; f < OPTK_NUM_FIELDS; ++f) off[f] += (long long)idx * P.in.stride[f][a];
+                off[OPTK_NUM_FIELDS] += (long long)idx * P.in.mask_stride[a];
+            }
+            r.w = __ldg(P.in.field[OPTK_WAVELENGTH] + off[OPTK_WAVELENGTH]);
+            r.px = __ldg(P.in.field[OPTK_PX] + off[OPTK_PX]);
+            r.py = __ldg(P.in.field[OPTK_PY] + off[OPTK_PY]);
+            r.pz = __ldg(P.in.field[OPTK_PZ] + off[OPTK_PZ]);
+            r.dx = __ldg(P.in.field[OPTK_DX] + off[OPTK_DX]);
+            r.dy = __ldg(P.in.field[OPTK_DY] + off[OPTK_DY]);
+            r.dz = __ldg(P.in.field[OPTK_DZ] + off[OPTK_DZ]);
+            r.intensity = __ldg(P.in.field[OPTK_INTENSITY] + off[OPTK_INTENSITY]);
+            r.att = __ldg(P.in.field[OPTK_ATTENUATION] + off[OPTK_ATTENUATION]);
+            r.n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + off[OPTK_INDEX_REFRACTION]);
+            r.unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + off[OPTK_NUM_FIELDS]) != 0) : true;
+        }
+
+        for (int s = 0; s < P.n_surf; ++s) {
+            surface_propagate(P.surf[s], r, newton_iterations);
+            if (P.accumulate) store_ray(P.out, (long long)s * P.accumulate_stride + i, r);
+        }
+        if (!P.accumulate) store_ray(P.out, i, r);
+    }
+
+    if (P.has_image) {
+        // AbstractImagingSensor.collect on the final rays in sensor-local coordinates
+        // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
+        // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
+        double x = r.px, y = r.py, z = r.pz, cx = r.dx, cy = r.dy, cz = r.dz;
+        if (valid && P.has_frame) {
+            affine_inverse(P.frame, x, y, z, false);
+            affine_inverse(P.frame, cx, cy, cz, true);
+        }
+        image_bin_ray(P.image, guess, valid, r.w, x, y, cz, 0.0, r.intensity, r.unv);
+    }
+
+    if (P.stats) {
+        const unsigned full = 0xffffffffu;
+        unsigned n_unv = __popc(__ballot_sync(full, valid && r.unv));
+        unsigned n_val = __popc(__ballot_sync(full, valid));
+        unsigned n_it = __reduce_add_sync(full, newton_iterations);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&P.stats->n_rays, (unsigned long long)n_val);
+            atomicAdd(&P.stats->n_unvignetted, (unsigned long long)n_unv);
+            if (n_it) atomicAdd(&P.stats->n_newton_iterations, (unsigned long long)n_it);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------
+int launch_trace(const TraceParams& P, cudaStream_t stream) {
+    if (P.n_rays <= 0) return OPTK_OK;
+    const int block = 256;
+    const long long grid = (P.n_rays + block - 1) / block;
+    if (grid > 0x7fffffffLL) {
+        set_error("optk_trace: too many rays for one launch (%lld)", P.n_rays);
+        return OPTK_ERR_INVALID;
+    }
+    trace_kernel<<<(unsigned)grid, block, 0, stream>>>(P);
+    OPTK_CUDA(cudaGetLastError());
+    return OPTK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// standalone binning kernel (kernel 2) for rays already in sensor coordinates
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bin_kernel(long long n_rays, const double* __restrict__ wavelength, const double* __restrict__ x,
+           const double* __restrict__ y, const double* __restrict__ dz, const double* __restrict__ intensity,
+           const uint8_t* __restrict__ unvignetted, const __grid_constant__ ImageDev im) {
+    __shared__ ImageGuess guess;
+    image_guess_init(im, &guess);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n_rays;
+    double w = 0, px = 0, py = 0, c = 1.0, in = 0;
+    bool unv = false;
+    if (valid) {
+        w = __ldg(wavelength + i);
+        px = __ldg(x + i);
+        py = __ldg(y + i);
+        c = dz ? __ldg(dz + i) : 1.0;
+        in = intensity ? __ldg(intensity + i) : 1.0;
+        unv = unvignetted ? (__ldg(unvignetted + i) != 0) : true;
+    }
+    image_bin_ray(im, guess, valid, w, px, py, c, 0.0, in, unv);
+}
+
+int launch_bin(long long n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
+               const double* intensity, const uint8_t* unvignetted, const ImageDev& im, cudaStream_t stream) {
+    if (n_rays <= 0) return OPTK_OK;
+    const int block = 256;
+    const long long grid = (n_rays + block - 1) / block;
+    if (grid > 0x7fffffffLL) {
+        set_error("optk_bin: too many rays for one launch (%lld)", n_rays);
+        return OPTK_ERR_INVALID;
+    }
+    bin_kernel<<<(unsigned)grid, block, 0, stream>>>(n_rays, wavelength, x, y, dz, intensity, unvignetted, im);
+    OPTK_CUDA(cudaGetLastError());
+    return OPTK_OK;
+}
+
+}  // namespace optk

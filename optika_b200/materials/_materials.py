@@ -1,0 +1,101 @@
+"""
+Optical materials: what happens to a ray when it meets a surface.
+
+Mirrors ``optika.materials`` (``optika/materials/_materials.py``): `Vacuum`
+(``:82-116``), `Mirror` (``:120-175``), `Glass` with the three-term Sellmeier
+equation (``:309-455``).  The classes hold parameters; index of refraction,
+attenuation, efficiency and the mirror flag are evaluated per ray inside the
+fused CUDA kernel.
+"""
+
+from __future__ import annotations
+import dataclasses
+from .. import named as na
+from .. import units as u
+
+__all__ = ["AbstractMaterial", "Vacuum", "AbstractMirror", "Mirror", "Glass"]
+
+
+@dataclasses.dataclass(eq=False)
+class AbstractMaterial:
+    """Interface of an optical material (``_materials.py:24-79``)."""
+
+    @property
+    def transformation(self) -> None:
+        return None
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return {}
+
+    @property
+    def is_mirror(self) -> bool:
+        return False
+
+
+@dataclasses.dataclass(eq=False)
+class Vacuum(AbstractMaterial):
+    """Empty space: n = 1, no attenuation, unit efficiency (``_materials.py:82-116``)."""
+
+
+@dataclasses.dataclass(eq=False)
+class AbstractMirror(AbstractMaterial):
+    """Reflects; index and attenuation pass through (``_materials.py:120-157``)."""
+
+    @property
+    def is_mirror(self) -> bool:
+        return True
+
+
+@dataclasses.dataclass(eq=False)
+class Mirror(AbstractMirror):
+    """An ideal mirror with unit efficiency (``_materials.py:160-175``)."""
+
+    substrate: object = None
+
+
+@dataclasses.dataclass(eq=False)
+class Glass(AbstractMaterial):
+    """
+    Transparent glass following the three-term Sellmeier equation
+    (``_materials.py:309-455``).  ``c1..c3`` are in mm^2 (use ``u.um ** 2``).
+    As in the reference, the equation is evaluated on ``rays.wavelength``,
+    which is the in-medium wavelength after a previous refraction.
+    """
+
+    b1: float | na.ScalarArray = 0
+    b2: float | na.ScalarArray = 0
+    b3: float | na.ScalarArray = 0
+    c1: float | na.ScalarArray = 0
+    c2: float | na.ScalarArray = 0
+    c3: float | na.ScalarArray = 0
+
+    @classmethod
+    def n_bk7(cls) -> "Glass":
+        """SCHOTT N-BK7 (``_materials.py:382-396``)."""
+        return cls(
+            b1=1.03961212,
+            b2=0.231792344,
+            b3=1.01046945,
+            c1=0.00600069867 * u.um**2,
+            c2=0.0200179144 * u.um**2,
+            c3=103.560653 * u.um**2,
+        )
+
+    @classmethod
+    def f2(cls) -> "Glass":
+        """SCHOTT F2 (``_materials.py:398-412``)."""
+        return cls(
+            b1=1.34533359,
+            b2=0.209073176,
+            b3=0.937357162,
+            c1=0.00997743871 * u.um**2,
+            c2=0.0470450767 * u.um**2,
+            c3=111.886764 * u.um**2,
+        )
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(
+            *[na.shape(p) for p in (self.b1, self.b2, self.b3, self.c1, self.c2, self.c3)]
+        )

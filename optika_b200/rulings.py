@@ -1,0 +1,141 @@
+"""
+Diffraction-grating rulings.
+
+Host-side descriptions with the field names of ``optika.rulings`` (reference:
+``optika/rulings/_rulings.py:131-251`` and ``optika/rulings/_spacing.py``).
+The grating equation is applied inside the fused CUDA kernel as an
+"effective incident direction" that is then fed to Snell's law, exactly as the
+reference does (``optika/rulings/_rulings.py:24-128``, ``optika/surfaces.py:150-154``).
+"""
+
+from __future__ import annotations
+import dataclasses
+from . import named as na
+from .transformations import AbstractTransformation
+
+__all__ = [
+    "AbstractRulingSpacing",
+    "ConstantRulingSpacing",
+    "Polynomial1dRulingSpacing",
+    "HolographicRulingSpacing",
+    "AbstractRulings",
+    "Rulings",
+]
+
+
+@dataclasses.dataclass(eq=False)
+class AbstractRulingSpacing:
+    """Interface: local ruling vector at a point (``optika/rulings/_spacing.py:14-41``)."""
+
+    def __call__(self, position: na.Cartesian3dVectorArray, normal: na.Cartesian3dVectorArray):
+        from . import _engine
+
+        return _engine.ruling_vector(self, position, normal)
+
+
+@dataclasses.dataclass(eq=False)
+class ConstantRulingSpacing(AbstractRulingSpacing):
+    """Constant spacing (``optika/rulings/_spacing.py:45-74``)."""
+
+    constant: float | na.ScalarArray = 0
+    normal: na.Cartesian3dVectorArray = dataclasses.field(
+        default_factory=lambda: na.Cartesian3dVectorArray(1, 0, 0)
+    )
+
+    @property
+    def transformation(self) -> None:
+        return None
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(na.shape(self.constant), na.shape(self.normal))
+
+
+@dataclasses.dataclass(eq=False)
+class Polynomial1dRulingSpacing(AbstractRulingSpacing):
+    """
+    Variable line spacing ``d(x) = sum_k c_k x^k`` with ``x = position . normal``
+    (``optika/rulings/_spacing.py:78-128``).  `coefficients` maps the integer
+    power ``k`` to ``c_k`` in mm^(1-k); `transformation` is applied (forwards) to
+    the position before the polynomial is evaluated.
+    """
+
+    coefficients: dict[int, float | na.ScalarArray] = None
+    normal: na.Cartesian3dVectorArray = dataclasses.field(
+        default_factory=lambda: na.Cartesian3dVectorArray(1, 0, 0)
+    )
+    transformation: None | AbstractTransformation = None
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(
+            *[na.shape(c) for c in self.coefficients.values()],
+            na.shape(self.normal),
+            na.shape(self.transformation),
+        )
+
+
+@dataclasses.dataclass(eq=False)
+class HolographicRulingSpacing(AbstractRulingSpacing):
+    """
+    Rulings recorded by the interference of two beams originating at `x1`, `x2`
+    (``optika/rulings/_spacing.py:132-328``).  As in the reference, the declared
+    `transformation` field is not applied by ``__call__`` (``_spacing.py:295-328``).
+    """
+
+    x1: na.Cartesian3dVectorArray = None
+    x2: na.Cartesian3dVectorArray = None
+    wavelength: float | na.ScalarArray = 0
+    is_diverging_1: bool | na.ScalarArray = True
+    is_diverging_2: bool | na.ScalarArray = False
+    transformation: None | AbstractTransformation = None
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(
+            na.shape(self.x1),
+            na.shape(self.x2),
+            na.shape(self.wavelength),
+            na.shape(self.is_diverging_1),
+            na.shape(self.is_diverging_2),
+        )
+
+
+@dataclasses.dataclass(eq=False)
+class AbstractRulings:
+    """Interface of a ruled surface (``optika/rulings/_rulings.py:131-221``)."""
+
+    @property
+    def spacing_(self) -> AbstractRulingSpacing:
+        """`spacing` normalised to an :class:`AbstractRulingSpacing` (``_rulings.py:156-168``)."""
+        spacing = self.spacing
+        if not isinstance(spacing, AbstractRulingSpacing):
+            spacing = ConstantRulingSpacing(
+                constant=spacing,
+                normal=na.Cartesian3dVectorArray(1, 0, 0),
+            )
+        return spacing
+
+    def incident_effective(self, rays, normal: na.Cartesian3dVectorArray):
+        """Effective incident direction (``optika/rulings/_rulings.py:170-204``)."""
+        from . import _engine
+
+        return _engine.rulings_incident_effective(self, rays, normal)
+
+
+@dataclasses.dataclass(eq=False)
+class Rulings(AbstractRulings):
+    """Ideal rulings with unit efficiency in every order (``_rulings.py:224-251``)."""
+
+    spacing: float | na.ScalarArray | AbstractRulingSpacing = None
+    diffraction_order: int | na.ScalarArray = 1
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(
+            na.shape(self.spacing),
+            na.shape(self.diffraction_order),
+        )
+
+    def efficiency(self, rays, normal) -> float:
+        return 1
