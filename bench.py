@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""
+bench.py -- ray-surface intercepts/s of the fused sequential raytrace on B200.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d cfg 2): spherical
+concave grating spectrograph with a constant line-spacing ruling,
+100 x 100 field x 100 x 100 pupil = 1e8 rays x 64 wavelengths, 3 surfaces
+(object, grating, sensor), fp64.
+
+One "step" is one pass of the hot path over the whole batch: 64 launches of the
+fused trace kernel, one per wavelength slab of 1e8 rays.
+
+* ``value``     device-resident: the 1e8-ray slab is a dense structure of arrays
+                in HBM (81 B/ray read, 81 B/ray written = 162 algorithmic bytes
+                per ray, HBM-bound; every launch streams 16 GB, far more than L2).
+* ``e2e``       the same metric through the public API with HOST buffers:
+                ``SequentialSystem.image_rays`` (separable wavelength / field /
+                pupil axes from host memory -> fused trace + detector binning ->
+                detector planes back on the host); copies inside the timed region.
+* ``--impl reference``  the reference's CPU algorithm (the NumPy oracle port:
+                the reference itself cannot be imported without named_arrays /
+                astropy) on all host cores, on a bounded sample of the workload.
+
+Launch:  python bench.py --gpus N --steps K --warmup W        (N = 1)
+         python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+
+from __future__ import annotations
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ray-surface intercepts/sec"
+UNIT = "intercepts/s"
+N_SURFACES = 3
+BYTES_PER_RAY = 162  # 10 fp64 + 1 mask byte in, the same out
+FLOP_PER_RAY = 410  # algorithmic flop of cfg 2 (119 + 165 + 126)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--num-field", type=int, default=100)
+    ap.add_argument("--num-pupil", type=int, default=100)
+    ap.add_argument("--num-wavelength", type=int, default=64)
+    ap.add_argument("--cpu-sample-rays", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args) -> str:
+    return (
+        f"cfg2 spherical concave grating, constant ruling spacing: "
+        f"{args.num_field}x{args.num_field} field x {args.num_pupil}x{args.num_pupil} pupil "
+        f"x {args.num_wavelength} wavelengths, {N_SURFACES} surfaces"
+    )
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores, bounded sample
+# ---------------------------------------------------------------------------
+def cpu_reference(args, sample_rays: int, repeats: int = 1) -> dict:
+    """Time ``oracle.raytrace.propagate_rays`` on `sample_rays` rays of the workload, all host threads."""
+    import configs
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import raytrace as ora
+
+    cores = os.cpu_count() or 1
+    n_pupil = max(2, int(round((sample_rays / 100) ** 0.5)))
+    system = configs.spherical_grating(num_field=10, num_pupil=n_pupil, num_wavelength=1)
+    _, rays = system._input(None, None, None, None, False, False)
+    r0, _ = configs.flatten_rays(rays)
+    r0 = {k: np.ascontiguousarray(v.reshape(-1)) for k, v in r0.items()}
+    n = r0["px"].size
+    surfaces = system.surfaces_all
+    chunks = np.array_split(np.arange(n), cores)
+
+    def work(idx):
+        sub = {k: v[idx[0] : idx[-1] + 1] for k, v in r0.items()}
+        return ora.propagate_rays(surfaces, sub)
+
+    best = None
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            list(pool.map(work, chunks))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return dict(
+        value=n * N_SURFACES / best,
+        unit=UNIT,
+        cores=cores,
+        kind="port",
+        sample=f"{n} rays x {N_SURFACES} surfaces of the cfg2 system (one wavelength), "
+        f"NumPy oracle port split over {cores} threads, best of {repeats}",
+        seconds=best,
+    )
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_start = time.perf_counter()
+    for _ in range(args.warmup):
+        cpu_reference(args, max(20000, args.cpu_sample_rays // 20))
+    values = []
+    seconds = []
+    for _ in range(args.steps):
+        r = cpu_reference(args, args.cpu_sample_rays)
+        values.append(r["value"])
+        seconds.append(r["seconds"])
+    value = float(np.mean(values))
+    line = dict(
+        impl="reference",
+        metric=METRIC,
+        value=value,
+        unit=UNIT,
+        n_gpus=args.gpus,
+        steps=args.steps,
+        warmup=args.warmup,
+        ms_per_step=1e3 * float(np.mean(seconds)),
+        higher_is_better=True,
+        scaling="weak",
+        vs_baseline=None,
+        dtype="f64",
+        data="synthetic",
+        config=dict(workload=workload_name(args), sample=r["sample"]),
+        cpu_baseline=dict(value=value, unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
+        e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        wall_s=time.perf_counter() - t_start,
+    )
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(
+            sm_mhz=float(np.median(sm)),
+            sm_max_mhz=float(np.max(smax)),
+            power_w_max=float(np.max(power)),
+            samples=len(sm),
+            reasons=sorted(reasons),
+        )
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import optika_b200 as optika
+    from optika_b200 import _engine, _lib, named as na, units as u
+    import configs
+
+    lib = _lib.lib()
+    stream = torch.cuda.current_stream(device)
+
+    # ---- the system and its separable grid; rank r traces its own pupil slab (weak scaling)
+    nf, npup, nw = args.num_field, args.num_pupil, args.num_wavelength
+    system = configs.spherical_grating(num_field=nf, num_pupil=npup, num_wavelength=nw)
+    grid = system.grid_input
+    if world > 1:
+        # shard by pupil slab: each rank owns the same number of pupil_x cells over its own strip
+        lo, hi = -45.0 + 90.0 * rank / world, -45.0 + 90.0 * (rank + 1) / world
+        grid.pupil = na.Cartesian2dVectorLinearSpace(
+            start=na.Cartesian2dVectorArray(lo, -45.0), stop=na.Cartesian2dVectorArray(hi, 45.0),
+            axis=na.Cartesian2dVectorArray("pupil_x", "pupil_y"), num=npup, centers=True,
+        )
+    compiled = system._compiled
+    n_slab = nf * nf * npup * npup
+    wavelengths = np.asarray(grid.wavelength.ndarray, dtype=np.float64)
+
+    # ---- FP64 peak (not in MEASURED_PEAKS.json): DFMA micro-benchmark
+    fp64_peak = C.c_double(0.0)
+    _lib.check(lib.optk_measure_fp64_peak(C.byref(fp64_peak), stream.cuda_stream))
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
+        peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        hbm_peak = 6650.0
+        peak_source = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+    # ---- dense structure-of-arrays slab resident in HBM
+    fx = torch.as_tensor(np.asarray(grid.field.x.ndarray), device=device)
+    fy = torch.as_tensor(np.asarray(grid.field.y.ndarray), device=device)
+    px = torch.as_tensor(np.asarray(grid.pupil.x.ndarray), device=device)
+    py = torch.as_tensor(np.asarray(grid.pupil.y.ndarray), device=device)
+    shape4 = (nf, nf, npup, npup)
+
+    def dense(t, pos):
+        view = [1, 1, 1, 1]
+        view[pos] = -1
+        return t.reshape(view).expand(shape4).contiguous().reshape(-1)
+
+    dx = (-torch.cos(fy).reshape(1, -1, 1, 1) * torch.sin(fx).reshape(-1, 1, 1, 1)).expand(shape4).contiguous().reshape(-1)
+    dy = (-torch.sin(fy)).reshape(1, -1, 1, 1).expand(shape4).contiguous().reshape(-1)
+    dz = (torch.cos(fy).reshape(1, -1, 1, 1) * torch.cos(fx).reshape(-1, 1, 1, 1)).expand(shape4).contiguous().reshape(-1)
+    fields_in = dict(
+        px=dense(px, 2), py=dense(py, 3), pz=torch.zeros(n_slab, dtype=torch.float64, device=device),
+        dx=dx, dy=dy, dz=dz,
+        intensity=torch.ones(n_slab, dtype=torch.float64, device=device),
+        attenuation=torch.zeros(n_slab, dtype=torch.float64, device=device),
+        index_refraction=torch.ones(n_slab, dtype=torch.float64, device=device),
+    )
+    mask_in = torch.ones(n_slab, dtype=torch.uint8, device=device)
+    w_dense = [torch.full((n_slab,), float(w), dtype=torch.float64, device=device) for w in wavelengths]
+    out = {name: torch.empty(n_slab, dtype=torch.float64, device=device) for name in _lib.FIELDS}
+    mask_out = torch.empty(n_slab, dtype=torch.uint8, device=device)
+
+    rin = [_lib.RaysIn() for _ in range(nw)]
+    rout = _lib.RaysOut()
+    for f, name in enumerate(_lib.FIELDS):
+        rout.field[f] = out[name].data_ptr()
+    rout.unvignetted = mask_out.data_ptr()
+    for k in range(nw):
+        r = rin[k]
+        r.n_axes = 1
+        r.dims[0] = n_slab
+        for f, name in enumerate(_lib.FIELDS):
+            t = w_dense[k] if name == "wavelength" else fields_in[name]
+            r.field[f] = t.data_ptr()
+            r.stride[f][0] = 1
+        r.unvignetted = mask_in.data_ptr()
+        r.mask_stride[0] = 1
+
+    launches = 0
+
+    def step():
+        nonlocal launches
+        for k in range(nw):
+            _lib.check(
+                lib.optk_trace(
+                    compiled.handle, 0, C.byref(rin[k]), C.byref(rout), 0, N_SURFACES, 1, 0, 0,
+                    None, None, None, stream.cuda_stream,
+                )
+            )
+            launches += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- value: device-resident
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    timed_launches = launches
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    ms_per_step = ms_total_max / args.steps
+    rays_per_step = n_slab * nw * world
+    value = rays_per_step * N_SURFACES / (ms_per_step * 1e-3)
+
+    ms_per_launch = ms_total / timed_launches
+    achieved_gbs = BYTES_PER_RAY * n_slab / (ms_per_launch * 1e-3) / 1e9
+    achieved_tflops = FLOP_PER_RAY * n_slab / (ms_per_launch * 1e-3) / 1e12
+
+    # sanity: the traced rays are physical (most of them reach the sensor)
+    unv_frac = float(mask_out.float().mean().item())
+
+    # ---- e2e: public API, host buffers in, detector planes out (copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        del w_dense, out
+        torch.cuda.empty_cache()
+        edges = na.ScalarArray(np.array([wavelengths.min() - 1e-9, wavelengths.max() + 1e-9]), "wavelength")
+        h2d = 8 * (nw + 2 * npup + 3 * nf * nf + 5)  # the separable axes the engine uploads
+        image_host = {}
+
+        def e2e_step():
+            image = system.image_rays(edges, device=device, counts=True)
+            if world > 1:
+                dist.all_reduce(image.flux)
+                dist.all_reduce(image.moment_real)
+                dist.all_reduce(image.counts)
+            if rank == 0 or world == 1:
+                image_host["flux"] = image.flux.cpu()
+                image_host["moment"] = image.moment_real.cpu()
+                image_host["counts"] = image.counts.cpu()
+            return image
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 2))
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        d2h = sum(int(v.numel() * v.element_size()) for v in image_host.values()) if image_host else 0
+        binned = int(image_host["counts"].sum().item()) if image_host else 0
+        e2e = dict(
+            value=rays_per_step * N_SURFACES / float(tt.item()),
+            unit=UNIT,
+            h2d_bytes_per_step=int(h2d),
+            d2h_bytes_per_step=int(d2h),
+            api="SequentialSystem.image_rays (fused trace + detector binning), host grids in, host image planes out",
+            seconds_per_step=float(tt.item()),
+            rays_binned=binned,
+        )
+
+    # ---- CPU baseline beside it (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(args, args.cpu_sample_rays)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = dict(
+            metric=METRIC,
+            value=value,
+            unit=UNIT,
+            n_gpus=world,
+            steps=args.steps,
+            warmup=args.warmup,
+            ms_per_step=ms_per_step,
+            higher_is_better=True,
+            scaling="weak",
+            vs_baseline=None,
+            dtype="f64",
+            data="synthetic",
+            config=dict(
+                workload=workload_name(args),
+                rays_per_step=rays_per_step,
+                launches_per_step=nw,
+                l2="inputs exceed L2: every launch streams 16.2 GB of dense rays through HBM",
+                unvignetted_fraction=unv_frac,
+                sharding="pupil slab per rank, no data-path collective" if world > 1 else "single GPU",
+            ),
+            roofline=dict(
+                bound="hbm",
+                achieved=achieved_gbs,
+                peak=hbm_peak,
+                unit="GB/s",
+                frac=achieved_gbs / hbm_peak,
+                traffic=None,
+                kernel="optk::trace_kernel",
+                algorithmic_bytes_per_launch=BYTES_PER_RAY * n_slab,
+                ms_per_launch=ms_per_launch,
+                peak_source=peak_source,
+                fp64=dict(
+                    achieved=achieved_tflops,
+                    peak=fp64_peak.value / 1e12,
+                    unit="TFLOP/s",
+                    frac=achieved_tflops / (fp64_peak.value / 1e12) if fp64_peak.value else None,
+                    algorithmic_flop_per_ray=FLOP_PER_RAY,
+                    peak_source="optk_measure_fp64_peak (DFMA micro-benchmark, this run)",
+                ),
+            ),
+            cpu_baseline=cpu,
+            e2e=e2e,
+            gpu_launches=timed_launches,
+            clocks=clocks,
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

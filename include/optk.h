@@ -102,6 +102,9 @@ typedef enum optk_aperture_kind {
 #define OPTK_F_APERTURE_ANGULAR 0x040   /* clip on direction instead of position   */
 #define OPTK_F_HOLO_DIVERGING_1 0x080
 #define OPTK_F_HOLO_DIVERGING_2 0x100
+#define OPTK_F_LOCAL_OUT 0x200 /* skip the final local -> global step: the rays leave the
+                                  surface in its LOCAL frame (sensor.transformation.inverse,
+                                  optika/systems/_sequential.py:983-986)                    */
 
 /*
  * optk_surface_t.stages: which steps of AbstractSurface.propagate_rays
@@ -183,6 +186,12 @@ typedef struct optk_rays_in {
     int64_t stride[OPTK_NUM_FIELDS][OPTK_MAX_AXES];
     const uint8_t* unvignetted; /* NULL = all true */
     int64_t mask_stride[OPTK_MAX_AXES];
+    /* Optional caller-supplied surface normal (NULL = use sag.normal): the `normal`
+     * argument of rulings.incident_effective (optika/rulings/_rulings.py:170-204),
+     * AbstractRulingSpacing.__call__ (optika/rulings/_spacing.py:27-41) and
+     * snells_law (optika/materials/_snells_law.py:41-47).  Applies to every surface. */
+    const double* normal[3];
+    int64_t normal_stride[3][OPTK_MAX_AXES];
 } optk_rays_in_t;
 
 /* Dense outputs, prod(dims) elements each (times the number of traced surfaces

@@ -1,0 +1,529 @@
+"""
+Host side of the device engine: flattening named ray grids into strided
+structure-of-arrays buffers, launching ``liboptk`` through ctypes, and wrapping
+the results back into named arrays.
+
+This module is the drop-in boundary of SURVEY.md section 8b: everything above it
+keeps the reference's Python signatures, everything below it is the C ABI of
+``include/optk.h``.  PyTorch is used for device memory, streams and (in
+:mod:`optika_b200.distributed`) NCCL only; all arithmetic on rays happens in the
+CUDA kernels of ``optika_b200/csrc``.
+"""
+
+from __future__ import annotations
+import ctypes as C
+import dataclasses
+import math
+import numpy as np
+from . import named as na
+from . import units as u
+from . import _lib as L
+from . import _lowering
+from .rays import RayVectorArray
+
+__all__ = [
+    "CompiledSystem",
+    "DeviceRays",
+    "DeviceImage",
+    "trace",
+    "require_cuda",
+]
+
+_MAX_LAUNCH = 2**31 - 1
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def require_cuda(device=None):
+    """The torch CUDA device to run on; raises when there is none (no CPU fallback)."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise L.OptkError(
+            "optika_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback"
+        )
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream_ptr(device) -> int:
+    return _torch().cuda.current_stream(device).cuda_stream
+
+
+@dataclasses.dataclass(eq=False)
+class DeviceRays:
+    """
+    Rays resident in HBM: one dense fp64 tensor per field (structure of arrays)
+    plus the uint8 ``unvignetted`` mask, all of the named `shape` (C order).
+    """
+
+    fields: dict
+    unvignetted: object
+    shape: dict[str, int]
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(list(self.shape.values()), dtype=np.int64)) if self.shape else 1
+
+    def to_host(self) -> RayVectorArray:
+        axes = tuple(self.shape)
+        dims = tuple(self.shape.values())
+
+        def get(name):
+            return na.ScalarArray(self.fields[name].reshape(dims).cpu().numpy(), axes)
+
+        return RayVectorArray(
+            wavelength=get("wavelength"),
+            position=na.Cartesian3dVectorArray(get("px"), get("py"), get("pz")),
+            direction=na.Cartesian3dVectorArray(get("dx"), get("dy"), get("dz")),
+            intensity=get("intensity"),
+            attenuation=get("attenuation"),
+            index_refraction=get("index_refraction"),
+            unvignetted=na.ScalarArray(
+                self.unvignetted.reshape(dims).cpu().numpy().astype(bool), axes
+            ),
+        )
+
+    def __getitem__(self, item: dict) -> "DeviceRays":
+        axes = tuple(self.shape)
+        dims = tuple(self.shape.values())
+        index = tuple(item.get(ax, slice(None)) for ax in axes)
+        new_axes = [ax for ax in axes if not (ax in item and not isinstance(item[ax], slice))]
+
+        def get(t):
+            return t.reshape(dims)[index].contiguous()
+
+        fields = {k: get(v) for k, v in self.fields.items()}
+        mask = get(self.unvignetted)
+        shape_ = dict(zip(new_axes, fields["wavelength"].shape))
+        return DeviceRays(fields, mask, shape_)
+
+
+@dataclasses.dataclass(eq=False)
+class DeviceImage:
+    """Detector planes in HBM, ``[n_wavelength][n_x][n_y]`` (optionally with leading config axes)."""
+
+    edges_wavelength: object
+    edges_x: object
+    edges_y: object
+    flux: object
+    moment_real: object = None
+    moment_imag: object = None
+    counts: object = None
+
+    @classmethod
+    def zeros(cls, edges_wavelength, edges_x, edges_y, device, leading=(), moments=True, counts=True):
+        torch = _torch()
+
+        def dev(e):
+            return torch.as_tensor(np.ascontiguousarray(e, dtype=np.float64)).to(device)
+
+        ew, ex, ey = dev(edges_wavelength), dev(edges_x), dev(edges_y)
+        dims = tuple(leading) + (len(ew) - 1, len(ex) - 1, len(ey) - 1)
+        z = lambda dt: torch.zeros(dims, dtype=dt, device=device)  # noqa: E731
+        return cls(
+            ew, ex, ey,
+            flux=z(torch.float64),
+            moment_real=z(torch.float64) if moments else None,
+            moment_imag=None,
+            counts=z(torch.int64) if counts else None,
+        )
+
+    def struct(self, plane_index: int = 0) -> L.Image:
+        im = L.Image()
+        im.n_wavelength = len(self.edges_wavelength) - 1
+        im.n_x = len(self.edges_x) - 1
+        im.n_y = len(self.edges_y) - 1
+        im.edges_wavelength = self.edges_wavelength.data_ptr()
+        im.edges_x = self.edges_x.data_ptr()
+        im.edges_y = self.edges_y.data_ptr()
+        n = im.n_wavelength * im.n_x * im.n_y
+
+        def ptr(t):
+            return None if t is None else t.data_ptr() + plane_index * n * 8
+
+        im.flux = ptr(self.flux)
+        im.moment_real = ptr(self.moment_real)
+        im.moment_imag = ptr(self.moment_imag)
+        im.counts = ptr(self.counts)
+        return im
+
+
+class CompiledSystem:
+    """
+    A surface list lowered to the device table (``optk_system_create``): the
+    replacement for iterating ``SequentialSystem.surfaces_all`` in Python
+    (``optika/propagators.py:38-39, 67-71``).
+    """
+
+    def __init__(self, surfaces, stages: int = L.STAGE_ALL, local_last: bool = False):
+        self.surfaces = list(surfaces)
+        table, shape_ = _lowering.lower_system(self.surfaces, stages=stages)
+        if local_last:
+            # leave the rays in the local frame of the last surface
+            n = len(self.surfaces)
+            for k in range(n - 1, len(table), n):
+                table[k].flags |= L.F_LOCAL_OUT
+        self.table = table
+        self.shape = shape_
+        self.n_surface = len(self.surfaces)
+        self.n_config = len(table) // max(self.n_surface, 1)
+        handle = C.c_void_p()
+        L.check(L.lib().optk_system_create(table, self.n_surface, self.n_config, C.byref(handle)))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                L.lib().optk_system_destroy(self.handle)
+                self.handle = None
+        except Exception:  # pragma: no cover
+            pass
+
+
+# ---------------------------------------------------------------------------
+# flattening
+# ---------------------------------------------------------------------------
+_FIELD_GETTERS = (
+    ("wavelength", lambda r: r.wavelength),
+    ("px", lambda r: r.position.x),
+    ("py", lambda r: r.position.y),
+    ("pz", lambda r: r.position.z),
+    ("dx", lambda r: r.direction.x),
+    ("dy", lambda r: r.direction.y),
+    ("dz", lambda r: r.direction.z),
+    ("intensity", lambda r: r.intensity),
+    ("attenuation", lambda r: r.attenuation),
+    ("index_refraction", lambda r: r.index_refraction),
+)
+
+
+class _View:
+    """A device tensor plus its element stride along every axis of the full grid."""
+
+    def __init__(self, tensor, strides: dict[str, int]):
+        self.tensor = tensor
+        self.strides = strides
+
+
+def _view_of(value, device, is_mask=False) -> _View:
+    """Upload a (small, possibly broadcast) host value; strides are per named axis."""
+    torch = _torch()
+    dtype = np.uint8 if is_mask else np.float64
+    if isinstance(value, na.ScalarArray):
+        nd = np.ascontiguousarray(np.asarray(value.ndarray).astype(dtype, copy=False))
+        strides = {}
+        for ax, st, n in zip(value.axes, nd.strides, nd.shape):
+            strides[ax] = 0 if n == 1 else st // nd.itemsize
+        t = torch.from_numpy(nd.reshape(-1).copy() if nd.ndim == 0 else nd.reshape(-1)).to(device)
+        return _View(t, strides)
+    nd = np.asarray(u.length(value)).astype(dtype).reshape(1)
+    return _View(torch.from_numpy(nd).to(device), {})
+
+
+def _grid_shape(rays, config_shape_: dict[str, int], normal=None) -> tuple[dict[str, int], dict[str, int]]:
+    """(configuration axes, ray axes) of the full grid; configuration axes come first."""
+    rays_shape = na.broadcast_shapes(rays.shape, na.shape(normal))
+    total = na.broadcast_shapes(config_shape_, rays_shape)
+    config = {ax: total[ax] for ax in config_shape_}
+    ray = {ax: n for ax, n in total.items() if ax not in config}
+    return config, ray
+
+
+def _merge_axes(dims: list[int], strides: list[list[int]]):
+    """Drop size-1 axes and merge adjacent axes that are contiguous in every view."""
+    keep = [k for k, n in enumerate(dims) if n != 1]
+    dims = [dims[k] for k in keep]
+    strides = [[s[k] for k in keep] for s in strides]
+    k = len(dims) - 1
+    while k > 0:
+        if all(s[k - 1] == s[k] * dims[k] for s in strides):
+            dims[k - 1] *= dims[k]
+            del dims[k]
+            for s in strides:
+                s[k - 1] = s[k]
+                del s[k]
+        k -= 1
+    return dims, strides
+
+
+def trace(
+    system: CompiledSystem,
+    rays: RayVectorArray | DeviceRays,
+    accumulate: bool = False,
+    axis: str | None = None,
+    surf_begin: int = 0,
+    surf_count: int | None = None,
+    surf_step: int = 1,
+    image: DeviceImage | None = None,
+    image_frame=None,
+    write_rays: bool = True,
+    device=None,
+    stats: bool = False,
+    normal: na.Cartesian3dVectorArray | None = None,
+    ray_axes_order: list[str] | None = None,
+):
+    """
+    Trace `rays` through `system` on the device.  Returns :class:`DeviceRays`
+    (or ``None`` with ``write_rays=False``), plus a stats dict when requested.
+
+    With ``accumulate`` the result gains the axis `axis` of length `surf_count`
+    right after the configuration axes (``optika/propagators.py:44-73`` stacks
+    on a new leading axis; named axes make the position immaterial).
+    """
+    torch = _torch()
+    device = require_cuda(device)
+    lib = L.lib()
+    if surf_count is None:
+        surf_count = system.n_surface if surf_step > 0 else surf_begin + 1
+    if surf_count > L.MAX_SURFACES:
+        raise ValueError(f"at most {L.MAX_SURFACES} surfaces per launch; chain the trace")
+
+    config, ray = _grid_shape(rays, system.shape, normal)
+    if ray_axes_order is not None and not isinstance(rays, DeviceRays):
+        # named axes have no intrinsic order: put the requested axes last, in the given
+        # order (innermost = fastest varying = adjacent threads), e.g. pupil axes innermost
+        # so that the rays of one warp land on the same detector pixel
+        first = [ax for ax in ray if ax not in ray_axes_order]
+        ray = {ax: ray[ax] for ax in first + [ax for ax in ray_axes_order if ax in ray]}
+    config_axes, ray_axes = list(config), list(ray)
+    n_config = int(np.prod(list(config.values()), dtype=np.int64)) if config else 1
+    n_ray = int(np.prod(list(ray.values()), dtype=np.int64)) if ray else 1
+    if n_config != system.n_config:
+        # rays carry configuration axes the system does not vary over: they are ray axes
+        raise ValueError("internal error: configuration shape mismatch")
+
+    # ---- inputs as strided views
+    if isinstance(rays, DeviceRays):
+        full_axes = list(rays.shape)
+        full_dims = list(rays.shape.values())
+        dense = {}
+        st = 1
+        for ax, n in zip(reversed(full_axes), reversed(full_dims)):
+            dense[ax] = 0 if n == 1 else st
+            st *= n
+        views = [_View(rays.fields[name], dense) for name, _ in _FIELD_GETTERS]
+        mask_view = _View(rays.unvignetted, dense)
+    else:
+        views = [_view_of(get(rays), device) for _, get in _FIELD_GETTERS]
+        unv = rays.unvignetted
+        if isinstance(unv, na.ScalarArray) or not bool(unv):
+            mask_view = _view_of(unv, device, is_mask=True)
+        else:
+            mask_view = None
+
+    normal_views = []
+    if normal is not None:
+        normal_views = [_view_of(c, device) for c in (normal.x, normal.y, normal.z)]
+    all_views = views + normal_views + ([mask_view] if mask_view is not None else [])
+    dims = [ray[ax] for ax in ray_axes]
+    strides = [[v.strides.get(ax, 0) for ax in ray_axes] for v in all_views]
+    dims_m, strides_m = _merge_axes(dims, strides)
+    if len(dims_m) > L.MAX_AXES:
+        raise ValueError(f"ray grids with more than {L.MAX_AXES} non-mergeable axes are not supported")
+
+    # ---- outputs
+    n_states = surf_count if accumulate else 1
+    out_fields = None
+    out_mask = None
+    if write_rays:
+        out_fields = {
+            name: torch.empty((n_config, n_states, n_ray), dtype=torch.float64, device=device)
+            for name, _ in _FIELD_GETTERS
+        }
+        out_mask = torch.empty((n_config, n_states, n_ray), dtype=torch.uint8, device=device)
+
+    stats_dev = torch.zeros(4, dtype=torch.int64, device=device) if stats else None
+    frame = None
+    if image_frame is not None:
+        frame_shape = system.shape
+
+    # ---- launches: one per configuration (the surface table is a kernel parameter),
+    #      split along the outermost ray axis when a configuration exceeds 2^31 - 1 rays
+    stream = _stream_ptr(device)
+    rin = L.RaysIn()
+    rout = L.RaysOut()
+    config_dims = list(config.values())
+    for c, cindex in enumerate(np.ndindex(*config_dims) if config_dims else [()]):
+        if n_ray == 0:
+            break
+        base_off = [
+            sum(i * v.strides.get(ax, 0) for i, ax in zip(cindex, config_axes)) for v in all_views
+        ]
+        if image_frame is not None:
+            frame = _lowering.affine_struct(image_frame, frame_shape, tuple(cindex))
+        inner = n_ray // dims_m[0] if dims_m else 1
+        n0 = dims_m[0] if dims_m else 1
+        step0 = max(1, min(n0, _MAX_LAUNCH // max(inner, 1)))
+        if inner > _MAX_LAUNCH:
+            raise ValueError("a single index of the outermost ray axis exceeds 2^31 - 1 rays")
+        for i0 in range(0, n0, step0):
+            m0 = min(step0, n0 - i0)
+            rin.n_axes = len(dims_m)
+            for a, n in enumerate(dims_m):
+                rin.dims[a] = m0 if a == 0 else n
+            for f, v in enumerate(views):
+                off = base_off[f] + (i0 * strides_m[f][0] if dims_m else 0)
+                rin.field[f] = v.tensor.data_ptr() + 8 * off
+                for a in range(len(dims_m)):
+                    rin.stride[f][a] = strides_m[f][a]
+            for k, v in enumerate(normal_views):
+                f = len(views) + k
+                off = base_off[f] + (i0 * strides_m[f][0] if dims_m else 0)
+                rin.normal[k] = v.tensor.data_ptr() + 8 * off
+                for a in range(len(dims_m)):
+                    rin.normal_stride[k][a] = strides_m[f][a]
+            if mask_view is not None:
+                off = base_off[-1] + (i0 * strides_m[-1][0] if dims_m else 0)
+                rin.unvignetted = mask_view.tensor.data_ptr() + off
+                for a in range(len(dims_m)):
+                    rin.mask_stride[a] = strides_m[-1][a]
+            else:
+                rin.unvignetted = None
+            if write_rays:
+                o = c * n_states * n_ray + i0 * inner
+                for f, (name, _) in enumerate(_FIELD_GETTERS):
+                    rout.field[f] = out_fields[name].data_ptr() + 8 * o
+                rout.unvignetted = out_mask.data_ptr() + o
+            im = image.struct(c) if image is not None else None
+            L.check(
+                lib.optk_trace(
+                    system.handle, c, C.byref(rin), C.byref(rout) if write_rays else None,
+                    surf_begin, surf_count, surf_step, 1 if accumulate else 0, n_ray,
+                    C.byref(im) if im is not None else None,
+                    C.byref(frame) if frame is not None else None,
+                    stats_dev.data_ptr() if stats_dev is not None else None,
+                    stream,
+                )
+            )
+
+    result = None
+    if write_rays:
+        shape_ = dict(config)
+        if accumulate:
+            shape_[axis if axis is not None else "surface"] = n_states
+        shape_.update(ray)
+        result = DeviceRays(out_fields, out_mask, shape_)
+    if stats:
+        s = stats_dev.cpu().numpy()
+        return result, dict(
+            n_rays=int(s[0]), n_unvignetted=int(s[1]), n_newton_iterations=int(s[2]), n_binned=int(s[3])
+        )
+    return result
+
+
+# ---------------------------------------------------------------------------
+# unit operations of the reference API, executed by one-surface traces that are
+# restricted to the relevant stages of the surface operator
+# ---------------------------------------------------------------------------
+@dataclasses.dataclass(eq=False)
+class _Bare:
+    """A surface made of exactly one element; everything else is inert."""
+
+    sag: object = None
+    material: object = None
+    aperture: object = None
+    rulings: object = None
+    transformation: object = None
+
+    def __post_init__(self):
+        from . import sags, materials
+
+        if self.sag is None:
+            self.sag = sags.NoSag()
+        if self.material is None:
+            self.material = materials.Vacuum()
+
+    @property
+    def shape(self):
+        return na.broadcast_shapes(
+            na.shape(self.sag), na.shape(self.material), na.shape(self.aperture),
+            na.shape(self.rulings), na.shape(self.transformation),
+        )
+
+
+def _position_rays(position: na.Cartesian3dVectorArray, direction=None) -> RayVectorArray:
+    if direction is None:
+        direction = na.Cartesian3dVectorArray(0.0, 0.0, 1.0)
+    return RayVectorArray(
+        position=na.Cartesian3dVectorArray(
+            u.length(position.x), u.length(position.y), u.length(position.z)
+        ),
+        direction=direction,
+    )
+
+
+def sag_intercept(sag, rays, attenuate: bool):
+    """``sag.intercept`` / ``sag.propagate_rays`` (``optika/sags/_abc.py:76-122``)."""
+    stages = L.STAGE_INTERCEPT | (L.STAGE_ATTENUATE if attenuate else 0)
+    on_device = isinstance(rays, DeviceRays)
+    out = trace(CompiledSystem([_Bare(sag=sag)], stages=stages), rays)
+    return out if on_device else out.to_host()
+
+
+def sag_normal(sag, position) -> na.Cartesian3dVectorArray:
+    """``sag.normal(position)`` (``optika/sags/_abc.py:63-74``)."""
+    out = trace(CompiledSystem([_Bare(sag=sag)], stages=L.STAGE_NORMAL_OUT), _position_rays(position))
+    return out.to_host().direction
+
+
+def sag_value(sag, position) -> na.ScalarArray:
+    """``sag(position)`` (``optika/sags/_abc.py:48-61``)."""
+    out = trace(CompiledSystem([_Bare(sag=sag)], stages=L.STAGE_SAG_OUT), _position_rays(position))
+    return out.to_host().position.z
+
+
+def aperture_mask(aperture, position) -> na.ScalarArray:
+    """``aperture(position)`` (``optika/apertures/_apertures.py:69-80``): always tests the given vector."""
+    import copy
+
+    ap = copy.copy(aperture)
+    ap.angular = False
+    out = trace(CompiledSystem([_Bare(aperture=ap)], stages=L.STAGE_CLIP), _position_rays(position))
+    return out.to_host().unvignetted
+
+
+def aperture_clip(aperture, rays):
+    """``aperture.clip_rays(rays)`` (``optika/apertures/_apertures.py:82-102``)."""
+    on_device = isinstance(rays, DeviceRays)
+    out = trace(CompiledSystem([_Bare(aperture=aperture)], stages=L.STAGE_CLIP), rays)
+    return out if on_device else out.to_host()
+
+
+def ruling_vector(spacing, position, normal) -> na.Cartesian3dVectorArray:
+    """``spacing(position, normal)`` (``optika/rulings/_spacing.py:27-41``)."""
+    from . import rulings as _rulings
+
+    r = _rulings.Rulings(spacing=spacing, diffraction_order=1)
+    out = trace(
+        CompiledSystem([_Bare(rulings=r)], stages=L.STAGE_KAPPA_OUT), _position_rays(position), normal=normal
+    )
+    return out.to_host().direction
+
+
+def rulings_incident_effective(rulings, rays, normal):
+    """``rulings.incident_effective(rays, normal)`` (``optika/rulings/_rulings.py:170-204``)."""
+    on_device = isinstance(rays, DeviceRays)
+    out = trace(CompiledSystem([_Bare(rulings=rulings)], stages=L.STAGE_RULINGS), rays, normal=normal)
+    return out if on_device else out.to_host()
+
+
+def snells_law(direction, index_refraction, index_refraction_new, normal=None, is_mirror=False):
+    """``optika.materials.snells_law`` (``optika/materials/_snells_law.py:41-291``)."""
+    from . import materials
+
+    if normal is None:
+        normal = na.Cartesian3dVectorArray(0.0, 0.0, -1.0)  # _snells_law.py:268-269
+    n2 = index_refraction_new
+    if is_mirror:
+        material = materials.Mirror()
+    else:
+        # a Glass whose Sellmeier sum is constant: n^2 = 1 + b1 w^2 / (w^2 - 0) = 1 + b1
+        material = materials.Glass(b1=n2 * n2 - 1)
+    rays = RayVectorArray(wavelength=1.0, direction=direction, index_refraction=index_refraction)
+    out = trace(CompiledSystem([_Bare(material=material)], stages=L.STAGE_REFRACT), rays, normal=normal)
+    return out.to_host().direction

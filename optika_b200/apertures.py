@@ -208,7 +208,8 @@ class RectangularAperture(AbstractPolygonalAperture):
     def vertices(self) -> na.Cartesian3dVectorArray:
         # optika/apertures/_apertures.py:970-986: sqrt(2) * (cos, sin)(45deg + k 90deg) * half_width
         h = self.half_width_xy
-        az = na.linspace(0, 360, axis="vertex", num=4, endpoint=False) * u.deg + 45 * u.deg
+        # degrees first, one conversion to radians (as astropy does inside np.cos)
+        az = (na.linspace(0, 360, axis="vertex", num=4, endpoint=False) + 45) * u.deg
         r = np.sqrt(2)
         return na.Cartesian3dVectorArray(
             x=r * np.cos(az) * h.x,
@@ -236,7 +237,7 @@ class RegularPolygonalAperture(AbstractPolygonalAperture):
     def vertices(self) -> na.Cartesian3dVectorArray:
         # optika/apertures/_apertures.py:1009-1027
         radius = u.length(self.radius)
-        angle = na.linspace(0, 360 * u.deg, axis="vertex", num=self.num_vertices, endpoint=False)
+        angle = na.linspace(0, 360, axis="vertex", num=self.num_vertices, endpoint=False) * u.deg
         return na.Cartesian3dVectorArray(
             x=radius * np.cos(angle),
             y=radius * np.sin(angle),

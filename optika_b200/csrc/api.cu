@@ -147,6 +147,9 @@ bool stride_is_dense(const int64_t* stride, const int64_t* dims, int n_axes) {
 bool all_dense(const optk_rays_in_t& in) {
     for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
         if (!stride_is_dense(in.stride[f], in.dims, in.n_axes)) return false;
+    if (in.normal[0])
+        for (int k = 0; k < 3; ++k)
+            if (!in.normal[k] || !stride_is_dense(in.normal_stride[k], in.dims, in.n_axes)) return false;
     if (in.unvignetted && !stride_is_dense(in.mask_stride, in.dims, in.n_axes)) return false;
     return true;
 }
@@ -335,6 +338,10 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const opt
         return OPTK_ERR_INVALID;
     }
     if (n == 0) return OPTK_OK;
+    if (in->normal[0]) {
+        set_error("optk_trace_host: caller-supplied normals are only supported with device pointers");
+        return OPTK_ERR_UNSUPPORTED;
+    }
 
     std::lock_guard<std::mutex> lock(g_pipeline.mutex);
     HostPipeline& pl = g_pipeline;

@@ -325,7 +325,8 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
 // ---------------------------------------------------------------------------
 // one surface: AbstractSurface.propagate_rays, optika/surfaces.py:123-198
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& r, unsigned& newton_iterations) {
+__device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& r, unsigned& newton_iterations,
+                                                  bool normal_given, double gnx, double gny, double gnz) {
     const int stages = S.stages;
     const int flags = S.flags;
 
@@ -389,6 +390,9 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
     // 3. normal = sag.normal(position_1)  (surfaces.py:146-148)
     double nx, ny, nz;
     sag_normal(S, qx, qy, nx, ny, nz);
+    if (normal_given) {  // unit operations with a caller-supplied normal
+        nx = gnx; ny = gny; nz = gnz;
+    }
 
     if (stages & OPTK_STAGE_SAG_OUT) {
         double z = sag_value(S, qx, qy);
@@ -466,7 +470,7 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
     }
 
     // 10. local -> global  (surfaces.py:195-196)
-    if (flags & OPTK_F_TRANSFORM) {
+    if ((flags & OPTK_F_TRANSFORM) && !(flags & OPTK_F_LOCAL_OUT)) {
         affine_forward(S.transform, r.px, r.py, r.pz, false);
         affine_forward(S.transform, r.dx, r.dy, r.dz, true);
     }
@@ -494,6 +498,8 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     const bool valid = i < P.n_rays;
     unsigned newton_iterations = 0;
     Ray r = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, false};
+    const bool normal_given = P.in.normal[0] != nullptr;
+    double gnx = 0.0, gny = 0.0, gnz = -1.0;
 
     if (valid) {
         if (P.dense_in) {
@@ -508,11 +514,17 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
             r.att = __ldg(P.in.field[OPTK_ATTENUATION] + i);
             r.n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + i);
             r.unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + i) != 0) : true;
+            if (normal_given) {
+                gnx = __ldg(P.in.normal[0] + i);
+                gny = __ldg(P.in.normal[1] + i);
+                gnz = __ldg(P.in.normal[2] + i);
+            }
         } else {
             // broadcast view: decompose the flat index in C order of dims
             long long off[OPTK_NUM_FIELDS + 1];
 #pragma unroll
             for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] = 0;
+            long long offn[3] = {0, 0, 0};
             uint32_t rem = (uint32_t)(i + P.index_offset);
             for (int a = P.in.n_axes - 1; a >= 0; --a) {
                 uint32_t q, idx;
@@ -525,6 +537,15 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
 #pragma unroll
                 for (int f = 0; f < OPTK_NUM_FIELDS; ++f) off[f] += (long long)idx * P.in.stride[f][a];
                 off[OPTK_NUM_FIELDS] += (long long)idx * P.in.mask_stride[a];
+                if (normal_given) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) offn[k] += (long long)idx * P.in.normal_stride[k][a];
+                }
+            }
+            if (normal_given) {
+                gnx = __ldg(P.in.normal[0] + offn[0]);
+                gny = __ldg(P.in.normal[1] + offn[1]);
+                gnz = __ldg(P.in.normal[2] + offn[2]);
             }
             r.w = __ldg(P.in.field[OPTK_WAVELENGTH] + off[OPTK_WAVELENGTH]);
             r.px = __ldg(P.in.field[OPTK_PX] + off[OPTK_PX]);
@@ -540,7 +561,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
         }
 
         for (int s = 0; s < P.n_surf; ++s) {
-            surface_propagate(P.surf[s], r, newton_iterations);
+            surface_propagate(P.surf[s], r, newton_iterations, normal_given, gnx, gny, gnz);
             if (P.accumulate) store_ray(P.out, (long long)s * P.accumulate_stride + i, r);
         }
         if (!P.accumulate) store_ray(P.out, i, r);
