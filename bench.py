@@ -266,10 +266,10 @@ def run_b200(args):
         peak_source = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
     # ---- dense structure-of-arrays slab resident in HBM
-    fx = torch.as_tensor(np.asarray(grid.field.x.ndarray), device=device)
-    fy = torch.as_tensor(np.asarray(grid.field.y.ndarray), device=device)
-    px = torch.as_tensor(np.asarray(grid.pupil.x.ndarray), device=device)
-    py = torch.as_tensor(np.asarray(grid.pupil.y.ndarray), device=device)
+    fx = torch.as_tensor(np.array(grid.field.x.ndarray), device=device)
+    fy = torch.as_tensor(np.array(grid.field.y.ndarray), device=device)
+    px = torch.as_tensor(np.array(grid.pupil.x.ndarray), device=device)
+    py = torch.as_tensor(np.array(grid.pupil.y.ndarray), device=device)
     shape4 = (nf, nf, npup, npup)
 
     def dense(t, pos):

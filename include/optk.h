@@ -102,6 +102,7 @@ typedef enum optk_aperture_kind {
 #define OPTK_F_APERTURE_ANGULAR 0x040   /* clip on direction instead of position   */
 #define OPTK_F_HOLO_DIVERGING_1 0x080
 #define OPTK_F_HOLO_DIVERGING_2 0x100
+#define OPTK_F_TRANSLATION_ONLY 0x400 /* set by the library: `transform` has R == identity */
 #define OPTK_F_LOCAL_OUT 0x200 /* skip the final local -> global step: the rays leave the
                                   surface in its LOCAL frame (sensor.transformation.inverse,
                                   optika/systems/_sequential.py:983-986)                    */
@@ -148,7 +149,8 @@ typedef struct optk_surface {
     optk_affine_t ruling_transform;   /* applied FORWARDS to the position (spacing.py:118-119) */
 
     /* sag: [0] radius (spherical/cylindrical/conic/toroidal minor) or focal length
-     * (parabolic); [1] conic constant; [2] radius of rotation (toroidal).        */
+     * (parabolic); [1] conic constant; [2] radius of rotation (toroidal);
+     * [3] reserved: optk_system_create stores 1 / [0] there.                      */
     double sag[4];
 
     /* Glass: Sellmeier b1 b2 b3 c1 c2 c3 (c in mm^2). */

@@ -219,7 +219,7 @@ def _view_of(value, device, is_mask=False) -> _View:
         strides = {}
         for ax, st, n in zip(value.axes, nd.strides, nd.shape):
             strides[ax] = 0 if n == 1 else st // nd.itemsize
-        t = torch.from_numpy(nd.reshape(-1).copy() if nd.ndim == 0 else nd.reshape(-1)).to(device)
+        t = torch.from_numpy(nd.reshape(-1).copy()).to(device)
         return _View(t, strides)
     nd = np.asarray(u.length(value)).astype(dtype).reshape(1)
     return _View(torch.from_numpy(nd).to(device), {})

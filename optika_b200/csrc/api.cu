@@ -250,6 +250,15 @@ OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, 
     sys->n_surface = n_surface;
     sys->n_config = n_config;
     sys->table.assign(table, table + (size_t)n_surface * n_config);
+    for (optk_surface_t& s : sys->table) {
+        // per-surface constants every ray would otherwise recompute
+        s.sag[3] = 1.0 / s.sag[0];
+        s.flags &= ~OPTK_F_TRANSLATION_ONLY;
+        const double* r = s.transform.r;
+        const bool identity = r[0] == 1.0 && r[4] == 1.0 && r[8] == 1.0 && r[1] == 0.0 && r[2] == 0.0 &&
+                              r[3] == 0.0 && r[5] == 0.0 && r[6] == 0.0 && r[7] == 0.0;
+        if ((s.flags & OPTK_F_TRANSFORM) && identity) s.flags |= OPTK_F_TRANSLATION_ONLY;
+    }
     *out = sys;
     return OPTK_OK;
 }

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "bin.cuh"
 #include "params.cuh"
+#include <cstdlib>
 
 namespace optk {
 
@@ -29,45 +30,64 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
     switch (S.sag_kind) {
         case OPTK_SAG_FLAT:
             // optika/sags/_flat.py:58: d = -o.z / u.z
-            return -oz / uz;
+            return fdiv(-oz, uz);
         case OPTK_SAG_SPHERICAL: {
             // optika/sags/_spherical.py:176-184
             const double r = S.sag[0];
             const double pz = oz - r;
             const double up = ux * ox + uy * oy + uz * pz;
             const double disc = up * up - (ox * ox + oy * oy + pz * pz - r * r);
-            return -up - sign0(r * uz) * sqrt(disc);
+            return -up - sign0(r * uz) * fsqrt(disc);
         }
         case OPTK_SAG_PARABOLIC: {
-            // optika/sags/_parabolic.py:142-151
+            // optika/sags/_parabolic.py:142-151: root of a t^2 + 2 h t + c = 0 with
+            //   a = ux^2 + uy^2,  h = ox ux + oy uy - 2 f uz,  c = ox^2 + oy^2 - 4 f oz,
+            // the reference takes t = (-h - s sqrt(h^2 - a c)) / a with s = sign(f uz).
+            // For near-axial rays -h and s sqrt() nearly cancel (the reference loses
+            // ~eps |2f| / a to rounding there, see DESIGN.md "conditioning"); the same root
+            // is evaluated here in its cancellation-free form c / (-h + s sqrt()).
             const double f = S.sag[0];
-            const double uxy2 = ux * ux + uy * uy;
-            if (uxy2 > 1e-10) {
-                const double oyux = oy * ux, oxuy = ox * uy;
-                const double disc = -(oyux * oyux) - oxuy * oxuy + 2 * oy * uy * (ox * ux - 2 * f * uz) +
-                                    4 * f * (oz * uxy2 - ox * ux * uz + f * uz * uz);
-                return (-ox * ux - oy * uy + 2 * f * uz - sign0(f * uz) * sqrt(disc)) / uxy2;
+            const double a = ux * ux + uy * uy;
+            if (a > 1e-10) {
+                const double h = ox * ux + oy * uy - 2.0 * f * uz;
+                const double c = ox * ox + oy * oy - 4.0 * f * oz;
+                const double s = sign0(f * uz);
+                const double root = s * fsqrt(h * h - a * c);
+                // -h and root have the same sign: divide; otherwise the direct form is the stable one
+                return (-h * s >= 0.0) ? fdiv(c, -h + root) : fdiv(-h - root, a);
             }
-            return (ox * ox + oy * oy - 4 * f * oz) / (4 * f * uz);
+            // the reference's paraxial branch, verbatim (it drops the ox ux + oy uy terms)
+            return fdiv(ox * ox + oy * oy - 4.0 * f * oz, 4.0 * f * uz);
         }
         case OPTK_SAG_CONIC: {
-            // optika/sags/_conic.py:126-162
-            const double c = 1.0 / S.sag[0];
+            // optika/sags/_conic.py:126-162: A t^2 + B t + C = 0, both roots tested for the
+            // vertex sheet, the smaller |t| wins.  root(-1) = (-B - sqrt)/(2A) and
+            // root(+1) = (-B + sqrt)/(2A) are formed from q = -(B + sign(B) sqrt)/2 as q/A and
+            // C/q so that neither suffers the cancellation of the textbook formula (A -> 0
+            // for k -> -1 and near-axial rays).
+            const double c = S.sag[3];
             const double kp1 = 1.0 + S.sag[1];
             const double a = c * (ux * ux + uy * uy + kp1 * uz * uz);
-            const double b = 2 * (c * (ox * ux + oy * uy + kp1 * oz * uz) - uz);
-            const double cc = c * (ox * ox + oy * oy + kp1 * oz * oz) - 2 * oz;
-            const double disc = b * b - 4 * a * cc;
+            const double b = 2.0 * (c * (ox * ux + oy * uy + kp1 * oz * uz) - uz);
+            const double cc = c * (ox * ox + oy * oy + kp1 * oz * oz) - 2.0 * oz;
+            const double disc = b * b - 4.0 * a * cc;
             const bool real = disc >= 0;
-            const double sq_disc = sqrt(real ? disc : 0.0);
+            const double sq_disc = fsqrt(real ? disc : 0.0);
             const bool degenerate = fabs(a) < 1e-12;
-            const double denom = degenerate ? 1.0 : 2 * a;
-            const double t_linear = -cc / b;
-            double t_root[2];
+            double t_minus, t_plus;  // root(-1), root(+1)
+            if (degenerate) {
+                t_minus = t_plus = fdiv(-cc, b);
+            } else {
+                const double q = -0.5 * (b + copysign(sq_disc, b));
+                const double t_q = fdiv(q, a), t_c = (q != 0.0) ? fdiv(cc, q) : t_q;
+                // b >= 0: q/a = (-b - sqrt)/(2a) = root(-1);  b < 0: q/a = root(+1)
+                t_minus = (b >= 0.0) ? t_q : t_c;
+                t_plus = (b >= 0.0) ? t_c : t_q;
+            }
+            double t_root[2] = {t_minus, t_plus};
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const double sgn = k == 0 ? -1.0 : 1.0;
-                const double t = degenerate ? t_linear : (-b + sgn * sq_disc) / denom;
+                const double t = t_root[k];
                 const double x = ox + ux * t, y = oy + uy * t, z = oz + uz * t;
                 const double r2 = x * x + y * y;
                 const bool on_vertex_sheet = (z * (c * r2 - z)) >= 0;
@@ -84,8 +104,8 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
             const double negative_b = ncx * (-bz) + ncz * bx;
             const double dot = bx * ncx + bz * ncz;
             const double disc = nca2 * (r * r) - dot * dot;
-            if (disc > 0) return (negative_b - sign0(r * uz) * sqrt(disc)) / nca2;
-            return -oz / uz;
+            if (disc > 0) return fdiv(negative_b - sign0(r * uz) * fsqrt(disc), nca2);
+            return fdiv(-oz, uz);
         }
     }
     return NAN;
@@ -95,14 +115,14 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
 __device__ __forceinline__ void toroid_eval(double c, double r, double x, double y, double& z, double& dzdx,
                                             double& dzdy) {
     const double y2 = y * y;
-    const double g = sqrt(1.0 - c * c * y2);
-    const double zy = c * y2 / (1.0 + g);
+    const double g = fsqrt(1.0 - c * c * y2);
+    const double zy = fdiv(c * y2, 1.0 + g);
     const double rz = r - zy;
-    const double f = sqrt(rz * rz - x * x);
+    const double f = fsqrt(rz * rz - x * x);
     z = r - f;
-    const double inv_f = 1.0 / f;
+    const double inv_f = frcp(f);
     dzdx = x * inv_f;
-    dzdy = rz * (c * y / g) * inv_f;
+    dzdy = rz * fdiv(c * y, g) * inv_f;
 }
 
 // Unit normal at a point of the sag frame (not rotated back, as in the reference).
@@ -114,24 +134,24 @@ __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, do
             return;
         case OPTK_SAG_SPHERICAL: {
             // optika/sags/_spherical.py:141-146
-            const double c = 1.0 / S.sag[0];
+            const double c = S.sag[3];
             nx = c * x;
             ny = c * y;
-            nz = -sqrt(1.0 - nx * nx - ny * ny);
+            nz = -fsqrt(1.0 - nx * nx - ny * ny);
             return;
         }
         case OPTK_SAG_CYLINDRICAL: {
             // optika/sags/_cylindrical.py:107-113
-            nx = x / S.sag[0];
+            nx = x * S.sag[3];
             ny = 0.0;
-            nz = -sqrt(1.0 - nx * nx);
+            nz = -fsqrt(1.0 - nx * nx);
             return;
         }
         case OPTK_SAG_PARABOLIC: {
             // optika/sags/_parabolic.py:56-63: (x, y, -R) / sqrt((x/R)^2 + (y/R)^2 + 1) / R
-            const double r = 2.0 * S.sag[0];
-            const double xr = x / r, yr = y / r;
-            const double inv = 1.0 / sqrt(xr * xr + yr * yr + 1.0);
+            const double ir = 0.5 * S.sag[3];  // 1 / (2 f)
+            const double xr = x * ir, yr = y * ir;
+            const double inv = frsqrt(xr * xr + yr * yr + 1.0);
             nx = xr * inv;
             ny = yr * inv;
             nz = -inv;
@@ -139,10 +159,10 @@ __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, do
         }
         case OPTK_SAG_CONIC: {
             // optika/sags/_conic.py:69-81
-            const double c = 1.0 / S.sag[0];
-            const double g = sqrt(1.0 - (1.0 + S.sag[1]) * c * c * (x * x + y * y));
-            const double dzdx = c * x / g, dzdy = c * y / g;
-            const double inv = 1.0 / sqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+            const double c = S.sag[3];
+            const double ig = frsqrt(1.0 - (1.0 + S.sag[1]) * c * c * (x * x + y * y));
+            const double dzdx = c * x * ig, dzdy = c * y * ig;
+            const double inv = frsqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
             nx = dzdx * inv;
             ny = dzdy * inv;
             nz = -inv;
@@ -151,8 +171,8 @@ __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, do
         case OPTK_SAG_TOROIDAL: {
             // optika/sags/_toroidal.py:71-88
             double z, dzdx, dzdy;
-            toroid_eval(1.0 / S.sag[0], S.sag[2], x, y, z, dzdx, dzdy);
-            const double inv = 1.0 / sqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+            toroid_eval(S.sag[3], S.sag[2], x, y, z, dzdx, dzdy);
+            const double inv = frsqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
             nx = dzdx * inv;
             ny = dzdy * inv;
             nz = -inv;
@@ -168,12 +188,12 @@ __device__ __forceinline__ double sag_value(const optk_surface_t& S, double x, d
         case OPTK_SAG_FLAT:
             return 0.0;
         case OPTK_SAG_SPHERICAL: {
-            const double c = 1.0 / S.sag[0];
+            const double c = S.sag[3];
             const double r2 = x * x + y * y;
             return c * r2 / (1.0 + sqrt(1.0 - c * c * r2));
         }
         case OPTK_SAG_CYLINDRICAL: {
-            const double c = 1.0 / S.sag[0];
+            const double c = S.sag[3];
             const double r2 = x * x;
             return c * r2 / (1.0 + sqrt(1.0 - c * c * r2));
         }
@@ -187,7 +207,7 @@ __device__ __forceinline__ double sag_value(const optk_surface_t& S, double x, d
         }
         case OPTK_SAG_TOROIDAL: {
             double z, dzdx, dzdy;
-            toroid_eval(1.0 / S.sag[0], S.sag[2], x, y, z, dzdx, dzdy);
+            toroid_eval(S.sag[3], S.sag[2], x, y, z, dzdx, dzdy);
             return z;
         }
     }
@@ -237,13 +257,13 @@ __device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px
             const double d2 = (S.flags & OPTK_F_HOLO_DIVERGING_2) ? 1.0 : -1.0;
             double ax = px - S.holo_x1[0], ay = py - S.holo_x1[1], az = pz - S.holo_x1[2];
             double bx = px - S.holo_x2[0], by = py - S.holo_x2[1], bz = pz - S.holo_x2[2];
-            const double ia = d1 / sqrt(ax * ax + ay * ay + az * az);
-            const double ib = d2 / sqrt(bx * bx + by * by + bz * bz);
+            const double ia = d1 * frsqrt(ax * ax + ay * ay + az * az);
+            const double ib = d2 * frsqrt(bx * bx + by * by + bz * bz);
             const double rx = ax * ia - bx * ib, ry = ay * ia - by * ib, rz = az * ia - bz * ib;
             // aq = n x dr
             const double qx = ny * rz - nz * ry, qy = nz * rx - nx * rz, qz = nx * ry - ny * rx;
             // spacing * (q/a) x n  with spacing = w / a   =>  (w / a^2) (aq x n)
-            const double s = S.holo_wavelength / (qx * qx + qy * qy + qz * qz);
+            const double s = fdiv(S.holo_wavelength, qx * qx + qy * qy + qz * qz);
             kx = s * (qy * nz - qz * ny);
             ky = s * (qz * nx - qx * nz);
             kz = s * (qx * ny - qy * nx);
@@ -331,7 +351,11 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
     const int flags = S.flags;
 
     // 1. global -> surface-local (surfaces.py:141-142)
-    if (flags & OPTK_F_TRANSFORM) {
+    if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
+        r.px -= S.transform.t[0];
+        r.py -= S.transform.t[1];
+        r.pz -= S.transform.t[2];
+    } else if (flags & OPTK_F_TRANSFORM) {
         affine_inverse(S.transform, r.px, r.py, r.pz, false);
         affine_inverse(S.transform, r.dx, r.dy, r.dz, true);
     }
@@ -353,14 +377,14 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
             // f(t) = (o + t u).z - sag(T^-1 (o + t u)) from t = 0.  Newton with the
             // analytic gradient, iterated to convergence (the reference's secant
             // stops at |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
-            const double c = 1.0 / S.sag[0], rr = S.sag[2];
+            const double c = S.sag[3], rr = S.sag[2];
             t = 0.0;
             for (int it = 0; it < 64; ++it) {
                 double z, dzdx, dzdy;
                 toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
                 const double f = (r.pz + r.dz * t) - z;
                 const double df = r.dz - (dzdx * vx + dzdy * vy);
-                const double step = f / df;
+                const double step = fdiv(f, df);
                 t -= step;
                 ++newton_iterations;
                 if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(t)))) break;
@@ -374,7 +398,7 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
             const double ex = nx_ - r.px, ey = ny_ - r.py, ez = nz_ - r.pz;
             const double len2 = ex * ex + ey * ey + ez * ez;
             if (r.att != 0.0) {
-                r.intensity = exp(-r.att * sqrt(len2)) * r.intensity;
+                r.intensity = exp(-r.att * fsqrt(len2)) * r.intensity;
             } else if (!(len2 <= 1.7976931348623157e308)) {
                 r.intensity = NAN;  // exp(-0 * inf) = exp(-0 * nan) = nan in the reference
             }
@@ -418,7 +442,7 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
             // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
             const double k2 = kx * kx + ky * ky + kz * kz;
             const double s = sign0(r.dx * nx + r.dy * ny + r.dz * nz);
-            const double f = s * S.ruling_order * r.w / (r.n * k2);
+            const double f = fdiv(s * S.ruling_order * r.w, r.n * k2);
             r.dx += f * kx;
             r.dy += f * ky;
             r.dz += f * kz;
@@ -433,8 +457,8 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
         if (S.material_kind == OPTK_MAT_GLASS) {
             // optika/materials/_materials.py:428-438
             const double w2 = r.w * r.w;
-            n2 = sqrt(1.0 + (S.material[0] * w2 / (w2 - S.material[3]) + S.material[1] * w2 / (w2 - S.material[4]) +
-                             S.material[2] * w2 / (w2 - S.material[5])));
+            n2 = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
+                              S.material[2] * fdiv(w2, w2 - S.material[5])));
         } else if (mirror) {
             n2 = n1;  // _materials.py:135-139
         } else {
@@ -445,12 +469,24 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
         const double au = r.dx * nx + r.dy * ny + r.dz * nz;
         double ratio = 1.0, inv_r2 = 1.0;
         if (n1 != n2) {  // n1 == n2: r = 1 and 1 / r^2 = 1 exactly, skip the divisions
-            ratio = n1 / n2;
-            inv_r2 = 1.0 / (ratio * ratio);
-            r.w = r.w / ratio;  // surfaces.py:165
+            ratio = fdiv(n1, n2);
+            inv_r2 = frcp(ratio * ratio);
+            r.w = fdiv(r.w, ratio);  // surfaces.py:165
         }
         const double sgn = -copysign(1.0, au);
-        const double d = -au + sgn * (mirror ? 1.0 : -1.0) * sqrt(inv_r2 + au * au - a2);
+        // sqrt(1/r^2 + (a.u)^2 - |a|^2).  For an undiffracted ray in an unchanged medium
+        // the radicand is (a.u)^2 + e with e = 1/r^2 - |a|^2 ~ 1e-16: the root is
+        // |a.u| + e / (2 |a.u|) to better than 1e-26 relative, no square root needed.
+        const double au2 = au * au;
+        const double e = inv_r2 - a2;
+        double root;
+        if (fabs(e) < 1e-13 * au2) {
+            const double m = fabs(au);
+            root = fma(0.5 * e, frcp(m), m);
+        } else {
+            root = fsqrt(au2 + e);
+        }
+        const double d = -au + sgn * (mirror ? 1.0 : -1.0) * root;
         r.dx = ratio * (r.dx + d * nx);
         r.dy = ratio * (r.dy + d * ny);
         r.dz = ratio * (r.dz + d * nz);
@@ -470,9 +506,15 @@ __device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& 
     }
 
     // 10. local -> global  (surfaces.py:195-196)
-    if ((flags & OPTK_F_TRANSFORM) && !(flags & OPTK_F_LOCAL_OUT)) {
-        affine_forward(S.transform, r.px, r.py, r.pz, false);
-        affine_forward(S.transform, r.dx, r.dy, r.dz, true);
+    if (!(flags & OPTK_F_LOCAL_OUT)) {
+        if (flags & OPTK_F_TRANSLATION_ONLY) {
+            r.px += S.transform.t[0];
+            r.py += S.transform.t[1];
+            r.pz += S.transform.t[2];
+        } else if (flags & OPTK_F_TRANSFORM) {
+            affine_forward(S.transform, r.px, r.py, r.pz, false);
+            affine_forward(S.transform, r.dx, r.dy, r.dz, true);
+        }
     }
 }
 
@@ -490,7 +532,7 @@ __device__ __forceinline__ void store_ray(const optk_rays_out_t& out, long long 
     if (out.unvignetted) out.unvignetted[o] = r.unv ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams P) {
+__device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
     if (P.has_image) image_guess_init(P.image, &guess);
 
@@ -592,6 +634,12 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     }
 }
 
+// The same body at three occupancy targets (registers per thread capped at 128 / 80 / 64).
+// OPTK_TRACE_OCC=2|3|4 selects one at run time; the default is the measured best.
+__global__ void __launch_bounds__(256, 2) trace_kernel(const __grid_constant__ TraceParams P) { trace_body(P); }
+__global__ void __launch_bounds__(256, 3) trace_kernel_occ3(const __grid_constant__ TraceParams P) { trace_body(P); }
+__global__ void __launch_bounds__(256, 4) trace_kernel_occ4(const __grid_constant__ TraceParams P) { trace_body(P); }
+
 // ---------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------
@@ -603,7 +651,16 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         set_error("optk_trace: too many rays for one launch (%lld)", P.n_rays);
         return OPTK_ERR_INVALID;
     }
-    trace_kernel<<<(unsigned)grid, block, 0, stream>>>(P);
+    static const int occ = [] {
+        const char* e = getenv("OPTK_TRACE_OCC");
+        return e ? atoi(e) : 3;
+    }();
+    if (occ == 4)
+        trace_kernel_occ4<<<(unsigned)grid, block, 0, stream>>>(P);
+    else if (occ == 2)
+        trace_kernel<<<(unsigned)grid, block, 0, stream>>>(P);
+    else
+        trace_kernel_occ3<<<(unsigned)grid, block, 0, stream>>>(P);
     OPTK_CUDA(cudaGetLastError());
     return OPTK_OK;
 }

@@ -352,11 +352,21 @@ def _intercept_secant(sag, o, d, min_step_size=1e-6, max_iterations=100, converg
     return t1
 
 
-def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False) -> dict:
+def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False, extended: bool = False) -> dict:
     """
     ``sag.intercept(rays)``: rays moved to the surface, direction unchanged.
     ``generic=True`` forces the iterative ``AbstractSag.intercept`` for any sag
     (used to restate ``optika/sags/_tests/_abc_test.py:100-102``).
+
+    ``extended=True`` evaluates the SAME closed-form expressions of the parabolic
+    and conic sags in ``numpy.longdouble`` (80-bit on x86) and rounds the path
+    length to float64 at the end.  Those two reference formulas subtract nearly
+    equal numbers for near-axial rays -- in float64 they carry a rounding noise of
+    about ``eps * |2 f| / (ux^2 + uy^2)`` (1e-6 mm in the Newtonian example), which
+    any 1-ulp change upstream re-samples -- so "the reference's answer" is only
+    defined to that noise.  The extended evaluation is the reference's formula
+    without that noise; parity tests compare against it and report the float64
+    noise separately ("conditioning of the reference's closed forms").
     """
     name = _name(sag)
     t = getattr(sag, "transformation", None)
@@ -375,6 +385,9 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
     r = _rays_transform(t, rays, inverse=True)
     ox, oy, oz = r["px"], r["py"], r["pz"]
     ux, uy, uz = r["dx"], r["dy"], r["dz"]
+    o64, u64 = (ox, oy, oz), (ux, uy, uz)
+    if extended and name in ("ParabolicSag", "ConicSag"):
+        ox, oy, oz, ux, uy, uz = [np.asarray(v, dtype=np.longdouble) for v in (ox, oy, oz, ux, uy, uz)]
     with np.errstate(invalid="ignore", divide="ignore"):
         if name == "NoSag":
             # optika/sags/_flat.py:49-64
@@ -388,6 +401,8 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
         elif name == "ParabolicSag":
             # optika/sags/_parabolic.py:65-158
             f = _f(sag.focal_length)
+            if extended:
+                f = np.longdouble(f)
             tt = np.where(
                 (ux**2 + uy**2) > 1e-10,
                 (
@@ -407,6 +422,8 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
             radius, conic = _sag_radius_conic(sag)
             c = 1 / radius
             kp1 = 1 + conic
+            if extended:
+                c, kp1 = np.longdouble(c), np.longdouble(kp1)
             a = c * (np.square(ux) + np.square(uy) + kp1 * np.square(uz))
             b = 2 * (c * (ox * ux + oy * uy + kp1 * oz * uz) - uz)
             cc = c * (np.square(ox) + np.square(oy) + kp1 * np.square(oz)) - 2 * oz
@@ -447,14 +464,16 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
             )
         else:
             raise NotImplementedError(f"oracle: sag {name}")
+        tt = np.asarray(tt, dtype=np.float64)
+        (ox, oy, oz), (ux, uy, uz) = o64, u64
         r = dict(r)
         r["px"], r["py"], r["pz"] = ox + ux * tt, oy + uy * tt, oz + uz * tt
     return _rays_transform(t, r, inverse=False)
 
 
-def sag_propagate(sag, rays: dict, converge: bool = False) -> dict:
+def sag_propagate(sag, rays: dict, converge: bool = False, extended: bool = False) -> dict:
     """``AbstractSag.propagate_rays``, ``optika/sags/_abc.py:109-122``."""
-    result = sag_intercept(sag, rays, converge=converge)
+    result = sag_intercept(sag, rays, converge=converge, extended=extended)
     with np.errstate(invalid="ignore", over="ignore"):
         length = np.sqrt(
             np.square(result["px"] - rays["px"])
@@ -778,7 +797,7 @@ def aperture_clip(aperture, rays: dict) -> dict:
 # ---------------------------------------------------------------------------
 # the surface operator and the sequential loop
 # ---------------------------------------------------------------------------
-def surface_propagate(surface, rays: dict, converge: bool = False) -> dict:
+def surface_propagate(surface, rays: dict, converge: bool = False, extended: bool = False) -> dict:
     """``AbstractSurface.propagate_rays``, ``optika/surfaces.py:123-198``, step by step."""
     sag = surface.sag
     material = surface.material
@@ -789,7 +808,7 @@ def surface_propagate(surface, rays: dict, converge: bool = False) -> dict:
     if transformation is not None:  # :141-142
         rays = _rays_transform(transformation, rays, inverse=True)
 
-    rays_1 = sag_propagate(sag, rays, converge=converge)  # :144
+    rays_1 = sag_propagate(sag, rays, converge=converge, extended=extended)  # :144
     normal = sag_normal(sag, rays_1["px"], rays_1["py"], rays_1["pz"])  # :146-148
 
     if rulings is not None:  # :150-154
@@ -822,18 +841,18 @@ def surface_propagate(surface, rays: dict, converge: bool = False) -> dict:
     return rays_2
 
 
-def propagate_rays(surfaces, rays: dict, converge: bool = False) -> dict:
+def propagate_rays(surfaces, rays: dict, converge: bool = False, extended: bool = False) -> dict:
     """``optika.propagators.propagate_rays``, ``optika/propagators.py:19-41``."""
     for surface in surfaces:
-        rays = surface_propagate(surface, rays, converge=converge)
+        rays = surface_propagate(surface, rays, converge=converge, extended=extended)
     return rays
 
 
-def accumulate_rays(surfaces, rays: dict, converge: bool = False) -> dict:
+def accumulate_rays(surfaces, rays: dict, converge: bool = False, extended: bool = False) -> dict:
     """``optika.propagators.accumulate_rays``, ``optika/propagators.py:44-73`` (new leading axis)."""
     result = []
     for surface in surfaces:
-        rays = surface_propagate(surface, rays, converge=converge)
+        rays = surface_propagate(surface, rays, converge=converge, extended=extended)
         result.append(rays)
     return {k: np.stack([r[k] for r in result]) for k in result[0]}
 

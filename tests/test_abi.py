@@ -1,0 +1,148 @@
+"""
+The C-ABI library loads on a CPU-only box, exports every symbol that
+``include/optk.h`` declares, agrees with the ctypes mirror on struct layout, and
+fails loudly (no CPU fallback) when there is no CUDA device.
+"""
+
+import ctypes as C
+import pathlib
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "optk.h"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+
+    if not (ROOT / "optika_b200" / "liboptk.so").exists():
+        __graft_entry__.build()
+    from optika_b200 import _lib
+
+    return _lib.lib()
+
+
+def declared_symbols():
+    text = HEADER.read_text()
+    return re.findall(r"OPTK_API\s+[\w\s\*]+?\b(optk_\w+)\s*\(", text)
+
+
+def test_exports_every_declared_symbol(lib):
+    from optika_b200 import _lib
+
+    names = declared_symbols()
+    assert len(names) >= 11
+    assert set(names) == set(_lib.SYMBOLS)
+    for name in names:
+        assert getattr(lib, name) is not None
+    out = subprocess.run(["nm", "-D", str(ROOT / "optika_b200" / "liboptk.so")], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (optk_\w+)", out))
+    assert set(names) <= exported
+
+
+def test_struct_layout_matches_c(tmp_path, lib):
+    from optika_b200 import _lib
+
+    structs = {
+        "optk_affine_t": _lib.Affine,
+        "optk_surface_t": _lib.Surface,
+        "optk_rays_in_t": _lib.RaysIn,
+        "optk_rays_out_t": _lib.RaysOut,
+        "optk_image_t": _lib.Image,
+        "optk_trace_stats_t": _lib.TraceStats,
+        "optk_ml_layer_t": _lib.MlLayer,
+        "optk_ml_segment_t": _lib.MlSegment,
+        "optk_ml_input_t": _lib.MlInput,
+    }
+    probes = [
+        ("optk_surface_t", "transform"), ("optk_surface_t", "sag"), ("optk_surface_t", "ruling_power"),
+        ("optk_surface_t", "holo_wavelength"), ("optk_surface_t", "vertices_y"),
+        ("optk_rays_in_t", "field"), ("optk_rays_in_t", "stride"), ("optk_rays_in_t", "mask_stride"),
+        ("optk_rays_in_t", "normal_stride"), ("optk_image_t", "edges_wavelength"), ("optk_image_t", "counts"),
+        ("optk_ml_layer_t", "width_stride"), ("optk_ml_layer_t", "profile_kind"),
+        ("optk_ml_input_t", "direction_stride"), ("optk_ml_input_t", "n_stride"),
+    ]
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "optk.h"', "int main(void) {"]
+    for name in structs:
+        src.append(f'printf("sizeof {name} %zu\\n", sizeof({name}));')
+    for s, f in probes:
+        src.append(f'printf("offsetof {s} {f} %zu\\n", offsetof({s}, {f}));')
+    src += ["return 0;", "}"]
+    c_file = tmp_path / "layout.c"
+    c_file.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(c_file), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.splitlines():
+        parts = line.split()
+        if parts[0] == "sizeof":
+            assert C.sizeof(structs[parts[1]]) == int(parts[2]), line
+        else:
+            assert getattr(structs[parts[1]], parts[2]).offset == int(parts[3]), line
+
+
+def test_constants_match_header():
+    from optika_b200 import _lib
+
+    text = HEADER.read_text()
+
+    def define(name):
+        return int(re.search(rf"#define {name} (\w+)", text).group(1), 0)
+
+    assert define("OPTK_MAX_SURFACES") == _lib.MAX_SURFACES
+    assert define("OPTK_MAX_VERTICES") == _lib.MAX_VERTICES
+    assert define("OPTK_MAX_COEFF") == _lib.MAX_COEFF
+    assert define("OPTK_MAX_AXES") == _lib.MAX_AXES
+    assert define("OPTK_ML_MAX_AXES") == _lib.ML_MAX_AXES
+    assert define("OPTK_STAGE_ALL") == _lib.STAGE_ALL
+    assert define("OPTK_F_LOCAL_OUT") == _lib.F_LOCAL_OUT
+    assert define("OPTK_STAGE_KAPPA_OUT") == _lib.STAGE_KAPPA_OUT
+
+
+def test_system_create_validates_without_a_gpu(lib):
+    from optika_b200 import _lib
+
+    table = (_lib.Surface * 1)()
+    table[0].sag_kind = 99
+    handle = C.c_void_p()
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.optk_system_create(table, 1, 1, C.byref(handle)))
+    table[0].sag_kind = _lib.SAG_FLAT
+    table[0].aperture_kind = _lib.APERTURE_POLYGON
+    table[0].n_vertices = 2
+    with pytest.raises(ValueError):
+        _lib.check(lib.optk_system_create(table, 1, 1, C.byref(handle)))
+    table[0].aperture_kind = _lib.APERTURE_NONE
+    _lib.check(lib.optk_system_create(table, 1, 1, C.byref(handle)))
+    n_s, n_c = C.c_int32(), C.c_int32()
+    _lib.check(lib.optk_system_size(handle, C.byref(n_s), C.byref(n_c)))
+    assert (n_s.value, n_c.value) == (1, 1)
+    _lib.check(lib.optk_system_destroy(handle))
+
+
+def test_no_cpu_fallback():
+    """Without CUDA the product path raises; it never routes to the oracle or any CPU code."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import optika_b200 as optika
+    from optika_b200 import _lib
+    import configs
+
+    system = configs.newtonian(num_field=1, num_pupil=2)
+    with pytest.raises(_lib.OptkError):
+        system.raytrace()
+    with pytest.raises(_lib.OptkError):
+        optika.materials.multilayer_efficiency(1e-5, 1, 1, [optika.materials.Layer("Si", thickness=1e-5)])
+    # the product package must not import the oracle
+    import subprocess, sys
+
+    code = "import sys, optika_b200, optika_b200.systems, optika_b200.sensors; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT)).stdout.strip()
+    assert out == "False"
