@@ -342,10 +342,183 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
     return mask;
 }
 
+// sign0(v) * root for root >= 0, in 3 instructions: copysign unless v == 0 (NaN v gives NaN upstream anyway)
+__device__ __forceinline__ double signed_root(double v, double root) {
+    return (v == 0.0) ? v * root : copysign(root, v);
+}
+
 // ---------------------------------------------------------------------------
-// one surface: AbstractSurface.propagate_rays, optika/surfaces.py:123-198
+// one surface, FULL operator (every stage, sag normal): the streamlined path that
+// SequentialSystem.raytrace / propagate_rays / accumulate_rays take.  Intercept
+// and normal share one switch on the sag kind; no stage tests.
+// AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void surface_propagate(const optk_surface_t& S, Ray& r, unsigned& newton_iterations,
+__device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray& r, unsigned& newton_iterations) {
+    const int flags = S.flags;
+
+    // 1. global -> surface-local (surfaces.py:141-142)
+    if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
+        r.px -= S.transform.t[0];
+        r.py -= S.transform.t[1];
+        r.pz -= S.transform.t[2];
+    } else if (flags & OPTK_F_TRANSFORM) {
+        affine_inverse(S.transform, r.px, r.py, r.pz, false);
+        affine_inverse(S.transform, r.dx, r.dy, r.dz, true);
+    }
+
+    // the ray in the sag's own frame (sag.transformation)
+    double qx = r.px, qy = r.py, qz = r.pz;
+    double vx = r.dx, vy = r.dy, vz = r.dz;
+    if (flags & OPTK_F_SAG_TRANSFORM) {
+        affine_inverse(S.sag_transform, qx, qy, qz, false);
+        affine_inverse(S.sag_transform, vx, vy, vz, true);
+    }
+
+    // 2 + 3. path length to the sag and the unit normal at the hit point (surfaces.py:144-148)
+    double t, nx, ny, nz;
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            t = fdiv(-qz, vz);  // optika/sags/_flat.py:58
+            nx = 0.0; ny = 0.0; nz = -1.0;  // :43-47
+            break;
+        case OPTK_SAG_SPHERICAL: {
+            // optika/sags/_spherical.py:176-184, 141-146
+            const double rad = S.sag[0], c = S.sag[3];
+            const double pz = qz - rad;
+            const double up = vx * qx + vy * qy + vz * pz;
+            const double disc = up * up - (qx * qx + qy * qy + pz * pz - rad * rad);
+            t = -up - signed_root(rad * vz, fsqrt(disc));
+            nx = c * (qx + vx * t);
+            ny = c * (qy + vy * t);
+            nz = -fsqrt(1.0 - nx * nx - ny * ny);
+            break;
+        }
+        default: {
+            if (S.sag_kind == OPTK_SAG_TOROIDAL) {
+                // AbstractSag.intercept, optika/sags/_abc.py:76-107 (see surface_generic)
+                const double c = S.sag[3], rr = S.sag[2];
+                t = 0.0;
+                for (int it = 0; it < 64; ++it) {
+                    double z, dzdx, dzdy;
+                    toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
+                    const double f = (r.pz + r.dz * t) - z;
+                    const double df = r.dz - (dzdx * vx + dzdy * vy);
+                    const double step = fdiv(f, df);
+                    t -= step;
+                    ++newton_iterations;
+                    if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(t)))) break;
+                }
+            } else {
+                t = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
+            }
+            sag_normal(S, qx + vx * t, qy + vy * t, nx, ny, nz);
+            break;
+        }
+    }
+    {
+        const double hx = r.px + r.dx * t, hy = r.py + r.dy * t, hz = r.pz + r.dz * t;
+        // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|)
+        if (r.att != 0.0) {
+            const double ex = hx - r.px, ey = hy - r.py, ez = hz - r.pz;
+            r.intensity = exp(-r.att * fsqrt(ex * ex + ey * ey + ez * ez)) * r.intensity;
+        } else if (!(fabs(hx + hy + hz) <= 1.7976931348623157e308)) {
+            r.intensity = NAN;  // exp(-0 * inf) = exp(-0 * nan) = nan in the reference
+        }
+        r.px = hx; r.py = hy; r.pz = hz;
+    }
+
+    // 4. rulings.incident_effective  (surfaces.py:150-154, rulings/_rulings.py:107-128, 187-204)
+    if (S.ruling_kind != OPTK_RULING_NONE) {
+        double kx, ky, kz;
+        ruling_vector(S, r.px, r.py, r.pz, nx, ny, nz, kx, ky, kz);
+        // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
+        const double k2 = kx * kx + ky * ky + kz * kz;
+        const double an = r.dx * nx + r.dy * ny + r.dz * nz;
+        const double sg = (an == 0.0) ? an : copysign(1.0, an);  // numpy.sign
+        const double f = fdiv(sg * S.ruling_order * r.w, r.n * k2);
+        r.dx += f * kx;
+        r.dy += f * ky;
+        r.dz += f * kz;
+    }
+
+    // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
+    {
+        const double n1 = r.n;
+        double n2;
+        const bool mirror = S.material_kind == OPTK_MAT_MIRROR;
+        if (mirror) {
+            n2 = n1;  // _materials.py:135-139
+        } else if (S.material_kind == OPTK_MAT_GLASS) {
+            // optika/materials/_materials.py:428-438
+            const double w2 = r.w * r.w;
+            n2 = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
+                              S.material[2] * fdiv(w2, w2 - S.material[5])));
+        } else {
+            n2 = 1.0;  // _materials.py:95-99
+        }
+        // optika/materials/_snells_law.py:341-366
+        const double a2 = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
+        const double au = r.dx * nx + r.dy * ny + r.dz * nz;
+        double ratio = 1.0, inv_r2 = 1.0;
+        if (n1 != n2) {  // n1 == n2: r = 1 and 1 / r^2 = 1 exactly, skip the divisions
+            ratio = fdiv(n1, n2);
+            inv_r2 = frcp(ratio * ratio);
+            r.w = fdiv(r.w, ratio);  // surfaces.py:165
+        }
+        // sqrt(1/r^2 + (a.u)^2 - |a|^2): for an undiffracted ray in an unchanged medium the
+        // radicand is (a.u)^2 + e, e ~ 1e-16, and the root is |a.u| + e / (2 |a.u|) to 1e-26
+        const double au2 = au * au;
+        const double e = inv_r2 - a2;
+        double root;
+        if (fabs(e) < 1e-13 * au2) {
+            const double m = fabs(au);
+            root = fma(0.5 * e, frcp(m), m);
+        } else {
+            root = fsqrt(au2 + e);
+        }
+        // d = -au + sgn (2 mirror - 1) root with sgn = -copysign(1, au)
+        const double d = -au + copysign(root, mirror ? -au : au);
+        r.dx = ratio * (r.dx + d * nx);
+        r.dy = ratio * (r.dy + d * ny);
+        r.dz = ratio * (r.dz + d * nz);
+        if (!mirror) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
+        r.n = n2;
+    }
+
+    // 9. aperture.clip_rays on the outgoing ray, local coordinates  (surfaces.py:192-193)
+    if (S.aperture_kind != OPTK_APERTURE_NONE) {
+        bool m;
+        if (S.aperture_kind == OPTK_APERTURE_RECTANGULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
+            // optika/apertures/_apertures.py:962-963 (the common case, inlined)
+            m = (-S.aperture[0] <= r.px) && (r.px <= S.aperture[0]) && (-S.aperture[1] <= r.py) && (r.py <= S.aperture[1]);
+            if (flags & OPTK_F_APERTURE_INVERTED) m = !m;
+            if (!(flags & OPTK_F_APERTURE_ACTIVE)) m = true;
+        } else if (flags & OPTK_F_APERTURE_ANGULAR) {
+            m = aperture_test(S, r.dx, r.dy, r.dz);  // dimensionless aperture: test the direction
+        } else {
+            m = aperture_test(S, r.px, r.py, r.pz);
+        }
+        r.unv = r.unv && m;
+    }
+
+    // 10. local -> global  (surfaces.py:195-196)
+    if (!(flags & OPTK_F_LOCAL_OUT)) {
+        if (flags & OPTK_F_TRANSLATION_ONLY) {
+            r.px += S.transform.t[0];
+            r.py += S.transform.t[1];
+            r.pz += S.transform.t[2];
+        } else if (flags & OPTK_F_TRANSFORM) {
+            affine_forward(S.transform, r.px, r.py, r.pz, false);
+            affine_forward(S.transform, r.dx, r.dy, r.dz, true);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one surface, GENERIC path (partial stage masks, caller-supplied normals: the unit
+// operations of the reference API): AbstractSurface.propagate_rays, optika/surfaces.py:123-198
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray& r, unsigned& newton_iterations,
                                                   bool normal_given, double gnx, double gny, double gnz) {
     const int stages = S.stages;
     const int flags = S.flags;
@@ -532,19 +705,24 @@ __device__ __forceinline__ void store_ray(const optk_rays_out_t& out, long long 
     if (out.unvignetted) out.unvignetted[o] = r.unv ? 1 : 0;
 }
 
+// FULL:  every surface runs the full operator with the sag normal (surface_full);
+//        otherwise the generic path with stage masks / caller normals is used.
+// DENSE: every input is a dense array indexed by the thread index.
+// ACC:   write the state after every surface.   IMAGE: bin the final rays.
+template <bool FULL, bool DENSE, bool ACC, bool IMAGE>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
-    if (P.has_image) image_guess_init(P.image, &guess);
+    if (IMAGE) image_guess_init(P.image, &guess);
 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < P.n_rays;
     unsigned newton_iterations = 0;
     Ray r = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, false};
-    const bool normal_given = P.in.normal[0] != nullptr;
+    const bool normal_given = !FULL && P.in.normal[0] != nullptr;
     double gnx = 0.0, gny = 0.0, gnz = -1.0;
 
     if (valid) {
-        if (P.dense_in) {
+        if (DENSE) {
             r.w = __ldg(P.in.field[OPTK_WAVELENGTH] + i);
             r.px = __ldg(P.in.field[OPTK_PX] + i);
             r.py = __ldg(P.in.field[OPTK_PY] + i);
@@ -603,13 +781,16 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         }
 
         for (int s = 0; s < P.n_surf; ++s) {
-            surface_propagate(P.surf[s], r, newton_iterations, normal_given, gnx, gny, gnz);
-            if (P.accumulate) store_ray(P.out, (long long)s * P.accumulate_stride + i, r);
+            if (FULL)
+                surface_full(P.surf[s], r, newton_iterations);
+            else
+                surface_generic(P.surf[s], r, newton_iterations, normal_given, gnx, gny, gnz);
+            if (ACC) store_ray(P.out, (long long)s * P.accumulate_stride + i, r);
         }
-        if (!P.accumulate) store_ray(P.out, i, r);
+        if (!ACC) store_ray(P.out, i, r);
     }
 
-    if (P.has_image) {
+    if (IMAGE) {
         // AbstractImagingSensor.collect on the final rays in sensor-local coordinates
         // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
         // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
@@ -634,11 +815,39 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     }
 }
 
-// The same body at three occupancy targets (registers per thread capped at 128 / 80 / 64).
-// OPTK_TRACE_OCC=2|3|4 selects one at run time; the default is the measured best.
-__global__ void __launch_bounds__(256, 2) trace_kernel(const __grid_constant__ TraceParams P) { trace_body(P); }
-__global__ void __launch_bounds__(256, 3) trace_kernel_occ3(const __grid_constant__ TraceParams P) { trace_body(P); }
-__global__ void __launch_bounds__(256, 4) trace_kernel_occ4(const __grid_constant__ TraceParams P) { trace_body(P); }
+// One kernel per (occupancy target, FULL, DENSE, ACC, IMAGE): uniform decisions are made once
+// on the host instead of per ray per surface.  OPTK_TRACE_OCC=3|4 selects the register cap
+// (80 / 64 registers per thread, 3 / 4 CTAs of 256 threads per SM); default = measured best.
+template <int MINB, bool FULL, bool DENSE, bool ACC, bool IMAGE>
+__global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
+    trace_body<FULL, DENSE, ACC, IMAGE>(P);
+}
+
+typedef void (*trace_kernel_t)(const TraceParams);
+
+template <int MINB>
+static trace_kernel_t select_kernel(bool full, bool dense, bool acc, bool image) {
+#define OPTK_PICK(F, D, A, I) \
+    if (full == F && dense == D && acc == A && image == I) return (trace_kernel_t)trace_kernel<MINB, F, D, A, I>;
+    OPTK_PICK(true, true, false, false)
+    OPTK_PICK(true, true, true, false)
+    OPTK_PICK(true, true, false, true)
+    OPTK_PICK(true, true, true, true)
+    OPTK_PICK(true, false, false, false)
+    OPTK_PICK(true, false, true, false)
+    OPTK_PICK(true, false, false, true)
+    OPTK_PICK(true, false, true, true)
+    OPTK_PICK(false, true, false, false)
+    OPTK_PICK(false, true, true, false)
+    OPTK_PICK(false, true, false, true)
+    OPTK_PICK(false, true, true, true)
+    OPTK_PICK(false, false, false, false)
+    OPTK_PICK(false, false, true, false)
+    OPTK_PICK(false, false, false, true)
+    OPTK_PICK(false, false, true, true)
+#undef OPTK_PICK
+    return nullptr;
+}
 
 // ---------------------------------------------------------------------------
 // host launcher
@@ -653,15 +862,14 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     }
     static const int occ = [] {
         const char* e = getenv("OPTK_TRACE_OCC");
-        return e ? atoi(e) : 3;
+        return e ? atoi(e) : 4;
     }();
-    if (occ == 4)
-        trace_kernel_occ4<<<(unsigned)grid, block, 0, stream>>>(P);
-    else if (occ == 2)
-        trace_kernel<<<(unsigned)grid, block, 0, stream>>>(P);
-    else
-        trace_kernel_occ3<<<(unsigned)grid, block, 0, stream>>>(P);
-    OPTK_CUDA(cudaGetLastError());
+    bool full = P.in.normal[0] == nullptr;
+    for (int s = 0; s < P.n_surf; ++s) full = full && (P.surf[s].stages == OPTK_STAGE_ALL);
+    const bool dense = P.dense_in != 0, acc = P.accumulate != 0, image = P.has_image != 0;
+    trace_kernel_t kernel = occ == 3 ? select_kernel<3>(full, dense, acc, image) : select_kernel<4>(full, dense, acc, image);
+    void* args[] = {(void*)&P};
+    OPTK_CUDA(cudaLaunchKernel((const void*)kernel, dim3((unsigned)grid), dim3(block), args, 0, stream));
     return OPTK_OK;
 }
 
