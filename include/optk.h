@@ -345,6 +345,9 @@ OPTK_API int optk_multilayer(const optk_ml_input_t* input,
  * FP64 DFMA peak micro-benchmark (the roofline denominator that
  * MEASURED_PEAKS.json does not record): returns achieved FLOP/s. */
 OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream);
+/* Bandwidth (GB/s, 162 B per ray) of the trace kernel's access pattern with no arithmetic:
+ * ten fp64 arrays + a byte mask in, the same out.  Allocates 162 * n_rays bytes. */
+OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, void* stream);
 
 #ifdef __cplusplus
 }

@@ -209,6 +209,7 @@ SYMBOLS = (
     "optk_bin",
     "optk_multilayer",
     "optk_measure_fp64_peak",
+    "optk_measure_soa_copy",
 )
 
 _lib = None
@@ -245,6 +246,7 @@ def lib() -> C.CDLL:
         C.POINTER(MlInput), i32, C.POINTER(MlLayer), i32, C.POINTER(MlSegment), vp, vp, vp, vp, vp,
     ]
     L.optk_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
+    L.optk_measure_soa_copy.argtypes = [i64, C.POINTER(C.c_double), vp]
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int

@@ -4,6 +4,7 @@
 #include "bin.cuh"
 #include "params.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -258,6 +259,19 @@ OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, 
         const bool identity = r[0] == 1.0 && r[4] == 1.0 && r[8] == 1.0 && r[1] == 0.0 && r[2] == 0.0 &&
                               r[3] == 0.0 && r[5] == 0.0 && r[6] == 0.0 && r[7] == 0.0;
         if ((s.flags & OPTK_F_TRANSFORM) && identity) s.flags |= OPTK_F_TRANSLATION_ONLY;
+        if (s.aperture_kind == OPTK_APERTURE_CIRCULAR || s.aperture_kind == OPTK_APERTURE_SECTOR) {
+            // T = max{v : sqrt(v) <= radius} (correctly rounded sqrt): "sqrt(x^2 + y^2) <= radius"
+            // (optika/apertures/_apertures.py:309) becomes "x^2 + y^2 <= T" with identical results
+            const double radius = s.aperture[0];
+            double t = radius * radius;
+            if (radius >= 0.0 && t < INFINITY) {
+                while (std::sqrt(t) > radius) t = std::nextafter(t, 0.0);
+                while (std::sqrt(std::nextafter(t, INFINITY)) <= radius) t = std::nextafter(t, INFINITY);
+            } else if (!(radius >= 0.0)) {
+                t = -1.0;  // negative or NaN radius: nothing is inside
+            }
+            s.aperture[3] = t;
+        }
     }
     *out = sys;
     return OPTK_OK;
@@ -634,6 +648,14 @@ OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream) {
         return OPTK_ERR_INVALID;
     }
     return measure_fp64_peak(flops_per_second, (cudaStream_t)stream);
+}
+
+OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, void* stream) {
+    if (!gbytes_per_second || n_rays < 2) {
+        set_error("optk_measure_soa_copy: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    return measure_soa_copy(n_rays, gbytes_per_second, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@ struct TraceParams {
     long long n_rays;
     long long index_offset;  // added to the thread index before decomposing it into grid indices
     long long accumulate_stride;
+    long long prefetch_distance;  // rays; 0 = off.  L2 prefetch of the rays a later CTA will load
     int32_t n_surf;
     int32_t accumulate;
     int32_t dense_in;  // every input is a dense array indexed by the thread index
@@ -58,5 +59,6 @@ struct MultilayerParams {
 
 int launch_multilayer(const MultilayerParams& P, cudaStream_t stream);
 int measure_fp64_peak(double* flops, cudaStream_t stream);
+int measure_soa_copy(long long n_rays, double* gbytes_per_second, cudaStream_t stream);
 
 }  // namespace optk

@@ -24,6 +24,32 @@ struct Ray {
 // sag profiles, evaluated in the sag's own frame
 // ---------------------------------------------------------------------------
 
+// sign0(v) * root for root >= 0, in 3 instructions: copysign unless v == 0 (NaN v gives NaN upstream anyway)
+__device__ __forceinline__ double signed_root(double v, double root) {
+    return (v == 0.0) ? v * root : copysign(root, v);
+}
+
+// optika/sags/_parabolic.py:142-151: root of a t^2 + 2 h t + c = 0 with
+//   a = ux^2 + uy^2,  h = ox ux + oy uy - 2 f uz,  c = ox^2 + oy^2 - 4 f oz;
+// the reference takes t = (-h - s sqrt(h^2 - a c)) / a with s = sign(f uz), and for
+// a <= 1e-10 its paraxial form t = c / (4 f uz) (which drops ox ux + oy uy; kept verbatim).
+// For near-axial rays -h and s sqrt() nearly cancel (the reference loses ~eps |2f| / a to
+// rounding there, see DESIGN.md "conditioning"); the same root is evaluated in its
+// cancellation-free form c / (-h + s sqrt()).  One division, no branch.
+__device__ __forceinline__ double parabola_intercept(double f, double ox, double oy, double oz, double ux, double uy,
+                                                     double uz) {
+    const double a = ux * ux + uy * uy;
+    const double h = ox * ux + oy * uy - 2.0 * f * uz;
+    const double c = ox * ox + oy * oy - 4.0 * f * oz;
+    const double fuz = f * uz;
+    const double root = signed_root(fuz, fsqrt(h * h - a * c));
+    const bool general = a > 1e-10;
+    const bool stable = -h * fuz >= 0.0;  // -h and root have the same sign (or one of them is zero)
+    const double num = (general && !stable) ? (-h - root) : c;
+    const double den = general ? (stable ? (-h + root) : a) : 4.0 * fuz;
+    return fdiv(num, den);
+}
+
 // Path length t to the surface for a ray o + t u (closed forms), or NaN/inf on a miss.
 __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, double ox, double oy, double oz,
                                                        double ux, double uy, double uz) {
@@ -39,26 +65,8 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
             const double disc = up * up - (ox * ox + oy * oy + pz * pz - r * r);
             return -up - sign0(r * uz) * fsqrt(disc);
         }
-        case OPTK_SAG_PARABOLIC: {
-            // optika/sags/_parabolic.py:142-151: root of a t^2 + 2 h t + c = 0 with
-            //   a = ux^2 + uy^2,  h = ox ux + oy uy - 2 f uz,  c = ox^2 + oy^2 - 4 f oz,
-            // the reference takes t = (-h - s sqrt(h^2 - a c)) / a with s = sign(f uz).
-            // For near-axial rays -h and s sqrt() nearly cancel (the reference loses
-            // ~eps |2f| / a to rounding there, see DESIGN.md "conditioning"); the same root
-            // is evaluated here in its cancellation-free form c / (-h + s sqrt()).
-            const double f = S.sag[0];
-            const double a = ux * ux + uy * uy;
-            if (a > 1e-10) {
-                const double h = ox * ux + oy * uy - 2.0 * f * uz;
-                const double c = ox * ox + oy * oy - 4.0 * f * oz;
-                const double s = sign0(f * uz);
-                const double root = s * fsqrt(h * h - a * c);
-                // -h and root have the same sign: divide; otherwise the direct form is the stable one
-                return (-h * s >= 0.0) ? fdiv(c, -h + root) : fdiv(-h - root, a);
-            }
-            // the reference's paraxial branch, verbatim (it drops the ox ux + oy uy terms)
-            return fdiv(ox * ox + oy * oy - 4.0 * f * oz, 4.0 * f * uz);
-        }
+        case OPTK_SAG_PARABOLIC:
+            return parabola_intercept(S.sag[0], ox, oy, oz, ux, uy, uz);
         case OPTK_SAG_CONIC: {
             // optika/sags/_conic.py:126-162: A t^2 + B t + C = 0, both roots tested for the
             // vertex sheet, the smaller |t| wins.  root(-1) = (-B - sqrt)/(2A) and
@@ -289,7 +297,10 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
     switch (S.aperture_kind) {
         case OPTK_APERTURE_CIRCULAR:
             // optika/apertures/_apertures.py:309: position.xy.length <= radius
-            mask = sqrt(add_rn(mul_rn(x, x), mul_rn(y, y))) <= S.aperture[0];
+            // sqrt is monotone and correctly rounded in the reference, so "sqrt(r2) <= radius" is
+            // exactly "r2 <= T" with T = max{v : sqrt(v) <= radius}, which optk_system_create
+            // stores in aperture[3]: same decision bit for bit, no square root per ray
+            mask = add_rn(mul_rn(x, x), mul_rn(y, y)) <= S.aperture[3];
             break;
         case OPTK_APERTURE_RECTANGULAR:
             // optika/apertures/_apertures.py:962-963
@@ -303,7 +314,7 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
         }
         case OPTK_APERTURE_SECTOR: {
             // optika/apertures/_apertures.py:466-476
-            const bool mask_radius = sqrt(add_rn(mul_rn(x, x), mul_rn(y, y))) <= S.aperture[0];
+            const bool mask_radius = add_rn(mul_rn(x, x), mul_rn(y, y)) <= S.aperture[3];
             const double a0 = S.aperture[1], a1 = S.aperture[2];
             const double angle = atan2(y, x);
             const double two_pi = 6.283185307179586;
@@ -342,174 +353,233 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
     return mask;
 }
 
-// sign0(v) * root for root >= 0, in 3 instructions: copysign unless v == 0 (NaN v gives NaN upstream anyway)
-__device__ __forceinline__ double signed_root(double v, double root) {
-    return (v == 0.0) ? v * root : copysign(root, v);
-}
-
 // ---------------------------------------------------------------------------
-// one surface, FULL operator (every stage, sag normal): the streamlined path that
-// SequentialSystem.raytrace / propagate_rays / accumulate_rays take.  Intercept
-// and normal share one switch on the sag kind; no stage tests.
+// one surface, FULL operator (every stage, sag normal, no sag transformation): the
+// streamlined path that SequentialSystem.raytrace / propagate_rays / accumulate_rays
+// take.  R rays per thread walk the surface together: every decision that depends
+// only on the surface (transform kind, sag kind, rulings, material, aperture kind) is
+// taken once for the R rays, whose arithmetic then interleaves (instruction-level
+// parallelism for the long fp64 dependency chains).
 // AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray& r, unsigned& newton_iterations) {
+template <int R>
+__device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations) {
     const int flags = S.flags;
 
     // 1. global -> surface-local (surfaces.py:141-142)
     if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
-        r.px -= S.transform.t[0];
-        r.py -= S.transform.t[1];
-        r.pz -= S.transform.t[2];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            r[k].px -= S.transform.t[0];
+            r[k].py -= S.transform.t[1];
+            r[k].pz -= S.transform.t[2];
+        }
     } else if (flags & OPTK_F_TRANSFORM) {
-        affine_inverse(S.transform, r.px, r.py, r.pz, false);
-        affine_inverse(S.transform, r.dx, r.dy, r.dz, true);
-    }
-
-    // the ray in the sag's own frame (sag.transformation)
-    double qx = r.px, qy = r.py, qz = r.pz;
-    double vx = r.dx, vy = r.dy, vz = r.dz;
-    if (flags & OPTK_F_SAG_TRANSFORM) {
-        affine_inverse(S.sag_transform, qx, qy, qz, false);
-        affine_inverse(S.sag_transform, vx, vy, vz, true);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            affine_inverse(S.transform, r[k].px, r[k].py, r[k].pz, false);
+            affine_inverse(S.transform, r[k].dx, r[k].dy, r[k].dz, true);
+        }
     }
 
     // 2 + 3. path length to the sag and the unit normal at the hit point (surfaces.py:144-148)
-    double t, nx, ny, nz;
+    double t[R], nx[R], ny[R], nz[R];
     switch (S.sag_kind) {
         case OPTK_SAG_FLAT:
-            t = fdiv(-qz, vz);  // optika/sags/_flat.py:58
-            nx = 0.0; ny = 0.0; nz = -1.0;  // :43-47
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                t[k] = fdiv(-r[k].pz, r[k].dz);  // optika/sags/_flat.py:58
+                nx[k] = 0.0; ny[k] = 0.0; nz[k] = -1.0;  // :43-47
+            }
             break;
         case OPTK_SAG_SPHERICAL: {
             // optika/sags/_spherical.py:176-184, 141-146
             const double rad = S.sag[0], c = S.sag[3];
-            const double pz = qz - rad;
-            const double up = vx * qx + vy * qy + vz * pz;
-            const double disc = up * up - (qx * qx + qy * qy + pz * pz - rad * rad);
-            t = -up - signed_root(rad * vz, fsqrt(disc));
-            nx = c * (qx + vx * t);
-            ny = c * (qy + vy * t);
-            nz = -fsqrt(1.0 - nx * nx - ny * ny);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double qx = r[k].px, qy = r[k].py, pz = r[k].pz - rad;
+                const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
+                const double up = vx * qx + vy * qy + vz * pz;
+                const double disc = up * up - (qx * qx + qy * qy + pz * pz - rad * rad);
+                t[k] = -up - signed_root(rad * vz, fsqrt(disc));
+                nx[k] = c * (qx + vx * t[k]);
+                ny[k] = c * (qy + vy * t[k]);
+                nz[k] = -fsqrt(1.0 - nx[k] * nx[k] - ny[k] * ny[k]);
+            }
+            break;
+        }
+        case OPTK_SAG_PARABOLIC: {
+            // optika/sags/_parabolic.py:142-151, 56-63
+            const double f = S.sag[0], ir = 0.5 * S.sag[3];  // 1 / (2 f)
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                t[k] = parabola_intercept(f, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
+                const double xr = (r[k].px + r[k].dx * t[k]) * ir, yr = (r[k].py + r[k].dy * t[k]) * ir;
+                const double inv = frsqrt(xr * xr + yr * yr + 1.0);
+                nx[k] = xr * inv;
+                ny[k] = yr * inv;
+                nz[k] = -inv;
+            }
             break;
         }
         default: {
-            if (S.sag_kind == OPTK_SAG_TOROIDAL) {
-                // AbstractSag.intercept, optika/sags/_abc.py:76-107 (see surface_generic)
-                const double c = S.sag[3], rr = S.sag[2];
-                t = 0.0;
-                for (int it = 0; it < 64; ++it) {
-                    double z, dzdx, dzdy;
-                    toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
-                    const double f = (r.pz + r.dz * t) - z;
-                    const double df = r.dz - (dzdx * vx + dzdy * vy);
-                    const double step = fdiv(f, df);
-                    t -= step;
-                    ++newton_iterations;
-                    if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(t)))) break;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double qx = r[k].px, qy = r[k].py, qz = r[k].pz;
+                const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
+                if (S.sag_kind == OPTK_SAG_TOROIDAL) {
+                    // AbstractSag.intercept, optika/sags/_abc.py:76-107: root of
+                    // f(t) = (o + t u).z - sag(o + t u) from t = 0.  Newton with the analytic
+                    // gradient, iterated to convergence (the reference's secant stops at
+                    // |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
+                    const double c = S.sag[3], rr = S.sag[2];
+                    double tt = 0.0;
+                    for (int it = 0; it < 64; ++it) {
+                        double z, dzdx, dzdy;
+                        toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
+                        const double f = (qz + vz * tt) - z;
+                        const double df = vz - (dzdx * vx + dzdy * vy);
+                        const double step = fdiv(f, df);
+                        tt -= step;
+                        ++newton_iterations;
+                        if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(tt)))) break;
+                    }
+                    t[k] = tt;
+                } else {
+                    t[k] = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
                 }
-            } else {
-                t = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
+                sag_normal(S, qx + vx * t[k], qy + vy * t[k], nx[k], ny[k], nz[k]);
             }
-            sag_normal(S, qx + vx * t, qy + vy * t, nx, ny, nz);
             break;
         }
     }
     {
-        const double hx = r.px + r.dx * t, hy = r.py + r.dy * t, hz = r.pz + r.dz * t;
-        // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|)
-        if (r.att != 0.0) {
-            const double ex = hx - r.px, ey = hy - r.py, ez = hz - r.pz;
-            r.intensity = exp(-r.att * fsqrt(ex * ex + ey * ey + ez * ez)) * r.intensity;
-        } else if (!(fabs(hx + hy + hz) <= 1.7976931348623157e308)) {
-            r.intensity = NAN;  // exp(-0 * inf) = exp(-0 * nan) = nan in the reference
+        // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|).
+        // With attenuation == 0 the factor is exactly 1 unless the displacement is not finite
+        // (exp(-0 * inf) = exp(-0 * nan) = nan in the reference).
+        bool attenuating = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k) attenuating = attenuating || (r[k].att != 0.0);
+        if (attenuating) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double ex = r[k].dx * t[k], ey = r[k].dy * t[k], ez = r[k].dz * t[k];
+                r[k].intensity = exp(-r[k].att * fsqrt(ex * ex + ey * ey + ez * ez)) * r[k].intensity;
+            }
         }
-        r.px = hx; r.py = hy; r.pz = hz;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const double hx = r[k].px + r[k].dx * t[k], hy = r[k].py + r[k].dy * t[k], hz = r[k].pz + r[k].dz * t[k];
+            const bool finite = fabs(hx + hy + hz) <= 1.7976931348623157e308;
+            r[k].intensity = finite ? r[k].intensity : OPTK_NAN;
+            r[k].px = hx; r[k].py = hy; r[k].pz = hz;
+        }
     }
 
     // 4. rulings.incident_effective  (surfaces.py:150-154, rulings/_rulings.py:107-128, 187-204)
     if (S.ruling_kind != OPTK_RULING_NONE) {
-        double kx, ky, kz;
-        ruling_vector(S, r.px, r.py, r.pz, nx, ny, nz, kx, ky, kz);
-        // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
-        const double k2 = kx * kx + ky * ky + kz * kz;
-        const double an = r.dx * nx + r.dy * ny + r.dz * nz;
-        const double sg = (an == 0.0) ? an : copysign(1.0, an);  // numpy.sign
-        const double f = fdiv(sg * S.ruling_order * r.w, r.n * k2);
-        r.dx += f * kx;
-        r.dy += f * ky;
-        r.dz += f * kz;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double kx, ky, kz;
+            ruling_vector(S, r[k].px, r[k].py, r[k].pz, nx[k], ny[k], nz[k], kx, ky, kz);
+            // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
+            const double k2 = kx * kx + ky * ky + kz * kz;
+            const double an = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
+            const double sg = (an == 0.0) ? an : copysign(1.0, an);  // numpy.sign
+            const double f = fdiv(sg * S.ruling_order * r[k].w, r[k].n * k2);
+            r[k].dx += f * kx;
+            r[k].dy += f * ky;
+            r[k].dz += f * kz;
+        }
     }
 
     // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
     {
-        const double n1 = r.n;
-        double n2;
         const bool mirror = S.material_kind == OPTK_MAT_MIRROR;
-        if (mirror) {
-            n2 = n1;  // _materials.py:135-139
-        } else if (S.material_kind == OPTK_MAT_GLASS) {
-            // optika/materials/_materials.py:428-438
-            const double w2 = r.w * r.w;
-            n2 = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
-                              S.material[2] * fdiv(w2, w2 - S.material[5])));
-        } else {
-            n2 = 1.0;  // _materials.py:95-99
+        const bool glass = S.material_kind == OPTK_MAT_GLASS;
+        double n2[R];
+        bool same_medium = true;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (mirror) {
+                n2[k] = r[k].n;  // _materials.py:135-139
+            } else if (glass) {
+                // optika/materials/_materials.py:428-438
+                const double w2 = r[k].w * r[k].w;
+                n2[k] = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) +
+                                     S.material[1] * fdiv(w2, w2 - S.material[4]) +
+                                     S.material[2] * fdiv(w2, w2 - S.material[5])));
+            } else {
+                n2[k] = 1.0;  // _materials.py:95-99
+            }
+            same_medium = same_medium && (r[k].n == n2[k]);
         }
-        // optika/materials/_snells_law.py:341-366
-        const double a2 = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
-        const double au = r.dx * nx + r.dy * ny + r.dz * nz;
-        double ratio = 1.0, inv_r2 = 1.0;
-        if (n1 != n2) {  // n1 == n2: r = 1 and 1 / r^2 = 1 exactly, skip the divisions
-            ratio = fdiv(n1, n2);
-            inv_r2 = frcp(ratio * ratio);
-            r.w = fdiv(r.w, ratio);  // surfaces.py:165
+        // n1 == n2: r = 1 and 1 / r^2 = 1 exactly (no divisions, wavelength unchanged)
+        double ratio[R], inv_r2[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) ratio[k] = inv_r2[k] = 1.0;
+        if (!same_medium) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                ratio[k] = fdiv(r[k].n, n2[k]);
+                inv_r2[k] = frcp(ratio[k] * ratio[k]);
+                r[k].w = fdiv(r[k].w, ratio[k]);  // surfaces.py:165
+            }
         }
-        // sqrt(1/r^2 + (a.u)^2 - |a|^2): for an undiffracted ray in an unchanged medium the
-        // radicand is (a.u)^2 + e, e ~ 1e-16, and the root is |a.u| + e / (2 |a.u|) to 1e-26
-        const double au2 = au * au;
-        const double e = inv_r2 - a2;
-        double root;
-        if (fabs(e) < 1e-13 * au2) {
-            const double m = fabs(au);
-            root = fma(0.5 * e, frcp(m), m);
-        } else {
-            root = fsqrt(au2 + e);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            // optika/materials/_snells_law.py:341-366
+            const double a2 = r[k].dx * r[k].dx + r[k].dy * r[k].dy + r[k].dz * r[k].dz;
+            const double au = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
+            const double root = fsqrt(inv_r2[k] + au * au - a2);
+            // d = -au + sgn (2 mirror - 1) root with sgn = -copysign(1, au)
+            const double d = -au + copysign(root, mirror ? -au : au);
+            r[k].dx = ratio[k] * (r[k].dx + d * nx[k]);
+            r[k].dy = ratio[k] * (r[k].dy + d * ny[k]);
+            r[k].dz = ratio[k] * (r[k].dz + d * nz[k]);
+            if (!mirror) r[k].att = 0.0;  // _materials.py:101-105, 141-145, 440-444
+            r[k].n = n2[k];
         }
-        // d = -au + sgn (2 mirror - 1) root with sgn = -copysign(1, au)
-        const double d = -au + copysign(root, mirror ? -au : au);
-        r.dx = ratio * (r.dx + d * nx);
-        r.dy = ratio * (r.dy + d * ny);
-        r.dz = ratio * (r.dz + d * nz);
-        if (!mirror) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
-        r.n = n2;
     }
 
     // 9. aperture.clip_rays on the outgoing ray, local coordinates  (surfaces.py:192-193)
     if (S.aperture_kind != OPTK_APERTURE_NONE) {
-        bool m;
         if (S.aperture_kind == OPTK_APERTURE_RECTANGULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
             // optika/apertures/_apertures.py:962-963 (the common case, inlined)
-            m = (-S.aperture[0] <= r.px) && (r.px <= S.aperture[0]) && (-S.aperture[1] <= r.py) && (r.py <= S.aperture[1]);
-            if (flags & OPTK_F_APERTURE_INVERTED) m = !m;
-            if (!(flags & OPTK_F_APERTURE_ACTIVE)) m = true;
-        } else if (flags & OPTK_F_APERTURE_ANGULAR) {
-            m = aperture_test(S, r.dx, r.dy, r.dz);  // dimensionless aperture: test the direction
+            const double hx = S.aperture[0], hy = S.aperture[1];
+            const bool inverted = flags & OPTK_F_APERTURE_INVERTED, active = flags & OPTK_F_APERTURE_ACTIVE;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                bool m = (-hx <= r[k].px) && (r[k].px <= hx) && (-hy <= r[k].py) && (r[k].py <= hy);
+                m = (m != inverted) || !active;
+                r[k].unv = r[k].unv && m;
+            }
         } else {
-            m = aperture_test(S, r.px, r.py, r.pz);
+            const bool angular = flags & OPTK_F_APERTURE_ANGULAR;  // dimensionless aperture: test the direction
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const bool m = angular ? aperture_test(S, r[k].dx, r[k].dy, r[k].dz)
+                                       : aperture_test(S, r[k].px, r[k].py, r[k].pz);
+                r[k].unv = r[k].unv && m;
+            }
         }
-        r.unv = r.unv && m;
     }
 
     // 10. local -> global  (surfaces.py:195-196)
     if (!(flags & OPTK_F_LOCAL_OUT)) {
         if (flags & OPTK_F_TRANSLATION_ONLY) {
-            r.px += S.transform.t[0];
-            r.py += S.transform.t[1];
-            r.pz += S.transform.t[2];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                r[k].px += S.transform.t[0];
+                r[k].py += S.transform.t[1];
+                r[k].pz += S.transform.t[2];
+            }
         } else if (flags & OPTK_F_TRANSFORM) {
-            affine_forward(S.transform, r.px, r.py, r.pz, false);
-            affine_forward(S.transform, r.dx, r.dy, r.dz, true);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                affine_forward(S.transform, r[k].px, r[k].py, r[k].pz, false);
+                affine_forward(S.transform, r[k].dx, r[k].dy, r[k].dz, true);
+            }
         }
     }
 }
@@ -705,35 +775,30 @@ __device__ __forceinline__ void store_ray(const optk_rays_out_t& out, long long 
     if (out.unvignetted) out.unvignetted[o] = r.unv ? 1 : 0;
 }
 
-// FULL:  every surface runs the full operator with the sag normal (surface_full);
-//        otherwise the generic path with stage masks / caller normals is used.
-// DENSE: every input is a dense array indexed by the thread index.
+// FULL:  every surface runs the full operator with the sag normal (surface_full, R = 2 rays
+//        per thread); otherwise the generic path with stage masks / caller normals (R = 1).
+// DENSE: every input is a dense array indexed by the ray index.  VEC: the dense arrays are
+//        16-byte aligned, so the two rays of a thread move as one 128-bit load / store.
 // ACC:   write the state after every surface.   IMAGE: bin the final rays.
-template <bool FULL, bool DENSE, bool ACC, bool IMAGE>
-__device__ __forceinline__ void trace_body(const TraceParams& P) {
-    __shared__ ImageGuess guess;
-    if (IMAGE) image_guess_init(P.image, &guess);
-
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < P.n_rays;
-    unsigned newton_iterations = 0;
-    Ray r = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, false};
-    const bool normal_given = !FULL && P.in.normal[0] != nullptr;
-    double gnx = 0.0, gny = 0.0, gnz = -1.0;
-
-    if (valid) {
+template <int R, bool DENSE>
+__device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, const bool (&valid)[R], Ray (&r)[R],
+                                          bool normal_given, double& gnx, double& gny, double& gnz) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        if (!valid[k]) continue;
+        const long long i = i0 + k;
         if (DENSE) {
-            r.w = __ldg(P.in.field[OPTK_WAVELENGTH] + i);
-            r.px = __ldg(P.in.field[OPTK_PX] + i);
-            r.py = __ldg(P.in.field[OPTK_PY] + i);
-            r.pz = __ldg(P.in.field[OPTK_PZ] + i);
-            r.dx = __ldg(P.in.field[OPTK_DX] + i);
-            r.dy = __ldg(P.in.field[OPTK_DY] + i);
-            r.dz = __ldg(P.in.field[OPTK_DZ] + i);
-            r.intensity = __ldg(P.in.field[OPTK_INTENSITY] + i);
-            r.att = __ldg(P.in.field[OPTK_ATTENUATION] + i);
-            r.n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + i);
-            r.unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + i) != 0) : true;
+            r[k].w = __ldg(P.in.field[OPTK_WAVELENGTH] + i);
+            r[k].px = __ldg(P.in.field[OPTK_PX] + i);
+            r[k].py = __ldg(P.in.field[OPTK_PY] + i);
+            r[k].pz = __ldg(P.in.field[OPTK_PZ] + i);
+            r[k].dx = __ldg(P.in.field[OPTK_DX] + i);
+            r[k].dy = __ldg(P.in.field[OPTK_DY] + i);
+            r[k].dz = __ldg(P.in.field[OPTK_DZ] + i);
+            r[k].intensity = __ldg(P.in.field[OPTK_INTENSITY] + i);
+            r[k].att = __ldg(P.in.field[OPTK_ATTENUATION] + i);
+            r[k].n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + i);
+            r[k].unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + i) != 0) : true;
             if (normal_given) {
                 gnx = __ldg(P.in.normal[0] + i);
                 gny = __ldg(P.in.normal[1] + i);
@@ -759,7 +824,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                 off[OPTK_NUM_FIELDS] += (long long)idx * P.in.mask_stride[a];
                 if (normal_given) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) offn[k] += (long long)idx * P.in.normal_stride[k][a];
+                    for (int c = 0; c < 3; ++c) offn[c] += (long long)idx * P.in.normal_stride[c][a];
                 }
             }
             if (normal_given) {
@@ -767,45 +832,164 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                 gny = __ldg(P.in.normal[1] + offn[1]);
                 gnz = __ldg(P.in.normal[2] + offn[2]);
             }
-            r.w = __ldg(P.in.field[OPTK_WAVELENGTH] + off[OPTK_WAVELENGTH]);
-            r.px = __ldg(P.in.field[OPTK_PX] + off[OPTK_PX]);
-            r.py = __ldg(P.in.field[OPTK_PY] + off[OPTK_PY]);
-            r.pz = __ldg(P.in.field[OPTK_PZ] + off[OPTK_PZ]);
-            r.dx = __ldg(P.in.field[OPTK_DX] + off[OPTK_DX]);
-            r.dy = __ldg(P.in.field[OPTK_DY] + off[OPTK_DY]);
-            r.dz = __ldg(P.in.field[OPTK_DZ] + off[OPTK_DZ]);
-            r.intensity = __ldg(P.in.field[OPTK_INTENSITY] + off[OPTK_INTENSITY]);
-            r.att = __ldg(P.in.field[OPTK_ATTENUATION] + off[OPTK_ATTENUATION]);
-            r.n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + off[OPTK_INDEX_REFRACTION]);
-            r.unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + off[OPTK_NUM_FIELDS]) != 0) : true;
+            r[k].w = __ldg(P.in.field[OPTK_WAVELENGTH] + off[OPTK_WAVELENGTH]);
+            r[k].px = __ldg(P.in.field[OPTK_PX] + off[OPTK_PX]);
+            r[k].py = __ldg(P.in.field[OPTK_PY] + off[OPTK_PY]);
+            r[k].pz = __ldg(P.in.field[OPTK_PZ] + off[OPTK_PZ]);
+            r[k].dx = __ldg(P.in.field[OPTK_DX] + off[OPTK_DX]);
+            r[k].dy = __ldg(P.in.field[OPTK_DY] + off[OPTK_DY]);
+            r[k].dz = __ldg(P.in.field[OPTK_DZ] + off[OPTK_DZ]);
+            r[k].intensity = __ldg(P.in.field[OPTK_INTENSITY] + off[OPTK_INTENSITY]);
+            r[k].att = __ldg(P.in.field[OPTK_ATTENUATION] + off[OPTK_ATTENUATION]);
+            r[k].n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + off[OPTK_INDEX_REFRACTION]);
+            r[k].unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + off[OPTK_NUM_FIELDS]) != 0) : true;
         }
+    }
+}
 
+// 128-bit access to two consecutive rays of one field
+__device__ __forceinline__ void load_pair(const double* p, long long i, double& a, double& b) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
+    a = v.x;
+    b = v.y;
+}
+__device__ __forceinline__ void store_pair(double* p, long long i, double a, double b) {
+    if (p) *reinterpret_cast<double2*>(p + i) = make_double2(a, b);
+}
+
+__device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long long o, const Ray (&r)[2]) {
+    store_pair(out.field[OPTK_WAVELENGTH], o, r[0].w, r[1].w);
+    store_pair(out.field[OPTK_PX], o, r[0].px, r[1].px);
+    store_pair(out.field[OPTK_PY], o, r[0].py, r[1].py);
+    store_pair(out.field[OPTK_PZ], o, r[0].pz, r[1].pz);
+    store_pair(out.field[OPTK_DX], o, r[0].dx, r[1].dx);
+    store_pair(out.field[OPTK_DY], o, r[0].dy, r[1].dy);
+    store_pair(out.field[OPTK_DZ], o, r[0].dz, r[1].dz);
+    store_pair(out.field[OPTK_INTENSITY], o, r[0].intensity, r[1].intensity);
+    store_pair(out.field[OPTK_ATTENUATION], o, r[0].att, r[1].att);
+    store_pair(out.field[OPTK_INDEX_REFRACTION], o, r[0].n, r[1].n);
+    if (out.unvignetted)
+        *reinterpret_cast<uchar2*>(out.unvignetted + o) = make_uchar2(r[0].unv ? 1 : 0, r[1].unv ? 1 : 0);
+}
+
+template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
+__device__ __forceinline__ void trace_body(const TraceParams& P) {
+    __shared__ ImageGuess guess;
+    if (IMAGE) image_guess_init(P.image, &guess);
+
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
+    bool valid[R];
+    Ray r[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        valid[k] = i0 + k < P.n_rays;
+        r[k] = Ray{1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, false};  // dummy ray for idle lanes
+    }
+    unsigned newton_iterations = 0;
+    const bool normal_given = !FULL && P.in.normal[0] != nullptr;
+    double gnx = 0.0, gny = 0.0, gnz = -1.0;
+
+    // Memory-level parallelism: each CTA computes for ~10k cycles between its loads and
+    // its stores, so too few bytes are in flight to cover HBM latency.  Every thread asks L2
+    // for the lines that the CTA scheduled one "wave" later will load, so DRAM streams while
+    // the SMs compute and those loads become L2 hits.
+    if (DENSE && P.prefetch_distance > 0) {
+        const long long ip = i0 + P.prefetch_distance;
+        if (ip < P.n_rays) {
+#pragma unroll
+            for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.in.field[f] + ip));
+        }
+    }
+
+    // the whole thread is "vector" when both of its rays exist (only the last thread may not be)
+    const bool pair = R == 2 && VEC && valid[R - 1];
+    if (pair) {
+        load_pair(P.in.field[OPTK_WAVELENGTH], i0, r[0].w, r[R - 1].w);
+        load_pair(P.in.field[OPTK_PX], i0, r[0].px, r[R - 1].px);
+        load_pair(P.in.field[OPTK_PY], i0, r[0].py, r[R - 1].py);
+        load_pair(P.in.field[OPTK_PZ], i0, r[0].pz, r[R - 1].pz);
+        load_pair(P.in.field[OPTK_DX], i0, r[0].dx, r[R - 1].dx);
+        load_pair(P.in.field[OPTK_DY], i0, r[0].dy, r[R - 1].dy);
+        load_pair(P.in.field[OPTK_DZ], i0, r[0].dz, r[R - 1].dz);
+        load_pair(P.in.field[OPTK_INTENSITY], i0, r[0].intensity, r[R - 1].intensity);
+        load_pair(P.in.field[OPTK_ATTENUATION], i0, r[0].att, r[R - 1].att);
+        load_pair(P.in.field[OPTK_INDEX_REFRACTION], i0, r[0].n, r[R - 1].n);
+        if (P.in.unvignetted) {
+            const uchar2 m = *reinterpret_cast<const uchar2*>(P.in.unvignetted + i0);
+            r[0].unv = m.x != 0;
+            r[R - 1].unv = m.y != 0;
+        } else {
+            r[0].unv = r[R - 1].unv = true;
+        }
+    } else {
+        load_rays<R, DENSE>(P, i0, valid, r, normal_given, gnx, gny, gnz);
+    }
+
+    // No `if (valid)` around the walk: threads past the end trace a harmless dummy ray, so the
+    // surface loop stays warp-convergent and its per-surface decisions and parameter loads
+    // can use the uniform datapath (only the stores are predicated).
+    {
         for (int s = 0; s < P.n_surf; ++s) {
             if (FULL)
-                surface_full(P.surf[s], r, newton_iterations);
+                surface_full<R>(P.surf[s], r, newton_iterations);
             else
-                surface_generic(P.surf[s], r, newton_iterations, normal_given, gnx, gny, gnz);
-            if (ACC) store_ray(P.out, (long long)s * P.accumulate_stride + i, r);
+                surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz);
+            if (ACC) {
+                const long long o = (long long)s * P.accumulate_stride + i0;
+                bool done = false;
+                if constexpr (R == 2 && VEC) {
+                    if (pair) {
+                        store_rays_vec(P.out, o, r);
+                        done = true;
+                    }
+                }
+                if (!done) {
+#pragma unroll
+                    for (int k = 0; k < R; ++k)
+                        if (valid[k]) store_ray(P.out, o + k, r[k]);
+                }
+            }
         }
-        if (!ACC) store_ray(P.out, i, r);
+        if (!ACC) {
+            bool done = false;
+            if constexpr (R == 2 && VEC) {
+                if (pair) {
+                    store_rays_vec(P.out, i0, r);
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    if (valid[k]) store_ray(P.out, i0 + k, r[k]);
+            }
+        }
     }
 
     if (IMAGE) {
         // AbstractImagingSensor.collect on the final rays in sensor-local coordinates
         // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
         // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
-        double x = r.px, y = r.py, z = r.pz, cx = r.dx, cy = r.dy, cz = r.dz;
-        if (valid && P.has_frame) {
-            affine_inverse(P.frame, x, y, z, false);
-            affine_inverse(P.frame, cx, cy, cz, true);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double x = r[k].px, y = r[k].py, z = r[k].pz, cx = r[k].dx, cy = r[k].dy, cz = r[k].dz;
+            if (valid[k] && P.has_frame) {
+                affine_inverse(P.frame, x, y, z, false);
+                affine_inverse(P.frame, cx, cy, cz, true);
+            }
+            image_bin_ray(P.image, guess, valid[k], r[k].w, x, y, cz, 0.0, r[k].intensity, r[k].unv);
         }
-        image_bin_ray(P.image, guess, valid, r.w, x, y, cz, 0.0, r.intensity, r.unv);
     }
 
     if (P.stats) {
         const unsigned full = 0xffffffffu;
-        unsigned n_unv = __popc(__ballot_sync(full, valid && r.unv));
-        unsigned n_val = __popc(__ballot_sync(full, valid));
+        unsigned n_unv = 0, n_val = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            n_unv += __popc(__ballot_sync(full, valid[k] && r[k].unv));
+            n_val += __popc(__ballot_sync(full, valid[k]));
+        }
         unsigned n_it = __reduce_add_sync(full, newton_iterations);
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&P.stats->n_rays, (unsigned long long)n_val);
@@ -815,20 +999,20 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     }
 }
 
-// One kernel per (occupancy target, FULL, DENSE, ACC, IMAGE): uniform decisions are made once
-// on the host instead of per ray per surface.  OPTK_TRACE_OCC=3|4 selects the register cap
-// (80 / 64 registers per thread, 3 / 4 CTAs of 256 threads per SM); default = measured best.
-template <int MINB, bool FULL, bool DENSE, bool ACC, bool IMAGE>
+// One kernel per (FULL, DENSE, VEC, ACC, IMAGE): uniform decisions are made once on the host
+// instead of per ray per surface.  The streamlined kernels carry two rays per thread in
+// <= 80 registers (3 CTAs of 256 threads per SM, the measured best); OPTK_TRACE_OCC=2 allows 128.
+template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
 __global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
-    trace_body<FULL, DENSE, ACC, IMAGE>(P);
+    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE>(P);
 }
 
 typedef void (*trace_kernel_t)(const TraceParams);
 
 template <int MINB>
-static trace_kernel_t select_kernel(bool full, bool dense, bool acc, bool image) {
-#define OPTK_PICK(F, D, A, I) \
-    if (full == F && dense == D && acc == A && image == I) return (trace_kernel_t)trace_kernel<MINB, F, D, A, I>;
+static trace_kernel_t select_full(bool dense, bool vec, bool acc, bool image) {
+#define OPTK_PICK(D, V, A, I) \
+    if (dense == D && vec == V && acc == A && image == I) return (trace_kernel_t)trace_kernel<MINB, 2, true, D, V, A, I>;
     OPTK_PICK(true, true, false, false)
     OPTK_PICK(true, true, true, false)
     OPTK_PICK(true, true, false, true)
@@ -837,10 +1021,6 @@ static trace_kernel_t select_kernel(bool full, bool dense, bool acc, bool image)
     OPTK_PICK(true, false, true, false)
     OPTK_PICK(true, false, false, true)
     OPTK_PICK(true, false, true, true)
-    OPTK_PICK(false, true, false, false)
-    OPTK_PICK(false, true, true, false)
-    OPTK_PICK(false, true, false, true)
-    OPTK_PICK(false, true, true, true)
     OPTK_PICK(false, false, false, false)
     OPTK_PICK(false, false, true, false)
     OPTK_PICK(false, false, false, true)
@@ -849,25 +1029,68 @@ static trace_kernel_t select_kernel(bool full, bool dense, bool acc, bool image)
     return nullptr;
 }
 
+static trace_kernel_t select_generic(bool dense, bool acc, bool image) {
+#define OPTK_PICK(D, A, I) \
+    if (dense == D && acc == A && image == I) return (trace_kernel_t)trace_kernel<4, 1, false, D, false, A, I>;
+    OPTK_PICK(true, false, false)
+    OPTK_PICK(true, true, false)
+    OPTK_PICK(true, false, true)
+    OPTK_PICK(true, true, true)
+    OPTK_PICK(false, false, false)
+    OPTK_PICK(false, true, false)
+    OPTK_PICK(false, false, true)
+    OPTK_PICK(false, true, true)
+#undef OPTK_PICK
+    return nullptr;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // ---------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------
 int launch_trace(const TraceParams& P, cudaStream_t stream) {
     if (P.n_rays <= 0) return OPTK_OK;
+    static const int occ = [] {
+        const char* e = getenv("OPTK_TRACE_OCC");
+        return e ? atoi(e) : 3;
+    }();
+    bool full = P.in.normal[0] == nullptr;
+    for (int s = 0; s < P.n_surf; ++s)
+        full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM);
+    const bool dense = P.dense_in != 0, acc = P.accumulate != 0, image = P.has_image != 0;
+    // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
+    bool vec = full && dense && (P.accumulate_stride % 2 == 0);
+    for (int f = 0; f < OPTK_NUM_FIELDS && vec; ++f)
+        vec = aligned16(P.in.field[f]) && aligned16(P.out.field[f]);
+    if (vec && P.in.unvignetted) vec = (reinterpret_cast<uintptr_t>(P.in.unvignetted) & 1u) == 0;
+    if (vec && P.out.unvignetted) vec = (reinterpret_cast<uintptr_t>(P.out.unvignetted) & 1u) == 0;
+    const int rays_per_thread = full ? 2 : 1;
     const int block = 256;
-    const long long grid = (P.n_rays + block - 1) / block;
+    const long long threads = (P.n_rays + rays_per_thread - 1) / rays_per_thread;
+    const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) {
         set_error("optk_trace: too many rays for one launch (%lld)", P.n_rays);
         return OPTK_ERR_INVALID;
     }
-    static const int occ = [] {
-        const char* e = getenv("OPTK_TRACE_OCC");
-        return e ? atoi(e) : 4;
+    trace_kernel_t kernel;
+    if (full)
+        kernel = occ == 3 ? select_full<3>(dense, vec, acc, image) : select_full<2>(dense, vec, acc, image);
+    else
+        kernel = select_generic(dense, acc, image);
+    static const int prefetch_waves = [] {
+        const char* e = getenv("OPTK_TRACE_PREFETCH");
+        return e ? atoi(e) : 1;
     }();
-    bool full = P.in.normal[0] == nullptr;
-    for (int s = 0; s < P.n_surf; ++s) full = full && (P.surf[s].stages == OPTK_STAGE_ALL);
-    const bool dense = P.dense_in != 0, acc = P.accumulate != 0, image = P.has_image != 0;
-    trace_kernel_t kernel = occ == 3 ? select_kernel<3>(full, dense, acc, image) : select_kernel<4>(full, dense, acc, image);
+    TraceParams& Q = const_cast<TraceParams&>(P);
+    Q.prefetch_distance = 0;
+    if (dense && prefetch_waves > 0) {
+        int device = 0, sms = 0, ctas = 0;
+        OPTK_CUDA(cudaGetDevice(&device));
+        OPTK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        OPTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, (const void*)kernel, block, 0));
+        Q.prefetch_distance = (long long)prefetch_waves * sms * ctas * block * rays_per_thread;
+    }
     void* args[] = {(void*)&P};
     OPTK_CUDA(cudaLaunchKernel((const void*)kernel, dim3((unsigned)grid), dim3(block), args, 0, stream));
     return OPTK_OK;
