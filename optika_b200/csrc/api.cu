@@ -312,6 +312,7 @@ OPTK_API int optk_trace(const optk_system_t* sys, int32_t config, const optk_ray
         P.div[a] = make_fastdiv(a < in->n_axes ? (uint32_t)in->dims[a] : 1u);
     P.n_rays = n;
     P.index_offset = 0;
+    P.flat_index = 0;
     P.accumulate_stride = accumulate ? accumulate_stride : 0;
     if (accumulate && accumulate_stride < n) {
         set_error("accumulate_stride %lld is smaller than the number of rays %lld", (long long)accumulate_stride, n);
@@ -522,6 +523,7 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const opt
             if (out->unvignetted) P.out.unvignetted = (uint8_t*)cout;
         }
         P.n_rays = m;
+        P.flat_index = 1;
         P.index_offset = every_dense ? 0 : i0;
         P.accumulate_stride = accumulate ? slab_rays : 0;
         rc = launch_trace(P, st);

@@ -23,9 +23,9 @@ struct ImageDev {
     unsigned long long* counts;
 };
 
-// first edge and 1 / mean bin width of the pixel axes: the first guess of the lookup
+// first / last edge and 1 / mean bin width of the pixel axes: range test and first guess
 struct ImageGuess {
-    double x0, inv_dx, y0, inv_dy;
+    double x0, x1, inv_dx, y0, y1, inv_dy, w0, w1;
 };
 
 // Computed once per block into shared memory (edges live in device memory).
@@ -34,28 +34,42 @@ __device__ __forceinline__ void image_guess_init(const ImageDev& im, ImageGuess*
         const double x0 = __ldg(im.e_x), x1 = __ldg(im.e_x + im.n_x);
         const double y0 = __ldg(im.e_y), y1 = __ldg(im.e_y + im.n_y);
         g->x0 = x0;
+        g->x1 = x1;
         g->inv_dx = (double)im.n_x / (x1 - x0);
         g->y0 = y0;
+        g->y1 = y1;
         g->inv_dy = (double)im.n_y / (y1 - y0);
+        g->w0 = __ldg(im.e_w);
+        g->w1 = __ldg(im.e_w + im.n_w);
     }
     __syncthreads();
 }
 
 // Uniform-ish edges: guess then correct against the exact edge values.
-__device__ __forceinline__ int find_bin_guess(const double* __restrict__ e, int n, double v, double e0,
+// numpy.histogramdd: bin i holds e[i] <= v < e[i+1]; the last bin also holds v == e[n].
+__device__ __forceinline__ int find_bin_guess(const double* __restrict__ e, int n, double v, double e0, double e1,
                                               double inv_d) {
-    if (!(v >= __ldg(e)) || !(v <= __ldg(e + n))) return -1;  // also rejects NaN
-    double g = (v - e0) * inv_d;
-    int i = (int)g;
+    if (!(v >= e0) || !(v <= e1)) return -1;  // also rejects NaN
+    int i = (int)((v - e0) * inv_d);
     i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
-    while (i > 0 && v < __ldg(e + i)) --i;
-    while (i < n - 1 && v >= __ldg(e + i + 1)) ++i;
+    double lo = __ldg(e + i), hi = __ldg(e + i + 1);
+    // the guess is off by at most a bin for linspace edges; loop only in the rare other cases
+    while (v < lo) {
+        --i;
+        hi = lo;
+        lo = __ldg(e + i);
+    }
+    while (v >= hi && i < n - 1) {
+        ++i;
+        lo = hi;
+        hi = __ldg(e + i + 1);
+    }
     return i;
 }
 
 // Arbitrary monotonic edges (wavelength): binary search, searchsorted(side="right") - 1.
-__device__ __forceinline__ int find_bin_search(const double* __restrict__ e, int n, double v) {
-    if (!(v >= __ldg(e)) || !(v <= __ldg(e + n))) return -1;
+__device__ __forceinline__ int find_bin_search(const double* __restrict__ e, int n, double v, double e0, double e1) {
+    if (!(v >= e0) || !(v <= e1)) return -1;
     int lo = 0, hi = n;  // invariant: e[lo] <= v, (hi == n or v < e[hi])
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -71,74 +85,63 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Must be called by all 32 lanes of a converged warp.  `bin` < 0 means "drop".
-// Warp-aggregated: lanes that hit the same bin are summed in registers and one
-// lane issues the global reductions (RED.ADD.F64 / RED.ADD.U64 at L2).
+// Warp aggregation by a butterfly "merge if equal" network: at each of the five steps a
+// lane and its partner (lane ^ o) compare bins; when they agree the lower lane absorbs the
+// partner's sums and the partner retires.  The rays of a warp are neighbours in the pupil, so
+// they land on a few adjacent pixels in runs and most lanes retire; whoever is left issues
+// its own global reductions (RED.ADD.F64 / RED.ADD.U64 at L2).  No loops, no match_any;
+// exact for the integer counts, order-independent up to rounding for the fp64 sums.
 __device__ __forceinline__ void image_add(const ImageDev& im, long long bin, double w_flux, double w_real,
-                                          double w_imag) {
+                                          double w_imag, unsigned count) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    unsigned peers = __match_any_sync(full, bin);
-    if (peers == full) {
-        if (bin < 0) return;
-        double f = warp_sum(w_flux);
-        double r = im.moment_real ? warp_sum(w_real) : 0.0;
-        double m = im.moment_imag ? warp_sum(w_imag) : 0.0;
-        if (lane == 0) {
-            if (im.flux) atomicAdd(im.flux + bin, f);
-            if (im.moment_real) atomicAdd(im.moment_real + bin, r);
-            if (im.moment_imag) atomicAdd(im.moment_imag + bin, m);
-            if (im.counts) atomicAdd(im.counts + bin, 32ull);
+    if (__all_sync(full, bin < 0)) return;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long pb = __shfl_xor_sync(full, bin, o);
+        const double pf = __shfl_xor_sync(full, w_flux, o);
+        const double pr = __shfl_xor_sync(full, w_real, o);
+        const unsigned pc = __shfl_xor_sync(full, count, o);
+        const bool same = (pb == bin) && (bin >= 0);
+        const bool lower = (lane & o) == 0;
+        if (same && lower) {
+            w_flux += pf;
+            w_real += pr;
+            count += pc;
         }
-        return;
-    }
-    // mixed bins: the lowest lane of each peer group gathers its group serially
-    const int leader = __ffs(peers) - 1;
-    const int n_peers = __popc(peers);
-    const int max_peers = __reduce_max_sync(full, (unsigned)n_peers);
-    if (max_peers == 1) {
-        if (bin >= 0) {
-            if (im.flux) atomicAdd(im.flux + bin, w_flux);
-            if (im.moment_real) atomicAdd(im.moment_real + bin, w_real);
-            if (im.moment_imag) atomicAdd(im.moment_imag + bin, w_imag);
-            if (im.counts) atomicAdd(im.counts + bin, 1ull);
+        if (im.moment_imag) {
+            const double pi = __shfl_xor_sync(full, w_imag, o);
+            if (same && lower) w_imag += pi;
         }
-        return;
+        if (same && !lower) bin = -1;
     }
-    double f = 0.0, r = 0.0, m = 0.0;
-    for (int k = 0; k < 32; ++k) {
-        double fk = __shfl_sync(full, w_flux, k);
-        double rk = __shfl_sync(full, w_real, k);
-        double mk = __shfl_sync(full, w_imag, k);
-        if ((peers >> k) & 1u) {
-            f += fk;
-            r += rk;
-            m += mk;
-        }
+    if (bin >= 0) {
+        if (im.flux) atomicAdd(im.flux + bin, w_flux);
+        if (im.moment_real) atomicAdd(im.moment_real + bin, w_real);
+        if (im.moment_imag) atomicAdd(im.moment_imag + bin, w_imag);
+        if (im.counts) atomicAdd(im.counts + bin, (unsigned long long)count);
     }
-    if (lane == leader && bin >= 0) {
-        if (im.flux) atomicAdd(im.flux + bin, f);
-        if (im.moment_real) atomicAdd(im.moment_real + bin, r);
-        if (im.moment_imag) atomicAdd(im.moment_imag + bin, m);
-        if (im.counts) atomicAdd(im.counts + bin, (unsigned long long)n_peers);
-    }
+}
+
+// Bin index of one ray given in sensor-local coordinates, or -1 (dropped / vignetted).
+// flux = intensity * where (optika/sensors/_sensors.py:139): vignetted rays carry weight
+// zero and are not counted.
+__device__ __forceinline__ long long image_bin_index(const ImageDev& im, const ImageGuess& g, bool valid,
+                                                     double wavelength, double x, double y, bool unvignetted) {
+    if (!valid || !unvignetted) return -1;
+    const int iw = find_bin_search(im.e_w, im.n_w, wavelength, g.w0, g.w1);
+    const int ix = find_bin_guess(im.e_x, im.n_x, x, g.x0, g.x1, g.inv_dx);
+    const int iy = find_bin_guess(im.e_y, im.n_y, y, g.y0, g.y1, g.inv_dy);
+    if (iw < 0 || ix < 0 || iy < 0) return -1;
+    return ((long long)iw * im.n_x + ix) * im.n_y + iy;
 }
 
 // Bin one ray given in sensor-local coordinates.  All lanes of the warp call this.
 __device__ __forceinline__ void image_bin_ray(const ImageDev& im, const ImageGuess& g, bool valid, double wavelength, double x,
                                               double y, double cos_real, double cos_imag, double intensity,
                                               bool unvignetted) {
-    long long bin = -1;
-    // flux = intensity * where (optika/sensors/_sensors.py:139): vignetted rays are
-    // binned with weight zero and are not counted.
-    double flux = unvignetted ? intensity : 0.0 * intensity;
-    if (valid) {
-        int iw = find_bin_search(im.e_w, im.n_w, wavelength);
-        int ix = find_bin_guess(im.e_x, im.n_x, x, g.x0, g.inv_dx);
-        int iy = find_bin_guess(im.e_y, im.n_y, y, g.y0, g.inv_dy);
-        if (iw >= 0 && ix >= 0 && iy >= 0 && unvignetted)
-            bin = ((long long)iw * im.n_x + ix) * im.n_y + iy;
-    }
-    image_add(im, bin, flux, flux * cos_real, flux * cos_imag);
+    const long long bin = image_bin_index(im, g, valid, wavelength, x, y, unvignetted);
+    image_add(im, bin, intensity, intensity * cos_real, intensity * cos_imag, 1u);
 }
 
 }  // namespace optk

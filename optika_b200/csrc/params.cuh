@@ -15,6 +15,12 @@ struct TraceParams {
     long long index_offset;  // added to the thread index before decomposing it into grid indices
     long long accumulate_stride;
     long long prefetch_distance;  // rays; 0 = off.  L2 prefetch of the rays a later CTA will load
+    // Broadcast (strided) inputs are addressed in two levels: the leading `n_axes - n_inner_axes`
+    // axes are fixed per CTA (offsets computed once per CTA), the trailing ones per thread.
+    long long inner_size;       // product of the trailing n_inner_axes dims
+    long long tiles_per_outer;  // CTAs per index of the leading axes
+    int32_t n_inner_axes;
+    int32_t flat_index;  // host slab path: n_rays is a slab of the grid, decompose every axis per thread
     int32_t n_surf;
     int32_t accumulate;
     int32_t dense_in;  // every input is a dense array indexed by the thread index

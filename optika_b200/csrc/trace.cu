@@ -781,8 +781,9 @@ __device__ __forceinline__ void store_ray(const optk_rays_out_t& out, long long 
 //        16-byte aligned, so the two rays of a thread move as one 128-bit load / store.
 // ACC:   write the state after every surface.   IMAGE: bin the final rays.
 template <int R, bool DENSE>
-__device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, const bool (&valid)[R], Ray (&r)[R],
-                                          bool normal_given, double& gnx, double& gny, double& gnz) {
+__device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, long long j0, const long long* base,
+                                          const bool (&valid)[R], Ray (&r)[R], bool normal_given, double& gnx,
+                                          double& gny, double& gnz) {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         if (!valid[k]) continue;
@@ -805,15 +806,17 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, co
                 gnz = __ldg(P.in.normal[2] + i);
             }
         } else {
-            // broadcast view: decompose the flat index in C order of dims
+            // broadcast view: the CTA-level offsets (leading axes) are in `base`, the thread adds
+            // the trailing axes of its own ray
             long long off[OPTK_NUM_FIELDS + 1];
 #pragma unroll
-            for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] = 0;
-            long long offn[3] = {0, 0, 0};
-            uint32_t rem = (uint32_t)(i + P.index_offset);
-            for (int a = P.in.n_axes - 1; a >= 0; --a) {
+            for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] = base[f];
+            long long offn[3] = {base[OPTK_NUM_FIELDS + 1], base[OPTK_NUM_FIELDS + 2], base[OPTK_NUM_FIELDS + 3]};
+            uint32_t rem = (uint32_t)(j0 + k + P.index_offset);
+            const int first = P.in.n_axes - P.n_inner_axes;
+            for (int a = P.in.n_axes - 1; a >= first; --a) {
                 uint32_t q, idx;
-                if (a == 0) {
+                if (a == first) {
                     idx = rem;
                 } else {
                     divmod(rem, P.div[a], q, idx);
@@ -877,12 +880,46 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
     if (IMAGE) image_guess_init(P.image, &guess);
 
-    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
+    // Dense input: ray index = thread index.  Broadcast input: the CTA owns one index of the
+    // leading ("outer") axes and a tile of the trailing ("inner") axes; its outer offsets are
+    // computed once by OPTK_NUM_FIELDS + 4 threads and shared.
+    __shared__ long long base[OPTK_NUM_FIELDS + 4];
+    long long i0, j0 = 0;
+    long long limit = P.n_rays;
+    if (DENSE) {
+        i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
+    } else {
+        const long long outer = blockIdx.x / P.tiles_per_outer;
+        const long long tile = blockIdx.x - outer * P.tiles_per_outer;
+        j0 = (tile * blockDim.x + threadIdx.x) * R;
+        i0 = outer * P.inner_size + j0;
+        limit = (outer + 1) * P.inner_size;
+        if (threadIdx.x < OPTK_NUM_FIELDS + 4) {
+            const int f = threadIdx.x;
+            long long o = 0;
+            uint32_t rem = (uint32_t)outer;
+            for (int a = P.in.n_axes - P.n_inner_axes - 1; a >= 0; --a) {
+                uint32_t q, idx;
+                if (a == 0) {
+                    idx = rem;
+                } else {
+                    divmod(rem, P.div[a], q, idx);
+                    rem = q;
+                }
+                const long long st = f < OPTK_NUM_FIELDS ? P.in.stride[f][a]
+                                     : (f == OPTK_NUM_FIELDS ? P.in.mask_stride[a]
+                                                             : P.in.normal_stride[f - OPTK_NUM_FIELDS - 1][a]);
+                o += (long long)idx * st;
+            }
+            base[f] = o;
+        }
+        __syncthreads();
+    }
     bool valid[R];
     Ray r[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        valid[k] = i0 + k < P.n_rays;
+        valid[k] = i0 + k < limit;
         r[k] = Ray{1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, false};  // dummy ray for idle lanes
     }
     unsigned newton_iterations = 0;
@@ -923,7 +960,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             r[0].unv = r[R - 1].unv = true;
         }
     } else {
-        load_rays<R, DENSE>(P, i0, valid, r, normal_given, gnx, gny, gnz);
+        load_rays<R, DENSE>(P, i0, j0, base, valid, r, normal_given, gnx, gny, gnz);
     }
 
     // No `if (valid)` around the walk: threads past the end trace a harmless dummy ray, so the
@@ -971,15 +1008,30 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         // AbstractImagingSensor.collect on the final rays in sensor-local coordinates
         // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
         // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
+        long long bin[R];
+        double w_flux[R], w_real[R];
+        unsigned count[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             double x = r[k].px, y = r[k].py, z = r[k].pz, cx = r[k].dx, cy = r[k].dy, cz = r[k].dz;
-            if (valid[k] && P.has_frame) {
+            if (P.has_frame) {
                 affine_inverse(P.frame, x, y, z, false);
                 affine_inverse(P.frame, cx, cy, cz, true);
             }
-            image_bin_ray(P.image, guess, valid[k], r[k].w, x, y, cz, 0.0, r[k].intensity, r[k].unv);
+            bin[k] = image_bin_index(P.image, guess, valid[k], r[k].w, x, y, r[k].unv);
+            w_flux[k] = r[k].intensity;
+            w_real[k] = r[k].intensity * cz;
+            count[k] = 1u;
         }
+        // the two rays of a thread are pupil neighbours: usually the same pixel, merged here
+        if (R == 2 && bin[0] == bin[R - 1] && bin[0] >= 0) {
+            w_flux[0] += w_flux[R - 1];
+            w_real[0] += w_real[R - 1];
+            count[0] += count[R - 1];
+            bin[R - 1] = -1;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) image_add(P.image, bin[k], w_flux[k], w_real[k], 0.0, count[k]);
     }
 
     if (P.stats) {
@@ -1067,8 +1119,30 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     if (vec && P.out.unvignetted) vec = (reinterpret_cast<uintptr_t>(P.out.unvignetted) & 1u) == 0;
     const int rays_per_thread = full ? 2 : 1;
     const int block = 256;
-    const long long threads = (P.n_rays + rays_per_thread - 1) / rays_per_thread;
-    const long long grid = (threads + block - 1) / block;
+    TraceParams& Q = const_cast<TraceParams&>(P);
+    long long grid;
+    if (dense) {
+        const long long threads = (P.n_rays + rays_per_thread - 1) / rays_per_thread;
+        grid = (threads + block - 1) / block;
+        Q.n_inner_axes = 0;
+        Q.inner_size = P.n_rays;
+        Q.tiles_per_outer = grid;
+    } else {
+        // trailing axes until a CTA-sized tile wastes little; a slab offset (host path) or a
+        // normal array keeps the flat scheme (every axis per thread)
+        int n_inner = 0;
+        long long inner = 1;
+        while (n_inner < P.in.n_axes && (inner < 16LL * block * rays_per_thread || P.flat_index)) {
+            inner *= P.in.dims[P.in.n_axes - 1 - n_inner];
+            ++n_inner;
+        }
+        if (P.flat_index) inner = P.n_rays;  // slab of a larger grid: one "outer" index
+        const long long per_tile = (long long)block * rays_per_thread;
+        Q.n_inner_axes = n_inner;
+        Q.inner_size = inner;
+        Q.tiles_per_outer = (inner + per_tile - 1) / per_tile;
+        grid = (inner > 0 ? P.n_rays / inner : 0) * Q.tiles_per_outer;
+    }
     if (grid > 0x7fffffffLL) {
         set_error("optk_trace: too many rays for one launch (%lld)", P.n_rays);
         return OPTK_ERR_INVALID;
@@ -1082,7 +1156,6 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         const char* e = getenv("OPTK_TRACE_PREFETCH");
         return e ? atoi(e) : 1;
     }();
-    TraceParams& Q = const_cast<TraceParams&>(P);
     Q.prefetch_distance = 0;
     if (dense && prefetch_waves > 0) {
         int device = 0, sms = 0, ctas = 0;
