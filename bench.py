@@ -374,9 +374,7 @@ def run_b200(args):
                 dist.all_reduce(image.moment_real)
                 dist.all_reduce(image.counts)
             if rank == 0 or world == 1:
-                image_host["flux"] = image.flux.cpu()
-                image_host["moment"] = image.moment_real.cpu()
-                image_host["counts"] = image.counts.cpu()
+                image_host.update(image.to_host(pinned=True))
             return image
 
         e2e_step()

@@ -133,6 +133,35 @@ class DeviceImage:
             counts=z(torch.int64) if counts else None,
         )
 
+    _pinned = {}
+
+    def to_host(self, pinned: bool = True) -> dict:
+        """
+        Copy the planes to host memory.  With ``pinned`` the destination buffers are
+        page-locked and cached per (name, shape): the copy then runs at PCIe speed instead of
+        being staged through pageable memory.  Returns ``{name: torch tensor}``; the buffers are
+        reused by the next call with the same shapes.
+        """
+        torch = _torch()
+        out = {}
+        for name in ("flux", "moment_real", "moment_imag", "counts"):
+            t = getattr(self, name)
+            if t is None:
+                continue
+            if pinned:
+                key = (name, tuple(t.shape), t.dtype)
+                buf = DeviceImage._pinned.get(key)
+                if buf is None:
+                    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    DeviceImage._pinned[key] = buf
+                buf.copy_(t, non_blocking=True)
+                out[name] = buf
+            else:
+                out[name] = t.cpu()
+        if pinned:
+            torch.cuda.current_stream(self.flux.device).synchronize()
+        return out
+
     def struct(self, plane_index: int = 0) -> L.Image:
         im = L.Image()
         im.n_wavelength = len(self.edges_wavelength) - 1

@@ -90,6 +90,15 @@ class CircularAperture(AbstractAperture):
         b = na.Cartesian3dVectorArray(r, r, 0 * r)
         return _bound(self, b, lower=False)
 
+    def wire(self, num: int = 101) -> na.Cartesian3dVectorArray:
+        """Points on the edge, on a new ``"wire"`` axis (``_apertures.py:337-356``)."""
+        az = na.linspace(0, 360, axis="wire", num=num) * u.deg
+        r = u.length(self.radius)
+        result = na.Cartesian3dVectorArray(x=r * np.cos(az), y=r * np.sin(az), z=0 * az)
+        if self.transformation is not None:
+            result = self.transformation(result)
+        return result
+
 
 @dataclasses.dataclass(eq=False)
 class CircularSectorAperture(AbstractAperture):
@@ -164,6 +173,39 @@ class AbstractPolygonalAperture(AbstractAperture):
         if self.transformation is not None:
             v = self.transformation(v)
         return v.max(axis="vertex")
+
+    def wire(self, num: int = 101) -> na.Cartesian3dVectorArray:
+        """`num` points along the polygon's sides on a new ``"wire"`` axis (``_apertures.py:794-836``)."""
+        v = self.vertices
+        shape_ = na.shape(v)
+        n = shape_["vertex"]
+        vx = na.broadcast_to(na.as_named_array(v.x), shape_)
+        vy = na.broadcast_to(na.as_named_array(v.y), shape_)
+        vz = na.broadcast_to(na.as_named_array(v.z), shape_)
+        per_side = num / n
+        pieces = []
+        cumulative = 0
+        for k in range(n):
+            num_k = int((k + 1) * per_side - cumulative)
+            cumulative += num_k
+            endpoint = cumulative == num
+            t = na.linspace(0, 1, axis="wire", num=num_k, endpoint=endpoint)
+            left = [c[dict(vertex=k)] for c in (vx, vy, vz)]
+            right = [c[dict(vertex=(k + 1) % n)] for c in (vx, vy, vz)]
+            pieces.append([a + (b - a) * t for a, b in zip(left, right)])
+        comps = []
+        for c in range(3):
+            arrays = [p[c] for p in pieces]
+            shp = na.shape_broadcasted(*[a[dict(wire=0)] for a in arrays])
+            nd = np.concatenate(
+                [np.broadcast_to(na.aligned(a, dict(wire=a.shape["wire"], **shp)), (a.shape["wire"],) + tuple(shp.values())) for a in arrays],
+                axis=0,
+            )
+            comps.append(na.ScalarArray(nd, ("wire",) + tuple(shp)))
+        result = na.Cartesian3dVectorArray(*comps)
+        if self.transformation is not None:
+            result = self.transformation(result)
+        return result
 
 
 @dataclasses.dataclass(eq=False)

@@ -143,11 +143,51 @@ class SequentialSystem(AbstractSequentialSystem):
         self._ray_axes_order = order
         return result, rays
 
-    def denormalize(self, grid: ObjectVectorArray, normalized_field=True, normalized_pupil=True):
+    def denormalize(self, grid: ObjectVectorArray, normalized_field=True, normalized_pupil=True, backend=None):
         """Map normalised field / pupil coordinates to physical ones (``:748-789``)."""
         from . import _stops
 
-        return _stops.denormalize_grid(self, grid, normalized_field, normalized_pupil)
+        return _stops.denormalize_grid(self, grid, normalized_field, normalized_pupil, backend=backend)
+
+    def rayfunction_stops(self, wavelength=None, samples_pupil_stop=101, samples_field_stop=101, backend=None):
+        """Rays through the edges of both stops, at the object (``:625-678``): ``(inputs, rays)``."""
+        from . import _stops
+
+        if wavelength is None:
+            wavelength = self.grid_input.wavelength
+        return _stops.rayfunction_stops(self, wavelength, samples_pupil_stop, samples_field_stop, backend=backend)
+
+    def _stop_extent(self, backend=None):
+        from . import _stops
+
+        _, rays = self.rayfunction_stops(backend=backend)
+        axes = (_stops.AXIS_FIELD_STOP, _stops.AXIS_PUPIL_STOP)
+        if self.object_is_at_infinity:
+            field = _util.angles(rays.direction)
+            pupil = na.Cartesian2dVectorArray(rays.position.x, rays.position.y)
+        else:
+            field = na.Cartesian2dVectorArray(rays.position.x, rays.position.y)
+            pupil = _util.angles(rays.direction)
+        return field, pupil, axes
+
+    def field_min(self, backend=None) -> na.Cartesian2dVectorArray:
+        """Lower-left corner of the field of view (``_sequential.py:697-708``)."""
+        field, _, axes = self._stop_extent(backend)
+        return field.min(axes)
+
+    def field_max(self, backend=None) -> na.Cartesian2dVectorArray:
+        """Upper-right corner of the field of view (``_sequential.py:710-720``)."""
+        field, _, axes = self._stop_extent(backend)
+        return field.max(axes)
+
+    def pupil_min(self, backend=None) -> na.Cartesian2dVectorArray:
+        _, pupil, axes = self._stop_extent(backend)
+        return pupil.min(axes)
+
+    def pupil_max(self, backend=None) -> na.Cartesian2dVectorArray:
+        """Upper-right corner of the entrance pupil (``_sequential.py:736-746``)."""
+        _, pupil, axes = self._stop_extent(backend)
+        return pupil.max(axes)
 
     # -- tracing -----------------------------------------------------------
     def raytrace(
