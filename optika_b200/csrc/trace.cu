@@ -1154,7 +1154,7 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         kernel = select_generic(dense, acc, image);
     static const int prefetch_waves = [] {
         const char* e = getenv("OPTK_TRACE_PREFETCH");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 0;  // measured: no gain once 24 warps per SM are resident
     }();
     Q.prefetch_distance = 0;
     if (dense && prefetch_waves > 0) {

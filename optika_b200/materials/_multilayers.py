@@ -19,7 +19,7 @@ from .. import _lib as L
 from ..vectors import PolarizationVectorArray
 from ._layers import AbstractLayer, Layer, LayerSequence, PeriodicLayerSequence
 
-__all__ = ["multilayer_efficiency", "flatten_layers"]
+__all__ = ["multilayer_efficiency", "multilayer_efficiency_device", "flatten_layers"]
 
 
 def flatten_layers(layers) -> tuple[list[Layer], list[tuple[int, int, int]]]:
@@ -88,7 +88,7 @@ def _split_complex(value):
     return v.real, (v.imag if v.imag != 0 else None)
 
 
-def multilayer_efficiency(
+def multilayer_efficiency_device(
     wavelength,
     direction=1,
     n=1,
@@ -97,13 +97,8 @@ def multilayer_efficiency(
     device=None,
 ) -> tuple[PolarizationVectorArray, PolarizationVectorArray]:
     """
-    Reflectivity and transmissivity of a multilayer stack for s and p
-    polarisation (``optika/materials/_multilayers.py:240-532``).
-
-    Parameters keep the reference's meaning: `wavelength` in vacuum (mm),
-    `direction` the cosine of the incidence angle in the ambient medium, `n` the
-    (complex) ambient index, `layers` from the ambient side down, `substrate`
-    the medium below (its thickness is ignored).
+    Device-resident variant of :func:`multilayer_efficiency`: returns
+    ``(tensor[4, n_eval], axes, dims)`` with rows R_s, R_p, T_s, T_p left in HBM.
     """
     from .. import _engine
 
@@ -197,9 +192,30 @@ def multilayer_efficiency(
             ptrs[0], ptrs[1], ptrs[2], ptrs[3], _engine._stream_ptr(device),
         )
     )
-    host = out.cpu().numpy().reshape([4] + dims)
     torch.cuda.current_stream(device).synchronize()
     del keepalive
+    return out, axes, dims
+
+
+def multilayer_efficiency(
+    wavelength,
+    direction=1,
+    n=1,
+    layers: None | AbstractLayer | list = None,
+    substrate: None | Layer = None,
+    device=None,
+) -> tuple[PolarizationVectorArray, PolarizationVectorArray]:
+    """
+    Reflectivity and transmissivity of a multilayer stack for s and p
+    polarisation (``optika/materials/_multilayers.py:240-532``).
+
+    Parameters keep the reference's meaning: `wavelength` in vacuum (mm),
+    `direction` the cosine of the incidence angle in the ambient medium, `n` the
+    (complex) ambient index, `layers` from the ambient side down, `substrate`
+    the medium below (its thickness is ignored).
+    """
+    out, axes, dims = multilayer_efficiency_device(wavelength, direction, n, layers, substrate, device)
+    host = out.cpu().numpy().reshape([4] + dims)
 
     def wrap(a):
         return na.ScalarArray(a, tuple(axes))
