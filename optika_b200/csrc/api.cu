@@ -633,6 +633,19 @@ OPTK_API int optk_multilayer(const optk_ml_input_t* input, int32_t n_layers, con
         }
         d.profile_kind = l.width ? l.profile_kind : 0;
         d.pad = 0;
+        auto single_axis = [&](const long long* st) -> int8_t {
+            int axis = -1;
+            for (int a = 0; a < input->n_axes; ++a) {
+                if (st[a] != 0 && input->dims[a] > 1) {
+                    if (axis >= 0) return (int8_t)-2;
+                    axis = a;
+                }
+            }
+            return (int8_t)axis;
+        };
+        d.n_axis = single_axis(d.n_stride);
+        d.t_axis = single_axis(d.t_stride);
+        d.w_axis = single_axis(d.w_stride);
     }
     OPTK_CUDA(cudaMemcpyAsync(table_dev.ptr, table_pinned, sizeof(LayerDev) * n_layers, cudaMemcpyHostToDevice,
                               (cudaStream_t)stream));

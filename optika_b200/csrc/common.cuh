@@ -132,6 +132,78 @@ __device__ __forceinline__ double frsqrt(double x) {
     return (fabs(y) < OPTK_INF) ? y : y0;
 }
 
+// ---------------------------------------------------------------------------
+// exp and sincos for the multilayer kernel: straight-line, ~20 / ~32 instructions instead of
+// the library's 40-75 with their slow-path calls.  exp: |error| < 2 ulp for |x| <= 700, inputs
+// beyond are clamped (exp(700) ~ 1e304 is already past every guard in the model), NaN
+// propagates.  sincos: three-term Cody-Waite reduction, absolute error < 1e-15 for
+// |x| < 1e5; larger arguments (a layer thousands of wavelengths thick) take the library path.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fexp(double x) {
+    const double xc = fmin(fmax(x, -700.0), 700.0);
+    const double shifter = 6755399441055744.0;  // 1.5 * 2^52: rounds to integer in the low word
+    const double kd = fma(xc, 1.4426950408889634, shifter);
+    const int k = __double2loint(kd);
+    const double kf = kd - shifter;
+    double r = fma(kf, -6.93147180369123816490e-01, xc);  // ln2 hi
+    r = fma(kf, -1.90821492927058770002e-10, r);          // ln2 lo
+    double p = 1.6059043836821613e-10;                    // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                 // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                 // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                  // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                 // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                 // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                 // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    // scale by 2^k in two halves so that k in [-1010, 1010] never leaves the normal range midway
+    const int k1 = k >> 1, k2 = k - k1;
+    const double s1 = __hiloint2double((k1 + 1023) << 20, 0), s2 = __hiloint2double((k2 + 1023) << 20, 0);
+    const double y = p * s1 * s2;
+    return (x != x) ? x : y;
+}
+
+__device__ __forceinline__ void fsincos(double x, double* s, double* c) {
+    if (!(fabs(x) < 1.0e5)) {
+        sincos(x, s, c);
+        return;
+    }
+    const double shifter = 6755399441055744.0;
+    const double kd = fma(x, 6.36619772367581382433e-01, shifter);  // x * 2/pi
+    const int q = __double2loint(kd);
+    const double kf = kd - shifter;
+    double r = fma(kf, -1.57079632673412561417e+00, x);   // pi/2, first 33 bits
+    r = fma(kf, -6.07710050650619224932e-11, r);          // next 33 bits
+    r = fma(kf, -2.02226624879595063154e-21, r);          // tail
+    const double r2 = r * r;
+    // sin(r) on [-pi/4, pi/4]
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, r2, -2.50507602534068634195e-08);
+    ps = fma(ps, r2, 2.75573137070700676789e-06);
+    ps = fma(ps, r2, -1.98412698298579493134e-04);
+    ps = fma(ps, r2, 8.33333333332248946124e-03);
+    ps = fma(ps, r2, -1.66666666666666324348e-01);
+    const double sr = fma(ps * r2, r, r);
+    // cos(r) on [-pi/4, pi/4]
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, r2, 2.08757232129817482790e-09);
+    pc = fma(pc, r2, -2.75573143513906633035e-07);
+    pc = fma(pc, r2, 2.48015872894767294178e-05);
+    pc = fma(pc, r2, -1.38888888888741095749e-03);
+    pc = fma(pc, r2, 4.16666666666666019037e-02);
+    const double cr = fma(pc * r2, r2, fma(-0.5, r2, 1.0));
+    // quadrant: q mod 4 = 0: (s, c); 1: (c, -s); 2: (-s, -c); 3: (-c, s)
+    const bool swap = q & 1;
+    const double ss = swap ? cr : sr, cc = swap ? sr : cr;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
+
 // x -> R x + t
 __device__ __forceinline__ void affine_forward(const optk_affine_t& a, double& x, double& y, double& z,
                                                bool is_direction) {

@@ -46,7 +46,8 @@ struct LayerDev {
     long long t_stride[OPTK_ML_MAX_AXES];
     long long w_stride[OPTK_ML_MAX_AXES];
     int32_t profile_kind;
-    int32_t pad;
+    // fast addressing: the single grid axis each array varies along (-1: none, -2: several, use strides)
+    int8_t n_axis, t_axis, w_axis, pad;
 };
 
 struct MultilayerParams {
