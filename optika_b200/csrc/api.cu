@@ -650,6 +650,19 @@ OPTK_API int optk_multilayer(const optk_ml_input_t* input, int32_t n_layers, con
     OPTK_CUDA(cudaMemcpyAsync(table_dev.ptr, table_pinned, sizeof(LayerDev) * n_layers, cudaMemcpyHostToDevice,
                               (cudaStream_t)stream));
     P.layers = (const LayerDev*)table_dev.ptr;
+    // cross-configuration reuse: an axis that only the thicknesses depend on
+    P.reuse_axis = -1;
+    for (int a = input->n_axes - 1; a >= 0 && P.reuse_axis < 0; --a) {
+        if (input->dims[a] < 2) continue;
+        bool only_thickness = input->wavelength_stride[a] == 0 && input->direction_stride[a] == 0 &&
+                              input->n_stride[a] == 0;
+        bool any_thickness = false;
+        for (int j = 0; j < n_layers && only_thickness; ++j) {
+            only_thickness = table_pinned[j].n_stride[a] == 0 && table_pinned[j].w_stride[a] == 0;
+            any_thickness = any_thickness || table_pinned[j].t_stride[a] != 0;
+        }
+        if (only_thickness && any_thickness) P.reuse_axis = a;
+    }
     P.r_s = reflectivity_s;
     P.r_p = reflectivity_p;
     P.t_s = transmissivity_s;

@@ -469,6 +469,161 @@ __global__ void __launch_bounds__(128, MINB) multilayer_explicit_kernel(const __
     if (P.t_p) P.t_p[e] = tripped ? 0.0 * (q_sub_p / ambient.q_p).re : fdiv(cp.d2, m_p * g2) * (q_sub_p / ambient.q_p).re;
 }
 
+// ---------------------------------------------------------------------------
+// Explicit stacks with a configuration axis that only the thicknesses depend on (BASELINE
+// cfg 4: the period scaled per configuration): the media, Fresnel terms and interface
+// factors depend on (wavelength, angle) only, so one thread carries NC configurations through
+// the stack and computes them once per layer; per configuration only the propagation phase
+// (one exp, one sincos) and the 2 x 5 complex products remain.
+// ---------------------------------------------------------------------------
+template <int NC, int MINB>
+__global__ void __launch_bounds__(128, MINB) multilayer_reuse_kernel(const __grid_constant__ MultilayerParams P,
+                                                                    long long n_outer, int n_groups) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LayerDev* layers = reinterpret_cast<LayerDev*>(smem_raw);
+    {
+        const int n_words = P.n_layers * (int)(sizeof(LayerDev) / sizeof(long long));
+        const long long* src = reinterpret_cast<const long long*>(P.layers);
+        long long* dst = reinterpret_cast<long long*>(layers);
+        for (int k = threadIdx.x; k < n_words; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_outer * n_groups) return;
+    const int ra = P.reuse_axis;
+    const int n_axes = P.in.n_axes;
+    const long long eo = tid % n_outer;  // index over the other axes (adjacent threads: adjacent outer points)
+    const int c0 = (int)(tid / n_outer) * NC;
+    const int n_c = (int)P.in.dims[ra];
+
+    // decompose eo over the axes other than `ra` (C order), idx[ra] = 0; dense output offset
+    unsigned idx[OPTK_ML_MAX_AXES] = {0, 0, 0, 0};
+    long long out_base = 0, out_stride_c = 1;
+    {
+        long long rem = eo, dense = 1;
+        for (int a = n_axes - 1; a >= 0; --a) {
+            if (a == ra) {
+                out_stride_c = dense;
+            } else {
+                const long long d = P.in.dims[a];
+                idx[a] = (unsigned)(rem % d);
+                rem /= d;
+                out_base += idx[a] * dense;
+            }
+            dense *= P.in.dims[a];
+        }
+    }
+    long long ow = 0, od = 0, on = 0;
+    for (int a = 0; a < n_axes; ++a) {
+        ow += (long long)idx[a] * P.in.wavelength_stride[a];
+        od += (long long)idx[a] * P.in.direction_stride[a];
+        on += (long long)idx[a] * P.in.n_stride[a];
+    }
+    const double wavelength = __ldg(P.in.wavelength + ow);
+    const cplx dir0 = C(__ldg(P.in.direction_re + od), P.in.direction_im ? __ldg(P.in.direction_im + od) : 0.0);
+    const cplx n0 = C(__ldg(P.in.n_re + on), P.in.n_im ? __ldg(P.in.n_im + on) : 0.0);
+    Medium ambient;
+    ambient.n = n0;
+    ambient.dir = dir0;
+    ambient.q_s = dir0 * n0;
+    ambient.q_p = conj(dir0) / n0;
+    const cplx k2 = (n0 * n0) * (C(1.0) - dir0 * dir0);
+    const double two_pi_over_w = 2.0 * 3.141592653589793 / wavelength;
+
+    int j_lo = P.n_layers - 1;
+    Medium lo = medium_of(layers[j_lo], idx, n_axes, k2);
+    const cplx q_sub_s = lo.q_s, q_sub_p = lo.q_p;
+    Column cs[NC], cp[NC];
+    double growth_total[NC];
+    bool tripped[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        cs[c] = Column{C(1.0), C(0.0), 1.0};
+        cp[c] = Column{C(1.0), C(0.0), 1.0};
+        growth_total[c] = 1.0;
+        tripped[c] = false;
+    }
+    bool lo_is_substrate = true;
+
+    for (int g = P.n_segments; g >= 0; --g) {
+        const int first = g > 0 ? P.segments[g - 1].first : 0;
+        const int count = g > 0 ? P.segments[g - 1].count : 1;
+        for (int jj = count - 1; jj >= 0; --jj) {
+            const bool up_is_ambient = g == 0;
+            const int j_up = first + jj;
+            const Medium up = up_is_ambient ? ambient : medium_of(layers[j_up], idx, n_axes, k2);
+            const LayerDev& L = layers[j_lo];
+
+            // per configuration: propagation through the lower layer
+            if (!lo_is_substrate && L.thickness) {
+                const long long t0 = layer_offset(L.t_axis == ra ? -1 : L.t_axis, L.t_stride, idx, n_axes);
+                const long long tc = L.t_stride[ra];
+                const double kr = two_pi_over_w * lo.q_s.re, ki = two_pi_over_w * lo.q_s.im;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int cc = min(c0 + c, n_c - 1);  // lanes past the end repeat the last configuration
+                    const double h = __ldg(L.thickness + t0 + (long long)cc * tc);
+                    const double growth = fexp(ki * h);
+                    const bool ok = growth < 1e10;
+                    double sn, cn;
+                    fsincos(kr * h, &sn, &cn);
+                    const double decay = frcp(growth * growth);
+                    const cplx w = C(decay * (cn * cn - sn * sn), decay * (2.0 * sn * cn));
+                    cs[c].v1 = ok ? cs[c].v1 * w : C(0.0);
+                    cp[c].v1 = ok ? cp[c].v1 * w : C(0.0);
+                    cs[c].v0 = ok ? cs[c].v0 : C(1.0);
+                    cp[c].v0 = ok ? cp[c].v0 : C(1.0);
+                    cs[c].d2 = ok ? cs[c].d2 : 1.0;
+                    cp[c].d2 = ok ? cp[c].d2 : 1.0;
+                    growth_total[c] = ok ? growth_total[c] * growth : 1.0;
+                    tripped[c] = tripped[c] || !ok;
+                }
+            }
+
+            // shared by all configurations: refraction at the top interface of the lower layer
+            double rough_s = 1.0, rough_p = 1.0;
+            if (L.profile_kind) {
+                const double width = L.width ? __ldg(L.width + layer_offset(L.w_axis, L.w_stride, idx, n_axes)) : 0.0;
+                const double k = 2.0 * two_pi_over_w;
+                rough_s = interface_factor(L.profile_kind, width, k * up.q_s.re);
+                rough_p = interface_factor(L.profile_kind, width, k * (up.n * conj(up.dir)).re);
+            }
+            const cplx a_s = up.q_s + lo.q_s, b_s = rough_s * (up.q_s - lo.q_s);
+            const cplx a_p = up.q_p + lo.q_p, b_p = rough_p * (up.q_p - lo.q_p);
+            const double f_s = 4.0 * norm2(up.q_s), f_p = 4.0 * norm2(up.q_p);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const cplx s0 = a_s * cs[c].v0 + b_s * cs[c].v1, s1 = b_s * cs[c].v0 + a_s * cs[c].v1;
+                cs[c].v0 = s0;
+                cs[c].v1 = s1;
+                cs[c].d2 *= f_s;
+                const cplx p0 = a_p * cp[c].v0 + b_p * cp[c].v1, p1 = b_p * cp[c].v0 + a_p * cp[c].v1;
+                cp[c].v0 = p0;
+                cp[c].v1 = p1;
+                cp[c].d2 *= f_p;
+            }
+            lo = up;
+            j_lo = j_up;
+            lo_is_substrate = false;
+        }
+    }
+
+    const double ratio_s = (q_sub_s / ambient.q_s).re, ratio_p = (q_sub_p / ambient.q_p).re;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (c0 + c < n_c) {
+            const long long e = out_base + (long long)(c0 + c) * out_stride_c;
+            const double m_s = norm2(cs[c].v0), m_p = norm2(cp[c].v0);
+            const double g2 = growth_total[c] * growth_total[c];
+            if (P.r_s) P.r_s[e] = fdiv(norm2(cs[c].v1), m_s);
+            if (P.r_p) P.r_p[e] = fdiv(norm2(cp[c].v1), m_p);
+            if (P.t_s) P.t_s[e] = tripped[c] ? 0.0 * ratio_s : fdiv(cs[c].d2, m_s * g2) * ratio_s;
+            if (P.t_p) P.t_p[e] = tripped[c] ? 0.0 * ratio_p : fdiv(cp[c].d2, m_p * g2) * ratio_p;
+        }
+    }
+}
+
 int launch_multilayer(const MultilayerParams& P, cudaStream_t stream) {
     if (P.n_eval <= 0) return OPTK_OK;
     const int block = 128;
@@ -484,6 +639,30 @@ int launch_multilayer(const MultilayerParams& P, cudaStream_t stream) {
         const char* e = getenv("OPTK_ML_OCC");
         return e ? atoi(e) : 4;
     }();
+    static const int reuse = [] {
+        const char* e = getenv("OPTK_ML_REUSE");
+        return e ? atoi(e) : 4;
+    }();
+    if (!periodic && P.reuse_axis >= 0 && reuse > 1) {
+        const int nc = reuse == 42 ? 4 : (reuse == 32 ? 3 : reuse);
+        const long long n_c = P.in.dims[P.reuse_axis];
+        const long long n_outer = P.n_eval / n_c;
+        const int n_groups = (int)((n_c + nc - 1) / nc);
+        const long long threads = n_outer * n_groups;
+        const long long g2 = (threads + block - 1) / block;
+        if (reuse == 42)
+            multilayer_reuse_kernel<4, 2><<<(unsigned)g2, block, smem, stream>>>(P, n_outer, n_groups);
+        else if (reuse == 32)
+            multilayer_reuse_kernel<3, 2><<<(unsigned)g2, block, smem, stream>>>(P, n_outer, n_groups);
+        else if (reuse == 3)
+            multilayer_reuse_kernel<3, 3><<<(unsigned)g2, block, smem, stream>>>(P, n_outer, n_groups);
+        else if (reuse == 2)
+            multilayer_reuse_kernel<2, 4><<<(unsigned)g2, block, smem, stream>>>(P, n_outer, n_groups);
+        else
+            multilayer_reuse_kernel<4, 3><<<(unsigned)g2, block, smem, stream>>>(P, n_outer, n_groups);
+        OPTK_CUDA(cudaGetLastError());
+        return OPTK_OK;
+    }
     if (periodic)
         multilayer_kernel<true, 2><<<(unsigned)grid, block, smem, stream>>>(P);
     else if (occ == 0)

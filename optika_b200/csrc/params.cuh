@@ -62,6 +62,10 @@ struct MultilayerParams {
     double* r_p;
     double* t_s;
     double* t_p;
+    // An axis along which ONLY layer thicknesses vary (-1: none): the Fresnel terms are shared by
+    // all its indices, so one thread evaluates several of them (cross-configuration reuse).
+    int32_t reuse_axis;
+    int32_t pad;
 };
 
 int launch_multilayer(const MultilayerParams& P, cudaStream_t stream);
