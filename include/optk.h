@@ -73,7 +73,11 @@ typedef enum optk_sag_kind {
 typedef enum optk_material_kind {
     OPTK_MAT_VACUUM = 0, /* optika/materials/_materials.py:82-116  */
     OPTK_MAT_MIRROR = 1, /* optika/materials/_materials.py:120-175 */
-    OPTK_MAT_GLASS = 2   /* optika/materials/_materials.py:428-455 */
+    OPTK_MAT_GLASS = 2,  /* optika/materials/_materials.py:428-455 */
+    /* unit operation optika.materials.snells_law (optika/materials/_snells_law.py:41-47):
+     * the new index is given explicitly in material[0]; transmit / reflect */
+    OPTK_MAT_INDEX = 3,
+    OPTK_MAT_INDEX_MIRROR = 4
 } optk_material_kind_t;
 
 typedef enum optk_ruling_kind {

@@ -475,6 +475,26 @@ class _Bare:
         )
 
 
+@dataclasses.dataclass(eq=False)
+class _FixedIndex:
+    """Material of the ``snells_law`` unit operation: an explicitly given new index."""
+
+    index: object = 1.0
+    mirror: bool = False
+
+    @property
+    def is_mirror(self) -> bool:
+        return self.mirror
+
+    @property
+    def shape(self):
+        return na.shape(self.index)
+
+    @property
+    def transformation(self):
+        return None
+
+
 def _position_rays(position: na.Cartesian3dVectorArray, direction=None) -> RayVectorArray:
     if direction is None:
         direction = na.Cartesian3dVectorArray(0.0, 0.0, 1.0)
@@ -547,12 +567,7 @@ def snells_law(direction, index_refraction, index_refraction_new, normal=None, i
 
     if normal is None:
         normal = na.Cartesian3dVectorArray(0.0, 0.0, -1.0)  # _snells_law.py:268-269
-    n2 = index_refraction_new
-    if is_mirror:
-        material = materials.Mirror()
-    else:
-        # a Glass whose Sellmeier sum is constant: n^2 = 1 + b1 w^2 / (w^2 - 0) = 1 + b1
-        material = materials.Glass(b1=n2 * n2 - 1)
+    material = _FixedIndex(index=index_refraction_new, mirror=bool(is_mirror))
     rays = RayVectorArray(wavelength=1.0, direction=direction, index_refraction=index_refraction)
     out = trace(CompiledSystem([_Bare(material=material)], stages=L.STAGE_REFRACT), rays, normal=normal)
     return out.to_host().direction

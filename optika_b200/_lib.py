@@ -45,7 +45,7 @@ FIELDS = (
 )
 
 SAG_FLAT, SAG_SPHERICAL, SAG_CYLINDRICAL, SAG_CONIC, SAG_PARABOLIC, SAG_TOROIDAL = range(6)
-MAT_VACUUM, MAT_MIRROR, MAT_GLASS = range(3)
+MAT_VACUUM, MAT_MIRROR, MAT_GLASS, MAT_INDEX, MAT_INDEX_MIRROR = range(5)
 RULING_NONE, RULING_CONSTANT, RULING_POLYNOMIAL, RULING_HOLOGRAPHIC = range(4)
 (
     APERTURE_NONE,

@@ -90,6 +90,9 @@ def _lower_material(material, S: L.Surface, shape_, index):
         S.material_kind = L.MAT_GLASS
         for k, v in enumerate((material.b1, material.b2, material.b3, material.c1, material.c2, material.c3)):
             S.material[k] = float(_scalar(v, shape_, index))
+    elif name == "_FixedIndex":
+        S.material_kind = L.MAT_INDEX_MIRROR if material.is_mirror else L.MAT_INDEX
+        S.material[0] = float(_scalar(material.index, shape_, index))
     else:
         raise NotImplementedError(f"material {name} is not supported by the device engine")
 

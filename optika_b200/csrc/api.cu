@@ -83,7 +83,7 @@ int validate_surface(const optk_surface_t& s, int index) {
         set_error("surface %d: unsupported sag kind %d", index, s.sag_kind);
         return OPTK_ERR_UNSUPPORTED;
     }
-    if (s.material_kind < OPTK_MAT_VACUUM || s.material_kind > OPTK_MAT_GLASS) {
+    if (s.material_kind < OPTK_MAT_VACUUM || s.material_kind > OPTK_MAT_INDEX_MIRROR) {
         set_error("surface %d: unsupported material kind %d", index, s.material_kind);
         return OPTK_ERR_UNSUPPORTED;
     }

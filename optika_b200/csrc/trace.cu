@@ -696,8 +696,10 @@ __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray& r, un
     if (stages & OPTK_STAGE_REFRACT) {
         const double n1 = r.n;
         double n2;
-        const bool mirror = S.material_kind == OPTK_MAT_MIRROR;
-        if (S.material_kind == OPTK_MAT_GLASS) {
+        const bool mirror = S.material_kind == OPTK_MAT_MIRROR || S.material_kind == OPTK_MAT_INDEX_MIRROR;
+        if (S.material_kind == OPTK_MAT_INDEX || S.material_kind == OPTK_MAT_INDEX_MIRROR) {
+            n2 = S.material[0];  // snells_law(direction, n1, n2, normal, is_mirror) unit operation
+        } else if (S.material_kind == OPTK_MAT_GLASS) {
             // optika/materials/_materials.py:428-438
             const double w2 = r.w * r.w;
             n2 = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
@@ -1109,7 +1111,8 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     }();
     bool full = P.in.normal[0] == nullptr;
     for (int s = 0; s < P.n_surf; ++s)
-        full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM);
+        full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM) &&
+               P.surf[s].material_kind <= OPTK_MAT_GLASS;
     const bool dense = P.dense_in != 0, acc = P.accumulate != 0, image = P.has_image != 0;
     // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
     bool vec = full && dense && (P.accumulate_stride % 2 == 0);
