@@ -218,6 +218,11 @@ typedef struct optk_image {
     double* moment_real;            /* sum of intensity * Re cos   (may be NULL) */
     double* moment_imag;            /* sum of intensity * Im cos   (may be NULL) */
     unsigned long long* counts;     /* number of rays              (may be NULL) */
+    /* Optional: the first and last edge of every axis, as known to the caller
+     * (wavelength, x, y).  With has_range != 0 the kernels do not have to fetch them from
+     * device memory at the start of every CTA.  Must equal the array values exactly. */
+    int32_t has_range;
+    double range[6];
 } optk_image_t;
 
 /* Counters returned by the trace (device-side reductions, optional). */

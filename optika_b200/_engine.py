@@ -114,6 +114,7 @@ class DeviceImage:
     moment_real: object = None
     moment_imag: object = None
     counts: object = None
+    range: object = None  # first / last edge of (wavelength, x, y) as host floats, when known
 
     @classmethod
     def zeros(cls, edges_wavelength, edges_x, edges_y, device, leading=(), moments=True, counts=True):
@@ -131,6 +132,7 @@ class DeviceImage:
             moment_real=z(torch.float64) if moments else None,
             moment_imag=None,
             counts=z(torch.int64) if counts else None,
+            range=[float(v) for e in (edges_wavelength, edges_x, edges_y) for v in (np.asarray(e)[0], np.asarray(e)[-1])],
         )
 
     _pinned = {}
@@ -175,6 +177,9 @@ class DeviceImage:
         def ptr(t):
             return None if t is None else t.data_ptr() + plane_index * n * 8
 
+        if self.range is not None:
+            im.has_range = 1
+            im.range[:] = self.range
         im.flux = ptr(self.flux)
         im.moment_real = ptr(self.moment_real)
         im.moment_imag = ptr(self.moment_imag)

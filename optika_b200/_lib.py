@@ -140,6 +140,8 @@ class Image(C.Structure):
         ("moment_real", C.c_void_p),
         ("moment_imag", C.c_void_p),
         ("counts", C.c_void_p),
+        ("has_range", C.c_int32),
+        ("range", C.c_double * 6),
     ]
 
 

@@ -185,6 +185,9 @@ int fill_image(const optk_image_t* image, ImageDev* dev) {
     dev->moment_real = image->moment_real;
     dev->moment_imag = image->moment_imag;
     dev->counts = image->counts;
+    dev->has_range = image->has_range ? 1 : 0;
+    dev->pad2 = 0;
+    for (int k = 0; k < 6; ++k) dev->range[k] = image->range[k];
     return OPTK_OK;
 }
 
@@ -439,6 +442,13 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const opt
         image_dev.edges_wavelength = ew;
         image_dev.edges_x = ex;
         image_dev.edges_y = ey;
+        image_dev.has_range = 1;
+        image_dev.range[0] = image->edges_wavelength[0];
+        image_dev.range[1] = image->edges_wavelength[image->n_wavelength];
+        image_dev.range[2] = image->edges_x[0];
+        image_dev.range[3] = image->edges_x[image->n_x];
+        image_dev.range[4] = image->edges_y[0];
+        image_dev.range[5] = image->edges_y[image->n_y];
         void* host_planes[4] = {image->flux, image->moment_real, image->moment_imag, image->counts};
         void* dev_planes[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int k = 0; k < 4; ++k) {

@@ -21,6 +21,9 @@ struct ImageDev {
     double* moment_real;
     double* moment_imag;
     unsigned long long* counts;
+    int32_t has_range;  // range[] below is valid: no loads needed for the guess
+    int32_t pad2;
+    double range[6];    // first / last edge of wavelength, x, y
 };
 
 // first / last edge and 1 / mean bin width of the pixel axes: range test and first guess
@@ -28,20 +31,31 @@ struct ImageGuess {
     double x0, x1, inv_dx, y0, y1, inv_dy, w0, w1;
 };
 
-// Computed once per block into shared memory (edges live in device memory).
-__device__ __forceinline__ void image_guess_init(const ImageDev& im, ImageGuess* g) {
-    if (threadIdx.x == 0) {
-        const double x0 = __ldg(im.e_x), x1 = __ldg(im.e_x + im.n_x);
-        const double y0 = __ldg(im.e_y), y1 = __ldg(im.e_y + im.n_y);
-        g->x0 = x0;
-        g->x1 = x1;
-        g->inv_dx = (double)im.n_x / (x1 - x0);
-        g->y0 = y0;
-        g->y1 = y1;
-        g->inv_dy = (double)im.n_y / (y1 - y0);
-        g->w0 = __ldg(im.e_w);
-        g->w1 = __ldg(im.e_w + im.n_w);
+// Computed once per block into shared memory by ONE thread (the caller places the barrier).
+// Edges live in device memory; with the caller's range hint no load is needed.
+__device__ __forceinline__ void image_guess_fill(const ImageDev& im, ImageGuess* g) {
+    double w0, w1, x0, x1, y0, y1;
+    if (im.has_range) {
+        w0 = im.range[0]; w1 = im.range[1];
+        x0 = im.range[2]; x1 = im.range[3];
+        y0 = im.range[4]; y1 = im.range[5];
+    } else {
+        w0 = __ldg(im.e_w); w1 = __ldg(im.e_w + im.n_w);
+        x0 = __ldg(im.e_x); x1 = __ldg(im.e_x + im.n_x);
+        y0 = __ldg(im.e_y); y1 = __ldg(im.e_y + im.n_y);
     }
+    g->x0 = x0;
+    g->x1 = x1;
+    g->inv_dx = (double)im.n_x / (x1 - x0);
+    g->y0 = y0;
+    g->y1 = y1;
+    g->inv_dy = (double)im.n_y / (y1 - y0);
+    g->w0 = w0;
+    g->w1 = w1;
+}
+
+__device__ __forceinline__ void image_guess_init(const ImageDev& im, ImageGuess* g) {
+    if (threadIdx.x == 0) image_guess_fill(im, g);
     __syncthreads();
 }
 

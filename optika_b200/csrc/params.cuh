@@ -21,6 +21,11 @@ struct TraceParams {
     long long tiles_per_outer;  // CTAs per index of the leading axes
     int32_t n_inner_axes;
     int32_t flat_index;  // host slab path: n_rays is a slab of the grid, decompose every axis per thread
+    // broadcast views whose offsets fit 32 bits (the usual case: small separable arrays):
+    // element strides of the fields (and the mask, index OPTK_NUM_FIELDS) as int32
+    int32_t offsets32;
+    int32_t pad3;
+    int32_t stride32[OPTK_NUM_FIELDS + 1][OPTK_MAX_AXES];
     int32_t n_surf;
     int32_t accumulate;
     int32_t dense_in;  // every input is a dense array indexed by the thread index

@@ -816,6 +816,25 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
             long long offn[3] = {base[OPTK_NUM_FIELDS + 1], base[OPTK_NUM_FIELDS + 2], base[OPTK_NUM_FIELDS + 3]};
             uint32_t rem = (uint32_t)(j0 + k + P.index_offset);
             const int first = P.in.n_axes - P.n_inner_axes;
+            if (P.offsets32 && !normal_given) {
+                // small broadcast arrays: 32-bit multiply-adds, one widening add per field at the end
+                int o32[OPTK_NUM_FIELDS + 1];
+#pragma unroll
+                for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) o32[f] = 0;
+                for (int a = P.in.n_axes - 1; a >= first; --a) {
+                    uint32_t q, idx;
+                    if (a == first) {
+                        idx = rem;
+                    } else {
+                        divmod(rem, P.div[a], q, idx);
+                        rem = q;
+                    }
+#pragma unroll
+                    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) o32[f] += (int)idx * P.stride32[f][a];
+                }
+#pragma unroll
+                for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] += o32[f];
+            } else
             for (int a = P.in.n_axes - 1; a >= first; --a) {
                 uint32_t q, idx;
                 if (a == first) {
@@ -880,7 +899,9 @@ __device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long 
 template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
-    if (IMAGE) image_guess_init(P.image, &guess);
+    // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
+    // second warp while the first warp computes the outer offsets
+    if (IMAGE && threadIdx.x == 32) image_guess_fill(P.image, &guess);
 
     // Dense input: ray index = thread index.  Broadcast input: the CTA owns one index of the
     // leading ("outer") axes and a tile of the trailing ("inner") axes; its outer offsets are
@@ -915,8 +936,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             }
             base[f] = o;
         }
-        __syncthreads();
     }
+    if (IMAGE || !DENSE) __syncthreads();
     bool valid[R];
     Ray r[R];
 #pragma unroll
@@ -1160,6 +1181,21 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         return e ? atoi(e) : 0;  // measured: no gain once 24 warps per SM are resident
     }();
     Q.prefetch_distance = 0;
+    Q.offsets32 = 0;
+    if (!dense) {
+        bool fits = true;
+        for (int f = 0; f <= OPTK_NUM_FIELDS && fits; ++f) {
+            const int64_t* st = f < OPTK_NUM_FIELDS ? P.in.stride[f] : P.in.mask_stride;
+            long long extent = 0;
+            for (int a = 0; a < P.in.n_axes; ++a) {
+                if (st[a] < 0) fits = false;
+                extent += (P.in.dims[a] - 1) * st[a];
+                Q.stride32[f][a] = (int32_t)st[a];
+            }
+            if (extent >= 0x7fffffffLL) fits = false;
+        }
+        Q.offsets32 = fits ? 1 : 0;
+    }
     if (dense && prefetch_waves > 0) {
         int device = 0, sms = 0, ctas = 0;
         OPTK_CUDA(cudaGetDevice(&device));

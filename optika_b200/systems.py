@@ -274,13 +274,15 @@ class SequentialSystem(AbstractSequentialSystem):
         result, rays = self._input(intensity, wavelength, field, pupil, normalized_field, normalized_pupil)
         ex, ey = self.sensor.pixel_edges()
         edges_w = np.asarray(na.as_named_array(u.length(wavelength_edges)).ndarray, dtype=float)
-        compiled = self._compiled
+        # trace in the sensor's local frame straight away (no final local -> global step, no
+        # inverse frame transformation before binning)
+        compiled = self._compiled_local
         if image is None:
             image = _engine.DeviceImage.zeros(
                 edges_w, ex, ey, device, leading=tuple(compiled.shape.values()), moments=True, counts=counts
             )
         _engine.trace(
-            compiled, rays, image=image, image_frame=self.sensor.transformation, write_rays=False, device=device,
+            compiled, rays, image=image, image_frame=None, write_rays=False, device=device,
             ray_axes_order=self._ray_axes_order,
         )
         return image

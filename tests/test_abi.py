@@ -63,7 +63,7 @@ def test_struct_layout_matches_c(tmp_path, lib):
         ("optk_surface_t", "transform"), ("optk_surface_t", "sag"), ("optk_surface_t", "ruling_power"),
         ("optk_surface_t", "holo_wavelength"), ("optk_surface_t", "vertices_y"),
         ("optk_rays_in_t", "field"), ("optk_rays_in_t", "stride"), ("optk_rays_in_t", "mask_stride"),
-        ("optk_rays_in_t", "normal_stride"), ("optk_image_t", "edges_wavelength"), ("optk_image_t", "counts"),
+        ("optk_rays_in_t", "normal_stride"), ("optk_image_t", "edges_wavelength"), ("optk_image_t", "counts"), ("optk_image_t", "range"),
         ("optk_ml_layer_t", "width_stride"), ("optk_ml_layer_t", "profile_kind"),
         ("optk_ml_input_t", "direction_stride"), ("optk_ml_input_t", "n_stride"),
     ]
