@@ -121,6 +121,24 @@ def test_fused_trace_bin_equals_trace_then_collect(cuda_device):
         assert np.allclose(fused.flux.cpu().numpy().reshape(flux.shape), flux, rtol=1e-9)
 
 
+def test_fused_image_with_explicit_frame_equals_local_trace(cuda_device):
+    """optk_trace(image, image_frame = sensor.transformation) on the GLOBAL trace == binning the local trace."""
+    system = configs.newtonian(num_field=4, num_pupil=20, num_pixel=64)
+    edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
+    local = system.image_rays(edges)
+    _, rays = system._input(None, None, None, None, False, False)
+    ex, ey = system.sensor.pixel_edges()
+    image = _engine.DeviceImage.zeros(edges.ndarray, ex, ey, cuda_device, moments=True, counts=True)
+    _engine.trace(
+        system._compiled, rays, image=image, image_frame=system.sensor.transformation, write_rays=False,
+        ray_axes_order=system._ray_axes_order,
+    )
+    a, b = local.counts.cpu().numpy().reshape(-1), image.counts.cpu().numpy().reshape(-1)
+    assert a.sum() == b.sum() > 0
+    assert (a != b).sum() <= 4  # a ray within rounding of a pixel edge may move
+    assert np.allclose(local.flux.sum().item(), image.flux.sum().item(), rtol=1e-12)
+
+
 def test_fused_image_with_configuration_axis(cuda_device):
     system = configs.misaligned_telescope(num_field=3, num_pupil=12, num_pixel=64, num_tilt=3)
     edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
