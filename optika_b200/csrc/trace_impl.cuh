@@ -1,0 +1,1092 @@
+// Kernel 1: the fused sequential raytrace (sm_100a, fp64).
+//
+// One thread owns one ray and walks the whole surface list, which arrives as a
+// kernel parameter (constant bank, broadcast to the warp).  Ray state stays in
+// registers; per surface the thread runs AbstractSurface.propagate_rays
+// (optika/surfaces.py:123-198): global->local, sag intercept + Beer-Lambert,
+// sag normal, grating equation, index / wavelength rescale, vector Snell,
+// aperture clip, local->global.  Rays touch HBM on entry and exit only (plus one
+// store per surface when accumulating), and optionally never leave the chip:
+// the final rays can be binned straight into the detector image.
+#pragma once
+#include "common.cuh"
+#include "bin.cuh"
+#include "params.cuh"
+#include <cstdlib>
+
+namespace optk {
+
+struct Ray {
+    double w, px, py, pz, dx, dy, dz, intensity, att, n;
+    bool unv;
+};
+
+// ---------------------------------------------------------------------------
+// sag profiles, evaluated in the sag's own frame
+// ---------------------------------------------------------------------------
+
+// sign0(v) * root for root >= 0, in 3 instructions: copysign unless v == 0 (NaN v gives NaN upstream anyway)
+__device__ __forceinline__ double signed_root(double v, double root) {
+    return (v == 0.0) ? v * root : copysign(root, v);
+}
+
+// optika/sags/_parabolic.py:142-151: root of a t^2 + 2 h t + c = 0 with
+//   a = ux^2 + uy^2,  h = ox ux + oy uy - 2 f uz,  c = ox^2 + oy^2 - 4 f oz;
+// the reference takes t = (-h - s sqrt(h^2 - a c)) / a with s = sign(f uz), and for
+// a <= 1e-10 its paraxial form t = c / (4 f uz) (which drops ox ux + oy uy; kept verbatim).
+// For near-axial rays -h and s sqrt() nearly cancel (the reference loses ~eps |2f| / a to
+// rounding there, see DESIGN.md "conditioning"); the same root is evaluated in its
+// cancellation-free form c / (-h + s sqrt()).  One division, no branch.
+__device__ __forceinline__ double parabola_intercept(double f, double ox, double oy, double oz, double ux, double uy,
+                                                     double uz) {
+    const double a = ux * ux + uy * uy;
+    const double h = ox * ux + oy * uy - 2.0 * f * uz;
+    const double c = ox * ox + oy * oy - 4.0 * f * oz;
+    const double fuz = f * uz;
+    const double root = signed_root(fuz, fsqrt(h * h - a * c));
+    const bool general = a > 1e-10;
+    const bool stable = -h * fuz >= 0.0;  // -h and root have the same sign (or one of them is zero)
+    const double num = (general && !stable) ? (-h - root) : c;
+    const double den = general ? (stable ? (-h + root) : a) : 4.0 * fuz;
+    return fdiv(num, den);
+}
+
+// Path length t to the surface for a ray o + t u (closed forms), or NaN/inf on a miss.
+__device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, double ox, double oy, double oz,
+                                                       double ux, double uy, double uz) {
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            // optika/sags/_flat.py:58: d = -o.z / u.z
+            return fdiv(-oz, uz);
+        case OPTK_SAG_SPHERICAL: {
+            // optika/sags/_spherical.py:176-184
+            const double r = S.sag[0];
+            const double pz = oz - r;
+            const double up = ux * ox + uy * oy + uz * pz;
+            const double disc = up * up - (ox * ox + oy * oy + pz * pz - r * r);
+            return -up - sign0(r * uz) * fsqrt(disc);
+        }
+        case OPTK_SAG_PARABOLIC:
+            return parabola_intercept(S.sag[0], ox, oy, oz, ux, uy, uz);
+        case OPTK_SAG_CONIC: {
+            // optika/sags/_conic.py:126-162: A t^2 + B t + C = 0, both roots tested for the
+            // vertex sheet, the smaller |t| wins.  root(-1) = (-B - sqrt)/(2A) and
+            // root(+1) = (-B + sqrt)/(2A) are formed from q = -(B + sign(B) sqrt)/2 as q/A and
+            // C/q so that neither suffers the cancellation of the textbook formula (A -> 0
+            // for k -> -1 and near-axial rays).
+            const double c = S.sag[3];
+            const double kp1 = 1.0 + S.sag[1];
+            const double a = c * (ux * ux + uy * uy + kp1 * uz * uz);
+            const double b = 2.0 * (c * (ox * ux + oy * uy + kp1 * oz * uz) - uz);
+            const double cc = c * (ox * ox + oy * oy + kp1 * oz * oz) - 2.0 * oz;
+            const double disc = b * b - 4.0 * a * cc;
+            const bool real = disc >= 0;
+            const double sq_disc = fsqrt(real ? disc : 0.0);
+            const bool degenerate = fabs(a) < 1e-12;
+            double t_minus, t_plus;  // root(-1), root(+1)
+            if (degenerate) {
+                t_minus = t_plus = fdiv(-cc, b);
+            } else {
+                const double q = -0.5 * (b + copysign(sq_disc, b));
+                const double t_q = fdiv(q, a), t_c = (q != 0.0) ? fdiv(cc, q) : t_q;
+                // b >= 0: q/a = (-b - sqrt)/(2a) = root(-1);  b < 0: q/a = root(+1)
+                t_minus = (b >= 0.0) ? t_q : t_c;
+                t_plus = (b >= 0.0) ? t_c : t_q;
+            }
+            double t_root[2] = {t_minus, t_plus};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const double t = t_root[k];
+                const double x = ox + ux * t, y = oy + uy * t, z = oz + uz * t;
+                const double r2 = x * x + y * y;
+                const bool on_vertex_sheet = (z * (c * r2 - z)) >= 0;
+                t_root[k] = (real && on_vertex_sheet) ? t : INFINITY;
+            }
+            return fabs(t_root[0]) <= fabs(t_root[1]) ? t_root[0] : t_root[1];
+        }
+        case OPTK_SAG_CYLINDRICAL: {
+            // optika/sags/_cylindrical.py:126-152, cross products with a = y-hat written out
+            const double r = S.sag[0];
+            const double bx = -ox, bz = r - oz;
+            const double ncx = -uz, ncz = ux;
+            const double nca2 = ncx * ncx + ncz * ncz;
+            const double negative_b = ncx * (-bz) + ncz * bx;
+            const double dot = bx * ncx + bz * ncz;
+            const double disc = nca2 * (r * r) - dot * dot;
+            if (disc > 0) return fdiv(negative_b - sign0(r * uz) * fsqrt(disc), nca2);
+            return fdiv(-oz, uz);
+        }
+    }
+    return NAN;
+}
+
+// Toroid: z and its gradient (optika/sags/_toroidal.py:38-88).
+__device__ __forceinline__ void toroid_eval(double c, double r, double x, double y, double& z, double& dzdx,
+                                            double& dzdy) {
+    const double y2 = y * y;
+    const double g = fsqrt(1.0 - c * c * y2);
+    const double zy = fdiv(c * y2, 1.0 + g);
+    const double rz = r - zy;
+    const double f = fsqrt(rz * rz - x * x);
+    z = r - f;
+    const double inv_f = frcp(f);
+    dzdx = x * inv_f;
+    dzdy = rz * fdiv(c * y, g) * inv_f;
+}
+
+// Unit normal at a point of the sag frame (not rotated back, as in the reference).
+__device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, double y, double& nx, double& ny,
+                                           double& nz) {
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            nx = 0.0; ny = 0.0; nz = -1.0;  // optika/sags/_flat.py:43-47
+            return;
+        case OPTK_SAG_SPHERICAL: {
+            // optika/sags/_spherical.py:141-146
+            const double c = S.sag[3];
+            nx = c * x;
+            ny = c * y;
+            nz = -fsqrt(1.0 - nx * nx - ny * ny);
+            return;
+        }
+        case OPTK_SAG_CYLINDRICAL: {
+            // optika/sags/_cylindrical.py:107-113
+            nx = x * S.sag[3];
+            ny = 0.0;
+            nz = -fsqrt(1.0 - nx * nx);
+            return;
+        }
+        case OPTK_SAG_PARABOLIC: {
+            // optika/sags/_parabolic.py:56-63: (x, y, -R) / sqrt((x/R)^2 + (y/R)^2 + 1) / R
+            const double ir = 0.5 * S.sag[3];  // 1 / (2 f)
+            const double xr = x * ir, yr = y * ir;
+            const double inv = frsqrt(xr * xr + yr * yr + 1.0);
+            nx = xr * inv;
+            ny = yr * inv;
+            nz = -inv;
+            return;
+        }
+        case OPTK_SAG_CONIC: {
+            // optika/sags/_conic.py:69-81
+            const double c = S.sag[3];
+            const double ig = frsqrt(1.0 - (1.0 + S.sag[1]) * c * c * (x * x + y * y));
+            const double dzdx = c * x * ig, dzdy = c * y * ig;
+            const double inv = frsqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+            nx = dzdx * inv;
+            ny = dzdy * inv;
+            nz = -inv;
+            return;
+        }
+        case OPTK_SAG_TOROIDAL: {
+            // optika/sags/_toroidal.py:71-88
+            double z, dzdx, dzdy;
+            toroid_eval(S.sag[3], S.sag[2], x, y, z, dzdx, dzdy);
+            const double inv = frsqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+            nx = dzdx * inv;
+            ny = dzdy * inv;
+            nz = -inv;
+            return;
+        }
+    }
+    nx = ny = nz = NAN;
+}
+
+// z(x, y) in the sag frame, for OPTK_STAGE_SAG_OUT.
+__device__ __forceinline__ double sag_value(const optk_surface_t& S, double x, double y) {
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+            return 0.0;
+        case OPTK_SAG_SPHERICAL: {
+            const double c = S.sag[3];
+            const double r2 = x * x + y * y;
+            return c * r2 / (1.0 + sqrt(1.0 - c * c * r2));
+        }
+        case OPTK_SAG_CYLINDRICAL: {
+            const double c = S.sag[3];
+            const double r2 = x * x;
+            return c * r2 / (1.0 + sqrt(1.0 - c * c * r2));
+        }
+        case OPTK_SAG_PARABOLIC:
+        case OPTK_SAG_CONIC: {
+            const double radius = S.sag_kind == OPTK_SAG_PARABOLIC ? 2.0 * S.sag[0] : S.sag[0];
+            const double conic = S.sag_kind == OPTK_SAG_PARABOLIC ? -1.0 : S.sag[1];
+            const double c = 1.0 / radius;
+            const double r2 = x * x + y * y;
+            return c * r2 / (1.0 + sqrt(1.0 - (1.0 + conic) * c * c * r2));
+        }
+        case OPTK_SAG_TOROIDAL: {
+            double z, dzdx, dzdy;
+            toroid_eval(S.sag[3], S.sag[2], x, y, z, dzdx, dzdy);
+            return z;
+        }
+    }
+    return NAN;
+}
+
+// ---------------------------------------------------------------------------
+// rulings: kappa = spacing_(position, normal)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ipow(double x, int p) {
+    bool neg = p < 0;
+    unsigned e = neg ? (unsigned)(-p) : (unsigned)p;
+    double r = 1.0, b = x;
+    while (e) {
+        if (e & 1u) r *= b;
+        b *= b;
+        e >>= 1;
+    }
+    return neg ? 1.0 / r : r;
+}
+
+__device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px, double py, double pz, double nx,
+                                              double ny, double nz, double& kx, double& ky, double& kz) {
+    switch (S.ruling_kind) {
+        case OPTK_RULING_CONSTANT: {
+            // optika/rulings/_spacing.py:69-74
+            const double c = S.ruling_coeff[0];
+            kx = c * S.ruling_normal[0];
+            ky = c * S.ruling_normal[1];
+            kz = c * S.ruling_normal[2];
+            return;
+        }
+        case OPTK_RULING_POLYNOMIAL: {
+            // optika/rulings/_spacing.py:109-128
+            if (S.flags & OPTK_F_RULING_TRANSFORM) affine_forward(S.ruling_transform, px, py, pz, false);
+            const double x = px * S.ruling_normal[0] + py * S.ruling_normal[1] + pz * S.ruling_normal[2];
+            double d = 0.0;
+            for (int k = 0; k < S.n_coeff; ++k) d += S.ruling_coeff[k] * ipow(x, S.ruling_power[k]);
+            kx = d * S.ruling_normal[0];
+            ky = d * S.ruling_normal[1];
+            kz = d * S.ruling_normal[2];
+            return;
+        }
+        case OPTK_RULING_HOLOGRAPHIC: {
+            // optika/rulings/_spacing.py:295-328
+            const double d1 = (S.flags & OPTK_F_HOLO_DIVERGING_1) ? 1.0 : -1.0;
+            const double d2 = (S.flags & OPTK_F_HOLO_DIVERGING_2) ? 1.0 : -1.0;
+            double ax = px - S.holo_x1[0], ay = py - S.holo_x1[1], az = pz - S.holo_x1[2];
+            double bx = px - S.holo_x2[0], by = py - S.holo_x2[1], bz = pz - S.holo_x2[2];
+            const double ia = d1 * frsqrt(ax * ax + ay * ay + az * az);
+            const double ib = d2 * frsqrt(bx * bx + by * by + bz * bz);
+            const double rx = ax * ia - bx * ib, ry = ay * ia - by * ib, rz = az * ia - bz * ib;
+            // aq = n x dr
+            const double qx = ny * rz - nz * ry, qy = nz * rx - nx * rz, qz = nx * ry - ny * rx;
+            // spacing * (q/a) x n  with spacing = w / a   =>  (w / a^2) (aq x n)
+            const double s = fdiv(S.holo_wavelength, qx * qx + qy * qy + qz * qz);
+            kx = s * (qy * nz - qz * ny);
+            ky = s * (qz * nx - qx * nz);
+            kz = s * (qx * ny - qy * nx);
+            return;
+        }
+    }
+    kx = ky = kz = NAN;
+}
+
+// ---------------------------------------------------------------------------
+// apertures (edge-sensitive: products and sums are not contracted)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double py_mod(double a, double b) {
+    // numpy's float remainder: result takes the sign of the divisor
+    double r = fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+
+__device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x, double y, double z) {
+    if (S.flags & OPTK_F_APERTURE_TRANSFORM) affine_inverse(S.aperture_transform, x, y, z, false);
+    bool mask = false;
+    switch (S.aperture_kind) {
+        case OPTK_APERTURE_CIRCULAR:
+            // optika/apertures/_apertures.py:309: position.xy.length <= radius
+            // sqrt is monotone and correctly rounded in the reference, so "sqrt(r2) <= radius" is
+            // exactly "r2 <= T" with T = max{v : sqrt(v) <= radius}, which optk_system_create
+            // stores in aperture[3]: same decision bit for bit, no square root per ray
+            mask = add_rn(mul_rn(x, x), mul_rn(y, y)) <= S.aperture[3];
+            break;
+        case OPTK_APERTURE_RECTANGULAR:
+            // optika/apertures/_apertures.py:962-963
+            mask = (-S.aperture[0] <= x) && (x <= S.aperture[0]) && (-S.aperture[1] <= y) && (y <= S.aperture[1]);
+            break;
+        case OPTK_APERTURE_ELLIPTICAL: {
+            // optika/apertures/_apertures.py:657
+            const double a = x / S.aperture[0], b = y / S.aperture[1];
+            mask = add_rn(mul_rn(a, a), mul_rn(b, b)) <= 1.0;
+            break;
+        }
+        case OPTK_APERTURE_SECTOR: {
+            // optika/apertures/_apertures.py:466-476
+            const bool mask_radius = add_rn(mul_rn(x, x), mul_rn(y, y)) <= S.aperture[3];
+            const double a0 = S.aperture[1], a1 = S.aperture[2];
+            const double angle = atan2(y, x);
+            const double two_pi = 6.283185307179586;
+            const double ap = py_mod(angle, two_pi);
+            const double an = py_mod(angle, -two_pi);
+            mask = mask_radius && (((a0 < ap) && (ap < a1)) || ((a0 < an) && (an < a1)));
+            break;
+        }
+        case OPTK_APERTURE_POLYGON: {
+            // na.geometry.point_in_polygon (third party): even-odd crossing, boundary inside
+            if (!(S.flags & OPTK_F_APERTURE_ACTIVE)) return true;  // _apertures.py:751, 775-776
+            bool inside = false, on_edge = false;
+            const int nv = S.n_vertices;
+            double x0 = S.vertices_x[nv - 1], y0 = S.vertices_y[nv - 1];
+            for (int i = 0; i < nv; ++i) {
+                const double x1 = S.vertices_x[i], y1 = S.vertices_y[i];
+                const double ex = sub_rn(x1, x0), ey = sub_rn(y1, y0);
+                const double cross = sub_rn(mul_rn(ex, sub_rn(y, y0)), mul_rn(ey, sub_rn(x, x0)));
+                const bool within = (fmin(x0, x1) <= x) && (x <= fmax(x0, x1)) && (fmin(y0, y1) <= y) &&
+                                    (y <= fmax(y0, y1));
+                on_edge |= (cross == 0.0) && within;
+                const bool straddles = (y0 > y) != (y1 > y);
+                const double x_cross = add_rn(x0, mul_rn(sub_rn(y, y0), ex) / ey);
+                inside ^= straddles && (x < x_cross);
+                x0 = x1;
+                y0 = y1;
+            }
+            mask = inside || on_edge;
+            break;
+        }
+        default:
+            return true;
+    }
+    if (S.flags & OPTK_F_APERTURE_INVERTED) mask = !mask;
+    if (!(S.flags & OPTK_F_APERTURE_ACTIVE)) mask = true;
+    return mask;
+}
+
+// ---------------------------------------------------------------------------
+// one surface, FULL operator (every stage, sag normal, no sag transformation): the
+// streamlined path that SequentialSystem.raytrace / propagate_rays / accumulate_rays
+// take.  R rays per thread walk the surface together: every decision that depends
+// only on the surface (transform kind, sag kind, rulings, material, aperture kind) is
+// taken once for the R rays, whose arithmetic then interleaves (instruction-level
+// parallelism for the long fp64 dependency chains).
+// AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
+// ---------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations) {
+    const int flags = S.flags;
+
+    // 1. global -> surface-local (surfaces.py:141-142)
+    if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            r[k].px -= S.transform.t[0];
+            r[k].py -= S.transform.t[1];
+            r[k].pz -= S.transform.t[2];
+        }
+    } else if (flags & OPTK_F_TRANSFORM) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            affine_inverse(S.transform, r[k].px, r[k].py, r[k].pz, false);
+            affine_inverse(S.transform, r[k].dx, r[k].dy, r[k].dz, true);
+        }
+    }
+
+    // 2 + 3. path length to the sag and the unit normal at the hit point (surfaces.py:144-148)
+    double t[R], nx[R], ny[R], nz[R];
+    switch (S.sag_kind) {
+        case OPTK_SAG_FLAT:
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                t[k] = fdiv(-r[k].pz, r[k].dz);  // optika/sags/_flat.py:58
+                nx[k] = 0.0; ny[k] = 0.0; nz[k] = -1.0;  // :43-47
+            }
+            break;
+        case OPTK_SAG_SPHERICAL: {
+            // optika/sags/_spherical.py:176-184, 141-146
+            const double rad = S.sag[0], c = S.sag[3];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double qx = r[k].px, qy = r[k].py, pz = r[k].pz - rad;
+                const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
+                const double up = vx * qx + vy * qy + vz * pz;
+                const double disc = up * up - (qx * qx + qy * qy + pz * pz - rad * rad);
+                t[k] = -up - signed_root(rad * vz, fsqrt(disc));
+                nx[k] = c * (qx + vx * t[k]);
+                ny[k] = c * (qy + vy * t[k]);
+                nz[k] = -fsqrt(1.0 - nx[k] * nx[k] - ny[k] * ny[k]);
+            }
+            break;
+        }
+        case OPTK_SAG_PARABOLIC: {
+            // optika/sags/_parabolic.py:142-151, 56-63
+            const double f = S.sag[0], ir = 0.5 * S.sag[3];  // 1 / (2 f)
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                t[k] = parabola_intercept(f, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
+                const double xr = (r[k].px + r[k].dx * t[k]) * ir, yr = (r[k].py + r[k].dy * t[k]) * ir;
+                const double inv = frsqrt(xr * xr + yr * yr + 1.0);
+                nx[k] = xr * inv;
+                ny[k] = yr * inv;
+                nz[k] = -inv;
+            }
+            break;
+        }
+        default: {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double qx = r[k].px, qy = r[k].py, qz = r[k].pz;
+                const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
+                if (S.sag_kind == OPTK_SAG_TOROIDAL) {
+                    // AbstractSag.intercept, optika/sags/_abc.py:76-107: root of
+                    // f(t) = (o + t u).z - sag(o + t u) from t = 0.  Newton with the analytic
+                    // gradient, iterated to convergence (the reference's secant stops at
+                    // |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
+                    const double c = S.sag[3], rr = S.sag[2];
+                    double tt = 0.0;
+                    for (int it = 0; it < 64; ++it) {
+                        double z, dzdx, dzdy;
+                        toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
+                        const double f = (qz + vz * tt) - z;
+                        const double df = vz - (dzdx * vx + dzdy * vy);
+                        const double step = fdiv(f, df);
+                        tt -= step;
+                        ++newton_iterations;
+                        if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(tt)))) break;
+                    }
+                    t[k] = tt;
+                } else {
+                    t[k] = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
+                }
+                sag_normal(S, qx + vx * t[k], qy + vy * t[k], nx[k], ny[k], nz[k]);
+            }
+            break;
+        }
+    }
+    {
+        // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|).
+        // With attenuation == 0 the factor is exactly 1 unless the displacement is not finite
+        // (exp(-0 * inf) = exp(-0 * nan) = nan in the reference).
+        bool attenuating = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k) attenuating = attenuating || (r[k].att != 0.0);
+        if (attenuating) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double ex = r[k].dx * t[k], ey = r[k].dy * t[k], ez = r[k].dz * t[k];
+                r[k].intensity = exp(-r[k].att * fsqrt(ex * ex + ey * ey + ez * ez)) * r[k].intensity;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const double hx = r[k].px + r[k].dx * t[k], hy = r[k].py + r[k].dy * t[k], hz = r[k].pz + r[k].dz * t[k];
+            const bool finite = fabs(hx + hy + hz) <= 1.7976931348623157e308;
+            r[k].intensity = finite ? r[k].intensity : OPTK_NAN;
+            r[k].px = hx; r[k].py = hy; r[k].pz = hz;
+        }
+    }
+
+    // 4. rulings.incident_effective  (surfaces.py:150-154, rulings/_rulings.py:107-128, 187-204)
+    if (S.ruling_kind != OPTK_RULING_NONE) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double kx, ky, kz;
+            ruling_vector(S, r[k].px, r[k].py, r[k].pz, nx[k], ny[k], nz[k], kx, ky, kz);
+            // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
+            const double k2 = kx * kx + ky * ky + kz * kz;
+            const double an = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
+            const double sg = (an == 0.0) ? an : copysign(1.0, an);  // numpy.sign
+            const double f = fdiv(sg * S.ruling_order * r[k].w, r[k].n * k2);
+            r[k].dx += f * kx;
+            r[k].dy += f * ky;
+            r[k].dz += f * kz;
+        }
+    }
+
+    // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
+    {
+        const bool mirror = S.material_kind == OPTK_MAT_MIRROR;
+        const bool glass = S.material_kind == OPTK_MAT_GLASS;
+        double n2[R];
+        bool same_medium = true;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (mirror) {
+                n2[k] = r[k].n;  // _materials.py:135-139
+            } else if (glass) {
+                // optika/materials/_materials.py:428-438
+                const double w2 = r[k].w * r[k].w;
+                n2[k] = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) +
+                                     S.material[1] * fdiv(w2, w2 - S.material[4]) +
+                                     S.material[2] * fdiv(w2, w2 - S.material[5])));
+            } else {
+                n2[k] = 1.0;  // _materials.py:95-99
+            }
+            same_medium = same_medium && (r[k].n == n2[k]);
+        }
+        // n1 == n2: r = 1 and 1 / r^2 = 1 exactly (no divisions, wavelength unchanged)
+        double ratio[R], inv_r2[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) ratio[k] = inv_r2[k] = 1.0;
+        if (!same_medium) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                ratio[k] = fdiv(r[k].n, n2[k]);
+                inv_r2[k] = frcp(ratio[k] * ratio[k]);
+                r[k].w = fdiv(r[k].w, ratio[k]);  // surfaces.py:165
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            // optika/materials/_snells_law.py:341-366
+            const double a2 = r[k].dx * r[k].dx + r[k].dy * r[k].dy + r[k].dz * r[k].dz;
+            const double au = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
+            const double root = fsqrt(inv_r2[k] + au * au - a2);
+            // d = -au + sgn (2 mirror - 1) root with sgn = -copysign(1, au)
+            const double d = -au + copysign(root, mirror ? -au : au);
+            r[k].dx = ratio[k] * (r[k].dx + d * nx[k]);
+            r[k].dy = ratio[k] * (r[k].dy + d * ny[k]);
+            r[k].dz = ratio[k] * (r[k].dz + d * nz[k]);
+            if (!mirror) r[k].att = 0.0;  // _materials.py:101-105, 141-145, 440-444
+            r[k].n = n2[k];
+        }
+    }
+
+    // 9. aperture.clip_rays on the outgoing ray, local coordinates  (surfaces.py:192-193)
+    if (S.aperture_kind != OPTK_APERTURE_NONE) {
+        if (S.aperture_kind == OPTK_APERTURE_RECTANGULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
+            // optika/apertures/_apertures.py:962-963 (the common case, inlined)
+            const double hx = S.aperture[0], hy = S.aperture[1];
+            const bool inverted = flags & OPTK_F_APERTURE_INVERTED, active = flags & OPTK_F_APERTURE_ACTIVE;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                bool m = (-hx <= r[k].px) && (r[k].px <= hx) && (-hy <= r[k].py) && (r[k].py <= hy);
+                m = (m != inverted) || !active;
+                r[k].unv = r[k].unv && m;
+            }
+        } else {
+            const bool angular = flags & OPTK_F_APERTURE_ANGULAR;  // dimensionless aperture: test the direction
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const bool m = angular ? aperture_test(S, r[k].dx, r[k].dy, r[k].dz)
+                                       : aperture_test(S, r[k].px, r[k].py, r[k].pz);
+                r[k].unv = r[k].unv && m;
+            }
+        }
+    }
+
+    // 10. local -> global  (surfaces.py:195-196)
+    if (!(flags & OPTK_F_LOCAL_OUT)) {
+        if (flags & OPTK_F_TRANSLATION_ONLY) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                r[k].px += S.transform.t[0];
+                r[k].py += S.transform.t[1];
+                r[k].pz += S.transform.t[2];
+            }
+        } else if (flags & OPTK_F_TRANSFORM) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                affine_forward(S.transform, r[k].px, r[k].py, r[k].pz, false);
+                affine_forward(S.transform, r[k].dx, r[k].dy, r[k].dz, true);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// one surface, GENERIC path (partial stage masks, caller-supplied normals: the unit
+// operations of the reference API): AbstractSurface.propagate_rays, optika/surfaces.py:123-198
+// ---------------------------------------------------------------------------
+static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray& r, unsigned& newton_iterations,
+                                                  bool normal_given, double gnx, double gny, double gnz) {
+    const int stages = S.stages;
+    const int flags = S.flags;
+
+    // 1. global -> surface-local (surfaces.py:141-142)
+    if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
+        r.px -= S.transform.t[0];
+        r.py -= S.transform.t[1];
+        r.pz -= S.transform.t[2];
+    } else if (flags & OPTK_F_TRANSFORM) {
+        affine_inverse(S.transform, r.px, r.py, r.pz, false);
+        affine_inverse(S.transform, r.dx, r.dy, r.dz, true);
+    }
+
+    // sag frame copy of the ray (sag.transformation, e.g. optika/sags/_spherical.py:153-154)
+    double qx = r.px, qy = r.py, qz = r.pz;
+    double vx = r.dx, vy = r.dy, vz = r.dz;
+    const bool sag_t = flags & OPTK_F_SAG_TRANSFORM;
+    if (sag_t) {
+        affine_inverse(S.sag_transform, qx, qy, qz, false);
+        affine_inverse(S.sag_transform, vx, vy, vz, true);
+    }
+
+    // 2. sag.propagate_rays: intercept (+ Beer-Lambert)  (surfaces.py:144)
+    if (stages & OPTK_STAGE_INTERCEPT) {
+        double t;
+        if (S.sag_kind == OPTK_SAG_TOROIDAL) {
+            // AbstractSag.intercept, optika/sags/_abc.py:76-107: root of
+            // f(t) = (o + t u).z - sag(T^-1 (o + t u)) from t = 0.  Newton with the
+            // analytic gradient, iterated to convergence (the reference's secant
+            // stops at |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
+            const double c = S.sag[3], rr = S.sag[2];
+            t = 0.0;
+            for (int it = 0; it < 64; ++it) {
+                double z, dzdx, dzdy;
+                toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
+                const double f = (r.pz + r.dz * t) - z;
+                const double df = r.dz - (dzdx * vx + dzdy * vy);
+                const double step = fdiv(f, df);
+                t -= step;
+                ++newton_iterations;
+                if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(t)))) break;
+            }
+        } else {
+            t = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
+        }
+        const double nx_ = r.px + r.dx * t, ny_ = r.py + r.dy * t, nz_ = r.pz + r.dz * t;
+        if (stages & OPTK_STAGE_ATTENUATE) {
+            // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|)
+            const double ex = nx_ - r.px, ey = ny_ - r.py, ez = nz_ - r.pz;
+            const double len2 = ex * ex + ey * ey + ez * ez;
+            if (r.att != 0.0) {
+                r.intensity = exp(-r.att * fsqrt(len2)) * r.intensity;
+            } else if (!(len2 <= 1.7976931348623157e308)) {
+                r.intensity = NAN;  // exp(-0 * inf) = exp(-0 * nan) = nan in the reference
+            }
+        }
+        r.px = nx_; r.py = ny_; r.pz = nz_;
+        qx += vx * t; qy += vy * t; qz += vz * t;
+        if (sag_t) {  // keep the sag-frame position consistent with the surface-frame one
+            qx = r.px; qy = r.py; qz = r.pz;
+            affine_inverse(S.sag_transform, qx, qy, qz, false);
+        }
+    }
+
+    // 3. normal = sag.normal(position_1)  (surfaces.py:146-148)
+    double nx, ny, nz;
+    sag_normal(S, qx, qy, nx, ny, nz);
+    if (normal_given) {  // unit operations with a caller-supplied normal
+        nx = gnx; ny = gny; nz = gnz;
+    }
+
+    if (stages & OPTK_STAGE_SAG_OUT) {
+        double z = sag_value(S, qx, qy);
+        if (S.sag_kind == OPTK_SAG_FLAT && sag_t) {
+            // optika/sags/_flat.py:31-41: z of the transformed (x, y, 0)
+            double tx = qx, ty = qy, tz = 0.0;
+            affine_forward(S.sag_transform, tx, ty, tz, false);
+            z = tz;
+        }
+        r.pz = z;
+    }
+    if (stages & OPTK_STAGE_NORMAL_OUT) {
+        r.dx = nx; r.dy = ny; r.dz = nz;
+    }
+
+    // 4. rulings.incident_effective  (surfaces.py:150-154, rulings/_rulings.py:107-128, 187-204)
+    if ((stages & (OPTK_STAGE_RULINGS | OPTK_STAGE_KAPPA_OUT)) && S.ruling_kind != OPTK_RULING_NONE) {
+        double kx, ky, kz;
+        ruling_vector(S, r.px, r.py, r.pz, nx, ny, nz, kx, ky, kz);
+        if (stages & OPTK_STAGE_KAPPA_OUT) {
+            r.dx = kx; r.dy = ky; r.dz = kz;
+        } else {
+            // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
+            const double k2 = kx * kx + ky * ky + kz * kz;
+            const double s = sign0(r.dx * nx + r.dy * ny + r.dz * nz);
+            const double f = fdiv(s * S.ruling_order * r.w, r.n * k2);
+            r.dx += f * kx;
+            r.dy += f * ky;
+            r.dz += f * kz;
+        }
+    }
+
+    // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
+    if (stages & OPTK_STAGE_REFRACT) {
+        const double n1 = r.n;
+        double n2;
+        const bool mirror = S.material_kind == OPTK_MAT_MIRROR || S.material_kind == OPTK_MAT_INDEX_MIRROR;
+        if (S.material_kind == OPTK_MAT_INDEX || S.material_kind == OPTK_MAT_INDEX_MIRROR) {
+            n2 = S.material[0];  // snells_law(direction, n1, n2, normal, is_mirror) unit operation
+        } else if (S.material_kind == OPTK_MAT_GLASS) {
+            // optika/materials/_materials.py:428-438
+            const double w2 = r.w * r.w;
+            n2 = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
+                              S.material[2] * fdiv(w2, w2 - S.material[5])));
+        } else if (mirror) {
+            n2 = n1;  // _materials.py:135-139
+        } else {
+            n2 = 1.0;  // _materials.py:95-99
+        }
+        // optika/materials/_snells_law.py:341-366
+        const double a2 = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
+        const double au = r.dx * nx + r.dy * ny + r.dz * nz;
+        double ratio = 1.0, inv_r2 = 1.0;
+        if (n1 != n2) {  // n1 == n2: r = 1 and 1 / r^2 = 1 exactly, skip the divisions
+            ratio = fdiv(n1, n2);
+            inv_r2 = frcp(ratio * ratio);
+            r.w = fdiv(r.w, ratio);  // surfaces.py:165
+        }
+        const double sgn = -copysign(1.0, au);
+        // sqrt(1/r^2 + (a.u)^2 - |a|^2).  For an undiffracted ray in an unchanged medium
+        // the radicand is (a.u)^2 + e with e = 1/r^2 - |a|^2 ~ 1e-16: the root is
+        // |a.u| + e / (2 |a.u|) to better than 1e-26 relative, no square root needed.
+        const double au2 = au * au;
+        const double e = inv_r2 - a2;
+        double root;
+        if (fabs(e) < 1e-13 * au2) {
+            const double m = fabs(au);
+            root = fma(0.5 * e, frcp(m), m);
+        } else {
+            root = fsqrt(au2 + e);
+        }
+        const double d = -au + sgn * (mirror ? 1.0 : -1.0) * root;
+        r.dx = ratio * (r.dx + d * nx);
+        r.dy = ratio * (r.dy + d * ny);
+        r.dz = ratio * (r.dz + d * nz);
+        // efficiency = 1 for Vacuum / Mirror / Glass and ideal Rulings (surfaces.py:175-179)
+        if (!mirror) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
+        r.n = n2;
+    }
+
+    // 9. aperture.clip_rays on the outgoing ray, local coordinates  (surfaces.py:192-193)
+    if ((stages & OPTK_STAGE_CLIP) && S.aperture_kind != OPTK_APERTURE_NONE) {
+        bool m;
+        if (flags & OPTK_F_APERTURE_ANGULAR)
+            m = aperture_test(S, r.dx, r.dy, r.dz);  // dimensionless aperture: test the direction
+        else
+            m = aperture_test(S, r.px, r.py, r.pz);
+        r.unv = r.unv && m;
+    }
+
+    // 10. local -> global  (surfaces.py:195-196)
+    if (!(flags & OPTK_F_LOCAL_OUT)) {
+        if (flags & OPTK_F_TRANSLATION_ONLY) {
+            r.px += S.transform.t[0];
+            r.py += S.transform.t[1];
+            r.pz += S.transform.t[2];
+        } else if (flags & OPTK_F_TRANSFORM) {
+            affine_forward(S.transform, r.px, r.py, r.pz, false);
+            affine_forward(S.transform, r.dx, r.dy, r.dz, true);
+        }
+    }
+}
+
+__device__ __forceinline__ void store_ray(const optk_rays_out_t& out, long long o, const Ray& r) {
+    if (out.field[OPTK_WAVELENGTH]) out.field[OPTK_WAVELENGTH][o] = r.w;
+    if (out.field[OPTK_PX]) out.field[OPTK_PX][o] = r.px;
+    if (out.field[OPTK_PY]) out.field[OPTK_PY][o] = r.py;
+    if (out.field[OPTK_PZ]) out.field[OPTK_PZ][o] = r.pz;
+    if (out.field[OPTK_DX]) out.field[OPTK_DX][o] = r.dx;
+    if (out.field[OPTK_DY]) out.field[OPTK_DY][o] = r.dy;
+    if (out.field[OPTK_DZ]) out.field[OPTK_DZ][o] = r.dz;
+    if (out.field[OPTK_INTENSITY]) out.field[OPTK_INTENSITY][o] = r.intensity;
+    if (out.field[OPTK_ATTENUATION]) out.field[OPTK_ATTENUATION][o] = r.att;
+    if (out.field[OPTK_INDEX_REFRACTION]) out.field[OPTK_INDEX_REFRACTION][o] = r.n;
+    if (out.unvignetted) out.unvignetted[o] = r.unv ? 1 : 0;
+}
+
+// FULL:  every surface runs the full operator with the sag normal (surface_full, R = 2 rays
+//        per thread); otherwise the generic path with stage masks / caller normals (R = 1).
+// DENSE: every input is a dense array indexed by the ray index.  VEC: the dense arrays are
+//        16-byte aligned, so the two rays of a thread move as one 128-bit load / store.
+// ACC:   write the state after every surface.   IMAGE: bin the final rays.
+template <int R, bool DENSE>
+__device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, long long j0, const long long* base,
+                                          const bool (&valid)[R], Ray (&r)[R], bool normal_given, double& gnx,
+                                          double& gny, double& gnz) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        if (!valid[k]) continue;
+        const long long i = i0 + k;
+        if (DENSE) {
+            r[k].w = __ldg(P.in.field[OPTK_WAVELENGTH] + i);
+            r[k].px = __ldg(P.in.field[OPTK_PX] + i);
+            r[k].py = __ldg(P.in.field[OPTK_PY] + i);
+            r[k].pz = __ldg(P.in.field[OPTK_PZ] + i);
+            r[k].dx = __ldg(P.in.field[OPTK_DX] + i);
+            r[k].dy = __ldg(P.in.field[OPTK_DY] + i);
+            r[k].dz = __ldg(P.in.field[OPTK_DZ] + i);
+            r[k].intensity = __ldg(P.in.field[OPTK_INTENSITY] + i);
+            r[k].att = __ldg(P.in.field[OPTK_ATTENUATION] + i);
+            r[k].n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + i);
+            r[k].unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + i) != 0) : true;
+            if (normal_given) {
+                gnx = __ldg(P.in.normal[0] + i);
+                gny = __ldg(P.in.normal[1] + i);
+                gnz = __ldg(P.in.normal[2] + i);
+            }
+        } else {
+            // broadcast view: the CTA-level offsets (leading axes) are in `base`, the thread adds
+            // the trailing axes of its own ray
+            long long off[OPTK_NUM_FIELDS + 1];
+#pragma unroll
+            for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] = base[f];
+            long long offn[3] = {base[OPTK_NUM_FIELDS + 1], base[OPTK_NUM_FIELDS + 2], base[OPTK_NUM_FIELDS + 3]};
+            uint32_t rem = (uint32_t)(j0 + k + P.index_offset);
+            const int first = P.in.n_axes - P.n_inner_axes;
+            if (P.offsets32 && !normal_given) {
+                // small broadcast arrays: 32-bit multiply-adds, one widening add per field at the end
+                int o32[OPTK_NUM_FIELDS + 1];
+#pragma unroll
+                for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) o32[f] = 0;
+                for (int a = P.in.n_axes - 1; a >= first; --a) {
+                    uint32_t q, idx;
+                    if (a == first) {
+                        idx = rem;
+                    } else {
+                        divmod(rem, P.div[a], q, idx);
+                        rem = q;
+                    }
+#pragma unroll
+                    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) o32[f] += (int)idx * P.stride32[f][a];
+                }
+#pragma unroll
+                for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] += o32[f];
+            } else
+            for (int a = P.in.n_axes - 1; a >= first; --a) {
+                uint32_t q, idx;
+                if (a == first) {
+                    idx = rem;
+                } else {
+                    divmod(rem, P.div[a], q, idx);
+                    rem = q;
+                }
+#pragma unroll
+                for (int f = 0; f < OPTK_NUM_FIELDS; ++f) off[f] += (long long)idx * P.in.stride[f][a];
+                off[OPTK_NUM_FIELDS] += (long long)idx * P.in.mask_stride[a];
+                if (normal_given) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) offn[c] += (long long)idx * P.in.normal_stride[c][a];
+                }
+            }
+            if (normal_given) {
+                gnx = __ldg(P.in.normal[0] + offn[0]);
+                gny = __ldg(P.in.normal[1] + offn[1]);
+                gnz = __ldg(P.in.normal[2] + offn[2]);
+            }
+            r[k].w = __ldg(P.in.field[OPTK_WAVELENGTH] + off[OPTK_WAVELENGTH]);
+            r[k].px = __ldg(P.in.field[OPTK_PX] + off[OPTK_PX]);
+            r[k].py = __ldg(P.in.field[OPTK_PY] + off[OPTK_PY]);
+            r[k].pz = __ldg(P.in.field[OPTK_PZ] + off[OPTK_PZ]);
+            r[k].dx = __ldg(P.in.field[OPTK_DX] + off[OPTK_DX]);
+            r[k].dy = __ldg(P.in.field[OPTK_DY] + off[OPTK_DY]);
+            r[k].dz = __ldg(P.in.field[OPTK_DZ] + off[OPTK_DZ]);
+            r[k].intensity = __ldg(P.in.field[OPTK_INTENSITY] + off[OPTK_INTENSITY]);
+            r[k].att = __ldg(P.in.field[OPTK_ATTENUATION] + off[OPTK_ATTENUATION]);
+            r[k].n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + off[OPTK_INDEX_REFRACTION]);
+            r[k].unv = P.in.unvignetted ? (__ldg(P.in.unvignetted + off[OPTK_NUM_FIELDS]) != 0) : true;
+        }
+    }
+}
+
+// 128-bit access to two consecutive rays of one field
+__device__ __forceinline__ void load_pair(const double* p, long long i, double& a, double& b) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
+    a = v.x;
+    b = v.y;
+}
+__device__ __forceinline__ void store_pair(double* p, long long i, double a, double b) {
+    if (p) *reinterpret_cast<double2*>(p + i) = make_double2(a, b);
+}
+
+__device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long long o, const Ray (&r)[2]) {
+    store_pair(out.field[OPTK_WAVELENGTH], o, r[0].w, r[1].w);
+    store_pair(out.field[OPTK_PX], o, r[0].px, r[1].px);
+    store_pair(out.field[OPTK_PY], o, r[0].py, r[1].py);
+    store_pair(out.field[OPTK_PZ], o, r[0].pz, r[1].pz);
+    store_pair(out.field[OPTK_DX], o, r[0].dx, r[1].dx);
+    store_pair(out.field[OPTK_DY], o, r[0].dy, r[1].dy);
+    store_pair(out.field[OPTK_DZ], o, r[0].dz, r[1].dz);
+    store_pair(out.field[OPTK_INTENSITY], o, r[0].intensity, r[1].intensity);
+    store_pair(out.field[OPTK_ATTENUATION], o, r[0].att, r[1].att);
+    store_pair(out.field[OPTK_INDEX_REFRACTION], o, r[0].n, r[1].n);
+    if (out.unvignetted)
+        *reinterpret_cast<uchar2*>(out.unvignetted + o) = make_uchar2(r[0].unv ? 1 : 0, r[1].unv ? 1 : 0);
+}
+
+template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
+__device__ __forceinline__ void trace_body(const TraceParams& P) {
+    __shared__ ImageGuess guess;
+    // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
+    // second warp while the first warp computes the outer offsets
+    if (IMAGE && threadIdx.x == 32) image_guess_fill(P.image, &guess);
+
+    // Dense input: ray index = thread index.  Broadcast input: the CTA owns one index of the
+    // leading ("outer") axes and a tile of the trailing ("inner") axes; its outer offsets are
+    // computed once by OPTK_NUM_FIELDS + 4 threads and shared.
+    __shared__ long long base[OPTK_NUM_FIELDS + 4];
+    long long i0, j0 = 0;
+    long long limit = P.n_rays;
+    if (DENSE) {
+        i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
+    } else {
+        const long long outer = blockIdx.x / P.tiles_per_outer;
+        const long long tile = blockIdx.x - outer * P.tiles_per_outer;
+        j0 = (tile * blockDim.x + threadIdx.x) * R;
+        i0 = outer * P.inner_size + j0;
+        limit = (outer + 1) * P.inner_size;
+        if (threadIdx.x < OPTK_NUM_FIELDS + 4) {
+            const int f = threadIdx.x;
+            long long o = 0;
+            uint32_t rem = (uint32_t)outer;
+            for (int a = P.in.n_axes - P.n_inner_axes - 1; a >= 0; --a) {
+                uint32_t q, idx;
+                if (a == 0) {
+                    idx = rem;
+                } else {
+                    divmod(rem, P.div[a], q, idx);
+                    rem = q;
+                }
+                const long long st = f < OPTK_NUM_FIELDS ? P.in.stride[f][a]
+                                     : (f == OPTK_NUM_FIELDS ? P.in.mask_stride[a]
+                                                             : P.in.normal_stride[f - OPTK_NUM_FIELDS - 1][a]);
+                o += (long long)idx * st;
+            }
+            base[f] = o;
+        }
+    }
+    if (IMAGE || !DENSE) __syncthreads();
+    bool valid[R];
+    Ray r[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        valid[k] = i0 + k < limit;
+        r[k] = Ray{1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, false};  // dummy ray for idle lanes
+    }
+    unsigned newton_iterations = 0;
+    const bool normal_given = !FULL && P.in.normal[0] != nullptr;
+    double gnx = 0.0, gny = 0.0, gnz = -1.0;
+
+    // Memory-level parallelism: each CTA computes for ~10k cycles between its loads and
+    // its stores, so too few bytes are in flight to cover HBM latency.  Every thread asks L2
+    // for the lines that the CTA scheduled one "wave" later will load, so DRAM streams while
+    // the SMs compute and those loads become L2 hits.
+    if (DENSE && P.prefetch_distance > 0) {
+        const long long ip = i0 + P.prefetch_distance;
+        if (ip < P.n_rays) {
+#pragma unroll
+            for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.in.field[f] + ip));
+        }
+    }
+
+    // the whole thread is "vector" when both of its rays exist (only the last thread may not be)
+    const bool pair = R == 2 && VEC && valid[R - 1];
+    if (pair) {
+        load_pair(P.in.field[OPTK_WAVELENGTH], i0, r[0].w, r[R - 1].w);
+        load_pair(P.in.field[OPTK_PX], i0, r[0].px, r[R - 1].px);
+        load_pair(P.in.field[OPTK_PY], i0, r[0].py, r[R - 1].py);
+        load_pair(P.in.field[OPTK_PZ], i0, r[0].pz, r[R - 1].pz);
+        load_pair(P.in.field[OPTK_DX], i0, r[0].dx, r[R - 1].dx);
+        load_pair(P.in.field[OPTK_DY], i0, r[0].dy, r[R - 1].dy);
+        load_pair(P.in.field[OPTK_DZ], i0, r[0].dz, r[R - 1].dz);
+        load_pair(P.in.field[OPTK_INTENSITY], i0, r[0].intensity, r[R - 1].intensity);
+        load_pair(P.in.field[OPTK_ATTENUATION], i0, r[0].att, r[R - 1].att);
+        load_pair(P.in.field[OPTK_INDEX_REFRACTION], i0, r[0].n, r[R - 1].n);
+        if (P.in.unvignetted) {
+            const uchar2 m = *reinterpret_cast<const uchar2*>(P.in.unvignetted + i0);
+            r[0].unv = m.x != 0;
+            r[R - 1].unv = m.y != 0;
+        } else {
+            r[0].unv = r[R - 1].unv = true;
+        }
+    } else {
+        load_rays<R, DENSE>(P, i0, j0, base, valid, r, normal_given, gnx, gny, gnz);
+    }
+
+    // No `if (valid)` around the walk: threads past the end trace a harmless dummy ray, so the
+    // surface loop stays warp-convergent and its per-surface decisions and parameter loads
+    // can use the uniform datapath (only the stores are predicated).
+    {
+        for (int s = 0; s < P.n_surf; ++s) {
+            if (FULL)
+                surface_full<R>(P.surf[s], r, newton_iterations);
+            else
+                surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz);
+            if (ACC) {
+                const long long o = (long long)s * P.accumulate_stride + i0;
+                bool done = false;
+                if constexpr (R == 2 && VEC) {
+                    if (pair) {
+                        store_rays_vec(P.out, o, r);
+                        done = true;
+                    }
+                }
+                if (!done) {
+#pragma unroll
+                    for (int k = 0; k < R; ++k)
+                        if (valid[k]) store_ray(P.out, o + k, r[k]);
+                }
+            }
+        }
+        if (!ACC) {
+            bool done = false;
+            if constexpr (R == 2 && VEC) {
+                if (pair) {
+                    store_rays_vec(P.out, i0, r);
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    if (valid[k]) store_ray(P.out, i0 + k, r[k]);
+            }
+        }
+    }
+
+    if (IMAGE) {
+        // AbstractImagingSensor.collect on the final rays in sensor-local coordinates
+        // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
+        // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
+        long long bin[R];
+        double w_flux[R], w_real[R];
+        unsigned count[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double x = r[k].px, y = r[k].py, z = r[k].pz, cx = r[k].dx, cy = r[k].dy, cz = r[k].dz;
+            if (P.has_frame) {
+                affine_inverse(P.frame, x, y, z, false);
+                affine_inverse(P.frame, cx, cy, cz, true);
+            }
+            bin[k] = image_bin_index(P.image, guess, valid[k], r[k].w, x, y, r[k].unv);
+            w_flux[k] = r[k].intensity;
+            w_real[k] = r[k].intensity * cz;
+            count[k] = 1u;
+        }
+        // the two rays of a thread are pupil neighbours: usually the same pixel, merged here
+        if (R == 2 && bin[0] == bin[R - 1] && bin[0] >= 0) {
+            w_flux[0] += w_flux[R - 1];
+            w_real[0] += w_real[R - 1];
+            count[0] += count[R - 1];
+            bin[R - 1] = -1;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) image_add(P.image, bin[k], w_flux[k], w_real[k], 0.0, count[k]);
+    }
+
+    if (P.stats) {
+        const unsigned full = 0xffffffffu;
+        unsigned n_unv = 0, n_val = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            n_unv += __popc(__ballot_sync(full, valid[k] && r[k].unv));
+            n_val += __popc(__ballot_sync(full, valid[k]));
+        }
+        unsigned n_it = __reduce_add_sync(full, newton_iterations);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&P.stats->n_rays, (unsigned long long)n_val);
+            atomicAdd(&P.stats->n_unvignetted, (unsigned long long)n_unv);
+            if (n_it) atomicAdd(&P.stats->n_newton_iterations, (unsigned long long)n_it);
+        }
+    }
+}
+
+// One kernel per (FULL, DENSE, VEC, ACC, IMAGE): uniform decisions are made once on the host
+// instead of per ray per surface.  The streamlined kernels carry two rays per thread in
+// <= 80 registers (3 CTAs of 256 threads per SM: the measured best).
+template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
+__global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
+    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE>(P);
+}
+
+typedef void (*trace_kernel_t)(const TraceParams);
+
+// defined in trace_full.cu / trace_generic.cu (separate translation units: parallel compilation)
+trace_kernel_t select_full_kernel(bool dense, bool vec, bool acc, bool image);
+trace_kernel_t select_generic_kernel(bool dense, bool acc, bool image);
+
+}  // namespace optk

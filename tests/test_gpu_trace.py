@@ -473,3 +473,72 @@ def test_unsupported_and_invalid_arguments_raise(cuda_device):
     system = configs.newtonian(num_field=1, num_pupil=2)
     with pytest.raises(ValueError):
         _engine.trace(system._compiled, system._input(None, None, None, None, False, False)[1], surf_begin=4, surf_count=6)
+
+
+def test_host_pointer_entry_point_broadcast_inputs_and_image(cuda_device):
+    """
+    optk_trace_host with a separable (stride-0) host grid, several slabs, ray outputs AND a
+    fused detector image, all in host memory.
+    """
+    from oracle import binning as orb
+
+    system = configs.newtonian(num_field=3, num_pupil=24, num_pixel=64)
+    _, rays = system._input(None, None, None, None, False, False)
+    r0, shape_ = configs.flatten_rays(rays)  # axes: pupil_x, pupil_y, field_y, field_x
+    assert list(shape_) == ["pupil_x", "pupil_y", "field_y", "field_x"]
+    n = int(np.prod(list(shape_.values())))
+    npx, npy, nfy, nfx = shape_.values()
+    compiled = system._compiled_local
+    lib = _lib.lib()
+    small = {
+        "wavelength": (np.array([float(rays.wavelength)]), (0, 0, 0, 0)),
+        "px": (np.ascontiguousarray(rays.position.x.ndarray), (1, 0, 0, 0)),
+        "py": (np.ascontiguousarray(rays.position.y.ndarray), (0, 1, 0, 0)),
+        "pz": (np.array([0.0]), (0, 0, 0, 0)),
+        "intensity": (np.array([1.0]), (0, 0, 0, 0)),
+        "attenuation": (np.array([0.0]), (0, 0, 0, 0)),
+        "index_refraction": (np.array([1.0]), (0, 0, 0, 0)),
+    }
+    for name, comp in (("dx", rays.direction.x), ("dy", rays.direction.y), ("dz", rays.direction.z)):
+        nd = np.ascontiguousarray(comp.numpy(("field_y", "field_x")).astype(float) + np.zeros((nfy, nfx)))
+        small[name] = (nd, (0, 0, nfx, 1))
+    rin = _lib.RaysIn()
+    rin.n_axes = 4
+    for a, d in enumerate((npx, npy, nfy, nfx)):
+        rin.dims[a] = d
+    for f, name in enumerate(_lib.FIELDS):
+        nd, strides = small[name]
+        rin.field[f] = nd.ctypes.data
+        for a, st in enumerate(strides):
+            rin.stride[f][a] = st
+    rin.unvignetted = None
+    outs = [np.full(n, np.nan) for _ in _lib.FIELDS]
+    mask = np.zeros(n, dtype=np.uint8)
+    rout = _lib.RaysOut()
+    for f, a in enumerate(outs):
+        rout.field[f] = a.ctypes.data
+    rout.unvignetted = mask.ctypes.data
+    ex, ey = system.sensor.pixel_edges()
+    ew = np.array([4.99e-4, 5.01e-4])
+    flux = np.zeros((1, 64, 64))
+    counts = np.zeros((1, 64, 64), dtype=np.uint64)
+    image = _lib.Image()
+    image.n_wavelength, image.n_x, image.n_y = 1, 64, 64
+    image.edges_wavelength, image.edges_x, image.edges_y = ew.ctypes.data, ex.ctypes.data, ey.ctypes.data
+    image.flux, image.counts = flux.ctypes.data, counts.ctypes.data
+    stats = _lib.TraceStats()
+    _lib.check(
+        lib.optk_trace_host(
+            compiled.handle, 0, C.byref(rin), C.byref(rout), 0, compiled.n_surface, 1, 0, 0,
+            C.byref(image), None, C.byref(stats), 700, 0,
+        )
+    )
+    want = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
+    local = ora._rays_transform(system.sensor.transformation, want, inverse=True)
+    got = {name: a for name, a in zip(_lib.FIELDS, outs)}
+    got["unvignetted"] = mask.astype(bool)
+    parity.compare_states(got, local)
+    want_counts = orb.counts(local, ew, ex, ey)
+    assert counts.sum() == want_counts.sum() == stats.n_unvignetted
+    assert (counts.astype(np.int64) != want_counts).sum() <= 4
+    assert np.isclose(flux.sum(), want_counts.sum())
