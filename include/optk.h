@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 1
+#define OPTK_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -283,6 +283,57 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config,
                     int32_t accumulate, int64_t accumulate_stride,
                     const optk_image_t* image, const optk_affine_t* image_frame,
                     optk_trace_stats_t* stats_host, int64_t slab_rays, int32_t pinned);
+
+/* ---- on-device ray grid (kernel 1 with a generator in front) ------------------
+ * Replaces SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
+ * (optika/systems/_sequential.py:1002-1086, 791-828) for a separable grid given on
+ * cell VERTICES: grid.cell_centers(axis=(wavelength, field, pupil), random=True)
+ * (:1066-1069) becomes a stratified sample drawn inside the kernel, the flux
+ * radiance * cell_area (:1071-1077, optika/vectors/_vectors_object.py:42-133)
+ * becomes weight_scene * weight_pupil, and optika.direction (optika/_util.py:41-73)
+ * is evaluated per ray.  No input ray is ever read from memory.
+ *
+ * Axes (fixed order, C order of the outputs, pupil_y fastest):
+ *   0 wavelength [mm], 1 field_x, 2 field_y, 3 pupil_x, 4 pupil_y.
+ * at_infinity = 1 (object at infinity, :797-799): field = angles [rad], pupil =
+ * position [mm]: position = (pupil_x, pupil_y, 0), direction = direction(field).
+ * at_infinity = 0 (:800-802): field = position [mm], pupil = angles [rad].
+ * Every ray starts with attenuation 0, index_refraction 1, unvignetted = true and
+ * intensity = weight_scene[i0][i1][i2] * weight_pupil[i3][i4] (NULL = 1).
+ *
+ * Sample of ray (i0..i4), indices in the WHOLE grid n[]:
+ *   v_a = lo_a + t_a * (hi_a - lo_a),  lo_a = vertices[a][i_a], hi_a = vertices[a][i_a + 1];
+ *   jitter = 0: t_a = 1/2 exactly as (lo + hi) / 2;
+ *   jitter = 1: t_a = (x_a + 1/2) * 2^-32 with x_0..x_3 = Philox4x32-10(counter =
+ *   (cell_lo, cell_hi, 0, 0), key = (seed_lo, seed_hi)) and x_4 the first word of the
+ *   same generator at counter (cell_lo, cell_hi, 1, 0); cell = C-order index of the ray
+ *   in the whole grid.  The stream therefore does not depend on how the grid is split
+ *   into sub-boxes (begin/count), launches or GPUs.
+ * `frame`, when has_frame, maps the generated rays (object-local) to the coordinates
+ * the first traced surface expects: object.transformation followed by the inverse of
+ * the system transformation (:823-826, :908-909). */
+typedef struct optk_grid {
+    int32_t n[5];     /* cells of the whole grid along each axis                      */
+    int32_t begin[5]; /* first cell of the sub-box this call traces                   */
+    int32_t count[5]; /* cells of the sub-box; outputs are dense in C order over it   */
+    int32_t at_infinity;
+    int32_t jitter;
+    int32_t has_frame;
+    uint64_t seed;
+    const double* vertices[5];  /* device; n[a] + 1 values each                       */
+    const double* weight_scene; /* device; [n0][n1][n2] or NULL                       */
+    const double* weight_pupil; /* device; [n3][n4] or NULL                           */
+    optk_affine_t frame;
+} optk_grid_t;
+
+/* As optk_trace, with the rays of `grid` as input.  surf_count = 0 returns the
+ * generated rays themselves. */
+OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const optk_grid_t* grid,
+                    const optk_rays_out_t* out,
+                    int32_t surf_begin, int32_t surf_count, int32_t surf_step,
+                    int32_t accumulate, int64_t accumulate_stride,
+                    const optk_image_t* image, const optk_affine_t* image_frame,
+                    optk_trace_stats_t* stats_device, void* stream);
 
 /* ---- detector binning (kernel 2) --------------------------------------------
  * Replaces the three na.histogram calls of AbstractImagingSensor.collect

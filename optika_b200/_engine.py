@@ -121,7 +121,7 @@ class DeviceImage:
         torch = _torch()
 
         def dev(e):
-            return torch.as_tensor(np.ascontiguousarray(e, dtype=np.float64)).to(device)
+            return torch.from_numpy(np.array(e, dtype=np.float64)).to(device)
 
         ew, ex, ey = dev(edges_wavelength), dev(edges_x), dev(edges_y)
         dims = tuple(leading) + (len(ew) - 1, len(ex) - 1, len(ey) - 1)

@@ -1,0 +1,226 @@
+"""
+On-device ray grids: the host description of ``optk_grid_t`` and its launcher.
+
+``SequentialSystem.image`` (``optika/systems/_sequential.py:1088-1206``) samples one
+stratified random ray per cell of a (wavelength, field, pupil) vertex grid
+(``_rayfunction_from_vertices``, ``:1002-1086``) and weights it with
+``radiance * cell_area``.  For the separable grids the reference's own examples use, all of
+that is a few small 1-D / 2-D arrays; :func:`trace_grid` hands them to
+``optk_trace_grid``, which draws, traces and bins every ray inside one kernel launch.
+"""
+
+from __future__ import annotations
+import ctypes as C
+import dataclasses
+import numpy as np
+from . import _lib as L
+from . import _engine
+
+__all__ = ["RayGrid", "trace_grid", "AXES"]
+
+AXES = ("wavelength", "field_x", "field_y", "pupil_x", "pupil_y")
+_MAX_LAUNCH = 2**31 - 1
+
+
+@dataclasses.dataclass(eq=False)
+class RayGrid:
+    """
+    A separable grid of cell vertices in device units (mm, rad).
+
+    ``vertices``: five 1-D arrays (wavelength, field_x, field_y, pupil_x, pupil_y) of
+    ``n + 1`` values; ``weight_scene[n0, n1, n2]`` and ``weight_pupil[n3, n4]`` multiply
+    into the intensity of every ray; ``frame = (R[3, 3], t[3])`` maps the generated rays to
+    the coordinates of the first surface; ``begin`` / ``count`` select a sub-box (the
+    random stream does not depend on it, see ``include/optk.h``).
+    """
+
+    vertices: tuple
+    at_infinity: bool = True
+    weight_scene: np.ndarray | None = None
+    weight_pupil: np.ndarray | None = None
+    jitter: bool = True
+    seed: int = 0
+    frame: tuple | None = None
+    axes: tuple = AXES
+    begin: tuple | None = None
+    count: tuple | None = None
+
+    def __post_init__(self):
+        self.vertices = tuple(np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in self.vertices)
+        if len(self.vertices) != 5:
+            raise ValueError("a ray grid has five axes: wavelength, field x/y, pupil x/y")
+        n = self.n
+        if any(k < 1 for k in n):
+            raise ValueError(f"every axis needs at least two vertices, got cells {n}")
+        if self.weight_scene is not None:
+            self.weight_scene = np.ascontiguousarray(np.broadcast_to(self.weight_scene, n[:3]), dtype=np.float64)
+        if self.weight_pupil is not None:
+            self.weight_pupil = np.ascontiguousarray(np.broadcast_to(self.weight_pupil, n[3:]), dtype=np.float64)
+        if self.begin is None:
+            self.begin = (0,) * 5
+        if self.count is None:
+            self.count = tuple(n[a] - self.begin[a] for a in range(5))
+        self._device = {}
+
+    @property
+    def n(self) -> tuple:
+        return tuple(len(v) - 1 for v in self.vertices)
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return dict(zip(self.axes, self.count))
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.count, dtype=np.int64))
+
+    def sub(self, begin, count) -> "RayGrid":
+        """The same grid restricted to a sub-box (absolute cell indices)."""
+        g = dataclasses.replace(self, begin=tuple(begin), count=tuple(count))
+        g._device = self._device
+        return g
+
+    def shard(self, rank: int, world_size: int, axis: int = 3) -> "RayGrid":
+        """Contiguous slab of this grid's box for one rank (default: along pupil_x)."""
+        from .distributed import slab
+
+        s = slab(self.count[axis], rank, world_size)
+        begin, count = list(self.begin), list(self.count)
+        begin[axis] += s.start
+        count[axis] = s.stop - s.start
+        return self.sub(begin, count)
+
+    def on_device(self, device):
+        torch = _engine._torch()
+        key = str(device)
+        if key not in self._device:
+            up = lambda a: None if a is None else torch.from_numpy(np.array(a, dtype=np.float64)).to(device)  # noqa: E731
+            self._device[key] = dict(
+                vertices=[up(v) for v in self.vertices],
+                weight_scene=up(self.weight_scene),
+                weight_pupil=up(self.weight_pupil),
+            )
+        return self._device[key]
+
+    def struct(self, device, begin=None, count=None) -> L.Grid:
+        dev = self.on_device(device)
+        g = L.Grid()
+        g.n[:] = self.n
+        g.begin[:] = self.begin if begin is None else begin
+        g.count[:] = self.count if count is None else count
+        g.at_infinity = 1 if self.at_infinity else 0
+        g.jitter = 1 if self.jitter else 0
+        g.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
+        for a in range(5):
+            g.vertices[a] = dev["vertices"][a].data_ptr()
+        g.weight_scene = None if dev["weight_scene"] is None else dev["weight_scene"].data_ptr()
+        g.weight_pupil = None if dev["weight_pupil"] is None else dev["weight_pupil"].data_ptr()
+        if self.frame is not None:
+            g.has_frame = 1
+            g.frame.r[:] = list(np.asarray(self.frame[0], dtype=float).reshape(9))
+            g.frame.t[:] = list(np.asarray(self.frame[1], dtype=float).reshape(3))
+        return g
+
+
+def _boxes(begin, count, limit):
+    """Split a box into sub-boxes of at most `limit` cells, cutting the outermost axes first."""
+    begin, count = list(begin), list(count)
+    total = int(np.prod(count, dtype=np.int64))
+    if total <= limit:
+        yield tuple(begin), tuple(count)
+        return
+    for a in range(5):
+        if count[a] > 1:
+            inner = total // count[a]
+            step = max(1, limit // inner)
+            for i in range(0, count[a], step):
+                b, c = list(begin), list(count)
+                b[a] += i
+                c[a] = min(step, count[a] - i)
+                yield from _boxes(b, c, limit)
+            return
+    raise ValueError("cannot split the grid")  # pragma: no cover
+
+
+def trace_grid(
+    system: "_engine.CompiledSystem",
+    grid: RayGrid,
+    config: int = 0,
+    accumulate: bool = False,
+    axis: str | None = None,
+    surf_begin: int = 0,
+    surf_count: int | None = None,
+    surf_step: int = 1,
+    image: "_engine.DeviceImage | None" = None,
+    image_plane: int | None = None,
+    image_frame=None,
+    write_rays: bool = True,
+    device=None,
+    stats: bool = False,
+    max_launch: int = _MAX_LAUNCH,
+):
+    """
+    Generate the rays of `grid` on the device and trace them through configuration
+    `config` of `system` (``optk_trace_grid``).  Returns :class:`DeviceRays` over the
+    grid's box (or ``None`` with ``write_rays=False``), plus a stats dict when requested.
+    """
+    torch = _engine._torch()
+    device = _engine.require_cuda(device)
+    lib = L.lib()
+    if surf_count is None:
+        surf_count = system.n_surface if surf_step > 0 else surf_begin + 1
+    n_ray = grid.size
+    n_states = surf_count if accumulate else 1
+    out_fields = out_mask = None
+    if write_rays:
+        out_fields = {
+            name: torch.empty((n_states, n_ray), dtype=torch.float64, device=device)
+            for name, _ in _engine._FIELD_GETTERS
+        }
+        out_mask = torch.empty((n_states, n_ray), dtype=torch.uint8, device=device)
+    stats_dev = torch.zeros(4, dtype=torch.int64, device=device) if stats else None
+    frame = None
+    if image_frame is not None:
+        frame = L.Affine()
+        frame.r[:] = list(np.asarray(image_frame[0], dtype=float).reshape(9))
+        frame.t[:] = list(np.asarray(image_frame[1], dtype=float).reshape(3))
+    im = image.struct(config if image_plane is None else image_plane) if image is not None else None
+    stream = _engine._stream_ptr(device)
+    rout = L.RaysOut()
+    offset = 0
+    for begin, count in _boxes(grid.begin, grid.count, max_launch) if n_ray else ():
+        n_box = int(np.prod(count, dtype=np.int64))
+        if write_rays:
+            # sub-boxes are contiguous in the output only when they are slabs of the
+            # outermost non-trivial axis
+            lead = [a for a in range(5) if grid.count[a] > 1]
+            if any(count[a] != grid.count[a] for a in lead[1:]):
+                raise ValueError("ray output needs slabs of the outermost axis; lower the inner axes or skip write_rays")
+            for f, (name, _) in enumerate(_engine._FIELD_GETTERS):
+                rout.field[f] = out_fields[name].data_ptr() + 8 * offset
+            rout.unvignetted = out_mask.data_ptr() + offset
+        g = grid.struct(device, begin, count)
+        L.check(
+            lib.optk_trace_grid(
+                system.handle, config, C.byref(g), C.byref(rout) if write_rays else None,
+                surf_begin, surf_count, surf_step, 1 if accumulate else 0, n_ray,
+                C.byref(im) if im is not None else None,
+                C.byref(frame) if frame is not None else None,
+                stats_dev.data_ptr() if stats_dev is not None else None,
+                stream,
+            )
+        )
+        offset += n_box
+    result = None
+    if write_rays:
+        shape_ = {}
+        if accumulate:
+            shape_[axis if axis is not None else "surface"] = n_states
+        shape_.update(grid.shape)
+        result = _engine.DeviceRays(out_fields, out_mask, shape_)
+    if stats:
+        s = stats_dev.cpu().numpy()
+        return result, dict(
+            n_rays=int(s[0]), n_unvignetted=int(s[1]), n_newton_iterations=int(s[2]), n_binned=int(s[3])
+        )
+    return result

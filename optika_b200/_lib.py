@@ -145,6 +145,22 @@ class Image(C.Structure):
     ]
 
 
+class Grid(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32 * 5),
+        ("begin", C.c_int32 * 5),
+        ("count", C.c_int32 * 5),
+        ("at_infinity", C.c_int32),
+        ("jitter", C.c_int32),
+        ("has_frame", C.c_int32),
+        ("seed", C.c_uint64),
+        ("vertices", C.c_void_p * 5),
+        ("weight_scene", C.c_void_p),
+        ("weight_pupil", C.c_void_p),
+        ("frame", Affine),
+    ]
+
+
 class TraceStats(C.Structure):
     _fields_ = [
         ("n_rays", C.c_uint64),
@@ -192,6 +208,9 @@ class MlInput(C.Structure):
     ]
 
 
+ABI_VERSION = 2
+
+
 class OptkError(RuntimeError):
     pass
 
@@ -208,6 +227,7 @@ SYMBOLS = (
     "optk_system_size",
     "optk_trace",
     "optk_trace_host",
+    "optk_trace_grid",
     "optk_bin",
     "optk_multilayer",
     "optk_measure_fp64_peak",
@@ -243,6 +263,10 @@ def lib() -> C.CDLL:
         vp, i32, C.POINTER(RaysIn), C.POINTER(RaysOut), i32, i32, i32, i32, i64,
         C.POINTER(Image), C.POINTER(Affine), C.POINTER(TraceStats), i64, i32,
     ]
+    L.optk_trace_grid.argtypes = [
+        vp, i32, C.POINTER(Grid), C.POINTER(RaysOut), i32, i32, i32, i32, i64,
+        C.POINTER(Image), C.POINTER(Affine), vp, vp,
+    ]
     L.optk_bin.argtypes = [i64, vp, vp, vp, vp, vp, vp, C.POINTER(Image), vp]
     L.optk_multilayer.argtypes = [
         C.POINTER(MlInput), i32, C.POINTER(MlLayer), i32, C.POINTER(MlSegment), vp, vp, vp, vp, vp,
@@ -252,7 +276,7 @@ def lib() -> C.CDLL:
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int
-    if L.optk_abi_version() != 1:
+    if L.optk_abi_version() != ABI_VERSION:
         raise OptkError("liboptk.so ABI version mismatch; rebuild it")
     _lib = L
     return L

@@ -333,6 +333,66 @@ OPTK_API int optk_trace(const optk_system_t* sys, int32_t config, const optk_ray
     return launch_trace(P, (cudaStream_t)stream);
 }
 
+OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const optk_grid_t* grid, const optk_rays_out_t* out,
+                    int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
+                    int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
+                    optk_trace_stats_t* stats_device, void* stream) {
+    static thread_local TraceParams P;
+    if (!grid) {
+        set_error("optk_trace_grid: grid is NULL");
+        return OPTK_ERR_INVALID;
+    }
+    long long n = 1;
+    for (int a = 0; a < 5; ++a) {
+        if (grid->n[a] < 1 || grid->begin[a] < 0 || grid->count[a] < 0 ||
+            (long long)grid->begin[a] + grid->count[a] > grid->n[a]) {
+            set_error("optk_trace_grid: axis %d: sub-box [%d, %d + %d) does not fit %d cells", a, grid->begin[a],
+                      grid->begin[a], grid->count[a], grid->n[a]);
+            return OPTK_ERR_INVALID;
+        }
+        if (!grid->vertices[a]) {
+            set_error("optk_trace_grid: vertices[%d] is NULL", a);
+            return OPTK_ERR_INVALID;
+        }
+        n *= grid->count[a];
+        if (n > 0x7fffffffLL) {
+            set_error("optk_trace_grid: sub-box exceeds one launch (2^31 - 1 rays); split it");
+            return OPTK_ERR_INVALID;
+        }
+    }
+    int rc = pack_trace(sys, config, surf_begin, surf_count, surf_step, accumulate, &P);
+    if (rc) return rc;
+    if (accumulate && accumulate_stride < n) {
+        set_error("accumulate_stride %lld is smaller than the number of rays %lld", (long long)accumulate_stride, n);
+        return OPTK_ERR_INVALID;
+    }
+    memset(&P.in, 0, sizeof(P.in));
+    P.in.n_axes = 5;
+    for (int a = 0; a < OPTK_MAX_AXES; ++a) {
+        if (a < 5) P.in.dims[a] = grid->count[a];
+        P.div[a] = make_fastdiv(a < 5 ? (uint32_t)(grid->count[a] > 0 ? grid->count[a] : 1) : 1u);
+    }
+    if (out) P.out = *out; else memset(&P.out, 0, sizeof(P.out));
+    P.n_rays = n;
+    P.index_offset = 0;
+    P.flat_index = 0;
+    P.accumulate_stride = accumulate ? accumulate_stride : 0;
+    P.dense_in = 0;
+    P.from_grid = 1;
+    P.grid = *grid;
+    P.has_image = image ? 1 : 0;
+    P.has_frame = image_frame ? 1 : 0;
+    if (image) {
+        rc = fill_image(image, &P.image);
+        if (rc) return rc;
+    }
+    if (image_frame) P.frame = *image_frame;
+    P.stats = stats_device;
+    rc = launch_trace(P, (cudaStream_t)stream);
+    P.from_grid = 0;
+    return rc;
+}
+
 OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
              const double* intensity, const uint8_t* unvignetted, const optk_image_t* image, void* stream) {
     if (!wavelength || !x || !y || !image) {

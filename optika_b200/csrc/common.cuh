@@ -21,7 +21,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // ---------------------------------------------------------------------------
 // exact division of a 32-bit index by a runtime constant: q = umul64hi(n, M),
-// M = floor((2^64 - 1) / d) + 1, exact for all n < 2^32 and 2 <= d < 2^32.
+// M = floor((2^64 - 1) / d) + 1, exact for all n < 2^32 and 2 <= d < 2^32 (d = 1: M = 0 marks q = n).
 // ---------------------------------------------------------------------------
 struct FastDiv {
     uint64_t magic;
@@ -38,7 +38,7 @@ inline FastDiv make_fastdiv(uint32_t d) {
 }
 
 __device__ __forceinline__ void divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
-    q = (uint32_t)__umul64hi((uint64_t)n, f.magic);
+    q = f.magic ? (uint32_t)__umul64hi((uint64_t)n, f.magic) : n;  // magic 0: d = 1
     r = n - q * f.divisor;
 }
 

@@ -35,6 +35,11 @@ struct TraceParams {
     ImageDev image;
     optk_affine_t frame;
     optk_trace_stats_t* stats;
+    // on-device ray generator (optk_trace_grid): `in` then only carries n_axes = 5 and
+    // dims = grid.count (the sub-box), addressed in two levels like a broadcast view
+    int32_t from_grid;
+    int32_t pad4;
+    optk_grid_t grid;
     optk_surface_t surf[OPTK_MAX_SURFACES];
 };
 

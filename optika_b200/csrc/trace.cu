@@ -27,13 +27,14 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // ---------------------------------------------------------------------------
 int launch_trace(const TraceParams& P, cudaStream_t stream) {
     if (P.n_rays <= 0) return OPTK_OK;
+    const bool from_grid = P.from_grid != 0;
     bool full = P.in.normal[0] == nullptr;
     for (int s = 0; s < P.n_surf; ++s)
         full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM) &&
                P.surf[s].material_kind <= OPTK_MAT_GLASS;
-    const bool dense = P.dense_in != 0, acc = P.accumulate != 0, image = P.has_image != 0;
+    const bool dense = P.dense_in != 0 && !from_grid, acc = P.accumulate != 0, image = P.has_image != 0;
     // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
-    bool vec = full && dense && (P.accumulate_stride % 2 == 0);
+    bool vec = full && dense && !from_grid && (P.accumulate_stride % 2 == 0);
     for (int f = 0; f < OPTK_NUM_FIELDS && vec; ++f)
         vec = aligned16(P.in.field[f]) && aligned16(P.out.field[f]);
     if (vec && P.in.unvignetted) vec = (reinterpret_cast<uintptr_t>(P.in.unvignetted) & 1u) == 0;
@@ -69,7 +70,9 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         return OPTK_ERR_INVALID;
     }
     trace_kernel_t kernel;
-    if (full)
+    if (from_grid)
+        kernel = select_grid_kernel(full, acc, image);
+    else if (full)
         kernel = select_full_kernel(dense, vec, acc, image);
     else
         kernel = select_generic_kernel(dense, acc, image);

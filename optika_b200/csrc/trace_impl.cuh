@@ -872,6 +872,106 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
     }
 }
 
+// ---------------------------------------------------------------------------
+// on-device ray grid (optk_trace_grid)
+// ---------------------------------------------------------------------------
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so the draw of a ray depends only on
+// (seed, index of its cell in the whole grid), never on the launch geometry.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+__device__ __forceinline__ double grid_sample(const double* vertices, int i, bool jitter, uint32_t x) {
+    const double lo = __ldg(vertices + i), hi = __ldg(vertices + i + 1);
+    if (!jitter) return 0.5 * (lo + hi);
+    const double t = ((double)x + 0.5) * 2.3283064365386962890625e-10;  // 2^-32
+    return fma(t, hi - lo, lo);
+}
+
+// SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
+// (optika/systems/_sequential.py:1055-1086, 791-828) for one ray of a separable grid.
+template <int R>
+__device__ __forceinline__ void generate_rays(const TraceParams& P, long long j0, const int* outer_index,
+                                              const bool (&valid)[R], Ray (&r)[R]) {
+    const optk_grid_t& G = P.grid;
+    const int first = 5 - P.n_inner_axes;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        if (!valid[k]) continue;
+        int idx[5];
+        uint32_t rem = (uint32_t)(j0 + k);
+#pragma unroll
+        for (int a = 4; a >= 0; --a) {
+            if (a > first) {
+                uint32_t q, i;
+                divmod(rem, P.div[a], q, i);
+                idx[a] = (int)i;
+                rem = q;
+            } else if (a == first) {
+                idx[a] = (int)rem;
+            } else {
+                idx[a] = outer_index[a];
+            }
+            idx[a] += G.begin[a];
+        }
+        unsigned long long cell = (unsigned long long)idx[0];
+#pragma unroll
+        for (int a = 1; a < 5; ++a) cell = cell * (unsigned long long)G.n[a] + (unsigned long long)idx[a];
+        uint32_t x[4] = {0u, 0u, 0u, 0u}, y[4] = {0u, 0u, 0u, 0u};
+        const bool jitter = G.jitter != 0;
+        if (jitter) {
+            const uint32_t k0 = (uint32_t)G.seed, k1 = (uint32_t)(G.seed >> 32);
+            philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), 0u, 0u, k0, k1, x);
+            philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), 1u, 0u, k0, k1, y);
+        }
+        const double w = grid_sample(G.vertices[0], idx[0], jitter, x[0]);
+        const double fx = grid_sample(G.vertices[1], idx[1], jitter, x[1]);
+        const double fy = grid_sample(G.vertices[2], idx[2], jitter, x[2]);
+        const double px = grid_sample(G.vertices[3], idx[3], jitter, x[3]);
+        const double py = grid_sample(G.vertices[4], idx[4], jitter, y[0]);
+        // position / angles by the location of the object (:797-802)
+        const double ax = G.at_infinity ? fx : px, ay = G.at_infinity ? fy : py;
+        double sx, cx, sy, cy;
+        fsincos(ax, &sx, &cx);
+        fsincos(ay, &sy, &cy);
+        r[k].w = w;
+        r[k].px = G.at_infinity ? px : fx;
+        r[k].py = G.at_infinity ? py : fy;
+        r[k].pz = 0.0;
+        r[k].dx = -cy * sx;  // optika.direction, optika/_util.py:64-73
+        r[k].dy = -sy;
+        r[k].dz = cy * cx;
+        double weight = 1.0;
+        if (G.weight_scene)
+            weight = __ldg(G.weight_scene + ((long long)idx[0] * G.n[1] + idx[1]) * G.n[2] + idx[2]);
+        if (G.weight_pupil) weight *= __ldg(G.weight_pupil + (long long)idx[3] * G.n[4] + idx[4]);
+        r[k].intensity = weight;
+        r[k].att = 0.0;
+        r[k].n = 1.0;
+        r[k].unv = true;
+        if (G.has_frame) {
+            affine_forward(G.frame, r[k].px, r[k].py, r[k].pz, false);
+            affine_forward(G.frame, r[k].dx, r[k].dy, r[k].dz, true);
+        }
+    }
+}
+
 // 128-bit access to two consecutive rays of one field
 __device__ __forceinline__ void load_pair(const double* p, long long i, double& a, double& b) {
     const double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
@@ -897,7 +997,7 @@ __device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long 
         *reinterpret_cast<uchar2*>(out.unvignetted + o) = make_uchar2(r[0].unv ? 1 : 0, r[1].unv ? 1 : 0);
 }
 
-template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
+template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
     // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
@@ -908,6 +1008,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     // leading ("outer") axes and a tile of the trailing ("inner") axes; its outer offsets are
     // computed once by OPTK_NUM_FIELDS + 4 threads and shared.
     __shared__ long long base[OPTK_NUM_FIELDS + 4];
+    __shared__ int outer_index[5];
     long long i0, j0 = 0;
     long long limit = P.n_rays;
     if (DENSE) {
@@ -918,7 +1019,24 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         j0 = (tile * blockDim.x + threadIdx.x) * R;
         i0 = outer * P.inner_size + j0;
         limit = (outer + 1) * P.inner_size;
-        if (threadIdx.x < OPTK_NUM_FIELDS + 4) {
+        if (GRID) {
+            // indices of the leading grid axes, shared by the CTA
+            if (threadIdx.x == 0) {
+                uint32_t rem = (uint32_t)outer;
+                for (int a = 4; a >= 0; --a) {
+                    uint32_t q = 0, idx = 0;
+                    if (a < 5 - P.n_inner_axes) {
+                        if (a == 0) {
+                            idx = rem;
+                        } else {
+                            divmod(rem, P.div[a], q, idx);
+                            rem = q;
+                        }
+                    }
+                    outer_index[a] = (int)idx;
+                }
+            }
+        } else if (threadIdx.x < OPTK_NUM_FIELDS + 4) {
             const int f = threadIdx.x;
             long long o = 0;
             uint32_t rem = (uint32_t)outer;
@@ -983,6 +1101,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         } else {
             r[0].unv = r[R - 1].unv = true;
         }
+    } else if (GRID) {
+        generate_rays<R>(P, j0, outer_index, valid, r);
     } else {
         load_rays<R, DENSE>(P, i0, j0, base, valid, r, normal_given, gnx, gny, gnz);
     }
@@ -1078,9 +1198,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
 // One kernel per (FULL, DENSE, VEC, ACC, IMAGE): uniform decisions are made once on the host
 // instead of per ray per surface.  The streamlined kernels carry two rays per thread in
 // <= 80 registers (3 CTAs of 256 threads per SM: the measured best).
-template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE>
+template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID = false>
 __global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
-    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE>(P);
+    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE, GRID>(P);
 }
 
 typedef void (*trace_kernel_t)(const TraceParams);
@@ -1088,5 +1208,6 @@ typedef void (*trace_kernel_t)(const TraceParams);
 // defined in trace_full.cu / trace_generic.cu (separate translation units: parallel compilation)
 trace_kernel_t select_full_kernel(bool dense, bool vec, bool acc, bool image);
 trace_kernel_t select_generic_kernel(bool dense, bool acc, bool image);
+trace_kernel_t select_grid_kernel(bool full, bool acc, bool image);
 
 }  // namespace optk

@@ -15,7 +15,16 @@ import numpy as np
 from . import named as na
 from .vectors import ObjectVectorArray
 
-__all__ = ["slab", "shard_axis", "shard_grid", "reduce_image", "image_rays_sharded"]
+__all__ = ["slab", "shard_axis", "shard_grid", "reduce_image", "image_rays_sharded", "rank_world"]
+
+
+def rank_world() -> tuple[int, int]:
+    """(rank, world size) of the default process group; (0, 1) outside ``torch.distributed``."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def slab(n: int, rank: int, world: int) -> slice:

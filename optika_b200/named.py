@@ -258,12 +258,21 @@ class ScalarArray(np.lib.mixins.NDArrayOperatorsMixin):
     def ptp(self, axis=None):
         return self._reduce(np.ptp, axis)
 
-    def cell_centers(self, axis: str) -> "ScalarArray":
-        """Midpoints between adjacent vertices along `axis`."""
-        i = self.axes.index(axis)
-        nd = np.moveaxis(self.ndarray, i, 0)
-        nd = (nd[1:] + nd[:-1]) / 2
-        return ScalarArray(np.moveaxis(nd, 0, i), self.axes)
+    def cell_centers(self, axis) -> "ScalarArray":
+        """Midpoints between adjacent vertices along `axis` (one name or several)."""
+        result = self
+        for ax in (axis,) if isinstance(axis, str) else tuple(axis):
+            if ax not in result.axes:
+                continue
+            i = result.axes.index(ax)
+            nd = np.moveaxis(result.ndarray, i, 0)
+            nd = (nd[1:] + nd[:-1]) / 2
+            result = ScalarArray(np.moveaxis(nd, 0, i), result.axes)
+        return result
+
+    def volume_cell(self, axis: str) -> "ScalarArray":
+        """Signed length of the cells between adjacent vertices along `axis` (``na`` ``volume_cell``)."""
+        return self[{axis: slice(1, None)}] - self[{axis: slice(None, -1)}]
 
 
 def linspace(
@@ -423,11 +432,28 @@ class _VectorArray:
         return dataclasses.replace(self, **kwargs)
 
 
+def _corners(v: "_VectorArray", axis: tuple[str, str]):
+    """The four corner vertices (00, 10, 11, 01) of every cell of a 2-D vertex grid."""
+    ax, ay = axis
+    shape_ = v.shape
+    if ax not in shape_ or ay not in shape_:
+        raise ValueError(f"axes {axis} must both be present in {shape_}")
+    v = v.broadcast_to(shape_)
+    lo, hi = slice(None, -1), slice(1, None)
+    return v[{ax: lo, ay: lo}], v[{ax: hi, ay: lo}], v[{ax: hi, ay: hi}], v[{ax: lo, ay: hi}]
+
+
 @dataclasses.dataclass(eq=False)
 class Cartesian2dVectorArray(_VectorArray):
     x: float | ScalarArray = 0
     y: float | ScalarArray = 0
     _names = ("x", "y")
+
+    def volume_cell(self, axis: tuple[str, str]) -> ScalarArray:
+        """Signed area of every vertex quadrilateral: half the cross product of its diagonals."""
+        v00, v10, v11, v01 = _corners(self, axis)
+        d1, d2 = v11 - v00, v01 - v10
+        return (d1.x * d2.y - d1.y * d2.x) / 2
 
 
 @dataclasses.dataclass(eq=False)
@@ -440,6 +466,20 @@ class Cartesian3dVectorArray(_VectorArray):
     @property
     def xy(self) -> Cartesian2dVectorArray:
         return Cartesian2dVectorArray(self.x, self.y)
+
+    def solid_angle_cell(self, axis: tuple[str, str]) -> ScalarArray:
+        """
+        Signed solid angle [sr] of the spherical quadrilateral spanned by the four direction
+        vertices of every cell: two spherical triangles, each by Van Oosterom & Strackee (1983).
+        """
+        v00, v10, v11, v01 = (v.normalized for v in _corners(self, axis))
+
+        def triangle(a, b, c):
+            num = a @ b.cross(c)
+            den = 1 + a @ b + b @ c + c @ a
+            return 2 * np.arctan2(num, den)
+
+        return triangle(v00, v10, v11) + triangle(v00, v11, v01)
 
     def cross(self, o: "Cartesian3dVectorArray") -> "Cartesian3dVectorArray":
         return Cartesian3dVectorArray(

@@ -35,9 +35,13 @@ class IdealSensorMaterial(_materials.Vacuum):
     ``direction_refracted = -direction . normal`` and photons map 1:1 to electrons.
     """
 
-    def signal(self, photons, wavelength=None, direction=1, noise: bool = False, **kwargs):
+    def signal(self, photons, wavelength=None, direction=1, noise: bool = False, rng=None, **kwargs):
+        # optika/sensors/materials/_materials.py:1576-1601; shot noise is drawn on the host
+        # (per pixel, tiny) from a seeded NumPy generator
         if noise:
-            raise NotImplementedError("shot noise is outside the device hot path; use noise=False")
+            rng = np.random.default_rng(rng)
+            p = na.as_named_array(photons)
+            photons = na.ScalarArray(rng.poisson(np.maximum(p.ndarray, 0)).astype(np.int64), p.axes)
         return photons
 
 
@@ -173,18 +177,34 @@ class AbstractImagingSensor(AbstractSurface):
             na.ScalarArray(direction, axes_out),
         )
 
-    def expose(self, image: na.FunctionArray, direction=1, axis_wavelength=None, timedelta=None, noise: bool = False):
-        """Photons -> electrons (``_sensors.py:173-252``); the ideal, noise-free model only."""
+    def expose(
+        self, image: na.FunctionArray, direction=1, axis_wavelength=None, timedelta=None, noise: bool = False,
+        seed=None,
+    ):
+        """
+        Photons -> electrons (``_sensors.py:173-252``).  `noise` adds Poisson shot noise
+        (in the material) and zero-mean Gaussian read noise of ``read_noise`` electrons
+        (``:243-248``), drawn on the host from ``numpy.random.default_rng(seed)``.
+        """
         if timedelta is None:
             timedelta = self.timedelta_exposure
         photons = image.outputs * timedelta
-        electrons = self.material.signal(photons=photons, direction=direction, noise=noise)
+        rng = np.random.default_rng(seed) if noise else None
+        electrons = self.material.signal(photons=photons, direction=direction, noise=noise, rng=rng)
+        if noise:
+            e = na.as_named_array(electrons)
+            electrons = na.ScalarArray(rng.normal(loc=e.ndarray, scale=float(self.read_noise)), e.axes)
         return dataclasses.replace(image, outputs=electrons)
 
-    def measure(self, rays, wavelength, axis=None, where=True, axis_wavelength=None, timedelta=None, noise: bool = False):
+    def measure(
+        self, rays, wavelength, axis=None, where=True, axis_wavelength=None, timedelta=None, noise: bool = False,
+        seed=None,
+    ):
         """``collect`` then ``expose`` (``_sensors.py:374-428``)."""
         image, direction = self.collect(rays, wavelength, axis=axis, where=where)
-        return self.expose(image, direction, axis_wavelength=axis_wavelength, timedelta=timedelta, noise=noise)
+        return self.expose(
+            image, direction, axis_wavelength=axis_wavelength, timedelta=timedelta, noise=noise, seed=seed
+        )
 
 
 def _host_to_device(rays, device):

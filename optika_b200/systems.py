@@ -286,3 +286,222 @@ class SequentialSystem(AbstractSequentialSystem):
             ray_axes_order=self._ray_axes_order,
         )
         return image
+
+    # -- forward model: scene -> detector image ------------------------------
+    def _separable(self, value, axis: str, config_shape: dict, cindex: tuple, what: str) -> np.ndarray:
+        """
+        The 1-D vertex array of a grid component that varies along `axis` (and possibly the
+        configuration axes).  Other axes (e.g. the wavelength axis the stop solution is
+        broadcast over, ``_sequential.py:760-789``) are accepted when the values are constant
+        along them to 1e-9 of the extent of the grid.
+        """
+        v = na.as_named_array(value)
+        if axis not in v.axes:
+            raise ValueError(f"the {what} vertices must vary along axis {axis!r}, got axes {v.axes}")
+        shape_ = dict(config_shape)
+        for ax, n in v.shape.items():
+            if ax not in shape_:
+                shape_[ax] = n
+        nd = np.broadcast_to(na.aligned(v, shape_), tuple(shape_.values()))[cindex]
+        axes = [ax for ax in shape_ if ax not in config_shape]
+        nd = np.moveaxis(nd, axes.index(axis), -1).reshape(-1, v.shape[axis])
+        extent = float(np.ptp(nd)) or 1.0
+        if float(np.ptp(nd, axis=0).max()) > 1e-9 * extent:
+            raise NotImplementedError(
+                f"the {what} vertices vary along axes other than {axis!r}: only separable grids run on the "
+                "device generator; trace explicit rays with `image_rays` instead"
+            )
+        return np.asarray(nd.mean(axis=0), dtype=np.float64)
+
+    def _frame_input(self, config_shape: dict, cindex: tuple):
+        """Object-local -> first-surface coordinates as ``(R, t)`` (``_sequential.py:823-826, 908-909``)."""
+        t_obj = self.object.transformation if self.object is not None else None
+        if t_obj is None and self.transformation is None:
+            return None
+        affine = None
+        if t_obj is not None:
+            affine = t_obj.affine
+        if self.transformation is not None:
+            inv = self.transformation.affine.inverse
+            affine = inv if affine is None else inv @ affine
+        if not set(affine.shape).issubset(config_shape):
+            raise NotImplementedError("system transformations with their own named axes are not supported here")
+        r, t = affine.numpy(config_shape)
+        return (r[cindex], t[cindex]) if cindex else (r, t)
+
+    def ray_grids(
+        self,
+        radiance,
+        wavelength,
+        field,
+        pupil,
+        axis_wavelength: str,
+        axis_field: tuple[str, str],
+        axis_pupil: tuple[str, str],
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
+        random: bool = True,
+        seed: int = 0,
+    ) -> list:
+        """
+        ``_rayfunction_from_vertices`` (``_sequential.py:1002-1086``) for separable grids:
+        one :class:`~optika_b200._grid.RayGrid` per configuration, carrying the physical
+        vertices, ``flux = radiance * cell_area`` split into its scene and pupil factors,
+        and the object frame.  The rays themselves are only ever created on the device.
+        """
+        from ._grid import RayGrid
+
+        grid = ObjectVectorArray(wavelength=wavelength, field=field, pupil=pupil)
+        grid = self.denormalize(grid, normalized_field, normalized_pupil)
+        config_shape = self._compiled_local.shape
+        at_infinity = self.object_is_at_infinity
+        conv_field, conv_pupil = (u.angle, u.length) if at_infinity else (u.length, u.angle)
+        axes = (axis_wavelength,) + tuple(axis_field) + tuple(axis_pupil)
+        grids = []
+        for cindex in np.ndindex(*config_shape.values()) if config_shape else [()]:
+            get = lambda v, ax, what: self._separable(v, ax, config_shape, cindex, what)  # noqa: E731
+            vertices = (
+                get(u.length(grid.wavelength), axis_wavelength, "wavelength"),
+                get(conv_field(grid.field.x), axis_field[0], "field x"),
+                get(conv_field(grid.field.y), axis_field[1], "field y"),
+                get(conv_pupil(grid.pupil.x), axis_pupil[0], "pupil x"),
+                get(conv_pupil(grid.pupil.y), axis_pupil[1], "pupil y"),
+            )
+            cell = ObjectVectorArray(
+                wavelength=na.ScalarArray(vertices[0], axis_wavelength),
+                field=na.Cartesian2dVectorArray(
+                    na.ScalarArray(vertices[1], axis_field[0]), na.ScalarArray(vertices[2], axis_field[1])
+                ),
+                pupil=na.Cartesian2dVectorArray(
+                    na.ScalarArray(vertices[3], axis_pupil[0]), na.ScalarArray(vertices[4], axis_pupil[1])
+                ),
+            )
+            area_w, area_f, area_p = cell.cell_area(
+                axis_wavelength, axis_field, axis_pupil,
+                field_is_angular=at_infinity, pupil_is_angular=not at_infinity, factors=True,
+            )
+            n = [len(v) - 1 for v in vertices]
+            scene_shape = dict(zip(axes[:3], n[:3]))
+            rad = na.as_named_array(radiance)
+            extra = set(rad.axes) - set(scene_shape) - set(config_shape)
+            if extra:
+                raise ValueError(f"the radiance has axes {sorted(extra)} that are not scene or configuration axes")
+            full = dict(config_shape, **scene_shape)
+            rad = np.broadcast_to(na.aligned(rad, full), tuple(full.values()))[cindex]
+            weight_scene = rad * area_w.numpy(axes[:1])[:, None, None] * area_f.numpy(axes[1:3])[None]
+            grids.append(
+                RayGrid(
+                    vertices=vertices,
+                    at_infinity=at_infinity,
+                    weight_scene=weight_scene,
+                    weight_pupil=area_p.numpy(axes[3:]),
+                    jitter=random,
+                    seed=seed,
+                    frame=self._frame_input(config_shape, cindex),
+                    axes=axes,
+                )
+            )
+        return grids
+
+    def image(
+        self,
+        scene: na.FunctionArray,
+        pupil: None | na.Cartesian2dVectorArray = None,
+        axis_wavelength: None | str = None,
+        axis_field: None | tuple[str, str] = None,
+        axis_pupil: None | tuple[str, str] = None,
+        integrate: bool = True,
+        noise: bool = True,
+        normalized_field: bool = False,
+        normalized_pupil: bool = True,
+        seed: int = 0,
+        device=None,
+        reduce: bool = True,
+    ) -> na.FunctionArray:
+        """
+        Forward model: spectral radiance of a scene -> detector counts
+        (``optika/systems/_sequential.py:1088-1206``).
+
+        `scene.inputs` holds the cell VERTICES of the wavelength and field grids and
+        `scene.outputs` the radiance of every cell, per mm of wavelength, per sr (or mm^2)
+        of field and per mm^2 (or sr) of pupil; `pupil` the vertices of the pupil grid
+        (default: one cell spanning the whole normalised pupil, ``:1139-1146``).  One
+        stratified random ray per cell is drawn, traced and binned on the device in a single
+        fused launch per configuration (``optk_trace_grid``); ``sensor.expose`` then turns the
+        photon image into electrons (``:1200-1206``, ``sensors/_sensors.py:374-428``).
+
+        Differences from the reference signature: floats carry no unit, so
+        `normalized_field` / `normalized_pupil` say whether the vertices are normalised
+        (the reference infers it from the unit, ``:1148-1152``); `seed` selects the
+        counter-based random stream.  Under ``torch.distributed`` every rank traces a
+        slab of the pupil (or field) cells and the planes are summed (`reduce`).
+        """
+        from . import _grid, distributed
+
+        device = _engine.require_cuda(device)
+        wavelength = scene.inputs.wavelength
+        field = scene.inputs.position
+        if pupil is None:
+            axis_pupil = ("_pupil_x", "_pupil_y")
+            pupil = na.Cartesian2dVectorLinearSpace(-1, 1, na.Cartesian2dVectorArray(*axis_pupil), 2)
+            normalized_pupil = True
+        config_axes = set(self.shape)
+        if axis_wavelength is None:
+            cand = tuple(set(na.shape(wavelength)) - config_axes)
+            if len(cand) != 1:
+                raise ValueError(f"`scene` must vary along exactly one wavelength axis, got {cand} as possibilities.")
+            (axis_wavelength,) = cand
+        if axis_field is None:
+            fx = set(na.shape(field.x)) - config_axes - {axis_wavelength}
+            fy = set(na.shape(field.y)) - config_axes - {axis_wavelength}
+            if len(fx) != 1 or len(fy) != 1 or fx == fy:
+                raise ValueError(f"the two field axes must be unambiguous, got {sorted(fx | fy)} as possibilities.")
+            axis_field = (next(iter(fx)), next(iter(fy)))
+        if axis_pupil is None:
+            skip = config_axes | {axis_wavelength} | set(axis_field)
+            px, py = set(na.shape(pupil.x)) - skip, set(na.shape(pupil.y)) - skip
+            if len(px) != 1 or len(py) != 1 or px == py:
+                raise ValueError(f"the two pupil axes must be unambiguous, got {sorted(px | py)} as possibilities.")
+            axis_pupil = (next(iter(px)), next(iter(py)))
+
+        grids = self.ray_grids(
+            scene.outputs, wavelength, field, pupil, axis_wavelength, tuple(axis_field), tuple(axis_pupil),
+            normalized_field, normalized_pupil, random=True, seed=seed,
+        )
+        w_edges = np.asarray(na.as_named_array(u.length(wavelength)).ndarray, dtype=float)
+        if na.as_named_array(wavelength).ndim != 1:
+            raise NotImplementedError("the wavelength vertices of the scene must be one-dimensional")
+        if integrate:
+            w_edges = np.array([w_edges.min(), w_edges.max()])  # :1189-1196
+        compiled = self._compiled_local
+        ex, ey = self.sensor.pixel_edges()
+        image = _engine.DeviceImage.zeros(
+            w_edges, ex, ey, device, leading=tuple(compiled.shape.values()), moments=True, counts=False
+        )
+        rank, world = distributed.rank_world()
+        for c, grid in enumerate(grids):
+            if world > 1:
+                axis = 3 if grid.count[3] >= world else (1 if grid.count[1] >= world else 4)
+                grid = grid.shard(rank, world, axis=axis)
+            _grid.trace_grid(compiled, grid, config=c, image=image, write_rays=False, device=device)
+        if reduce and world > 1:
+            distributed.reduce_image(image)
+        planes = image.to_host(pinned=False)
+        flux = planes["flux"].numpy()
+        moment = planes["moment_real"].numpy()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            direction = np.where(flux > 0, moment / flux, 1) + 0j  # sensors/_sensors.py:163-169
+        sensor = self.sensor
+        axes_out = tuple(compiled.shape) + (axis_wavelength, sensor.axis_pixel.x, sensor.axis_pixel.y)
+        from .vectors import SpectralPositionalVectorArray
+
+        inputs = SpectralPositionalVectorArray(
+            wavelength=na.ScalarArray(w_edges, axis_wavelength),
+            position=na.Cartesian2dVectorArray(
+                x=na.ScalarArray(ex, (sensor.axis_pixel.x,)), y=na.ScalarArray(ey, (sensor.axis_pixel.y,))
+            ),
+        )
+        collected = na.FunctionArray(inputs=inputs, outputs=na.ScalarArray(flux, axes_out))
+        return sensor.expose(
+            collected, na.ScalarArray(direction, axes_out), axis_wavelength=axis_wavelength, noise=noise, seed=seed
+        )

@@ -359,8 +359,9 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
     (used to restate ``optika/sags/_tests/_abc_test.py:100-102``).
 
     ``extended=True`` evaluates the SAME closed-form expressions of the parabolic
-    and conic sags in ``numpy.longdouble`` (80-bit on x86) and rounds the path
-    length to float64 at the end.  Those two reference formulas subtract nearly
+    and conic sags in ``numpy.longdouble`` (80-bit on x86), polishes the root they
+    select by Newton steps on the quadratic it solves (still in 80 bits), and rounds
+    the path length to float64 at the end.  Those two reference formulas subtract nearly
     equal numbers for near-axial rays -- in float64 they carry a rounding noise of
     about ``eps * |2 f| / (ux^2 + uy^2)`` (1e-6 mm in the Newtonian example), which
     any 1-ulp change upstream re-samples -- so "the reference's answer" is only
@@ -417,6 +418,18 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
                 / (ux**2 + uy**2),
                 (ox**2 + oy**2 - 4 * f * oz) / (4 * f * uz),
             )
+            if extended:
+                # 80-bit evaluation still leaves ~eps_80 |2 f| / (ux^2 + uy^2) (1e-7 mm just above
+                # the 1e-10 switch): polish the root the formula selected on its own equation,
+                # z(t) = (x(t)^2 + y(t)^2) / (4 f), a quadratic in t with well-conditioned
+                # coefficients.  Newton from 1e-7 away converges to rounding in two steps.
+                qa = ux**2 + uy**2
+                qb = 2 * (ox * ux + oy * uy) - 4 * f * uz
+                qc = ox**2 + oy**2 - 4 * f * oz
+                quadratic = (qa > 1e-10) & np.isfinite(tt)
+                for _ in range(3):
+                    step = (qa * tt**2 + qb * tt + qc) / (2 * qa * tt + qb)
+                    tt = np.where(quadratic & np.isfinite(step), tt - step, tt)
         elif name == "ConicSag":
             # optika/sags/_conic.py:83-170
             radius, conic = _sag_radius_conic(sag)
@@ -445,6 +458,12 @@ def sag_intercept(sag, rays: dict, converge: bool = False, generic: bool = False
             t_a = root(-1)
             t_b = root(+1)
             tt = np.where(np.abs(t_a) <= np.abs(t_b), t_a, t_b)
+            if extended:
+                # as for the parabola: polish the selected root on a t^2 + b t + c = 0
+                quadratic = ~degenerate & np.isfinite(tt)
+                for _ in range(3):
+                    step = (a * tt**2 + b * tt + cc) / (2 * a * tt + b)
+                    tt = np.where(quadratic & np.isfinite(step), tt - step, tt)
         elif name == "CylindricalSag":
             # optika/sags/_cylindrical.py:115-160, cross products written out with a = y-hat:
             # n x a = (-n_z, 0, n_x);  b = (0,0,r) - o;  b x a = (-b_z, 0, b_x)

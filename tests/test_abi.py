@@ -55,6 +55,7 @@ def test_struct_layout_matches_c(tmp_path, lib):
         "optk_rays_out_t": _lib.RaysOut,
         "optk_image_t": _lib.Image,
         "optk_trace_stats_t": _lib.TraceStats,
+        "optk_grid_t": _lib.Grid,
         "optk_ml_layer_t": _lib.MlLayer,
         "optk_ml_segment_t": _lib.MlSegment,
         "optk_ml_input_t": _lib.MlInput,
@@ -64,6 +65,7 @@ def test_struct_layout_matches_c(tmp_path, lib):
         ("optk_surface_t", "holo_wavelength"), ("optk_surface_t", "vertices_y"),
         ("optk_rays_in_t", "field"), ("optk_rays_in_t", "stride"), ("optk_rays_in_t", "mask_stride"),
         ("optk_rays_in_t", "normal_stride"), ("optk_image_t", "edges_wavelength"), ("optk_image_t", "counts"), ("optk_image_t", "range"),
+        ("optk_grid_t", "seed"), ("optk_grid_t", "vertices"), ("optk_grid_t", "frame"),
         ("optk_ml_layer_t", "width_stride"), ("optk_ml_layer_t", "profile_kind"),
         ("optk_ml_input_t", "direction_stride"), ("optk_ml_input_t", "n_stride"),
     ]
