@@ -304,11 +304,12 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config,
  * Sample of ray (i0..i4), indices in the WHOLE grid n[]:
  *   v_a = lo_a + t_a * (hi_a - lo_a),  lo_a = vertices[a][i_a], hi_a = vertices[a][i_a + 1];
  *   jitter = 0: t_a = 1/2 exactly as (lo + hi) / 2;
- *   jitter = 1: t_a = (x_a + 1/2) * 2^-32 with x_0..x_3 = Philox4x32-10(counter =
- *   (cell_lo, cell_hi, 0, 0), key = (seed_lo, seed_hi)) and x_4 the first word of the
- *   same generator at counter (cell_lo, cell_hi, 1, 0); cell = C-order index of the ray
- *   in the whole grid.  The stream therefore does not depend on how the grid is split
- *   into sub-boxes (begin/count), launches or GPUs.
+ *   jitter = 1: t_a = (b_a + 1/2) * 2^-25 with five 25-bit integers b_a cut from the
+ *   four words x_0..x_3 = Philox4x32-10(counter = (cell_lo, cell_hi, 0, 0), key =
+ *   (seed_lo, seed_hi)): b_a = x_a >> 7 for a = 0..3 and b_4 = (x_0 & 127) |
+ *   (x_1 & 127) << 7 | (x_2 & 127) << 14 | (x_3 & 15) << 21; cell = C-order index of
+ *   the ray in the whole grid.  The stream therefore does not depend on how the grid is
+ *   split into sub-boxes (begin/count), launches or GPUs.  n[0] * n[1] < 2^31.
  * `frame`, when has_frame, maps the generated rays (object-local) to the coordinates
  * the first traced surface expects: object.transformation followed by the inverse of
  * the system transformation (:823-826, :908-909). */

@@ -380,6 +380,12 @@ OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const opt
     P.dense_in = 0;
     P.from_grid = 1;
     P.grid = *grid;
+    P.cell_stride[4] = 1;
+    for (int a = 3; a >= 0; --a) P.cell_stride[a] = P.cell_stride[a + 1] * (unsigned long long)grid->n[a + 1];
+    if ((long long)grid->n[0] * grid->n[1] > 0x7fffffffLL) {
+        set_error("optk_trace_grid: n[0] * n[1] exceeds 2^31 - 1");
+        return OPTK_ERR_INVALID;
+    }
     P.has_image = image ? 1 : 0;
     P.has_frame = image_frame ? 1 : 0;
     if (image) {

@@ -139,28 +139,38 @@ __device__ __forceinline__ double frsqrt(double x) {
 // propagates.  sincos: three-term Cody-Waite reduction, absolute error < 1e-15 for
 // |x| < 1e5; larger arguments (a layer thousands of wavelengths thick) take the library path.
 // ---------------------------------------------------------------------------
+static __constant__ double kExp[16] = {
+    1.6059043836821613e-10,  // 1/13!
+    2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+    2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
+    4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0,
+    -6.93147180369123816490e-01, -1.90821492927058770002e-10,  // -ln2 hi, lo
+};
+static __constant__ double kSin[6] = {
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+};
+static __constant__ double kCos[6] = {
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+};
+static __constant__ double kPio2[3] = {
+    -1.57079632673412561417e+00, -6.07710050650619224932e-11, -2.02226624879595063154e-21,  // pi/2 in three parts
+};
+
 __device__ __forceinline__ double fexp(double x) {
     const double xc = fmin(fmax(x, -700.0), 700.0);
     const double shifter = 6755399441055744.0;  // 1.5 * 2^52: rounds to integer in the low word
     const double kd = fma(xc, 1.4426950408889634, shifter);
     const int k = __double2loint(kd);
     const double kf = kd - shifter;
-    double r = fma(kf, -6.93147180369123816490e-01, xc);  // ln2 hi
-    r = fma(kf, -1.90821492927058770002e-10, r);          // ln2 lo
-    double p = 1.6059043836821613e-10;                    // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                 // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                 // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                  // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                 // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                 // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                 // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    double r = fma(kf, kExp[14], xc);  // -ln2 hi
+    r = fma(kf, kExp[15], r);          // -ln2 lo
+    // coefficients come from the constant bank (an operand of the DFMA itself); as immediates
+    // every one of them costs two UMOV issue slots
+    double p = kExp[0];
+#pragma unroll
+    for (int i = 1; i < 14; ++i) p = fma(p, r, kExp[i]);
     // scale by 2^k in two halves so that k in [-1010, 1010] never leaves the normal range midway
     const int k1 = k >> 1, k2 = k - k1;
     const double s1 = __hiloint2double((k1 + 1023) << 20, 0), s2 = __hiloint2double((k2 + 1023) << 20, 0);
@@ -177,25 +187,18 @@ __device__ __forceinline__ void fsincos(double x, double* s, double* c) {
     const double kd = fma(x, 6.36619772367581382433e-01, shifter);  // x * 2/pi
     const int q = __double2loint(kd);
     const double kf = kd - shifter;
-    double r = fma(kf, -1.57079632673412561417e+00, x);   // pi/2, first 33 bits
-    r = fma(kf, -6.07710050650619224932e-11, r);          // next 33 bits
-    r = fma(kf, -2.02226624879595063154e-21, r);          // tail
+    double r = fma(kf, kPio2[0], x);  // pi/2, first 33 bits
+    r = fma(kf, kPio2[1], r);         // next 33 bits
+    r = fma(kf, kPio2[2], r);         // tail
     const double r2 = r * r;
-    // sin(r) on [-pi/4, pi/4]
-    double ps = 1.58969099521155010221e-10;
-    ps = fma(ps, r2, -2.50507602534068634195e-08);
-    ps = fma(ps, r2, 2.75573137070700676789e-06);
-    ps = fma(ps, r2, -1.98412698298579493134e-04);
-    ps = fma(ps, r2, 8.33333333332248946124e-03);
-    ps = fma(ps, r2, -1.66666666666666324348e-01);
+    // sin(r), cos(r) on [-pi/4, pi/4]
+    double ps = kSin[0], pc = kCos[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        ps = fma(ps, r2, kSin[i]);
+        pc = fma(pc, r2, kCos[i]);
+    }
     const double sr = fma(ps * r2, r, r);
-    // cos(r) on [-pi/4, pi/4]
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, r2, 2.08757232129817482790e-09);
-    pc = fma(pc, r2, -2.75573143513906633035e-07);
-    pc = fma(pc, r2, 2.48015872894767294178e-05);
-    pc = fma(pc, r2, -1.38888888888741095749e-03);
-    pc = fma(pc, r2, 4.16666666666666019037e-02);
     const double cr = fma(pc * r2, r2, fma(-0.5, r2, 1.0));
     // quadrant: q mod 4 = 0: (s, c); 1: (c, -s); 2: (-s, -c); 3: (-c, s)
     const bool swap = q & 1;

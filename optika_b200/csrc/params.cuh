@@ -40,6 +40,7 @@ struct TraceParams {
     int32_t from_grid;
     int32_t pad4;
     optk_grid_t grid;
+    unsigned long long cell_stride[5];  // C-order strides of the whole grid n[] (Philox counter)
     optk_surface_t surf[OPTK_MAX_SURFACES];
 };
 

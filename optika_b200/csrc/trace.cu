@@ -43,7 +43,7 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     const int block = 256;
     TraceParams& Q = const_cast<TraceParams&>(P);
     long long grid;
-    if (dense) {
+    if (dense || from_grid) {
         const long long threads = (P.n_rays + rays_per_thread - 1) / rays_per_thread;
         grid = (threads + block - 1) / block;
         Q.n_inner_axes = 0;

@@ -897,54 +897,67 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[3] = c3;
 }
 
-__device__ __forceinline__ double grid_sample(const double* vertices, int i, bool jitter, uint32_t x) {
+// t = (bits + 1/2) 2^-25 of a 25-bit integer: strictly inside (0, 1)
+__device__ __forceinline__ double grid_sample(const double* vertices, int i, bool jitter, uint32_t bits25) {
     const double lo = __ldg(vertices + i), hi = __ldg(vertices + i + 1);
     if (!jitter) return 0.5 * (lo + hi);
-    const double t = ((double)x + 0.5) * 2.3283064365386962890625e-10;  // 2^-32
+    const double t = ((double)bits25 + 0.5) * 2.98023223876953125e-08;  // 2^-25
     return fma(t, hi - lo, lo);
 }
 
 // SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
-// (optika/systems/_sequential.py:1055-1086, 791-828) for one ray of a separable grid.
+// (optika/systems/_sequential.py:1055-1086, 791-828) for the R consecutive rays of a thread.
+// `j0` is the C-order index of the first ray in the sub-box of this launch (< 2^31).
 template <int R>
-__device__ __forceinline__ void generate_rays(const TraceParams& P, long long j0, const int* outer_index,
-                                              const bool (&valid)[R], Ray (&r)[R]) {
+__device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0, const bool (&valid)[R],
+                                              Ray (&r)[R]) {
     const optk_grid_t& G = P.grid;
-    const int first = 5 - P.n_inner_axes;
+    int idx[5];
+    {
+        uint32_t rem = j0;
+#pragma unroll
+        for (int a = 4; a >= 1; --a) {
+            uint32_t q, i;
+            divmod(rem, P.div[a], q, i);
+            idx[a] = (int)i;
+            rem = q;
+        }
+        idx[0] = (int)rem;
+    }
+    const bool jitter = G.jitter != 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        if (!valid[k]) continue;
-        int idx[5];
-        uint32_t rem = (uint32_t)(j0 + k);
+        if (k > 0) {
+            // next ray of the thread: increment with carry
+            ++idx[4];
 #pragma unroll
-        for (int a = 4; a >= 0; --a) {
-            if (a > first) {
-                uint32_t q, i;
-                divmod(rem, P.div[a], q, i);
-                idx[a] = (int)i;
-                rem = q;
-            } else if (a == first) {
-                idx[a] = (int)rem;
-            } else {
-                idx[a] = outer_index[a];
+            for (int a = 4; a >= 1; --a) {
+                if (idx[a] == (int)P.div[a].divisor) {
+                    idx[a] = 0;
+                    ++idx[a - 1];
+                }
             }
-            idx[a] += G.begin[a];
         }
-        unsigned long long cell = (unsigned long long)idx[0];
+        if (!valid[k]) continue;
+        int g[5];
+        unsigned long long cell = 0;
 #pragma unroll
-        for (int a = 1; a < 5; ++a) cell = cell * (unsigned long long)G.n[a] + (unsigned long long)idx[a];
-        uint32_t x[4] = {0u, 0u, 0u, 0u}, y[4] = {0u, 0u, 0u, 0u};
-        const bool jitter = G.jitter != 0;
-        if (jitter) {
-            const uint32_t k0 = (uint32_t)G.seed, k1 = (uint32_t)(G.seed >> 32);
-            philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), 0u, 0u, k0, k1, x);
-            philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), 1u, 0u, k0, k1, y);
+        for (int a = 0; a < 5; ++a) {
+            g[a] = idx[a] + G.begin[a];
+            cell += (unsigned long long)(unsigned)g[a] * P.cell_stride[a];
         }
-        const double w = grid_sample(G.vertices[0], idx[0], jitter, x[0]);
-        const double fx = grid_sample(G.vertices[1], idx[1], jitter, x[1]);
-        const double fy = grid_sample(G.vertices[2], idx[2], jitter, x[2]);
-        const double px = grid_sample(G.vertices[3], idx[3], jitter, x[3]);
-        const double py = grid_sample(G.vertices[4], idx[4], jitter, y[0]);
+        uint32_t x[4] = {0u, 0u, 0u, 0u};
+        if (jitter)
+            philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), 0u, 0u, (uint32_t)G.seed,
+                          (uint32_t)(G.seed >> 32), x);
+        // five 25-bit integers from the 128 bits: the top 25 bits of each word, and the
+        // low 7 bits of the four words side by side (include/optk.h)
+        const uint32_t low = (x[0] & 127u) | ((x[1] & 127u) << 7) | ((x[2] & 127u) << 14) | ((x[3] & 15u) << 21);
+        const double w = grid_sample(G.vertices[0], g[0], jitter, x[0] >> 7);
+        const double fx = grid_sample(G.vertices[1], g[1], jitter, x[1] >> 7);
+        const double fy = grid_sample(G.vertices[2], g[2], jitter, x[2] >> 7);
+        const double px = grid_sample(G.vertices[3], g[3], jitter, x[3] >> 7);
+        const double py = grid_sample(G.vertices[4], g[4], jitter, low);
         // position / angles by the location of the object (:797-802)
         const double ax = G.at_infinity ? fx : px, ay = G.at_infinity ? fy : py;
         double sx, cx, sy, cy;
@@ -958,9 +971,8 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, long long j0
         r[k].dy = -sy;
         r[k].dz = cy * cx;
         double weight = 1.0;
-        if (G.weight_scene)
-            weight = __ldg(G.weight_scene + ((long long)idx[0] * G.n[1] + idx[1]) * G.n[2] + idx[2]);
-        if (G.weight_pupil) weight *= __ldg(G.weight_pupil + (long long)idx[3] * G.n[4] + idx[4]);
+        if (G.weight_scene) weight = __ldg(G.weight_scene + (g[0] * G.n[1] + g[1]) * (long long)G.n[2] + g[2]);
+        if (G.weight_pupil) weight *= __ldg(G.weight_pupil + g[3] * (long long)G.n[4] + g[4]);
         r[k].intensity = weight;
         r[k].att = 0.0;
         r[k].n = 1.0;
@@ -1008,10 +1020,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     // leading ("outer") axes and a tile of the trailing ("inner") axes; its outer offsets are
     // computed once by OPTK_NUM_FIELDS + 4 threads and shared.
     __shared__ long long base[OPTK_NUM_FIELDS + 4];
-    __shared__ int outer_index[5];
     long long i0, j0 = 0;
     long long limit = P.n_rays;
-    if (DENSE) {
+    if (DENSE || GRID) {
         i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
     } else {
         const long long outer = blockIdx.x / P.tiles_per_outer;
@@ -1019,24 +1030,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         j0 = (tile * blockDim.x + threadIdx.x) * R;
         i0 = outer * P.inner_size + j0;
         limit = (outer + 1) * P.inner_size;
-        if (GRID) {
-            // indices of the leading grid axes, shared by the CTA
-            if (threadIdx.x == 0) {
-                uint32_t rem = (uint32_t)outer;
-                for (int a = 4; a >= 0; --a) {
-                    uint32_t q = 0, idx = 0;
-                    if (a < 5 - P.n_inner_axes) {
-                        if (a == 0) {
-                            idx = rem;
-                        } else {
-                            divmod(rem, P.div[a], q, idx);
-                            rem = q;
-                        }
-                    }
-                    outer_index[a] = (int)idx;
-                }
-            }
-        } else if (threadIdx.x < OPTK_NUM_FIELDS + 4) {
+        if (threadIdx.x < OPTK_NUM_FIELDS + 4) {
             const int f = threadIdx.x;
             long long o = 0;
             uint32_t rem = (uint32_t)outer;
@@ -1056,7 +1050,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             base[f] = o;
         }
     }
-    if (IMAGE || !DENSE) __syncthreads();
+    if (IMAGE || !(DENSE || GRID)) __syncthreads();
     bool valid[R];
     Ray r[R];
 #pragma unroll
@@ -1102,7 +1096,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             r[0].unv = r[R - 1].unv = true;
         }
     } else if (GRID) {
-        generate_rays<R>(P, j0, outer_index, valid, r);
+        generate_rays<R>(P, (uint32_t)i0, valid, r);
     } else {
         load_rays<R, DENSE>(P, i0, j0, base, valid, r, normal_given, gnx, gny, gnz);
     }

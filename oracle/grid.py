@@ -17,8 +17,9 @@ its published behaviour; **parity unpinned** for all three (no reference test pi
     from NumPy's global generator, so no implementation can reproduce its stream; the
     contract here is the *distribution* (one sample per cell, uniform inside it) and a
     documented counter-based stream: Philox4x32-10 (Salmon et al., SC'11; Random123
-    known-answer vectors in ``tests/test_oracle_grid.py``), counter = (cell index, call),
-    key = seed, ``t = (x + 1/2) 2^-32`` (see ``include/optk.h``).
+    known-answer vectors in ``tests/test_oracle_grid.py``), counter = cell index,
+    key = seed, five 25-bit integers ``b`` cut from the 128 output bits,
+    ``t = (b + 1/2) 2^-25`` (see ``include/optk.h``).
   * ``volume_cell(axis)``: scalar -> difference along the axis; 2-D vector over two axes ->
     signed area of the vertex quadrilateral (half the cross product of its diagonals).
   * ``solid_angle_cell(axis)``: solid angle of the spherical quadrilateral spanned by the
@@ -75,9 +76,10 @@ def jitter(cell: np.ndarray, seed: int) -> np.ndarray:
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     zero = np.zeros_like(lo)
     x = philox4x32_10((lo, hi, zero, zero), key)
-    y = philox4x32_10((lo, hi, zero + np.uint64(1), zero), key)
-    words = [x[0], x[1], x[2], x[3], y[0]]
-    return np.stack([(w.astype(np.float64) + 0.5) * 2.0**-32 for w in words])
+    m7, m4 = np.uint64(127), np.uint64(15)
+    low = (x[0] & m7) | ((x[1] & m7) << np.uint64(7)) | ((x[2] & m7) << np.uint64(14)) | ((x[3] & m4) << np.uint64(21))
+    words = [x[0] >> np.uint64(7), x[1] >> np.uint64(7), x[2] >> np.uint64(7), x[3] >> np.uint64(7), low]
+    return np.stack([(w.astype(np.float64) + 0.5) * 2.0**-25 for w in words])
 
 
 def cell_samples(vertices, begin=None, count=None, random: bool = True, seed: int = 0):
