@@ -355,6 +355,14 @@ def run_b200(args):
     achieved_gbs = BYTES_PER_RAY * n_slab / (ms_per_launch * 1e-3) / 1e9
     achieved_tflops = FLOP_PER_RAY * n_slab / (ms_per_launch * 1e-3) / 1e12
 
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture, scaled to
+    # this launch size (profiles/r01_traffic.json; null when the capture is absent)
+    traffic = None
+    traffic_file = ROOT / "profiles" / "r01_traffic.json"
+    if traffic_file.exists():
+        cap = json.loads(traffic_file.read_text())
+        traffic = cap["dram_bytes_per_launch"] / cap["rays_per_launch"] * n_slab
+
     # sanity: the traced rays are physical (most of them reach the sensor)
     unv_frac = float(mask_out.float().mean().item())
 
@@ -400,6 +408,56 @@ def run_b200(args):
             rays_binned=binned,
         )
 
+    # ---- cfg 2 "generated on chip": stratified random rays drawn, traced and binned inside
+    #      one launch per wavelength cell (optk_trace_grid); device-timed, no ray ever in HBM
+    on_chip = None
+    if not args.no_e2e:
+        from optika_b200 import _grid
+
+        def cell_edges(lo, hi, n):
+            return np.linspace(lo, hi, n + 1)
+
+        lo_w, hi_w = float(wavelengths.min()), float(wavelengths.max())
+        if hi_w == lo_w:
+            hi_w = lo_w * (1 + 1e-6)
+        half_field = 0.05 * u.deg
+        ray_grid = _grid.RayGrid(
+            [cell_edges(lo_w, hi_w, nw), cell_edges(-half_field, half_field, nf), cell_edges(-half_field, half_field, nf),
+             cell_edges(-45.0, 45.0, npup * world), cell_edges(-45.0, 45.0, npup)],
+            jitter=True, seed=0,
+        ).shard(rank, world, axis=3)
+        ex, ey = system.sensor.pixel_edges()
+        chip_image = _engine.DeviceImage.zeros(
+            np.array([lo_w, hi_w]), ex, ey, device, moments=True, counts=True
+        )
+        local = system._compiled_local
+        chip_launches = 0
+
+        def chip_step():
+            nonlocal chip_launches
+            before = _grid.LAUNCHES
+            _grid.trace_grid(local, ray_grid, image=chip_image, write_rays=False, device=device, max_launch=n_slab)
+            chip_launches = _grid.LAUNCHES - before
+
+        chip_step()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        chip_step()
+        c1.record(stream)
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        on_chip = dict(
+            value=ray_grid.size * world * N_SURFACES / (float(tc.item()) * 1e-3),
+            unit=UNIT,
+            ms_per_step=float(tc.item()),
+            launches_per_step=chip_launches,
+            api="optk_trace_grid: Philox-jittered vertex grid -> trace -> detector planes, one fused kernel",
+            rays_binned_fraction=float(chip_image.counts.sum().item()) / (2.0 * ray_grid.size),
+        )
+
     # ---- CPU baseline beside it (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -426,6 +484,7 @@ def run_b200(args):
                 launches_per_step=nw,
                 l2="inputs exceed L2: every launch streams 16.2 GB of dense rays through HBM",
                 unvignetted_fraction=unv_frac,
+                generated_on_chip=on_chip,
                 sharding="pupil slab per rank, no data-path collective" if world > 1 else "single GPU",
             ),
             roofline=dict(
@@ -434,7 +493,7 @@ def run_b200(args):
                 peak=hbm_peak,
                 unit="GB/s",
                 frac=achieved_gbs / hbm_peak,
-                traffic=None,
+                traffic=traffic,
                 kernel="optk::trace_kernel",
                 algorithmic_bytes_per_launch=BYTES_PER_RAY * n_slab,
                 ms_per_launch=ms_per_launch,

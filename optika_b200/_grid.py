@@ -19,6 +19,7 @@ from . import _engine
 __all__ = ["RayGrid", "trace_grid", "AXES"]
 
 AXES = ("wavelength", "field_x", "field_y", "pupil_x", "pupil_y")
+LAUNCHES = 0  # kernels launched by trace_grid in this process (bench accounting)
 _MAX_LAUNCH = 2**31 - 1
 
 
@@ -200,6 +201,8 @@ def trace_grid(
                 rout.field[f] = out_fields[name].data_ptr() + 8 * offset
             rout.unvignetted = out_mask.data_ptr() + offset
         g = grid.struct(device, begin, count)
+        global LAUNCHES
+        LAUNCHES += 1
         L.check(
             lib.optk_trace_grid(
                 system.handle, config, C.byref(g), C.byref(rout) if write_rays else None,
