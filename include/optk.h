@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 2
+#define OPTK_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -80,6 +80,21 @@ typedef enum optk_material_kind {
     OPTK_MAT_INDEX_MIRROR = 4
 } optk_material_kind_t;
 
+typedef enum optk_efficiency_kind {
+    OPTK_EFF_UNIT = 0,
+    OPTK_EFF_LUT = 1
+} optk_efficiency_kind_t;
+
+typedef enum optk_ruling_profile {
+    OPTK_PROFILE_IDEAL = 0,       /* Rulings.efficiency = 1, optika/rulings/_rulings.py:246-251 */
+    OPTK_PROFILE_SINUSOIDAL = 1,
+    OPTK_PROFILE_SQUARE = 2,
+    OPTK_PROFILE_SAWTOOTH = 3,
+    OPTK_PROFILE_TRIANGULAR = 4,
+    OPTK_PROFILE_RECTANGULAR = 5,
+    OPTK_PROFILE_MEASURED = 6
+} optk_ruling_profile_t;
+
 typedef enum optk_ruling_kind {
     OPTK_RULING_NONE = 0,
     OPTK_RULING_CONSTANT = 1,    /* optika/rulings/_spacing.py:45-74   */
@@ -125,6 +140,7 @@ typedef enum optk_aperture_kind {
 #define OPTK_STAGE_NORMAL_OUT 0x20 /* write sag.normal(position) into the direction fields */
 #define OPTK_STAGE_SAG_OUT 0x40    /* write sag(position) into the z position field        */
 #define OPTK_STAGE_KAPPA_OUT 0x80  /* write spacing_(position, normal) into direction      */
+#define OPTK_STAGE_EFFICIENCY_OUT 0x100 /* write material.efficiency * rulings.efficiency into intensity */
 #define OPTK_STAGE_ALL 0x1f
 
 /* x -> R x + t, row-major R.  The inverse is evaluated as R^T (x - t). */
@@ -173,6 +189,34 @@ typedef struct optk_surface {
     double aperture[4];
     double vertices_x[OPTK_MAX_VERTICES];
     double vertices_y[OPTK_MAX_VERTICES];
+
+    /* Efficiencies multiplied into the intensity next to Snell's law
+     * (optika/surfaces.py:175-179), evaluated on the ray AFTER rulings.incident_effective
+     * and BEFORE the wavelength rescale.  0 = unit efficiency (Vacuum / Mirror / Glass,
+     * ideal Rulings).
+     * material_efficiency OPTK_EFF_LUT: MeasuredMirror (optika/materials/_materials.py:279-305),
+     *   numpy.interp of the ray wavelength in (lut_x, lut_y), ends clamped.
+     * ruling_profile: the thin-grating groove efficiencies of optika/rulings/_rulings.py
+     *   (Magnusson & Gaylord 1978, Table 1), with the reference's
+     *   cos(theta) = -(a - (a . p)) . n  (p = normalized(n x g), the scalar a . p subtracted
+     *   from every component, :446-449) and gamma = pi ruling_depth / (wavelength cos(theta)):
+     *   SINUSOIDAL  J_m(2 gamma), unsquared as in the reference (:404-457);
+     *   SQUARE (:548-614), SAWTOOTH (:705-758), TRIANGULAR (:849-911), RECTANGULAR with
+     *   ruling_duty = ratio_duty (:1008-1073); `ruling_depth` is the physical depth in mm, the
+     *   per-profile amplitude normalisation is applied by the kernel;
+     *   MEASURED: MeasuredRulings (:287-313), numpy.interp like the mirror.
+     * LUT arrays are HOST pointers when the table is given to optk_system_create, which
+     * copies them to the current device; they must be ascending in x.                  */
+    int32_t material_efficiency;
+    int32_t ruling_profile;
+    int32_t material_lut_n;
+    int32_t ruling_lut_n;
+    double ruling_depth;
+    double ruling_duty;
+    const double* material_lut_x;
+    const double* material_lut_y;
+    const double* ruling_lut_x;
+    const double* ruling_lut_y;
 } optk_surface_t;
 
 typedef struct optk_system optk_system_t;

@@ -566,6 +566,18 @@ def rulings_incident_effective(rulings, rays, normal):
     return out if on_device else out.to_host()
 
 
+def surface_efficiency(rays, normal, material=None, rulings=None) -> na.ScalarArray:
+    """
+    ``material.efficiency(rays, normal)`` / ``rulings.efficiency(rays, normal)``
+    (``optika/materials/_materials.py:279-305``, ``optika/rulings/_rulings.py:205-221``): a one-surface
+    trace that writes the efficiency into the intensity field (``OPTK_STAGE_EFFICIENCY_OUT``).
+    """
+    on_device = isinstance(rays, DeviceRays)
+    system = CompiledSystem([_Bare(material=material, rulings=rulings)], stages=L.STAGE_EFFICIENCY_OUT)
+    out = trace(system, rays, normal=normal)
+    return out.fields["intensity"] if on_device else out.to_host().intensity
+
+
 def snells_law(direction, index_refraction, index_refraction_new, normal=None, is_mirror=False):
     """``optika.materials.snells_law`` (``optika/materials/_snells_law.py:41-291``)."""
     from . import materials

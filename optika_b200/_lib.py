@@ -75,7 +75,11 @@ STAGE_CLIP = 0x10
 STAGE_NORMAL_OUT = 0x20
 STAGE_SAG_OUT = 0x40
 STAGE_KAPPA_OUT = 0x80
+STAGE_EFFICIENCY_OUT = 0x100
 STAGE_ALL = 0x1F
+EFF_UNIT, EFF_LUT = range(2)
+(PROFILE_IDEAL, PROFILE_SINUSOIDAL, PROFILE_SQUARE, PROFILE_SAWTOOTH, PROFILE_TRIANGULAR, PROFILE_RECTANGULAR,
+ PROFILE_MEASURED) = range(7)
 
 
 class Affine(C.Structure):
@@ -108,6 +112,16 @@ class Surface(C.Structure):
         ("aperture", C.c_double * 4),
         ("vertices_x", C.c_double * MAX_VERTICES),
         ("vertices_y", C.c_double * MAX_VERTICES),
+        ("material_efficiency", C.c_int32),
+        ("ruling_profile", C.c_int32),
+        ("material_lut_n", C.c_int32),
+        ("ruling_lut_n", C.c_int32),
+        ("ruling_depth", C.c_double),
+        ("ruling_duty", C.c_double),
+        ("material_lut_x", C.c_void_p),
+        ("material_lut_y", C.c_void_p),
+        ("ruling_lut_x", C.c_void_p),
+        ("ruling_lut_y", C.c_void_p),
     ]
 
 
@@ -208,7 +222,7 @@ class MlInput(C.Structure):
     ]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class OptkError(RuntimeError):

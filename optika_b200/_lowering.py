@@ -80,12 +80,47 @@ def _lower_sag(sag, S: L.Surface, shape_, index):
     S.sag_transform = affine_struct(t, shape_, index)
 
 
-def _lower_material(material, S: L.Surface, shape_, index):
+def _measured_table(measured, shape_, index, keep: list):
+    """
+    ``(n, x pointer, y pointer)`` of a measured efficiency (``optika/materials/_materials.py:283-305``,
+    ``optika/rulings/_rulings.py:291-313``) at one configuration index; the host arrays are
+    appended to `keep` (``optk_system_create`` copies them to the device).
+    """
+    import ctypes as C
+
+    inputs = measured.inputs
+    wavelength = na.as_named_array(u.length(inputs.wavelength))
+    if na.as_named_array(getattr(inputs.direction, "x", inputs.direction)).size != 1 or any(
+        n != 1 for n in na.shape(inputs.direction).values()
+    ):
+        raise ValueError("Interpolating over different incidence angles is not supported.")
+    if wavelength.ndim != 1:
+        raise ValueError(f"wavelength must be one dimensional, got shape {wavelength.shape}")
+    (axis,) = wavelength.axes
+    full = dict(shape_)
+    full[axis] = wavelength.shape[axis]
+    values = np.broadcast_to(na.aligned(na.as_named_array(measured.outputs), full), tuple(full.values()))
+    x = np.ascontiguousarray(wavelength.ndarray, dtype=np.float64)
+    y = np.ascontiguousarray(values[index], dtype=np.float64)
+    if np.any(np.diff(x) < 0):  # numpy.interp wants ascending abscissae
+        order = np.argsort(x)
+        x, y = np.ascontiguousarray(x[order]), np.ascontiguousarray(y[order])
+    keep += [x, y]
+    return len(x), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)
+
+
+def _lower_material(material, S: L.Surface, shape_, index, keep: list):
     name = type(material).__name__
     if name in ("Vacuum", "IdealSensorMaterial"):
         S.material_kind = L.MAT_VACUUM
     elif name == "Mirror":
         S.material_kind = L.MAT_MIRROR
+    elif name == "MeasuredMirror":
+        S.material_kind = L.MAT_MIRROR
+        S.material_efficiency = L.EFF_LUT
+        S.material_lut_n, S.material_lut_x, S.material_lut_y = _measured_table(
+            material.efficiency_measured, shape_, index, keep
+        )
     elif name == "Glass":
         S.material_kind = L.MAT_GLASS
         for k, v in enumerate((material.b1, material.b2, material.b3, material.c1, material.c2, material.c3)):
@@ -97,13 +132,32 @@ def _lower_material(material, S: L.Surface, shape_, index):
         raise NotImplementedError(f"material {name} is not supported by the device engine")
 
 
-def _lower_rulings(rulings, S: L.Surface, shape_, index):
+_PROFILES = {
+    "Rulings": L.PROFILE_IDEAL,
+    "SinusoidalRulings": L.PROFILE_SINUSOIDAL,
+    "SquareRulings": L.PROFILE_SQUARE,
+    "SawtoothRulings": L.PROFILE_SAWTOOTH,
+    "TriangularRulings": L.PROFILE_TRIANGULAR,
+    "RectangularRulings": L.PROFILE_RECTANGULAR,
+    "MeasuredRulings": L.PROFILE_MEASURED,
+}
+
+
+def _lower_rulings(rulings, S: L.Surface, shape_, index, keep: list):
     if rulings is None:
         S.ruling_kind = L.RULING_NONE
         return
-    if type(rulings).__name__ != "Rulings":
-        raise NotImplementedError(
-            f"rulings {type(rulings).__name__} (non-unit efficiency) are not supported by the device engine"
+    kind = type(rulings).__name__
+    if kind not in _PROFILES:
+        raise NotImplementedError(f"rulings {kind} are not supported by the device engine")
+    S.ruling_profile = _PROFILES[kind]
+    if hasattr(rulings, "depth"):
+        S.ruling_depth = float(_scalar(u.length(rulings.depth), shape_, index))
+    if hasattr(rulings, "ratio_duty"):
+        S.ruling_duty = float(_scalar(rulings.ratio_duty, shape_, index))
+    if kind == "MeasuredRulings":
+        S.ruling_lut_n, S.ruling_lut_x, S.ruling_lut_y = _measured_table(
+            rulings.efficiency_measured, shape_, index, keep
         )
     spacing = rulings.spacing_
     name = type(spacing).__name__
@@ -189,14 +243,21 @@ def _lower_aperture(aperture, S: L.Surface, shape_, index):
     S.aperture_transform = affine_struct(aperture.transformation, shape_, index)
 
 
-def lower_surface(surface, shape_: dict[str, int], index: tuple, stages: int = L.STAGE_ALL) -> L.Surface:
-    """One surface at one configuration index -> ``optk_surface_t``."""
+def lower_surface(
+    surface, shape_: dict[str, int], index: tuple, stages: int = L.STAGE_ALL, keep: list | None = None
+) -> L.Surface:
+    """
+    One surface at one configuration index -> ``optk_surface_t``.  Host arrays the record
+    points to (measured-efficiency tables) are appended to `keep`, which must outlive the
+    ``optk_system_create`` call.
+    """
     S = L.Surface()
     S.stages = stages
     S.flags = 0
+    keep = [] if keep is None else keep
     _lower_sag(surface.sag, S, shape_, index)
-    _lower_material(surface.material, S, shape_, index)
-    _lower_rulings(surface.rulings, S, shape_, index)
+    _lower_material(surface.material, S, shape_, index, keep)
+    _lower_rulings(surface.rulings, S, shape_, index, keep)
     _lower_aperture(surface.aperture, S, shape_, index)
     if surface.transformation is not None:
         S.flags |= L.F_TRANSFORM
@@ -206,16 +267,25 @@ def lower_surface(surface, shape_: dict[str, int], index: tuple, stages: int = L
 
 def lower_system(surfaces, shape_: dict[str, int] | None = None, stages: int = L.STAGE_ALL):
     """
-    ``[n_config][n_surface]`` table as a ctypes array, plus the configuration shape.
+    ``[n_config][n_surface]`` table as a ctypes array, plus the configuration shape.  The
+    host arrays the table points to are returned in ``table.keep``.
     """
     surfaces = list(surfaces)
     if shape_ is None:
         shape_ = config_shape(surfaces)
     n_config = int(np.prod(list(shape_.values()), dtype=np.int64)) if shape_ else 1
-    table = (L.Surface * (n_config * len(surfaces)))()
+    table = _table_type(n_config * len(surfaces))()
+    table.keep = []
     k = 0
     for index in np.ndindex(*shape_.values()):
         for s in surfaces:
-            table[k] = lower_surface(s, shape_, index, stages)
+            table[k] = lower_surface(s, shape_, index, stages, table.keep)
             k += 1
     return table, shape_
+
+
+def _table_type(n: int):
+    class SurfaceTable(L.Surface * n):  # a Python subclass, so instances can carry `keep`
+        pass
+
+    return SurfaceTable

@@ -37,6 +37,7 @@ struct optk_system {
     int32_t n_surface;
     int32_t n_config;
     std::vector<optk_surface_t> table;
+    double* lut_device = nullptr;  // every efficiency table of the system, one allocation
 };
 
 // ---- scratch cache for the host-pointer path ------------------------------------
@@ -104,6 +105,34 @@ int validate_surface(const optk_surface_t& s, int index) {
         set_error("surface %d: polynomial ruling needs 1..%d coefficients, got %d", index, OPTK_MAX_COEFF,
                   s.n_coeff);
         return OPTK_ERR_INVALID;
+    }
+    if (s.material_efficiency < OPTK_EFF_UNIT || s.material_efficiency > OPTK_EFF_LUT) {
+        set_error("surface %d: unsupported material efficiency kind %d", index, s.material_efficiency);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.ruling_profile < OPTK_PROFILE_IDEAL || s.ruling_profile > OPTK_PROFILE_MEASURED) {
+        set_error("surface %d: unsupported ruling profile %d", index, s.ruling_profile);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.ruling_profile != OPTK_PROFILE_IDEAL && s.ruling_kind == OPTK_RULING_NONE) {
+        set_error("surface %d: a ruling profile needs a ruling spacing", index);
+        return OPTK_ERR_INVALID;
+    }
+    for (int which = 0; which < 2; ++which) {
+        const bool used = which == 0 ? s.material_efficiency == OPTK_EFF_LUT : s.ruling_profile == OPTK_PROFILE_MEASURED;
+        if (!used) continue;
+        const int n = which == 0 ? s.material_lut_n : s.ruling_lut_n;
+        const double* x = which == 0 ? s.material_lut_x : s.ruling_lut_x;
+        const double* y = which == 0 ? s.material_lut_y : s.ruling_lut_y;
+        if (n < 1 || !x || !y) {
+            set_error("surface %d: measured efficiency needs a table of at least one (wavelength, value) pair", index);
+            return OPTK_ERR_INVALID;
+        }
+        for (int i = 1; i < n; ++i)
+            if (!(x[i] > x[i - 1])) {
+                set_error("surface %d: measured efficiency wavelengths must be strictly ascending", index);
+                return OPTK_ERR_INVALID;
+            }
     }
     return OPTK_OK;
 }
@@ -276,11 +305,47 @@ OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, 
             s.aperture[3] = t;
         }
     }
+    // measured-efficiency tables: host arrays -> one device allocation owned by the handle
+    size_t lut_total = 0;
+    for (const optk_surface_t& s : sys->table) {
+        if (s.material_efficiency == OPTK_EFF_LUT) lut_total += 2 * (size_t)s.material_lut_n;
+        if (s.ruling_profile == OPTK_PROFILE_MEASURED) lut_total += 2 * (size_t)s.ruling_lut_n;
+    }
+    if (lut_total) {
+        std::vector<double> host;
+        host.reserve(lut_total);
+        cudaError_t e = cudaMalloc((void**)&sys->lut_device, lut_total * sizeof(double));
+        if (e != cudaSuccess) {
+            delete sys;
+            return cuda_fail(e, "cudaMalloc (efficiency tables)");
+        }
+        for (optk_surface_t& s : sys->table) {
+            for (int which = 0; which < 2; ++which) {
+                const bool used = which == 0 ? s.material_efficiency == OPTK_EFF_LUT : s.ruling_profile == OPTK_PROFILE_MEASURED;
+                if (!used) continue;
+                const int n = which == 0 ? s.material_lut_n : s.ruling_lut_n;
+                const double*& x = which == 0 ? s.material_lut_x : s.ruling_lut_x;
+                const double*& y = which == 0 ? s.material_lut_y : s.ruling_lut_y;
+                const size_t at = host.size();
+                host.insert(host.end(), x, x + n);
+                host.insert(host.end(), y, y + n);
+                x = sys->lut_device + at;
+                y = sys->lut_device + at + n;
+            }
+        }
+        e = cudaMemcpy(sys->lut_device, host.data(), lut_total * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(sys->lut_device);
+            delete sys;
+            return cuda_fail(e, "cudaMemcpy (efficiency tables)");
+        }
+    }
     *out = sys;
     return OPTK_OK;
 }
 
 OPTK_API int optk_system_destroy(optk_system_t* sys) {
+    if (sys && sys->lut_device) cudaFree(sys->lut_device);
     delete sys;
     return OPTK_OK;
 }

@@ -31,7 +31,8 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     bool full = P.in.normal[0] == nullptr;
     for (int s = 0; s < P.n_surf; ++s)
         full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM) &&
-               P.surf[s].material_kind <= OPTK_MAT_GLASS;
+               P.surf[s].material_kind <= OPTK_MAT_GLASS && P.surf[s].material_efficiency == OPTK_EFF_UNIT &&
+               P.surf[s].ruling_profile == OPTK_PROFILE_IDEAL;
     const bool dense = P.dense_in != 0 && !from_grid, acc = P.accumulate != 0, image = P.has_image != 0;
     // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
     bool vec = full && dense && !from_grid && (P.accumulate_stride % 2 == 0);

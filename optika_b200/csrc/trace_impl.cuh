@@ -586,6 +586,140 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 }
 
 // ---------------------------------------------------------------------------
+// efficiencies (optika/surfaces.py:175-179): cold code, only systems with measured
+// mirrors or groove profiles reach it (they run the generic kernels)
+// ---------------------------------------------------------------------------
+
+// numpy.interp(x, xp, fp): linear, ends clamped, NaN -> NaN
+// (MeasuredMirror / MeasuredRulings, optika/materials/_materials.py:301-305, rulings/_rulings.py:309-313)
+static __device__ __noinline__ double lut_interp(const double* __restrict__ xp, const double* __restrict__ fp, int n,
+                                                 double x) {
+    if (x != x) return x;
+    if (n == 1 || x <= __ldg(xp)) return __ldg(fp);
+    if (x >= __ldg(xp + n - 1)) return __ldg(fp + n - 1);
+    int lo = 0, hi = n - 1;  // xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= __ldg(xp + mid)) lo = mid; else hi = mid;
+    }
+    const double x0 = __ldg(xp + lo), x1 = __ldg(xp + lo + 1), f0 = __ldg(fp + lo), f1 = __ldg(fp + lo + 1);
+    const double slope = (f1 - f0) / (x1 - x0);
+    return slope * (x - x0) + f0;
+}
+
+// Bessel function of the first kind of integer order (scipy.special.jv in
+// SinusoidalRulings.efficiency, optika/rulings/_rulings.py:455): Miller's backward recurrence
+// J_{k-1} = (2 k / x) J_k - J_{k+1} from far above max(n, x), normalised with
+// 1 = J_0 + 2 (J_2 + J_4 + ...).  Absolute error ~1e-16 for |x| up to a few thousand.
+static __device__ __noinline__ double bessel_jn(int n, double x) {
+    if (x != x) return x;
+    double sign = 1.0;
+    if (n < 0) {
+        n = -n;
+        if (n & 1) sign = -sign;  // J_{-n} = (-1)^n J_n
+    }
+    if (x < 0.0) {
+        x = -x;
+        if (n & 1) sign = -sign;  // J_n(-x) = (-1)^n J_n(x)
+    }
+    if (x == 0.0) return n == 0 ? 1.0 : 0.0;
+    if (!(x < 1.0e6)) return 0.0 * x;  // inf -> nan like jv; huge arguments are outside the thin-grating model
+    if (x < 1e-8) {  // leading term of the series, exact to 1e-17 relative here
+        double term = 1.0;
+        for (int k = 1; k <= n; ++k) term *= 0.5 * x / k;
+        return sign * term;
+    }
+    const int top = (n > (int)x ? n : (int)x);
+    int m = top + 24 + (int)(8.0 * cbrt(x));
+    m += m & 1;  // even start
+    double jp = 0.0, j = 1e-300, sum = 0.0, result = 0.0;
+    const double two_over_x = 2.0 / x;
+    for (int k = m; k > 0; --k) {
+        const double jm = (double)k * two_over_x * j - jp;  // J_{k-1}
+        jp = j;
+        j = jm;
+        if (fabs(j) > 1e250) {  // rescale; every quantity scales together
+            j *= 1e-250;
+            jp *= 1e-250;
+            sum *= 1e-250;
+            result *= 1e-250;
+        }
+        if (((k - 1) & 1) == 0 && k - 1 > 0) sum += j;  // even orders >= 2
+        if (k - 1 == n) result = j;
+    }
+    sum = 2.0 * sum + j;  // j is J_0 now
+    return sign * result / sum;
+}
+
+// material.efficiency(rays_1, normal) * rulings.efficiency(rays_1, normal): `r` carries the
+// effective direction (after incident_effective) and the wavelength before the rescale.
+static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S, const Ray& r, double nx, double ny,
+                                                         double nz) {
+    double eff = 1.0;
+    if (S.material_efficiency == OPTK_EFF_LUT) eff = lut_interp(S.material_lut_x, S.material_lut_y, S.material_lut_n, r.w);
+    const int profile = S.ruling_profile;
+    if (profile == OPTK_PROFILE_IDEAL) return eff;
+    if (profile == OPTK_PROFILE_MEASURED)
+        return eff * lut_interp(S.ruling_lut_x, S.ruling_lut_y, S.ruling_lut_n, r.w);
+    // normal_rulings = spacing_(position, normal).normalized; parallel = (normal x normal_rulings).normalized
+    double gx, gy, gz;
+    ruling_vector(S, r.px, r.py, r.pz, nx, ny, nz, gx, gy, gz);
+    const double gi = 1.0 / sqrt(gx * gx + gy * gy + gz * gz);
+    gx *= gi; gy *= gi; gz *= gi;
+    double px = ny * gz - nz * gy, py = nz * gx - nx * gz, pz = nx * gy - ny * gx;
+    const double pi_ = 1.0 / sqrt(px * px + py * py + pz * pz);
+    px *= pi_; py *= pi_; pz *= pi_;
+    // direction - direction @ parallel: the reference subtracts the SCALAR from every component
+    const double dp = r.dx * px + r.dy * py + r.dz * pz;
+    const double cos_theta = -((r.dx - dp) * nx + (r.dy - dp) * ny + (r.dz - dp) * nz);
+    const double PI = 3.141592653589793;
+    const double m = S.ruling_order;
+    const bool even = fmod(m, 2.0) == 0.0;
+    switch (profile) {
+        case OPTK_PROFILE_SINUSOIDAL: {
+            const double gamma = PI * S.ruling_depth / (r.w * cos_theta);
+            return eff * bessel_jn((int)m, 2.0 * gamma);
+        }
+        case OPTK_PROFILE_SQUARE: {
+            const double gamma = PI * (S.ruling_depth / (PI / 4)) / (r.w * cos_theta);
+            double e;
+            if (m == 0.0) {
+                const double c = cos(PI * gamma / 2);
+                e = c * c;
+            } else if (even) {
+                e = 0.0;
+            } else {
+                const double q = 2 * sin(PI * gamma / 2) / (m * PI);
+                e = q * q;
+            }
+            return eff * e;
+        }
+        case OPTK_PROFILE_SAWTOOTH: {
+            const double gamma = PI * (S.ruling_depth / (PI / 2)) / (r.w * cos_theta);
+            const double q = sin(PI * gamma) / (PI * (gamma + m));
+            return eff * q * q;
+        }
+        case OPTK_PROFILE_TRIANGULAR: {
+            const double gamma = PI * (S.ruling_depth / (PI * PI / 8)) / (r.w * cos_theta);
+            const double h = PI * gamma / 2;
+            const double a = gamma / (h * h + m * m);  // "+" as written in the reference (:901)
+            const double q = a * (even ? sin(PI * PI * gamma / 4) : cos(PI * PI * gamma / 4));
+            return eff * q * q;
+        }
+        default: {  // OPTK_PROFILE_RECTANGULAR
+            const double a = 2 * PI * S.ruling_duty;
+            const double root = sqrt(2 * (1 - cos(a)));
+            const double gamma = PI * (S.ruling_depth / (PI / (2 * root))) / (r.w * cos_theta);
+            double b = sin(PI * gamma / root);
+            b = b * b;
+            const double e = (m == 0.0) ? 1 - ((2 * a / PI) - (a / PI) * (a / PI)) * b
+                                        : (2 / ((m * PI) * (m * PI))) * (1 - cos(m * a)) * b;
+            return eff * e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // one surface, GENERIC path (partial stage masks, caller-supplied normals: the unit
 // operations of the reference API): AbstractSurface.propagate_rays, optika/surfaces.py:123-198
 // ---------------------------------------------------------------------------
@@ -693,8 +827,17 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
         }
     }
 
+    // efficiency = material.efficiency(rays_1, normal) [* rulings.efficiency(rays_1, normal)]
+    // on the effective direction and the incoming wavelength (surfaces.py:175-179)
+    const bool has_efficiency = S.material_efficiency != OPTK_EFF_UNIT || S.ruling_profile != OPTK_PROFILE_IDEAL;
+    double efficiency = 1.0;
+    if (has_efficiency && (stages & (OPTK_STAGE_REFRACT | OPTK_STAGE_EFFICIENCY_OUT)))
+        efficiency = surface_efficiency(S, r, nx, ny, nz);
+    if (stages & OPTK_STAGE_EFFICIENCY_OUT) r.intensity = efficiency;
+
     // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
     if (stages & OPTK_STAGE_REFRACT) {
+        if (has_efficiency) r.intensity *= efficiency;
         const double n1 = r.n;
         double n2;
         const bool mirror = S.material_kind == OPTK_MAT_MIRROR || S.material_kind == OPTK_MAT_INDEX_MIRROR;
@@ -736,7 +879,6 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
         r.dx = ratio * (r.dx + d * nx);
         r.dy = ratio * (r.dy + d * ny);
         r.dz = ratio * (r.dz + d * nz);
-        // efficiency = 1 for Vacuum / Mirror / Glass and ideal Rulings (surfaces.py:175-179)
         if (!mirror) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
         r.n = n2;
     }

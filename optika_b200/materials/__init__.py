@@ -1,6 +1,6 @@
 """Optical materials (mirrors ``optika.materials``)."""
 
-from ._materials import AbstractMaterial, Vacuum, AbstractMirror, Mirror, Glass
+from ._materials import AbstractMaterial, Vacuum, AbstractMirror, Mirror, MeasuredMirror, Glass
 from . import profiles
 from ._layers import AbstractLayer, Layer, LayerSequence, PeriodicLayerSequence
 from ._snells_law import snells_law, snells_law_scalar
@@ -11,6 +11,7 @@ __all__ = [
     "Vacuum",
     "AbstractMirror",
     "Mirror",
+    "MeasuredMirror",
     "Glass",
     "profiles",
     "AbstractLayer",

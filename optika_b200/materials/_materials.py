@@ -13,7 +13,7 @@ import dataclasses
 from .. import named as na
 from .. import units as u
 
-__all__ = ["AbstractMaterial", "Vacuum", "AbstractMirror", "Mirror", "Glass"]
+__all__ = ["AbstractMaterial", "Vacuum", "AbstractMirror", "Mirror", "MeasuredMirror", "Glass"]
 
 
 @dataclasses.dataclass(eq=False)
@@ -52,6 +52,35 @@ class Mirror(AbstractMirror):
     """An ideal mirror with unit efficiency (``_materials.py:160-175``)."""
 
     substrate: object = None
+
+
+@dataclasses.dataclass(eq=False)
+class MeasuredMirror(AbstractMirror):
+    """
+    A mirror whose reflectivity was measured as a function of wavelength
+    (``optika/materials/_materials.py:177-305``): ``efficiency_measured`` is a
+    :class:`~optika_b200.named.FunctionArray` with inputs
+    :class:`~optika_b200.vectors.SpectralDirectionalVectorArray` (one-dimensional
+    ``wavelength``, a single ``direction``) and the reflectivity as outputs; the efficiency
+    of a ray is ``numpy.interp`` of its wavelength in that table (``:301-305``), evaluated
+    inside the trace kernel.
+    """
+
+    efficiency_measured: na.FunctionArray = None
+    substrate: object = None
+    serial_number: object = None
+
+    @property
+    def shape(self) -> dict[str, int]:
+        shape_ = dict(na.shape(self.efficiency_measured.outputs))
+        for ax in na.shape(self.efficiency_measured.inputs.wavelength):
+            shape_.pop(ax, None)
+        return shape_
+
+    def efficiency(self, rays, normal):
+        from .. import _engine
+
+        return _engine.surface_efficiency(rays, normal, material=self)
 
 
 @dataclasses.dataclass(eq=False)

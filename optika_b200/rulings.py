@@ -20,6 +20,12 @@ __all__ = [
     "HolographicRulingSpacing",
     "AbstractRulings",
     "Rulings",
+    "MeasuredRulings",
+    "SinusoidalRulings",
+    "SquareRulings",
+    "SawtoothRulings",
+    "TriangularRulings",
+    "RectangularRulings",
 ]
 
 
@@ -122,6 +128,12 @@ class AbstractRulings:
 
         return _engine.rulings_incident_effective(self, rays, normal)
 
+    def efficiency(self, rays, normal: na.Cartesian3dVectorArray):
+        """Fraction of the light diffracted into the order (``optika/rulings/_rulings.py:205-221``), on the device."""
+        from . import _engine
+
+        return _engine.surface_efficiency(rays, normal, rulings=self)
+
 
 @dataclasses.dataclass(eq=False)
 class Rulings(AbstractRulings):
@@ -139,3 +151,68 @@ class Rulings(AbstractRulings):
 
     def efficiency(self, rays, normal) -> float:
         return 1
+
+
+@dataclasses.dataclass(eq=False)
+class MeasuredRulings(AbstractRulings):
+    """
+    Rulings whose efficiency was measured as a function of wavelength
+    (``optika/rulings/_rulings.py:254-313``): ``numpy.interp`` of the ray wavelength in
+    ``efficiency_measured`` (a :class:`~optika_b200.named.FunctionArray` whose inputs carry
+    a one-dimensional ``wavelength`` and a single ``direction``).
+    """
+
+    spacing: float | na.ScalarArray | AbstractRulingSpacing = None
+    diffraction_order: int | na.ScalarArray = 1
+    efficiency_measured: na.FunctionArray = None
+
+    @property
+    def shape(self) -> dict[str, int]:
+        shape_ = dict(na.shape(self.efficiency_measured.outputs))
+        for ax in na.shape(self.efficiency_measured.inputs.wavelength):
+            shape_.pop(ax, None)
+        return na.broadcast_shapes(na.shape(self.spacing), na.shape(self.diffraction_order), shape_)
+
+
+@dataclasses.dataclass(eq=False)
+class _ProfileRulings(AbstractRulings):
+    spacing: float | na.ScalarArray | AbstractRulingSpacing = None
+    depth: float | na.ScalarArray = 0
+    diffraction_order: int | na.ScalarArray = 1
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(
+            na.shape(self.spacing), na.shape(self.depth), na.shape(self.diffraction_order)
+        )
+
+
+@dataclasses.dataclass(eq=False)
+class SinusoidalRulings(_ProfileRulings):
+    """Sinusoidal groove profile, efficiency ``J_m(2 gamma)`` (``optika/rulings/_rulings.py:316-457``)."""
+
+
+@dataclasses.dataclass(eq=False)
+class SquareRulings(_ProfileRulings):
+    """Square-wave groove profile (``optika/rulings/_rulings.py:460-614``)."""
+
+
+@dataclasses.dataclass(eq=False)
+class SawtoothRulings(_ProfileRulings):
+    """Sawtooth (blazed) groove profile (``optika/rulings/_rulings.py:617-758``)."""
+
+
+@dataclasses.dataclass(eq=False)
+class TriangularRulings(_ProfileRulings):
+    """Triangular groove profile (``optika/rulings/_rulings.py:761-911``)."""
+
+
+@dataclasses.dataclass(eq=False)
+class RectangularRulings(_ProfileRulings):
+    """Rectangular groove profile with a duty cycle (``optika/rulings/_rulings.py:914-1073``)."""
+
+    ratio_duty: float | na.ScalarArray = 0.5
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.broadcast_shapes(super().shape, na.shape(self.ratio_duty))

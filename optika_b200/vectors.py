@@ -9,7 +9,12 @@ import dataclasses
 import numpy as np
 from . import named as na
 
-__all__ = ["ObjectVectorArray", "PolarizationVectorArray", "SpectralPositionalVectorArray"]
+__all__ = [
+    "ObjectVectorArray",
+    "PolarizationVectorArray",
+    "SpectralPositionalVectorArray",
+    "SpectralDirectionalVectorArray",
+]
 
 
 @dataclasses.dataclass(eq=False)
@@ -84,3 +89,15 @@ class SpectralPositionalVectorArray:
     @property
     def shape(self) -> dict[str, int]:
         return na.shape_broadcasted(self.wavelength, self.position)
+
+
+@dataclasses.dataclass(eq=False)
+class SpectralDirectionalVectorArray:
+    """``na.SpectralDirectionalVectorArray``: a wavelength and a direction (measured efficiencies)."""
+
+    wavelength: float | na.ScalarArray = 0
+    direction: na.Cartesian3dVectorArray | float = 0
+
+    @property
+    def shape(self) -> dict[str, int]:
+        return na.shape_broadcasted(self.wavelength, self.direction)

@@ -641,6 +641,93 @@ def attenuation(material, rays: dict):
     return np.zeros_like(rays["wavelength"])  # _materials.py:101-105, 440-444
 
 
+def _measured_interp(measured, wavelength):
+    """
+    ``na.interp(x=rays.wavelength, xp=wavelength, fp=efficiency)`` of a measured efficiency
+    (``optika/materials/_materials.py:283-305``, ``optika/rulings/_rulings.py:291-313``);
+    third-party ``na.interp`` assumed to be ``numpy.interp`` (linear, clamped ends).
+    """
+    inputs = measured.inputs
+    xp = np.asarray(inputs.wavelength.ndarray, dtype=np.float64)
+    fp = np.asarray(measured.outputs.ndarray, dtype=np.float64)
+    if xp.ndim != 1:
+        raise ValueError(f"wavelength must be one dimensional, got shape {xp.shape}")
+    if fp.shape != xp.shape:
+        raise NotImplementedError("oracle: select the configuration first (select_config)")
+    order = np.argsort(xp)
+    return np.interp(wavelength, xp[order], fp[order])
+
+
+def material_efficiency(material, rays: dict, normal):
+    """``material.efficiency(rays, normal)``."""
+    name = _name(material)
+    if name == "MeasuredMirror":
+        return _measured_interp(material.efficiency_measured, rays["wavelength"])  # _materials.py:279-305
+    if name in ("Vacuum", "IdealSensorMaterial", "Mirror", "Glass", "_FixedIndex"):
+        return 1.0  # _materials.py:107-112, 147-152, 446-451
+    raise NotImplementedError(f"oracle: efficiency of material {name}")
+
+
+def rulings_efficiency(rulings, rays: dict, normal):
+    """
+    ``rulings.efficiency(rays, normal)``: the groove efficiencies of
+    ``optika/rulings/_rulings.py`` (Magnusson & Gaylord 1978, Table 1), line by line,
+    including ``direction - direction @ parallel_rulings`` (a scalar subtracted from a
+    vector, ``:446-447``), the unsquared Bessel function of the sinusoidal profile
+    (``:455``) and the ``+ i^2`` of the triangular profile (``:901``).
+    """
+    import scipy.special
+
+    name = _name(rulings)
+    if name == "Rulings":
+        return 1.0  # :246-251
+    if name == "MeasuredRulings":
+        return _measured_interp(rulings.efficiency_measured, rays["wavelength"])  # :287-313
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kappa = ruling_vector(_spacing_of(rulings), (rays["px"], rays["py"], rays["pz"]), normal)
+        length = np.sqrt(kappa[0] ** 2 + kappa[1] ** 2 + kappa[2] ** 2)
+        g = tuple(k / length for k in kappa)  # normal_rulings
+        nx, ny, nz = normal
+        p = (ny * g[2] - nz * g[1], nz * g[0] - nx * g[2], nx * g[1] - ny * g[0])  # normal.cross(normal_rulings)
+        length = np.sqrt(p[0] ** 2 + p[1] ** 2 + p[2] ** 2)
+        p = tuple(c / length for c in p)
+        d = (rays["dx"], rays["dy"], rays["dz"])
+        dp = d[0] * p[0] + d[1] * p[1] + d[2] * p[2]
+        d = tuple(c - dp for c in d)
+        wavelength = rays["wavelength"]
+        cos_theta = -(d[0] * nx + d[1] * ny + d[2] * nz)
+        depth = _f(rulings.depth)
+        i = _f(rulings.diffraction_order)
+        pi = np.pi
+        if name == "SinusoidalRulings":  # :442-457
+            gamma = pi * depth / (wavelength * cos_theta)
+            return scipy.special.jv(i, 2 * gamma)
+        if name == "SquareRulings":  # :590-614
+            gamma = pi * (depth / (pi / 4)) / (wavelength * cos_theta)
+            result = np.where(i % 2 == 0, 0, np.square(2 * np.sin(pi * gamma / 2) / (i * pi)) if i != 0 else 0)
+            return np.where(i == 0, np.square(np.cos(pi * gamma / 2)), result)
+        if name == "SawtoothRulings":  # :741-758
+            gamma = pi * (depth / (pi / 2)) / (wavelength * cos_theta)
+            return np.square(np.sin(pi * gamma) / (pi * (gamma + i)))
+        if name == "TriangularRulings":  # :887-911
+            gamma = pi * (depth / (np.square(pi) / 8)) / (wavelength * cos_theta)
+            a = gamma / (np.square(pi * gamma / 2) + np.square(i))
+            return np.where(
+                i % 2 == 0,
+                np.square(a * np.sin(np.square(pi) * gamma / 4)),
+                np.square(a * np.cos(np.square(pi) * gamma / 4)),
+            )
+        if name == "RectangularRulings":  # :1046-1073
+            a = 2 * pi * _f(rulings.ratio_duty)
+            amplitude = pi / (2 * np.sqrt(2 * (1 - np.cos(a))))
+            gamma = pi * (depth / amplitude) / (wavelength * cos_theta)
+            b = np.square(np.sin(pi * gamma / np.sqrt(2 * (1 - np.cos(a)))))
+            if i == 0:
+                return 1 - ((2 * a / pi) - np.square(a / pi)) * b
+            return (2 / np.square(i * pi)) * (1 - np.cos(i * a)) * b
+    raise NotImplementedError(f"oracle: rulings {name}")
+
+
 def snells_law(ax, ay, az, n1, n2, ux, uy, uz, mirror: bool):
     """
     Vector Snell's law, ``optika/materials/_snells_law.py:341-366``
@@ -843,7 +930,9 @@ def surface_propagate(surface, rays: dict, converge: bool = False, extended: boo
         rays_1["dx"], rays_1["dy"], rays_1["dz"], n1, n2, normal[0], normal[1], normal[2],
         is_mirror(material),
     )
-    efficiency = 1.0  # :175-177 (Vacuum/Mirror/Glass and ideal Rulings all return 1)
+    efficiency = material_efficiency(material, rays_1, normal)  # :175
+    if rulings is not None:  # :176-177
+        efficiency = efficiency * rulings_efficiency(rulings, rays_1, normal)
     rays_2 = dict(rays_1)  # :182-190
     rays_2["wavelength"] = wavelength_2
     rays_2["dx"], rays_2["dy"], rays_2["dz"] = bx, by, bz
