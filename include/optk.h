@@ -77,7 +77,10 @@ typedef enum optk_material_kind {
     /* unit operation optika.materials.snells_law (optika/materials/_snells_law.py:41-47):
      * the new index is given explicitly in material[0]; transmit / reflect */
     OPTK_MAT_INDEX = 3,
-    OPTK_MAT_INDEX_MIRROR = 4
+    OPTK_MAT_INDEX_MIRROR = 4,
+    /* index and attenuation pass through, no reflection: AbstractMultilayerFilm
+     * (optika/materials/_multilayers.py:795-805, 835-837) */
+    OPTK_MAT_PASS = 5
 } optk_material_kind_t;
 
 typedef enum optk_efficiency_kind {
@@ -249,6 +252,11 @@ typedef struct optk_rays_in {
 typedef struct optk_rays_out {
     double* field[OPTK_NUM_FIELDS];
     uint8_t* unvignetted;
+    /* Optional, one value per ray: -a . n at the LAST traced surface, a = the incident
+     * direction after rulings.incident_effective, n = the surface normal: the `direction`
+     * argument MultilayerMirror.efficiency / MultilayerFilm.efficiency hand to
+     * multilayer_efficiency (optika/materials/_multilayers.py:858, 927).  NULL = not wanted. */
+    double* cos_incidence;
 } optk_rays_out_t;
 
 /* Detector binning target (optika/sensors/_sensors.py:139-161). Planes are
@@ -445,6 +453,22 @@ OPTK_API int optk_multilayer(const optk_ml_input_t* input,
                     double* reflectivity_s, double* reflectivity_p,
                     double* transmissivity_s, double* transmissivity_p,
                     void* stream);
+
+/* ---- per-ray multilayer efficiency (rows a35) -----------------------------------
+ * MultilayerMirror.efficiency / MultilayerFilm.efficiency (optika/materials/
+ * _multilayers.py:839-866, 908-935) evaluate multilayer_efficiency for every ray.  The
+ * host chains: optk_trace up to the coated surface with `cos_incidence` captured ->
+ * optk_interp of every layer's optical constants at the ray wavelengths
+ * (Chemical.n, optika/chemicals/_chemicals.py:136-142) -> optk_multilayer on the dense
+ * per-ray arrays -> optk_apply_efficiency -> optk_trace of the remaining surfaces. */
+
+/* numpy.interp(x, xp, fp) for n device values x; fp complex as (re, im), im may be NULL
+ * (then out_im may be NULL); xp ascending, m >= 1 entries; ends clamped. */
+OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp, const double* fp_re,
+                const double* fp_im, double* out_re, double* out_im, void* stream);
+
+/* intensity[i] *= (e_s[i] + e_p[i]) / 2   (PolarizationVectorArray.average) */
+OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream);
 
 /* ---- measurement helpers ----------------------------------------------------
  * FP64 DFMA peak micro-benchmark (the roofline denominator that

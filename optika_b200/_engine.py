@@ -64,6 +64,40 @@ class DeviceRays:
     fields: dict
     unvignetted: object
     shape: dict[str, int]
+    cos_incidence: object = None  # -a . n at the last traced surface, when captured
+
+    def last_state(self, axis_position: int | None = None) -> "DeviceRays":
+        """The state after the last surface of an accumulated trace (`[config][surface][rays...]`)."""
+        axes = list(self.shape)
+        k = self._surface_axis
+        n_lead = int(np.prod([self.shape[a] for a in axes[:k]], dtype=np.int64)) if k else 1
+        n_s = self.shape[axes[k]]
+
+        def pick(t):
+            return t.reshape(n_lead, n_s, -1)[:, -1].contiguous().reshape(-1)
+
+        shape_ = {a: n for a, n in self.shape.items() if a != axes[k]}
+        return DeviceRays({f: pick(t) for f, t in self.fields.items()}, pick(self.unvignetted), shape_)
+
+    _surface_axis = 0
+
+    @classmethod
+    def concatenate(cls, parts: list, axis: str) -> "DeviceRays":
+        """Join accumulated traces of consecutive surface ranges along the surface axis."""
+        torch = _torch()
+        first = parts[0]
+        axes = list(first.shape)
+        k = axes.index(axis)
+        n_lead = int(np.prod([first.shape[a] for a in axes[:k]], dtype=np.int64)) if k else 1
+
+        def join(get):
+            return torch.cat([get(p).reshape(n_lead, p.shape[axis], -1) for p in parts], dim=1).reshape(-1)
+
+        shape_ = dict(first.shape)
+        shape_[axis] = sum(p.shape[axis] for p in parts)
+        out = cls({f: join(lambda p, f=f: p.fields[f]) for f in first.fields}, join(lambda p: p.unvignetted), shape_)
+        out._surface_axis = k
+        return out
 
     @property
     def size(self) -> int:
@@ -197,6 +231,12 @@ class CompiledSystem:
     def __init__(self, surfaces, stages: int = L.STAGE_ALL, local_last: bool = False):
         self.surfaces = list(surfaces)
         table, shape_ = _lowering.lower_system(self.surfaces, stages=stages)
+        # surfaces whose efficiency is a per-ray multilayer evaluation (MultilayerMirror /
+        # MultilayerFilm): the trace is chained around them, see `trace`
+        self.coatings = {
+            k: s.material for k, s in enumerate(self.surfaces)
+            if stages == L.STAGE_ALL and hasattr(s.material, "efficiency_device")
+        }
         if local_last:
             # leave the rays in the local frame of the last surface
             n = len(self.surfaces)
@@ -302,6 +342,105 @@ def trace(
     ray_axes_order: list[str] | None = None,
 ):
     """
+    Trace `rays` through `system` on the device (see :func:`_trace`).  Systems with
+    multilayer-coated surfaces (``MultilayerMirror`` / ``MultilayerFilm``, whose efficiency is
+    ``multilayer_efficiency`` evaluated for every ray, ``optika/materials/_multilayers.py:839-935``)
+    are traced in segments: up to and including a coated surface with the cosine of
+    incidence captured, the stack evaluated per ray by ``optk_multilayer`` and multiplied into
+    the intensity, then onwards.  Reverse traces (the stop solver) skip the coatings: they
+    only use positions and directions.
+    """
+    if surf_count is None:
+        surf_count = system.n_surface if surf_step > 0 else surf_begin + 1
+    coated = [k for k in system.coatings if surf_begin <= k < surf_begin + surf_count] if surf_step > 0 else []
+    if not coated:
+        return _trace(
+            system, rays, accumulate, axis, surf_begin, surf_count, surf_step, image, image_frame, write_rays,
+            device, stats, normal, ray_axes_order,
+        )
+    if normal is not None:
+        raise NotImplementedError("caller-supplied normals are not supported together with coated surfaces")
+    device = require_cuda(device)
+    torch = _torch()
+    end = surf_begin + surf_count
+    states, totals = [], dict(n_rays=0, n_unvignetted=0, n_newton_iterations=0, n_binned=0)
+    current, begin = rays, surf_begin
+    for k in sorted(coated) + [None]:
+        last = k is None
+        stop = end if last else k + 1
+        if stop == begin:
+            break
+        out = _trace(
+            system, current, accumulate, axis, begin, stop - begin, 1,
+            image if last else None, image_frame if last else None,
+            write_rays if last else True, device, stats, None,
+            ray_axes_order if current is rays else None, capture_cos=not last,
+        )
+        if stats:
+            out, st = out
+            totals.update(n_rays=st["n_rays"], n_unvignetted=st["n_unvignetted"], n_binned=st["n_binned"])
+            totals["n_newton_iterations"] += st["n_newton_iterations"]
+        if last:
+            if out is not None:
+                states.append(out)
+            break
+        apply_coating(system, k, out, device)
+        states.append(out)
+        current = out.last_state() if accumulate else out
+        begin = stop
+        if begin == end:
+            if image is not None:  # the coated surface was the last one: bin its rays
+                _trace(system, current, False, None, end, 0, 1, image, image_frame, False, device)
+            break
+    result = None
+    if write_rays and states:
+        result = states[-1] if not accumulate else DeviceRays.concatenate(states, axis if axis is not None else "surface")
+    return (result, totals) if stats else result
+
+
+def apply_coating(system: CompiledSystem, k: int, out: "DeviceRays", device) -> None:
+    """Multiply the per-ray multilayer efficiency of surface `k` into the (last) state of `out`."""
+    material = system.coatings[k]
+    n_config = system.n_config
+    n_ray = out.cos_incidence.shape[-1]
+    config_dims = tuple(system.shape.values())
+    for c, cindex in enumerate(np.ndindex(*config_dims) if config_dims else [()]):
+        def last(t):
+            return t.reshape(n_config, -1, n_ray)[c, -1]
+
+        intensity = last(out.fields["intensity"])
+        efficiency = material.efficiency_device(
+            wavelength=last(out.fields["wavelength"]),
+            cos_incidence=out.cos_incidence.reshape(n_config, n_ray)[c],
+            index_refraction=last(out.fields["index_refraction"]),
+            attenuation=last(out.fields["attenuation"]),
+            config_shape=system.shape, cindex=tuple(cindex), device=device,
+        )
+        L.check(
+            L.lib().optk_apply_efficiency(
+                n_ray, intensity.data_ptr(), efficiency[0].data_ptr(), efficiency[1].data_ptr(), _stream_ptr(device)
+            )
+        )
+
+
+def _trace(
+    system: CompiledSystem,
+    rays: RayVectorArray | DeviceRays,
+    accumulate: bool = False,
+    axis: str | None = None,
+    surf_begin: int = 0,
+    surf_count: int | None = None,
+    surf_step: int = 1,
+    image: DeviceImage | None = None,
+    image_frame=None,
+    write_rays: bool = True,
+    device=None,
+    stats: bool = False,
+    normal: na.Cartesian3dVectorArray | None = None,
+    ray_axes_order: list[str] | None = None,
+    capture_cos: bool = False,
+):
+    """
     Trace `rays` through `system` on the device.  Returns :class:`DeviceRays`
     (or ``None`` with ``write_rays=False``), plus a stats dict when requested.
 
@@ -370,6 +509,7 @@ def trace(
             for name, _ in _FIELD_GETTERS
         }
         out_mask = torch.empty((n_config, n_states, n_ray), dtype=torch.uint8, device=device)
+    out_cos = torch.empty((n_config, n_ray), dtype=torch.float64, device=device) if capture_cos else None
 
     stats_dev = torch.zeros(4, dtype=torch.int64, device=device) if stats else None
     frame = None
@@ -423,6 +563,8 @@ def trace(
                 for f, (name, _) in enumerate(_FIELD_GETTERS):
                     rout.field[f] = out_fields[name].data_ptr() + 8 * o
                 rout.unvignetted = out_mask.data_ptr() + o
+            if capture_cos:
+                rout.cos_incidence = out_cos.data_ptr() + 8 * (c * n_ray + i0 * inner)
             im = image.struct(c) if image is not None else None
             L.check(
                 lib.optk_trace(
@@ -442,6 +584,8 @@ def trace(
             shape_[axis if axis is not None else "surface"] = n_states
         shape_.update(ray)
         result = DeviceRays(out_fields, out_mask, shape_)
+        result.cos_incidence = out_cos
+        result._surface_axis = len(config)
     if stats:
         s = stats_dev.cpu().numpy()
         return result, dict(

@@ -45,7 +45,7 @@ FIELDS = (
 )
 
 SAG_FLAT, SAG_SPHERICAL, SAG_CYLINDRICAL, SAG_CONIC, SAG_PARABOLIC, SAG_TOROIDAL = range(6)
-MAT_VACUUM, MAT_MIRROR, MAT_GLASS, MAT_INDEX, MAT_INDEX_MIRROR = range(5)
+MAT_VACUUM, MAT_MIRROR, MAT_GLASS, MAT_INDEX, MAT_INDEX_MIRROR, MAT_PASS = range(6)
 RULING_NONE, RULING_CONSTANT, RULING_POLYNOMIAL, RULING_HOLOGRAPHIC = range(4)
 (
     APERTURE_NONE,
@@ -139,7 +139,7 @@ class RaysIn(C.Structure):
 
 
 class RaysOut(C.Structure):
-    _fields_ = [("field", C.c_void_p * NUM_FIELDS), ("unvignetted", C.c_void_p)]
+    _fields_ = [("field", C.c_void_p * NUM_FIELDS), ("unvignetted", C.c_void_p), ("cos_incidence", C.c_void_p)]
 
 
 class Image(C.Structure):
@@ -244,6 +244,8 @@ SYMBOLS = (
     "optk_trace_grid",
     "optk_bin",
     "optk_multilayer",
+    "optk_interp",
+    "optk_apply_efficiency",
     "optk_measure_fp64_peak",
     "optk_measure_soa_copy",
 )
@@ -285,6 +287,8 @@ def lib() -> C.CDLL:
     L.optk_multilayer.argtypes = [
         C.POINTER(MlInput), i32, C.POINTER(MlLayer), i32, C.POINTER(MlSegment), vp, vp, vp, vp, vp,
     ]
+    L.optk_interp.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.optk_apply_efficiency.argtypes = [i64, vp, vp, vp, vp]
     L.optk_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
     L.optk_measure_soa_copy.argtypes = [i64, C.POINTER(C.c_double), vp]
     for name in SYMBOLS:

@@ -121,6 +121,10 @@ def _lower_material(material, S: L.Surface, shape_, index, keep: list):
         S.material_lut_n, S.material_lut_x, S.material_lut_y = _measured_table(
             material.efficiency_measured, shape_, index, keep
         )
+    elif name == "MultilayerMirror":
+        S.material_kind = L.MAT_MIRROR  # the efficiency is applied by the engine's chained trace
+    elif name == "MultilayerFilm":
+        S.material_kind = L.MAT_PASS
     elif name == "Glass":
         S.material_kind = L.MAT_GLASS
         for k, v in enumerate((material.b1, material.b2, material.b3, material.c1, material.c2, material.c3)):

@@ -84,7 +84,7 @@ int validate_surface(const optk_surface_t& s, int index) {
         set_error("surface %d: unsupported sag kind %d", index, s.sag_kind);
         return OPTK_ERR_UNSUPPORTED;
     }
-    if (s.material_kind < OPTK_MAT_VACUUM || s.material_kind > OPTK_MAT_INDEX_MIRROR) {
+    if (s.material_kind < OPTK_MAT_VACUUM || s.material_kind > OPTK_MAT_PASS) {
         set_error("surface %d: unsupported material kind %d", index, s.material_kind);
         return OPTK_ERR_UNSUPPORTED;
     }
@@ -462,6 +462,23 @@ OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const opt
     rc = launch_trace(P, (cudaStream_t)stream);
     P.from_grid = 0;
     return rc;
+}
+
+OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp, const double* fp_re, const double* fp_im,
+                double* out_re, double* out_im, void* stream) {
+    if (n < 0 || m < 1 || !x || !xp || !fp_re || !out_re || (fp_im && !out_im)) {
+        set_error("optk_interp: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    return launch_interp(n, x, m, xp, fp_re, fp_im, out_re, out_im, (cudaStream_t)stream);
+}
+
+OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream) {
+    if (n < 0 || !intensity || !e_s || !e_p) {
+        set_error("optk_apply_efficiency: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    return launch_apply_efficiency(n, intensity, e_s, e_p, (cudaStream_t)stream);
 }
 
 OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y, const double* dz,

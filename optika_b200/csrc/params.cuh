@@ -80,6 +80,9 @@ struct MultilayerParams {
 };
 
 int launch_multilayer(const MultilayerParams& P, cudaStream_t stream);
+int launch_interp(long long n, const double* x, int m, const double* xp, const double* fp_re, const double* fp_im,
+                  double* out_re, double* out_im, cudaStream_t stream);
+int launch_apply_efficiency(long long n, double* intensity, const double* e_s, const double* e_p, cudaStream_t stream);
 int measure_fp64_peak(double* flops, cudaStream_t stream);
 int measure_soa_copy(long long n_rays, double* gbytes_per_second, cudaStream_t stream);
 

@@ -28,7 +28,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int launch_trace(const TraceParams& P, cudaStream_t stream) {
     if (P.n_rays <= 0) return OPTK_OK;
     const bool from_grid = P.from_grid != 0;
-    bool full = P.in.normal[0] == nullptr;
+    bool full = P.in.normal[0] == nullptr && P.out.cos_incidence == nullptr;
     for (int s = 0; s < P.n_surf; ++s)
         full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM) &&
                P.surf[s].material_kind <= OPTK_MAT_GLASS && P.surf[s].material_efficiency == OPTK_EFF_UNIT &&

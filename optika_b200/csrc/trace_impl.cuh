@@ -724,7 +724,8 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
 // operations of the reference API): AbstractSurface.propagate_rays, optika/surfaces.py:123-198
 // ---------------------------------------------------------------------------
 static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray& r, unsigned& newton_iterations,
-                                                  bool normal_given, double gnx, double gny, double gnz) {
+                                                  bool normal_given, double gnx, double gny, double gnz,
+                                                  double& cos_incidence) {
     const int stages = S.stages;
     const int flags = S.flags;
 
@@ -841,8 +842,11 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
         const double n1 = r.n;
         double n2;
         const bool mirror = S.material_kind == OPTK_MAT_MIRROR || S.material_kind == OPTK_MAT_INDEX_MIRROR;
+        const bool pass = S.material_kind == OPTK_MAT_PASS;  // multilayer film: index and attenuation unchanged
         if (S.material_kind == OPTK_MAT_INDEX || S.material_kind == OPTK_MAT_INDEX_MIRROR) {
             n2 = S.material[0];  // snells_law(direction, n1, n2, normal, is_mirror) unit operation
+        } else if (pass) {
+            n2 = n1;  // _multilayers.py:795-799
         } else if (S.material_kind == OPTK_MAT_GLASS) {
             // optika/materials/_materials.py:428-438
             const double w2 = r.w * r.w;
@@ -856,6 +860,7 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
         // optika/materials/_snells_law.py:341-366
         const double a2 = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
         const double au = r.dx * nx + r.dy * ny + r.dz * nz;
+        cos_incidence = -au;  // -direction @ normal on the effective direction (_multilayers.py:858, 927)
         double ratio = 1.0, inv_r2 = 1.0;
         if (n1 != n2) {  // n1 == n2: r = 1 and 1 / r^2 = 1 exactly, skip the divisions
             ratio = fdiv(n1, n2);
@@ -879,7 +884,7 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
         r.dx = ratio * (r.dx + d * nx);
         r.dy = ratio * (r.dy + d * ny);
         r.dz = ratio * (r.dz + d * nz);
-        if (!mirror) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
+        if (!mirror && !pass) r.att = 0.0;  // _materials.py:101-105, 141-145, 440-444
         r.n = n2;
     }
 
@@ -1201,6 +1206,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         r[k] = Ray{1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, false};  // dummy ray for idle lanes
     }
     unsigned newton_iterations = 0;
+    double cos_incidence = 0.0;  // generic path only: captured at the last traced surface
     const bool normal_given = !FULL && P.in.normal[0] != nullptr;
     double gnx = 0.0, gny = 0.0, gnz = -1.0;
 
@@ -1251,7 +1257,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             if (FULL)
                 surface_full<R>(P.surf[s], r, newton_iterations);
             else
-                surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz);
+                surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz, cos_incidence);
             if (ACC) {
                 const long long o = (long long)s * P.accumulate_stride + i0;
                 bool done = false;
@@ -1283,6 +1289,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             }
         }
     }
+
+    if (!FULL && P.out.cos_incidence && valid[0]) P.out.cos_incidence[i0] = cos_incidence;
 
     if (IMAGE) {
         // AbstractImagingSensor.collect on the final rays in sensor-local coordinates

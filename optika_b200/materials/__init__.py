@@ -1,6 +1,9 @@
 """Optical materials (mirrors ``optika.materials``)."""
 
-from ._materials import AbstractMaterial, Vacuum, AbstractMirror, Mirror, MeasuredMirror, Glass
+from ._materials import (
+    AbstractMaterial, Vacuum, AbstractMirror, Mirror, MeasuredMirror, Glass,
+    AbstractMultilayerMaterial, MultilayerFilm, MultilayerMirror,
+)
 from . import profiles
 from ._layers import AbstractLayer, Layer, LayerSequence, PeriodicLayerSequence
 from ._snells_law import snells_law, snells_law_scalar
@@ -12,6 +15,9 @@ __all__ = [
     "AbstractMirror",
     "Mirror",
     "MeasuredMirror",
+    "AbstractMultilayerMaterial",
+    "MultilayerFilm",
+    "MultilayerMirror",
     "Glass",
     "profiles",
     "AbstractLayer",

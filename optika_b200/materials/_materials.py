@@ -10,10 +10,21 @@ fused CUDA kernel.
 
 from __future__ import annotations
 import dataclasses
+import numpy as np
 from .. import named as na
 from .. import units as u
 
-__all__ = ["AbstractMaterial", "Vacuum", "AbstractMirror", "Mirror", "MeasuredMirror", "Glass"]
+__all__ = [
+    "AbstractMaterial",
+    "Vacuum",
+    "AbstractMirror",
+    "Mirror",
+    "MeasuredMirror",
+    "Glass",
+    "AbstractMultilayerMaterial",
+    "MultilayerFilm",
+    "MultilayerMirror",
+]
 
 
 @dataclasses.dataclass(eq=False)
@@ -128,3 +139,82 @@ class Glass(AbstractMaterial):
         return na.broadcast_shapes(
             *[na.shape(p) for p in (self.b1, self.b2, self.b3, self.c1, self.c2, self.c3)]
         )
+
+
+@dataclasses.dataclass(eq=False)
+class AbstractMultilayerMaterial(AbstractMaterial):
+    """
+    A multilayer coating as a surface material (``optika/materials/_multilayers.py:772-826``):
+    index of refraction and attenuation pass through; the efficiency of every ray is
+    ``multilayer_efficiency`` at its wavelength and cosine of incidence, evaluated on the
+    device (``_engine.trace`` chains the launches around the coated surface).
+    """
+
+    @property
+    def _substrate(self):
+        return None
+
+    @property
+    def _polarization_rows(self) -> tuple[int, int]:
+        raise NotImplementedError
+
+    @property
+    def shape(self) -> dict[str, int]:
+        from ._multilayers import flatten_layers
+
+        flat, _ = flatten_layers(self.layers)
+        parts = [na.shape(layer) for layer in flat]
+        if self._substrate is not None:
+            parts.append(na.shape(self._substrate))
+        return na.broadcast_shapes(*parts)
+
+    def efficiency_device(self, wavelength, cos_incidence, index_refraction, attenuation, config_shape, cindex, device):
+        """Device tensor ``[2, N]``: the s and p efficiencies of N rays (R for mirrors, T for films)."""
+        from ._multilayers import multilayer_efficiency_rays
+
+        out = multilayer_efficiency_rays(
+            wavelength, cos_incidence, index_refraction, attenuation, self.layers, self._substrate,
+            config_shape, cindex, device,
+        )
+        a, b = self._polarization_rows
+        return out[a : b + 1]
+
+    def efficiency(self, rays, normal):
+        """``efficiency(rays, normal)`` of the reference (``:839-866, 908-935``) for host rays."""
+        from ._multilayers import multilayer_efficiency
+
+        wavelength = u.length(rays.wavelength)
+        k = rays.attenuation * wavelength / (4 * np.pi)
+        n = rays.index_refraction + k * 1j
+        reflectivity, transmissivity = multilayer_efficiency(
+            wavelength=wavelength, direction=-(rays.direction @ normal), n=n, layers=self.layers,
+            substrate=self._substrate,
+        )
+        return (reflectivity if self.is_mirror else transmissivity).average
+
+
+@dataclasses.dataclass(eq=False)
+class MultilayerFilm(AbstractMultilayerMaterial):
+    """A free-standing thin-film stack: efficiency = transmissivity (``_multilayers.py:829-895``)."""
+
+    layers: object = None
+
+    @property
+    def _polarization_rows(self) -> tuple[int, int]:
+        return 2, 3  # T_s, T_p
+
+
+@dataclasses.dataclass(eq=False)
+class MultilayerMirror(AbstractMultilayerMaterial, AbstractMirror):
+    """A multilayer-coated mirror: efficiency = reflectivity (``_multilayers.py:898-987``)."""
+
+    layers: object = None
+    substrate: object = None
+
+    @property
+    def _substrate(self):
+        return self.substrate
+
+    @property
+    def _polarization_rows(self) -> tuple[int, int]:
+        return 0, 1  # R_s, R_p

@@ -223,3 +223,104 @@ def multilayer_efficiency(
     reflectivity = PolarizationVectorArray(s=wrap(host[0]), p=wrap(host[1]))
     transmissivity = PolarizationVectorArray(s=wrap(host[2]), p=wrap(host[3]))
     return reflectivity, transmissivity
+
+
+# ---------------------------------------------------------------------------
+# per-ray evaluation: multilayer coatings as surface materials
+# ---------------------------------------------------------------------------
+_nk_device = {}
+
+
+def _nk_table(chemical, device, torch):
+    """The ``.nk`` table of a chemical on the device: (wavelength [mm], n, k), cached."""
+    from .. import chemicals
+
+    key = (chemical.file_nk, str(device))
+    if key not in _nk_device:
+        wp, fp = chemicals._load_table(chemical.file_nk)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)  # noqa: E731
+        _nk_device[key] = (up(wp), up(fp.real), up(fp.imag), len(wp))
+    return _nk_device[key]
+
+
+def multilayer_efficiency_rays(
+    wavelength, cos_incidence, index_refraction, attenuation, layers, substrate, config_shape, cindex, device,
+):
+    """
+    ``multilayer_efficiency`` for N rays whose wavelength, cosine of incidence, ambient index
+    and attenuation are dense device tensors (``optika/materials/_multilayers.py:852-865,
+    921-934``): ``n = index_refraction + i attenuation wavelength / (4 pi)``, the optical
+    constants of every layer interpolated at the ray wavelengths on the device
+    (``optk_interp``), thicknesses / interface widths taken at configuration `cindex`.
+    Returns a device tensor ``[4, N]``: R_s, R_p, T_s, T_p.
+    """
+    from .. import _engine, _lowering
+
+    torch = _engine._torch()
+    lib = L.lib()
+    stream = _engine._stream_ptr(device)
+    n_ray = int(wavelength.numel())
+    if substrate is None:
+        substrate = Layer()
+    flat, segments = flatten_layers(layers)
+    stack = flat + [substrate]
+    if len(stack) > L.ML_MAX_LAYERS:
+        raise ValueError(f"at most {L.ML_MAX_LAYERS - 1} distinct layers are supported")
+    keep = []
+
+    def scalar(value):
+        v = float(_lowering._scalar(u.length(value), config_shape, cindex)) if value is not None else 0.0
+        t = torch.full((1,), v, dtype=torch.float64, device=device)
+        keep.append(t)
+        return t
+
+    inp = L.MlInput()
+    inp.n_axes = 1
+    inp.dims[0] = n_ray
+    inp.wavelength = wavelength.data_ptr()
+    inp.wavelength_stride[0] = 1
+    inp.direction_re = cos_incidence.data_ptr()
+    inp.direction_stride[0] = 1
+    inp.n_re = index_refraction.data_ptr()
+    inp.n_stride[0] = 1
+    if bool((attenuation != 0).any().item()):
+        k = attenuation * wavelength * (1.0 / (4 * np.pi))  # _multilayers.py:853
+        keep.append(k)
+        inp.n_im = k.data_ptr()
+
+    constants = {}
+    table = (L.MlLayer * len(stack))()
+    for j, layer in enumerate(stack):
+        chemical = layer._chemical if layer.chemical is not None else None
+        if chemical is None:
+            table[j].n_re = scalar(1.0).data_ptr()
+        else:
+            key = chemical.file_nk
+            if key not in constants:
+                xp, fr, fi, m = _nk_table(chemical, device, torch)
+                re = torch.empty(n_ray, dtype=torch.float64, device=device)
+                im = torch.empty(n_ray, dtype=torch.float64, device=device)
+                L.check(
+                    lib.optk_interp(
+                        n_ray, wavelength.data_ptr(), m, xp.data_ptr(), fr.data_ptr(), fi.data_ptr(),
+                        re.data_ptr(), im.data_ptr(), stream,
+                    )
+                )
+                constants[key] = (re, im)
+            re, im = constants[key]
+            table[j].n_re, table[j].n_im = re.data_ptr(), im.data_ptr()
+            table[j].n_stride[0] = 1
+        table[j].thickness = scalar(layer.thickness).data_ptr()
+        if layer.interface is not None:
+            table[j].width = scalar(layer.interface.width).data_ptr()
+            table[j].profile_kind = layer.interface.kind
+    segs = (L.MlSegment * max(len(segments), 1))()
+    for g, (first, count, repeat) in enumerate(segments):
+        segs[g].first, segs[g].count, segs[g].repeat = first, count, repeat
+    out = torch.empty((4, n_ray), dtype=torch.float64, device=device)
+    ptrs = [out.data_ptr() + 8 * n_ray * q for q in range(4)]
+    L.check(
+        lib.optk_multilayer(C.byref(inp), len(stack), table, len(segments), segs, ptrs[0], ptrs[1], ptrs[2], ptrs[3], stream)
+    )
+    torch.cuda.current_stream(device).synchronize()  # `keep` and `constants` may be released now
+    return out

@@ -617,12 +617,57 @@ def is_mirror(material) -> bool:
     return _name(material) in ("Mirror", "MeasuredMirror", "MultilayerMirror")
 
 
+def _passes_through(material) -> bool:
+    # AbstractMultilayerMaterial: index and attenuation of the incoming ray (_multilayers.py:795-805)
+    return _name(material) in ("MultilayerMirror", "MultilayerFilm")
+
+
+def _oracle_layers(layers, wavelength):
+    """Product-style layer objects -> the tuples of ``oracle.multilayer`` with ``n`` at the ray wavelengths."""
+    from . import multilayer as orm
+
+    out = []
+    if layers is None:
+        return out
+    if not isinstance(layers, (list, tuple)):
+        layers = [layers]
+    for layer in layers:
+        name = _name(layer)
+        if name == "PeriodicLayerSequence":
+            out.append(("periodic", _oracle_layers(list(layer.layers), wavelength), int(layer.num_periods)))
+        elif name == "LayerSequence":
+            out += _oracle_layers(list(layer.layers), wavelength)
+        else:
+            if layer.chemical is None:
+                n = 1.0 + 0j  # optika/materials/_layers.py:218-227
+            else:
+                chemical = layer._chemical
+                table = orm.load_nk(_nk_file(chemical.file_nk))  # optika/chemicals/_chemicals.py:116-142
+                n = orm.interp_nk(wavelength / 1e-7, table)
+            kind = 0 if layer.interface is None else layer.interface.kind
+            width = 0.0 if layer.interface is None else _f(layer.interface.width)
+            out.append((n, 0.0 if layer.thickness is None else _f(layer.thickness), kind, width))
+    return out
+
+
+def _nk_file(name: str) -> str:
+    import os
+    import pathlib
+
+    roots = [pathlib.Path(p) for p in os.environ.get("OPTIKA_NK_PATH", "").split(os.pathsep) if p]
+    roots.append(pathlib.Path(__file__).resolve().parent.parent / "optika_b200" / "data" / "nk")  # data, not code
+    for root in roots:
+        if (root / name).exists():
+            return str(root / name)
+    raise FileNotFoundError(name)
+
+
 def index_refraction(material, rays: dict):
     name = _name(material)
     if name in ("Vacuum", "IdealSensorMaterial"):
         return np.ones_like(rays["wavelength"])  # _materials.py:95-99
-    if is_mirror(material):
-        return rays["index_refraction"]  # _materials.py:135-139
+    if is_mirror(material) or _passes_through(material):
+        return rays["index_refraction"]  # _materials.py:135-139, _multilayers.py:795-799
     if name == "Glass":
         # optika/materials/_materials.py:428-438
         w2 = np.square(rays["wavelength"])
@@ -636,8 +681,8 @@ def index_refraction(material, rays: dict):
 
 
 def attenuation(material, rays: dict):
-    if is_mirror(material):
-        return rays["attenuation"]  # _materials.py:141-145
+    if is_mirror(material) or _passes_through(material):
+        return rays["attenuation"]  # _materials.py:141-145, _multilayers.py:801-805
     return np.zeros_like(rays["wavelength"])  # _materials.py:101-105, 440-444
 
 
@@ -665,6 +710,20 @@ def material_efficiency(material, rays: dict, normal):
         return _measured_interp(material.efficiency_measured, rays["wavelength"])  # _materials.py:279-305
     if name in ("Vacuum", "IdealSensorMaterial", "Mirror", "Glass", "_FixedIndex"):
         return 1.0  # _materials.py:107-112, 147-152, 446-451
+    if name in ("MultilayerMirror", "MultilayerFilm"):
+        # optika/materials/_multilayers.py:839-866 (film: T.average, substrate None), 908-935 (mirror: R.average)
+        from . import multilayer as orm
+
+        w = rays["wavelength"]
+        k = rays["attenuation"] * w / (4 * np.pi)
+        n = rays["index_refraction"] + k * 1j
+        cos = -(rays["dx"] * normal[0] + rays["dy"] * normal[1] + rays["dz"] * normal[2])
+        stack = _oracle_layers(material.layers, w)
+        substrate = None
+        if name == "MultilayerMirror" and material.substrate is not None:
+            (substrate,) = _oracle_layers([material.substrate], w)
+        r_s, r_p, t_s, t_p = orm.multilayer_efficiency(w, cos, n, stack, substrate)
+        return (r_s + r_p) / 2 if name == "MultilayerMirror" else (t_s + t_p) / 2
     raise NotImplementedError(f"oracle: efficiency of material {name}")
 
 

@@ -1,0 +1,147 @@
+"""
+Multilayer coatings as surface materials: ``MultilayerMirror`` /
+``MultilayerFilm`` efficiency evaluated for every ray inside a system trace
+(``optika/materials/_multilayers.py:839-866, 908-935``; chained launches around the coated
+surface) against the oracle, which applies ``multilayer_efficiency`` to the ray arrays.
+"""
+
+import numpy as np
+import pytest
+
+import optika_b200 as optika
+from optika_b200 import named as na
+from optika_b200 import units as u
+from oracle import raytrace as ora, binning as orb
+
+import configs
+import parity
+
+pytestmark = pytest.mark.gpu
+M = optika.materials
+
+
+def mo_si(num_periods=10, scale=1.0):
+    d, gamma = 6.65 * u.nm * scale, 0.6
+    rough = M.profiles.ErfInterfaceProfile(0.7 * u.nm)
+    return M.MultilayerMirror(
+        layers=[
+            M.Layer("SiO2", thickness=1 * u.nm),
+            M.PeriodicLayerSequence(
+                [M.Layer("Si", thickness=d * gamma, interface=rough), M.Layer("Mo", thickness=d * (1 - gamma), interface=rough)],
+                num_periods=num_periods,
+            ),
+        ],
+        substrate=M.Layer("SiO2", interface=rough),
+    )
+
+
+def coated_grating(material, rulings=None, num_wavelength=6):
+    system = configs.spherical_grating(num_field=4, num_pupil=10, num_wavelength=num_wavelength, num_pixel=512)
+    system.grid_input.wavelength = na.linspace(12.5 * u.nm, 14.5 * u.nm, axis="wavelength", num=num_wavelength)
+    grating = system.surfaces[0]
+    grating.material = material
+    # 13.5 nm leaves this grating where 40 nm leaves the 1200 / mm one: onto the sensor
+    spacing = (13.5 / 40 / 1200) * u.mm
+    grating.rulings = optika.rulings.Rulings(spacing=spacing, diffraction_order=1) if rulings is None else rulings(spacing)
+    return system
+
+
+def states_of(system, out, n_surfaces, order):
+    get = lambda a: na.as_named_array(a).numpy(("surface",) + order).reshape(n_surfaces, -1)  # noqa: E731
+    return dict(
+        wavelength=get(out.wavelength), px=get(out.position.x), py=get(out.position.y), pz=get(out.position.z),
+        dx=get(out.direction.x), dy=get(out.direction.y), dz=get(out.direction.z), intensity=get(out.intensity),
+        attenuation=get(out.attenuation), index_refraction=get(out.index_refraction),
+        unvignetted=get(out.unvignetted).astype(bool),
+    )
+
+
+def test_unit_operation_matches_multilayer_efficiency(cuda_device):
+    mirror = mo_si()
+    n = 300
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=(3, n)) * 0.2
+    d[2] = 1
+    d /= np.linalg.norm(d, axis=0)
+    rays = optika.rays.RayVectorArray(
+        wavelength=na.ScalarArray(rng.uniform(12 * u.nm, 15 * u.nm, n), "ray"),
+        direction=na.Cartesian3dVectorArray(*[na.ScalarArray(c, "ray") for c in d]),
+    )
+    normal = na.Cartesian3dVectorArray(0.0, 0.0, -1.0)
+    got = mirror.efficiency(rays, normal)
+    r0, _ = configs.flatten_rays(rays)
+    want = ora.material_efficiency(mirror, r0, (0.0, 0.0, -1.0))
+    assert np.allclose(got.ndarray, want, rtol=1e-9, atol=1e-15)
+    assert want.max() > 0.1  # the stack is tuned near 13.5 nm
+
+
+@pytest.mark.parametrize("with_profile", [False, True])
+def test_coated_grating_trace(cuda_device, with_profile):
+    rulings = None
+    if with_profile:
+        rulings = lambda spacing: optika.rulings.SawtoothRulings(spacing=spacing, depth=4 * u.nm, diffraction_order=1)  # noqa: E731
+    system = coated_grating(mo_si(), rulings)
+    result = system.raytrace(accumulate=True)
+    _, rays0 = system._input(None, None, None, None, False, False)
+    r0, _ = configs.flatten_rays(rays0)
+    states = ora.accumulate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
+    got = states_of(system, result.outputs, len(system.surfaces_all), tuple(rays0.shape))
+    parity.compare_states(got, states, system.surfaces_all)
+    final = states["intensity"][-1]
+    assert 0 < final.max() < 1 and np.ptp(final) > 1e-4
+    # without accumulate: the same final state
+    last = system.raytrace(accumulate=False).outputs
+    assert np.allclose(
+        na.as_named_array(last.intensity).numpy(tuple(rays0.shape)).reshape(-1), final, rtol=1e-9, atol=1e-15
+    )
+
+
+def test_film_and_mirror_in_one_system_with_a_configuration_axis(cuda_device):
+    scale = na.ScalarArray(np.array([0.97, 1.0, 1.03]), "period")
+    system = coated_grating(mo_si(num_periods=8, scale=scale))
+    film = optika.surfaces.Surface(
+        name="filter",
+        material=M.MultilayerFilm(layers=[M.Layer("Si", thickness=100 * u.nm), M.Layer("SiO2", thickness=2 * u.nm)]),
+        transformation=optika.transformations.Cartesian3dTranslation(z=500 * u.mm),
+    )
+    system.surfaces = [film] + list(system.surfaces)
+    system.invalidate()
+    assert system.shape == {"period": 3}
+    result = system.raytrace(accumulate=True)
+    _, rays0 = system._input(None, None, None, None, False, False)
+    r0, _ = configs.flatten_rays(rays0)
+    flat0 = {k: v.reshape(-1) for k, v in r0.items()}
+    out = result.outputs
+    order = tuple(rays0.shape)
+    n_s = len(system.surfaces_all)
+    totals = []
+    for c in range(3):
+        surfaces = ora.select_config(system.surfaces_all, {"period": c})
+        states = ora.accumulate_rays(surfaces, flat0, extended=True)
+        sel = lambda a: na.as_named_array(a).numpy(("period", "surface") + order)[c].reshape(n_s, -1)  # noqa: E731
+        got = dict(
+            wavelength=sel(out.wavelength), px=sel(out.position.x), py=sel(out.position.y), pz=sel(out.position.z),
+            dx=sel(out.direction.x), dy=sel(out.direction.y), dz=sel(out.direction.z), intensity=sel(out.intensity),
+            attenuation=sel(out.attenuation), index_refraction=sel(out.index_refraction),
+            unvignetted=sel(out.unvignetted).astype(bool),
+        )
+        parity.compare_states(got, states, surfaces)
+        assert np.all(states["intensity"][1] < 1)  # the film absorbs
+        totals.append(states["intensity"][-1].sum())
+    assert len({round(t, 6) for t in totals}) == 3  # the period scale changes the reflectivity
+
+
+def test_fused_image_of_a_coated_system(cuda_device):
+    system = coated_grating(mo_si())
+    edges = na.ScalarArray(np.array([12 * u.nm, 13.5 * u.nm, 15 * u.nm]), "wavelength")
+    image = system.image_rays(edges, counts=True)
+    _, rays0 = system._input(None, None, None, None, False, False)
+    r0, _ = configs.flatten_rays(rays0)
+    out = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
+    local = ora._rays_transform(system.sensor.transformation, out, inverse=True)
+    ex, ey = system.sensor.pixel_edges()
+    want, _, _ = orb.collect(local, edges.ndarray, ex, ey)
+    flux = image.flux.cpu().numpy()
+    assert want.sum() > 0 and np.isclose(flux.sum(), want.sum(), rtol=1e-9)
+    assert (~np.isclose(flux, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
+    assert np.array_equal(image.counts.cpu().numpy(), orb.counts(local, edges.ndarray, ex, ey))
