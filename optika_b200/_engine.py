@@ -398,13 +398,18 @@ def trace(
     return (result, totals) if stats else result
 
 
-def apply_coating(system: CompiledSystem, k: int, out: "DeviceRays", device) -> None:
-    """Multiply the per-ray multilayer efficiency of surface `k` into the (last) state of `out`."""
+def apply_coating(system: CompiledSystem, k: int, out: "DeviceRays", device, config: int | None = None) -> None:
+    """
+    Multiply the per-ray multilayer efficiency of surface `k` into the (last) state of `out`.
+    `out` holds every configuration of the system, or only configuration `config` when given.
+    """
     material = system.coatings[k]
-    n_config = system.n_config
     n_ray = out.cos_incidence.shape[-1]
     config_dims = tuple(system.shape.values())
-    for c, cindex in enumerate(np.ndindex(*config_dims) if config_dims else [()]):
+    indices = list(np.ndindex(*config_dims)) if config_dims else [()]
+    n_config = system.n_config if config is None else 1
+    todo = list(enumerate(indices)) if config is None else [(0, indices[config])]
+    for c, cindex in todo:
         def last(t):
             return t.reshape(n_config, -1, n_ray)[c, -1]
 

@@ -159,11 +159,13 @@ def trace_grid(
     device=None,
     stats: bool = False,
     max_launch: int = _MAX_LAUNCH,
+    capture_cos: bool = False,
 ):
     """
     Generate the rays of `grid` on the device and trace them through configuration
     `config` of `system` (``optk_trace_grid``).  Returns :class:`DeviceRays` over the
     grid's box (or ``None`` with ``write_rays=False``), plus a stats dict when requested.
+    Coated surfaces are NOT applied here (see :func:`trace_grid_coated`).
     """
     torch = _engine._torch()
     device = _engine.require_cuda(device)
@@ -179,6 +181,7 @@ def trace_grid(
             for name, _ in _engine._FIELD_GETTERS
         }
         out_mask = torch.empty((n_states, n_ray), dtype=torch.uint8, device=device)
+    out_cos = torch.empty(n_ray, dtype=torch.float64, device=device) if capture_cos else None
     stats_dev = torch.zeros(4, dtype=torch.int64, device=device) if stats else None
     frame = None
     if image_frame is not None:
@@ -200,6 +203,8 @@ def trace_grid(
             for f, (name, _) in enumerate(_engine._FIELD_GETTERS):
                 rout.field[f] = out_fields[name].data_ptr() + 8 * offset
             rout.unvignetted = out_mask.data_ptr() + offset
+            if capture_cos:
+                rout.cos_incidence = out_cos.data_ptr() + 8 * offset
         g = grid.struct(device, begin, count)
         global LAUNCHES
         LAUNCHES += 1
@@ -221,9 +226,73 @@ def trace_grid(
             shape_[axis if axis is not None else "surface"] = n_states
         shape_.update(grid.shape)
         result = _engine.DeviceRays(out_fields, out_mask, shape_)
+        result.cos_incidence = out_cos
     if stats:
         s = stats_dev.cpu().numpy()
         return result, dict(
             n_rays=int(s[0]), n_unvignetted=int(s[1]), n_newton_iterations=int(s[2]), n_binned=int(s[3])
         )
     return result
+
+
+def _trace_dense(system, config: int, rays, surf_begin: int, surf_count: int, image, write_rays: bool,
+                 capture_cos: bool, device):
+    """One ``optk_trace`` launch of configuration `config` on dense device rays (a link of the coated chain)."""
+    torch = _engine._torch()
+    n = rays.size
+    rin = L.RaysIn()
+    rin.n_axes = 1
+    rin.dims[0] = n
+    for f, (name, _) in enumerate(_engine._FIELD_GETTERS):
+        rin.field[f] = rays.fields[name].data_ptr()
+        rin.stride[f][0] = 1
+    rin.unvignetted = rays.unvignetted.data_ptr()
+    rin.mask_stride[0] = 1
+    rout = L.RaysOut()
+    result = None
+    if write_rays:
+        fields = {name: torch.empty(n, dtype=torch.float64, device=device) for name, _ in _engine._FIELD_GETTERS}
+        mask = torch.empty(n, dtype=torch.uint8, device=device)
+        for f, (name, _) in enumerate(_engine._FIELD_GETTERS):
+            rout.field[f] = fields[name].data_ptr()
+        rout.unvignetted = mask.data_ptr()
+        result = _engine.DeviceRays(fields, mask, dict(rays.shape))
+        if capture_cos:
+            result.cos_incidence = torch.empty(n, dtype=torch.float64, device=device)
+            rout.cos_incidence = result.cos_incidence.data_ptr()
+    im = image.struct(config) if image is not None else None
+    global LAUNCHES
+    LAUNCHES += 1
+    L.check(
+        L.lib().optk_trace(
+            system.handle, config, C.byref(rin), C.byref(rout) if write_rays else None, surf_begin, surf_count, 1,
+            0, 0, C.byref(im) if im is not None else None, None, None, _engine._stream_ptr(device),
+        )
+    )
+    return result
+
+
+def trace_grid_coated(system, grid: RayGrid, config: int, image, device=None, max_rays: int = 1 << 25) -> None:
+    """
+    Fused image of a system with multilayer-coated surfaces: the grid is cut into boxes of
+    at most `max_rays` rays (they do live in HBM between the links of the chain); each box is
+    generated and traced to the first coated surface, the coating evaluated per ray
+    (:func:`optika_b200._engine.apply_coating`), and so on; the last link bins into `image`.
+    """
+    device = _engine.require_cuda(device)
+    coated = sorted(system.coatings)
+    n_surface = system.n_surface
+    for begin, count in _boxes(grid.begin, grid.count, max_rays):
+        sub = grid.sub(begin, count)
+        last = coated[0] + 1 == n_surface
+        rays = trace_grid(system, sub, config=config, surf_count=coated[0] + 1, device=device, capture_cos=True)
+        _engine.apply_coating(system, coated[0], rays, device, config=config)
+        at = coated[0] + 1
+        for k in coated[1:] + [None]:
+            stop = n_surface if k is None else k + 1
+            final = k is None
+            rays = _trace_dense(system, config, rays, at, stop - at, image if final else None, not final, not final, device)
+            if not final:
+                _engine.apply_coating(system, k, rays, device, config=config)
+            at = stop
+        del last

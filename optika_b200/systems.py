@@ -483,7 +483,10 @@ class SequentialSystem(AbstractSequentialSystem):
             if world > 1:
                 axis = 3 if grid.count[3] >= world else (1 if grid.count[1] >= world else 4)
                 grid = grid.shard(rank, world, axis=axis)
-            _grid.trace_grid(compiled, grid, config=c, image=image, write_rays=False, device=device)
+            if compiled.coatings:
+                _grid.trace_grid_coated(compiled, grid, c, image, device=device)
+            else:
+                _grid.trace_grid(compiled, grid, config=c, image=image, write_rays=False, device=device)
         if reduce and world > 1:
             distributed.reduce_image(image)
         planes = image.to_host(pinned=False)

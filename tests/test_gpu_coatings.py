@@ -145,3 +145,35 @@ def test_fused_image_of_a_coated_system(cuda_device):
     assert want.sum() > 0 and np.isclose(flux.sum(), want.sum(), rtol=1e-9)
     assert (~np.isclose(flux, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
     assert np.array_equal(image.counts.cpu().numpy(), orb.counts(local, edges.ndarray, ex, ey))
+
+
+def test_image_of_a_scene_through_a_coated_system(cuda_device):
+    from oracle import grid as og
+
+    system = coated_grating(mo_si())
+    nf = 6
+    field = na.Cartesian2dVectorLinearSpace(
+        -0.05 * u.deg, 0.05 * u.deg, na.Cartesian2dVectorArray("field_x", "field_y"), nf + 1
+    )
+    w = na.linspace(12.8 * u.nm, 14.2 * u.nm, "wavelength", 4)
+    rng = np.random.default_rng(4)
+    scene = na.FunctionArray(
+        inputs=optika.vectors.SpectralPositionalVectorArray(wavelength=w, position=field),
+        outputs=na.ScalarArray(rng.uniform(1e9, 2e9, (3, nf, nf)), ("wavelength", "field_x", "field_y")),
+    )
+    pupil = na.Cartesian2dVectorLinearSpace(
+        -40 * u.mm, 40 * u.mm, na.Cartesian2dVectorArray("pupil_x", "pupil_y"), 15
+    )
+    image = system.image(scene, pupil=pupil, noise=False, normalized_pupil=False, seed=6)
+    v = [w.ndarray, field.x.ndarray, field.y.ndarray, pupil.x.ndarray, pupil.y.ndarray]
+    aw, af, ap = og.cell_area(v, True, False)
+    rays0 = og.input_rays(v, weight_scene=scene.outputs.ndarray * aw[:, None, None] * af[None], weight_pupil=ap, seed=6)
+    out = ora.propagate_rays(system.surfaces_all, rays0, extended=True)
+    local = ora._rays_transform(system.sensor.transformation, out, inverse=True)
+    ex, ey = system.sensor.pixel_edges()
+    want, _, _ = orb.collect(local, np.array([w.ndarray.min(), w.ndarray.max()]), ex, ey)
+    got = image.outputs.ndarray
+    assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
+    assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
+    # the coating matters: far from unit efficiency
+    assert got.sum() < 0.5 * rays0["intensity"].sum()
