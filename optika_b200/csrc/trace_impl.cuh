@@ -355,6 +355,79 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
 }
 
 // ---------------------------------------------------------------------------
+// Out-of-line versions of the rarer element kinds for the streamlined kernel.  The kernel
+// body is instruction-cache bound once the generator, the surface walk and the binning
+// network are all live (ncu: `no_instruction` is the top stall of the fused kernels), so
+// only the kinds the BASELINE systems spend their time in (flat / sphere / parabola,
+// constant rulings, rectangle / circle) are inlined twice (two rays per thread); the rest
+// costs one call per ray and keeps the hot loop short.
+// ---------------------------------------------------------------------------
+// Results come back BY VALUE: a reference parameter would pin the caller's ray state to
+// local memory for the whole kernel.
+struct SagHit {
+    double t, nx, ny, nz;
+    unsigned iterations;
+};
+struct Vec3 {
+    double x, y, z;
+};
+
+static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double qx, double qy, double qz, double vx,
+                                               double vy, double vz) {
+    SagHit hit;
+    hit.iterations = 0;
+    if (S.sag_kind == OPTK_SAG_TOROIDAL) {
+        // AbstractSag.intercept, optika/sags/_abc.py:76-107: root of
+        // f(t) = (o + t u).z - sag(o + t u) from t = 0.  Newton with the analytic
+        // gradient, iterated to convergence (the reference's secant stops at
+        // |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
+        const double c = S.sag[3], rr = S.sag[2];
+        double tt = 0.0;
+        for (int it = 0; it < 64; ++it) {
+            double z, dzdx, dzdy;
+            toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
+            const double f = (qz + vz * tt) - z;
+            const double df = vz - (dzdx * vx + dzdy * vy);
+            const double step = fdiv(f, df);
+            tt -= step;
+            ++hit.iterations;
+            if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(tt)))) break;
+        }
+        hit.t = tt;
+    } else {
+        hit.t = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
+    }
+    double nx, ny, nz;
+    sag_normal(S, qx + vx * hit.t, qy + vy * hit.t, nx, ny, nz);
+    hit.nx = nx;
+    hit.ny = ny;
+    hit.nz = nz;
+    return hit;
+}
+
+static __device__ __noinline__ Vec3 ruling_cold(const optk_surface_t& S, double px, double py, double pz, double nx,
+                                                double ny, double nz) {
+    Vec3 k;
+    double kx, ky, kz;
+    ruling_vector(S, px, py, pz, nx, ny, nz, kx, ky, kz);
+    k.x = kx;
+    k.y = ky;
+    k.z = kz;
+    return k;
+}
+
+static __device__ __noinline__ bool aperture_cold(const optk_surface_t& S, double x, double y, double z) {
+    return aperture_test(S, x, y, z);
+}
+
+static __device__ __noinline__ double glass_index(const optk_surface_t& S, double w) {
+    // optika/materials/_materials.py:428-438
+    const double w2 = w * w;
+    return fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
+                        S.material[2] * fdiv(w2, w2 - S.material[5])));
+}
+
+// ---------------------------------------------------------------------------
 // one surface, FULL operator (every stage, sag normal, no sag transformation): the
 // streamlined path that SequentialSystem.raytrace / propagate_rays / accumulate_rays
 // take.  R rays per thread walk the surface together: every decision that depends
@@ -423,36 +496,17 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             }
             break;
         }
-        default: {
+        default:
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const double qx = r[k].px, qy = r[k].py, qz = r[k].pz;
-                const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
-                if (S.sag_kind == OPTK_SAG_TOROIDAL) {
-                    // AbstractSag.intercept, optika/sags/_abc.py:76-107: root of
-                    // f(t) = (o + t u).z - sag(o + t u) from t = 0.  Newton with the analytic
-                    // gradient, iterated to convergence (the reference's secant stops at
-                    // |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
-                    const double c = S.sag[3], rr = S.sag[2];
-                    double tt = 0.0;
-                    for (int it = 0; it < 64; ++it) {
-                        double z, dzdx, dzdy;
-                        toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
-                        const double f = (qz + vz * tt) - z;
-                        const double df = vz - (dzdx * vx + dzdy * vy);
-                        const double step = fdiv(f, df);
-                        tt -= step;
-                        ++newton_iterations;
-                        if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(tt)))) break;
-                    }
-                    t[k] = tt;
-                } else {
-                    t[k] = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);
-                }
-                sag_normal(S, qx + vx * t[k], qy + vy * t[k], nx[k], ny[k], nz[k]);
+                const SagHit hit = sag_cold(S, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
+                t[k] = hit.t;
+                nx[k] = hit.nx;
+                ny[k] = hit.ny;
+                nz[k] = hit.nz;
+                newton_iterations += hit.iterations;
             }
             break;
-        }
     }
     {
         // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|).
@@ -482,7 +536,18 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             double kx, ky, kz;
-            ruling_vector(S, r[k].px, r[k].py, r[k].pz, nx[k], ny[k], nz[k], kx, ky, kz);
+            if (S.ruling_kind == OPTK_RULING_CONSTANT) {
+                // optika/rulings/_spacing.py:69-74
+                const double c = S.ruling_coeff[0];
+                kx = c * S.ruling_normal[0];
+                ky = c * S.ruling_normal[1];
+                kz = c * S.ruling_normal[2];
+            } else {
+                const Vec3 kappa = ruling_cold(S, r[k].px, r[k].py, r[k].pz, nx[k], ny[k], nz[k]);
+                kx = kappa.x;
+                ky = kappa.y;
+                kz = kappa.z;
+            }
             // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
             const double k2 = kx * kx + ky * ky + kz * kz;
             const double an = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
@@ -505,11 +570,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             if (mirror) {
                 n2[k] = r[k].n;  // _materials.py:135-139
             } else if (glass) {
-                // optika/materials/_materials.py:428-438
-                const double w2 = r[k].w * r[k].w;
-                n2[k] = fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) +
-                                     S.material[1] * fdiv(w2, w2 - S.material[4]) +
-                                     S.material[2] * fdiv(w2, w2 - S.material[5])));
+                n2[k] = glass_index(S, r[k].w);
             } else {
                 n2[k] = 1.0;  // _materials.py:95-99
             }
@@ -555,12 +616,22 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                 m = (m != inverted) || !active;
                 r[k].unv = r[k].unv && m;
             }
+        } else if (S.aperture_kind == OPTK_APERTURE_CIRCULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
+            // optika/apertures/_apertures.py:309 as "x^2 + y^2 <= T" (see aperture_test), inlined
+            const double threshold = S.aperture[3];
+            const bool inverted = flags & OPTK_F_APERTURE_INVERTED, active = flags & OPTK_F_APERTURE_ACTIVE;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                bool m = add_rn(mul_rn(r[k].px, r[k].px), mul_rn(r[k].py, r[k].py)) <= threshold;
+                m = (m != inverted) || !active;
+                r[k].unv = r[k].unv && m;
+            }
         } else {
             const bool angular = flags & OPTK_F_APERTURE_ANGULAR;  // dimensionless aperture: test the direction
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const bool m = angular ? aperture_test(S, r[k].dx, r[k].dy, r[k].dz)
-                                       : aperture_test(S, r[k].px, r[k].py, r[k].pz);
+                const bool m = angular ? aperture_cold(S, r[k].dx, r[k].dy, r[k].dz)
+                                       : aperture_cold(S, r[k].px, r[k].py, r[k].pz);
                 r[k].unv = r[k].unv && m;
             }
         }
