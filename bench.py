@@ -76,7 +76,7 @@ def workload_name(args) -> str:
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port on all host cores, bounded sample
 # ---------------------------------------------------------------------------
-def cpu_reference(args, sample_rays: int, repeats: int = 1) -> dict:
+def cpu_reference(args, sample_rays: int, repeats: int = 3) -> dict:
     """Time ``oracle.raytrace.propagate_rays`` on `sample_rays` rays of the workload, all host threads."""
     import configs
     from concurrent.futures import ThreadPoolExecutor

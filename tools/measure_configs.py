@@ -69,7 +69,7 @@ def trace_config(name, system, n_surfaces, flop_per_ray):
     )
 
 
-def multilayer_config(n_w=4096, n_t=1024, n_c=16, bilayers=30):
+def multilayer_config(n_w=4096, n_t=1024, n_c=256, bilayers=30):
     """cfg 4: 60-layer Mo/Si stack on SiO2, erf interfaces, thickness scaled per configuration."""
     device = torch.device("cuda", 0)
     M = optika.materials
@@ -85,7 +85,7 @@ def multilayer_config(n_w=4096, n_t=1024, n_c=16, bilayers=30):
     out = {}
     for name, layers in (("explicit_60_layers", explicit), ("periodic_30x2", periodic)):
         fn = lambda: M._multilayers.multilayer_efficiency_device(w, cos, 1, layers, substrate, device=device)  # noqa: E731
-        ms = time_ms(fn, warmup=2, reps=3)
+        ms = time_ms(fn, warmup=1, reps=2)
         n = n_w * n_t * n_c
         out[name] = dict(
             evaluations=n,

@@ -84,9 +84,9 @@ def main():
         6, 791,
     ))
     results.append(measure(
-        "cfg5 misaligned telescope, 8 tilts x 128x128 field x 100x100 pupil, 4096^2 sensor",
+        "cfg5 misaligned telescope, 8 tilts x 354x354 field x 100x100 pupil = 1.0e10 rays, 4096^2 sensor",
         configs.misaligned_telescope(6, 12, 4096, 8),
-        [edges(499 * u.nm, 501 * u.nm, 1), edges(-0.1 * deg, 0.1 * deg, 128), edges(-0.1 * deg, 0.1 * deg, 128),
+        [edges(499 * u.nm, 501 * u.nm, 1), edges(-0.1 * deg, 0.1 * deg, 354), edges(-0.1 * deg, 0.1 * deg, 354),
          edges(-40, 40, 100), edges(-40, 40, 100)],
         6, 791, rays_out=False,
     ))
