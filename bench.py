@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rays", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-rays", type=int, default=20_000_000, help="rays of the host-array e2e sample")
     return ap.parse_args()
 
 
@@ -408,6 +409,53 @@ def run_b200(args):
             rays_binned=binned,
         )
 
+    # ---- the seam itself with HOST ray arrays: propagate_rays(surfaces, rays) -> rays, every ray
+    #      crossing PCIe both ways (optk_trace_host: slabs on three streams).  Bounded sample.
+    host_rays = None
+    if not args.no_e2e and rank == 0:
+        n_host = min(n_slab, args.host_rays)
+        pin = lambda dt: torch.empty(n_host, dtype=dt, pin_memory=True)  # noqa: E731
+        hin = {name: pin(torch.float64) for name in _lib.FIELDS}
+        for name in _lib.FIELDS:
+            src = torch.full((n_host,), float(wavelengths[0]), dtype=torch.float64) if name == "wavelength" \
+                else fields_in[name][:n_host].cpu()
+            hin[name].copy_(src)
+        hout = {name: pin(torch.float64) for name in _lib.FIELDS}
+        hmask = pin(torch.uint8)
+        hr, ho = _lib.RaysIn(), _lib.RaysOut()
+        hr.n_axes = 1
+        hr.dims[0] = n_host
+        for f, name in enumerate(_lib.FIELDS):
+            hr.field[f] = hin[name].data_ptr()
+            hr.stride[f][0] = 1
+            ho.field[f] = hout[name].data_ptr()
+        hr.unvignetted = None
+        ho.unvignetted = hmask.data_ptr()
+
+        def host_step():
+            _lib.check(
+                lib.optk_trace_host(
+                    compiled.handle, 0, C.byref(hr), C.byref(ho), 0, N_SURFACES, 1, 0, 0, None, None, None, 1 << 22, 1
+                )
+            )
+
+        host_step()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            host_step()
+        dt_host = (time.perf_counter() - t0) / 2
+        host_rays = dict(
+            value=n_host * N_SURFACES / dt_host,
+            unit=UNIT,
+            rays=n_host,
+            h2d_bytes_per_step=80 * n_host,
+            d2h_bytes_per_step=81 * n_host,
+            pcie_gbytes_per_s_each_way=80 * n_host / dt_host / 1e9,
+            api="optk_trace_host (propagate_rays with host ray arrays in and out, pinned, 4M-ray slabs)",
+            unvignetted_fraction=float(hmask.float().mean().item()),
+        )
+        del hin, hout, hmask
+
     # ---- cfg 2 "generated on chip": stratified random rays drawn, traced and binned inside
     #      one launch per wavelength cell (optk_trace_grid); device-timed, no ray ever in HBM
     on_chip = None
@@ -508,7 +556,7 @@ def run_b200(args):
                 ),
             ),
             cpu_baseline=cpu,
-            e2e=e2e,
+            e2e=dict(e2e, rays_to_host=host_rays) if e2e is not None else None,
             gpu_launches=timed_launches,
             clocks=clocks,
         )
