@@ -45,6 +45,8 @@ struct TraceParams {
 };
 
 int launch_trace(const TraceParams& P, cudaStream_t stream);
+int launch_trace_tma(const TraceParams& P, cudaStream_t stream);  // full tiles of tma_tile_rays() rays only
+int tma_tile_rays();
 int launch_bin(long long n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
                const double* intensity, const uint8_t* unvignetted, const ImageDev& im, cudaStream_t stream);
 

@@ -43,6 +43,36 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     const int rays_per_thread = full ? 2 : 1;
     const int block = 256;
     TraceParams& Q = const_cast<TraceParams&>(P);
+    // HBM-streaming case (dense in, dense out, nothing else): the persistent bulk-copy pipeline
+    // takes the full 512-ray tiles, the ordinary kernel the remainder
+    static const bool use_tma = [] {
+        const char* e = getenv("OPTK_TRACE_TMA");
+        return e ? atoi(e) != 0 : true;
+    }();
+    if (use_tma && vec && !acc && !image && !from_grid && P.n_rays >= 64LL * tma_tile_rays()) {
+        bool all_out = P.out.unvignetted != nullptr;
+        for (int f = 0; f < OPTK_NUM_FIELDS; ++f) all_out = all_out && P.out.field[f] != nullptr;
+        if (all_out) {
+            const long long tile = tma_tile_rays();
+            const long long n_main = P.n_rays / tile * tile, n_tail = P.n_rays - n_main;
+            const long long n_all = P.n_rays;
+            Q.n_rays = n_main;
+            int rc = launch_trace_tma(P, stream);
+            Q.n_rays = n_all;
+            if (rc || n_tail == 0) return rc;
+            static thread_local TraceParams T;
+            T = P;
+            T.n_rays = n_tail;
+            for (int f = 0; f < OPTK_NUM_FIELDS; ++f) {
+                T.in.field[f] += n_main;
+                T.out.field[f] += n_main;
+            }
+            if (T.in.unvignetted) T.in.unvignetted += n_main;
+            T.out.unvignetted += n_main;
+            T.in.dims[0] = n_tail;  // dense: one flat axis is all the kernel looks at
+            return launch_trace(T, stream);
+        }
+    }
     long long grid;
     if (dense || from_grid) {
         const long long threads = (P.n_rays + rays_per_thread - 1) / rays_per_thread;

@@ -542,3 +542,49 @@ def test_host_pointer_entry_point_broadcast_inputs_and_image(cuda_device):
     assert counts.sum() == want_counts.sum() == stats.n_unvignetted
     assert (counts.astype(np.int64) != want_counts).sum() <= 4
     assert np.isclose(flux.sum(), want_counts.sum())
+
+
+def test_streaming_pipeline_kernel_is_bit_identical(cuda_device):
+    """
+    Dense device rays (>= 64 tiles of 512) take the persistent bulk-copy pipeline
+    (trace_tma.cu) plus the ordinary kernel for the remainder; broadcast host grids take the
+    ordinary kernels.  Same arithmetic, so the results must agree bit for bit.
+    """
+    from optika_b200 import sensors
+
+    system = configs.spherical_grating(num_field=40, num_pupil=9, num_wavelength=1, num_pixel=256)
+    _, rays = system._input(None, None, None, None, False, False)
+    order = system._ray_axes_order
+    compiled = system._compiled
+    want, want_stats = _engine.trace(compiled, rays, ray_axes_order=order, stats=True)
+    n = want.size
+    assert n == 129600 and n % 512 == 64  # 253 full tiles and a tail
+    # dense input in the same ray order as `want`
+    first = _engine.trace(compiled, rays, ray_axes_order=order, surf_count=0)
+    got, got_stats = _engine.trace(compiled, first, stats=True)
+    assert got_stats == want_stats
+    for name in want.fields:
+        assert torch_equal(got.fields[name], want.fields[name]), name
+    assert torch_equal(got.unvignetted, want.unvignetted)
+    # and against the oracle
+    r0, _ = configs.flatten_rays(rays)
+    state = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
+    host = got.to_host()
+    axes = tuple(rays.shape)
+    flat = lambda a: na.as_named_array(a).numpy(axes).reshape(-1)  # noqa: E731
+    dev = dict(
+        wavelength=flat(host.wavelength), px=flat(host.position.x), py=flat(host.position.y), pz=flat(host.position.z),
+        dx=flat(host.direction.x), dy=flat(host.direction.y), dz=flat(host.direction.z), intensity=flat(host.intensity),
+        attenuation=flat(host.attenuation), index_refraction=flat(host.index_refraction),
+        unvignetted=flat(host.unvignetted).astype(bool),
+    )
+    parity.compare_states(dev, state)
+
+
+def torch_equal(a, b) -> bool:
+    import torch
+
+    a, b = a.reshape(-1), b.reshape(-1)
+    if a.dtype.is_floating_point:
+        return bool(torch.equal(a.view(torch.int64), b.view(torch.int64)))  # NaNs compare by bit pattern
+    return bool(torch.equal(a, b))
