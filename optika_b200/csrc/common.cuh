@@ -103,8 +103,19 @@ __device__ __forceinline__ double fdiv(double a, double b) {
     e = fma(-b, y, 1.0);
     y = fma(y, e, y);
     const double q0 = a * y;
-    const double q = fma(fma(-b, q0, a), y, q0);
-    return (fabs(q) < OPTK_INF) ? q : a * y0;  // b = 0 / inf, a = inf, NaN: IEEE values from the seed
+    double q = fma(fma(-b, q0, a), y, q0);
+    // b = 0 / inf, a = inf, NaN: the IEEE value comes from the seed.  One predicated multiply
+    // instead of a multiply and a two-word select.
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .f64 t;\n"
+        "abs.f64 t, %0;\n"
+        "setp.lt.f64 p, t, 0d7FF0000000000000;\n"
+        "@!p mul.f64 %0, %1, %2;\n"
+        "}"
+        : "+d"(q)
+        : "d"(a), "d"(y0));
+    return q;
 }
 
 __device__ __forceinline__ double fsqrt(double x) {
@@ -117,9 +128,11 @@ __device__ __forceinline__ double fsqrt(double x) {
     g = fma(g, r, g);
     h = fma(h, r, h);
     g = fma(fma(-g, g, x), h, g);
-    // x = 0 (or subnormal), +inf, negative, NaN
-    const double special = (x >= 0.0) ? ((x == OPTK_INF) ? x : 0.0) : OPTK_NAN;
-    return (fabs(g) < OPTK_INF) ? g : special;
+    // x = 0 (seed inf), +inf (seed 0), negative or NaN (seed NaN) all leave g = NaN.  The
+    // first two have sqrt(x) = x and are exactly the non-negative fixed points of x + x = x;
+    // for the others NaN is the answer.  (A subnormal radicand is flushed by the seed and also
+    // yields NaN; radicands here are sums of squares of millimetre-scale quantities.)
+    return ((x + x == x) && (x >= 0.0)) ? x : g;
 }
 
 // 1 / sqrt(x)

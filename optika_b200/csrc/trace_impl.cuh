@@ -525,8 +525,8 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const double hx = r[k].px + r[k].dx * t[k], hy = r[k].py + r[k].dy * t[k], hz = r[k].pz + r[k].dz * t[k];
-            const bool finite = fabs(hx + hy + hz) <= 1.7976931348623157e308;
-            r[k].intensity = finite ? r[k].intensity : OPTK_NAN;
+            // 0 * (finite) = 0, 0 * (inf or NaN) = NaN: adds the reference's NaN without a select
+            r[k].intensity = fma(0.0, hx + hy + hz, r[k].intensity);
             r[k].px = hx; r[k].py = hy; r[k].pz = hz;
         }
     }

@@ -11,9 +11,9 @@ namespace optk {
 
 namespace {
 
-constexpr int TILE = 512;  // rays per tile = 256 threads x 2 rays
 constexpr int STAGES = 2;
 
+template <int TILE>
 struct alignas(128) TmaStage {
     double field[OPTK_NUM_FIELDS][TILE];
     uint8_t mask[TILE];
@@ -53,7 +53,8 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                  : "memory");
 }
 
-__device__ __forceinline__ void issue_tile(const TraceParams& P, TmaStage* stage, uint64_t* bar, long long tile,
+template <int TILE>
+__device__ __forceinline__ void issue_tile(const TraceParams& P, TmaStage<TILE>* stage, uint64_t* bar, long long tile,
                                            bool has_mask) {
     const unsigned bytes = OPTK_NUM_FIELDS * TILE * 8 + (has_mask ? TILE : 0);
     // the stage was last read through the generic proxy; order those reads before the
@@ -66,10 +67,13 @@ __device__ __forceinline__ void issue_tile(const TraceParams& P, TmaStage* stage
     if (has_mask) bulk_load(stage->mask, P.in.unvignetted + first, TILE, bar);
 }
 
-__global__ void __launch_bounds__(256, 2) trace_kernel_tma(const __grid_constant__ TraceParams P) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) trace_kernel_tma(const __grid_constant__ TraceParams P) {
+    constexpr int TILE = 2 * THREADS;  // two rays per thread
+    typedef TmaStage<TILE> Stage;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TmaStage* stages = reinterpret_cast<TmaStage*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * sizeof(TmaStage));
+    Stage* stages = reinterpret_cast<Stage*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * sizeof(Stage));
     const long long n_tiles = P.n_rays / TILE;
     const bool has_mask = P.in.unvignetted != nullptr;
 
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256, 2) trace_kernel_tma(const __grid_constant
 
         // the two rays of this thread: one 128-bit shared load per field
         Ray r[2];
-        const TmaStage& st = stages[s];
+        const Stage& st = stages[s];
         const int j = 2 * threadIdx.x;
         {
             double2 v;
@@ -144,21 +148,19 @@ __global__ void __launch_bounds__(256, 2) trace_kernel_tma(const __grid_constant
     }
 }
 
-}  // namespace
-
-int tma_tile_rays() { return TILE; }
-
-int launch_trace_tma(const TraceParams& P, cudaStream_t stream) {
+template <int THREADS, int MINB>
+int launch_shape(const TraceParams& P, cudaStream_t stream) {
+    constexpr int TILE = 2 * THREADS;
+    const void* kernel = (const void*)trace_kernel_tma<THREADS, MINB>;
     static int ctas_per_device = 0;
-    const size_t smem = STAGES * sizeof(TmaStage) + STAGES * sizeof(uint64_t);
+    const size_t smem = STAGES * sizeof(TmaStage<TILE>) + STAGES * sizeof(uint64_t);
     if (!ctas_per_device) {
         int device = 0, sms = 0;
         OPTK_CUDA(cudaGetDevice(&device));
         OPTK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        OPTK_CUDA(cudaFuncSetAttribute((const void*)trace_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+        OPTK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        OPTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)trace_kernel_tma, 256, smem));
+        OPTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
         if (per_sm < 1) per_sm = 1;
         ctas_per_device = sms * per_sm;
     }
@@ -166,8 +168,35 @@ int launch_trace_tma(const TraceParams& P, cudaStream_t stream) {
     if (n_tiles == 0) return OPTK_OK;
     const unsigned grid = (unsigned)(n_tiles < ctas_per_device ? n_tiles : ctas_per_device);
     void* args[] = {(void*)&P};
-    OPTK_CUDA(cudaLaunchKernel((const void*)trace_kernel_tma, dim3(grid), dim3(256), args, smem, stream));
+    OPTK_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream));
     return OPTK_OK;
+}
+
+// (threads per CTA, CTAs per SM) of the pipeline; OPTK_TMA_SHAPE selects one of the measured
+// alternatives
+int tma_shape() {
+    static const int shape = [] {
+        const char* e = getenv("OPTK_TMA_SHAPE");
+        const int v = e ? atoi(e) : 3;
+        return (v >= 0 && v <= 3) ? v : 3;
+    }();
+    return shape;
+}
+
+}  // namespace
+
+int tma_tile_rays() {
+    static const int tiles[4] = {512, 384, 256, 256};
+    return tiles[tma_shape()];
+}
+
+int launch_trace_tma(const TraceParams& P, cudaStream_t stream) {
+    switch (tma_shape()) {
+        case 1: return launch_shape<192, 3>(P, stream);
+        case 2: return launch_shape<128, 5>(P, stream);
+        case 3: return launch_shape<128, 4>(P, stream);
+        default: return launch_shape<256, 2>(P, stream);
+    }
 }
 
 }  // namespace optk
