@@ -284,7 +284,6 @@ def trace_grid_coated(system, grid: RayGrid, config: int, image, device=None, ma
     n_surface = system.n_surface
     for begin, count in _boxes(grid.begin, grid.count, max_rays):
         sub = grid.sub(begin, count)
-        last = coated[0] + 1 == n_surface
         rays = trace_grid(system, sub, config=config, surf_count=coated[0] + 1, device=device, capture_cos=True)
         _engine.apply_coating(system, coated[0], rays, device, config=config)
         at = coated[0] + 1
@@ -295,4 +294,3 @@ def trace_grid_coated(system, grid: RayGrid, config: int, image, device=None, ma
             if not final:
                 _engine.apply_coating(system, k, rays, device, config=config)
             at = stop
-        del last

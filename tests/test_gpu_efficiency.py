@@ -118,7 +118,6 @@ def test_system_trace_with_efficiencies(cuda_device):
     r0, _ = configs.flatten_rays(rays0)
     states = ora.accumulate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
     out = result.outputs
-    axes = ("surface",) + tuple(ax for ax in out.shape if ax != "surface")
     order = tuple(rays0.shape)  # the oracle's ray order
     get = lambda a: na.as_named_array(a).numpy(("surface",) + order).reshape(len(system.surfaces_all), -1)  # noqa: E731
     got = dict(
@@ -129,7 +128,6 @@ def test_system_trace_with_efficiencies(cuda_device):
     )
     parity.compare_states(got, states, system.surfaces_all)
     assert 0 < states["intensity"][-1].max() < 1 and np.ptp(states["intensity"][-1]) > 0.01
-    del axes
 
 
 def test_fused_image_with_efficiencies_and_a_configuration_axis(cuda_device):
