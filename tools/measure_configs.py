@@ -69,6 +69,34 @@ def trace_config(name, system, n_surfaces, flop_per_ray):
     )
 
 
+def bin_config():
+    """Kernel 2 alone: 1e8 traced cfg-2 rays resident in HBM -> 2048^2 image (41 B read per ray)."""
+    device = torch.device("cuda", 0)
+    system = configs.spherical_grating(100, 100, 1, 2048)
+    _, rays = system._input(None, None, None, None, False, False)
+    out = _engine.trace(system._compiled_local, rays, ray_axes_order=system._ray_axes_order, device=device)
+    n = out.size
+    ex, ey = system.sensor.pixel_edges()
+    image = _engine.DeviceImage.zeros(np.array([1e-6, 1e-2]), ex, ey, device, moments=True, counts=True)
+    im = image.struct(0)
+    f = out.fields
+    lib = _lib.lib()
+
+    def run():
+        _lib.check(
+            lib.optk_bin(
+                n, f["wavelength"].data_ptr(), f["px"].data_ptr(), f["py"].data_ptr(), f["dz"].data_ptr(),
+                f["intensity"].data_ptr(), out.unvignetted.data_ptr(), C.byref(im), None,
+            )
+        )
+
+    ms = time_ms(run)
+    return dict(
+        config="kernel 2 (optk_bin), cfg2 rays at the sensor", rays=n, ms=ms, rays_per_s=n / (ms * 1e-3),
+        hbm_gbs=41.0 * n / (ms * 1e-3) / 1e9, binned_fraction=float(image.counts.sum().item()) / (8.0 * n),
+    )
+
+
 def multilayer_config(n_w=4096, n_t=1024, n_c=256, bilayers=30):
     """cfg 4: 60-layer Mo/Si stack on SiO2, erf interfaces, thickness scaled per configuration."""
     device = torch.device("cuda", 0)
@@ -104,6 +132,7 @@ def main():
         trace_config("cfg5 misaligned telescope 8 tilts x 64x64 field x 100x100 pupil, 4096^2 sensor",
                      configs.misaligned_telescope(64, 100, 4096, 8), 6, 791)
     )
+    results.append(bin_config())
     results.append(multilayer_config())
     fp64 = C.c_double()
     _lib.check(_lib.lib().optk_measure_fp64_peak(C.byref(fp64), None))
