@@ -50,7 +50,8 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         return e ? atoi(e) != 0 : true;
     }();
     if (use_tma && vec && !acc && !image && !from_grid && P.n_rays >= 64LL * tma_tile_rays()) {
-        bool all_out = P.out.unvignetted != nullptr;
+        // bulk copies need 16-byte aligned sources (the fields are, `vec`; the mask may not be)
+        bool all_out = P.out.unvignetted != nullptr && aligned16(P.in.unvignetted);
         for (int f = 0; f < OPTK_NUM_FIELDS; ++f) all_out = all_out && P.out.field[f] != nullptr;
         if (all_out) {
             const long long tile = tma_tile_rays();
