@@ -566,6 +566,29 @@ def test_streaming_pipeline_kernel_is_bit_identical(cuda_device):
     for name in want.fields:
         assert torch_equal(got.fields[name], want.fields[name]), name
     assert torch_equal(got.unvignetted, want.unvignetted)
+    # the same through the bare C ABI without an input mask (one bulk copy fewer per tile)
+    import torch
+
+    rin, rout = _lib.RaysIn(), _lib.RaysOut()
+    rin.n_axes = 1
+    rin.dims[0] = n
+    outs = {name: torch.empty(n, dtype=torch.float64, device=cuda_device) for name in _lib.FIELDS}
+    mask = torch.empty(n, dtype=torch.uint8, device=cuda_device)
+    for f, name in enumerate(_lib.FIELDS):
+        rin.field[f] = first.fields[name].data_ptr()
+        rin.stride[f][0] = 1
+        rout.field[f] = outs[name].data_ptr()
+    rin.unvignetted = None
+    rout.unvignetted = mask.data_ptr()
+    _lib.check(
+        _lib.lib().optk_trace(
+            compiled.handle, 0, C.byref(rin), C.byref(rout), 0, compiled.n_surface, 1, 0, 0, None, None, None, None
+        )
+    )
+    torch.cuda.synchronize()
+    for name in want.fields:
+        assert torch_equal(outs[name], want.fields[name]), name
+    assert torch_equal(mask, want.unvignetted)
     # and against the oracle
     r0, _ = configs.flatten_rays(rays)
     state = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
