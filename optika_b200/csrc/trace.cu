@@ -45,10 +45,28 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     TraceParams& Q = const_cast<TraceParams&>(P);
     // HBM-streaming case (dense in, dense out, nothing else): the persistent bulk-copy pipeline
     // takes the full 512-ray tiles, the ordinary kernel the remainder
-    static const bool use_tma = [] {
+    // The pipeline runs 16 warps per SM (114 registers, no spills), the direct-load kernel 24:
+    // the pipeline wins while the walk is HBM-bound (cfg 2: 2.8 vs 3.2 ms per 1e8 rays) and
+    // loses once it is FP64/issue-bound (cfg 1, six surfaces: 4.5 vs 4.2 ms; cfg 3, toroid:
+    // 9.7 vs 8.2 ms).  Rough per-ray cost in units of a flat surface decides; OPTK_TRACE_TMA
+    // = 0 / 1 forces the choice.
+    static const int tma_mode = [] {
         const char* e = getenv("OPTK_TRACE_TMA");
-        return e ? atoi(e) != 0 : true;
+        return e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }();
+    bool use_tma = tma_mode == 1;
+    if (tma_mode < 0) {
+        double cost = 0.0;
+        for (int s = 0; s < P.n_surf; ++s) {
+            const optk_surface_t& S = P.surf[s];
+            cost += S.sag_kind == OPTK_SAG_FLAT ? 1.0
+                    : (S.sag_kind == OPTK_SAG_SPHERICAL || S.sag_kind == OPTK_SAG_PARABOLIC) ? 1.3
+                    : S.sag_kind == OPTK_SAG_TOROIDAL ? 4.0 : 2.0;
+            if (S.ruling_kind > OPTK_RULING_CONSTANT) cost += 1.0;
+            if (S.material_kind == OPTK_MAT_GLASS) cost += 0.5;
+        }
+        use_tma = cost <= 4.5;
+    }
     if (use_tma && vec && !acc && !image && !from_grid && P.n_rays >= 64LL * tma_tile_rays()) {
         // bulk copies need 16-byte aligned sources (the fields are, `vec`; the mask may not be)
         bool all_out = P.out.unvignetted != nullptr && aligned16(P.in.unvignetted);
