@@ -38,7 +38,8 @@ struct TraceParams {
     // on-device ray generator (optk_trace_grid): `in` then only carries n_axes = 5 and
     // dims = grid.count (the sub-box), addressed in two levels like a broadcast view
     int32_t from_grid;
-    int32_t pad4;
+    int32_t has_out;  // any output pointer is set (fused image calls usually write no rays)
+    FastDiv div_tiles;  // divisor tiles_per_outer
     optk_grid_t grid;
     unsigned long long cell_stride[5];  // C-order strides of the whole grid n[] (Philox counter)
     optk_surface_t surf[OPTK_MAX_SURFACES];

@@ -115,6 +115,10 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         Q.tiles_per_outer = (inner + per_tile - 1) / per_tile;
         grid = (inner > 0 ? P.n_rays / inner : 0) * Q.tiles_per_outer;
     }
+    Q.div_tiles = make_fastdiv((uint32_t)(Q.tiles_per_outer > 0 ? Q.tiles_per_outer : 1));
+    Q.has_out = (P.out.unvignetted != nullptr || P.out.cos_incidence != nullptr) ? 1 : 0;
+    for (int f = 0; f < OPTK_NUM_FIELDS; ++f)
+        if (P.out.field[f]) Q.has_out = 1;
     if (grid > 0x7fffffffLL) {
         set_error("optk_trace: too many rays for one launch (%lld)", P.n_rays);
         return OPTK_ERR_INVALID;

@@ -1005,6 +1005,10 @@ template <int R, bool DENSE>
 __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, long long j0, const long long* base,
                                           const bool (&valid)[R], Ray (&r)[R], bool normal_given, double& gnx,
                                           double& gny, double& gnz) {
+    long long off[OPTK_NUM_FIELDS + 1];
+    long long offn[3] = {0, 0, 0};
+    uint32_t last_index = 0;
+    bool have_offsets = false;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         if (!valid[k]) continue;
@@ -1028,11 +1032,21 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
             }
         } else {
             // broadcast view: the CTA-level offsets (leading axes) are in `base`, the thread adds
-            // the trailing axes of its own ray
-            long long off[OPTK_NUM_FIELDS + 1];
+            // the trailing axes of its own ray.  `off`, `offn` and `last_index` live across the
+            // rays of the thread: the second ray is the first one's neighbour along the last axis
+            // and only adds that axis' strides unless it wraps.
+            const int last = P.in.n_axes - 1;
+            if (k > 0 && have_offsets && !normal_given && last_index + 1u < P.div[last].divisor) {
+                ++last_index;
+#pragma unroll
+                for (int f = 0; f < OPTK_NUM_FIELDS; ++f) off[f] += P.in.stride[f][last];
+                off[OPTK_NUM_FIELDS] += P.in.mask_stride[last];
+            } else {
 #pragma unroll
             for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) off[f] = base[f];
-            long long offn[3] = {base[OPTK_NUM_FIELDS + 1], base[OPTK_NUM_FIELDS + 2], base[OPTK_NUM_FIELDS + 3]};
+            offn[0] = base[OPTK_NUM_FIELDS + 1];
+            offn[1] = base[OPTK_NUM_FIELDS + 2];
+            offn[2] = base[OPTK_NUM_FIELDS + 3];
             uint32_t rem = (uint32_t)(j0 + k + P.index_offset);
             const int first = P.in.n_axes - P.n_inner_axes;
             if (P.offsets32 && !normal_given) {
@@ -1048,6 +1062,7 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
                         divmod(rem, P.div[a], q, idx);
                         rem = q;
                     }
+                    if (a == last) last_index = idx;
 #pragma unroll
                     for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) o32[f] += (int)idx * P.stride32[f][a];
                 }
@@ -1062,6 +1077,7 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
                     divmod(rem, P.div[a], q, idx);
                     rem = q;
                 }
+                if (a == last) last_index = idx;
 #pragma unroll
                 for (int f = 0; f < OPTK_NUM_FIELDS; ++f) off[f] += (long long)idx * P.in.stride[f][a];
                 off[OPTK_NUM_FIELDS] += (long long)idx * P.in.mask_stride[a];
@@ -1069,6 +1085,8 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
 #pragma unroll
                     for (int c = 0; c < 3; ++c) offn[c] += (long long)idx * P.in.normal_stride[c][a];
                 }
+            }
+            have_offsets = P.n_inner_axes > 0;
             }
             if (normal_given) {
                 gnx = __ldg(P.in.normal[0] + offn[0]);
@@ -1243,8 +1261,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     if (DENSE || GRID) {
         i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
     } else {
-        const long long outer = blockIdx.x / P.tiles_per_outer;
-        const long long tile = blockIdx.x - outer * P.tiles_per_outer;
+        uint32_t outer32, tile32;
+        divmod(blockIdx.x, P.div_tiles, outer32, tile32);  // blockIdx.x / tiles_per_outer without a 64-bit division
+        const long long outer = outer32, tile = tile32;
         j0 = (tile * blockDim.x + threadIdx.x) * R;
         i0 = outer * P.inner_size + j0;
         limit = (outer + 1) * P.inner_size;
@@ -1329,7 +1348,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                 surface_full<R>(P.surf[s], r, newton_iterations);
             else
                 surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz, cos_incidence);
-            if (ACC) {
+            if (ACC && P.has_out) {
                 const long long o = (long long)s * P.accumulate_stride + i0;
                 bool done = false;
                 if constexpr (R == 2 && VEC) {
@@ -1345,7 +1364,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                 }
             }
         }
-        if (!ACC) {
+        if (!ACC && P.has_out) {  // one uniform test instead of eleven null checks per ray
             bool done = false;
             if constexpr (R == 2 && VEC) {
                 if (pair) {
