@@ -179,11 +179,18 @@ __device__ __forceinline__ double fexp(double x) {
     const double kf = kd - shifter;
     double r = fma(kf, kExp[14], xc);  // -ln2 hi
     r = fma(kf, kExp[15], r);          // -ln2 lo
-    // coefficients come from the constant bank (an operand of the DFMA itself); as immediates
-    // every one of them costs two UMOV issue slots
-    double p = kExp[0];
-#pragma unroll
-    for (int i = 1; i < 14; ++i) p = fma(p, r, kExp[i]);
+    // Coefficients come from the constant bank (an operand of the DFMA itself).  Estrin's
+    // scheme: 16 operations in a dependency chain of depth 5 instead of Horner's 13 dependent
+    // FMAs -- the multilayer kernel is bound by fp64 latency ("wait" stalls), not by the pipe.
+    // a_j (degree j) = kExp[13 - j].
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double q0 = fma(kExp[12], r, kExp[13]), q1 = fma(kExp[10], r, kExp[11]);
+    const double q2 = fma(kExp[8], r, kExp[9]), q3 = fma(kExp[6], r, kExp[7]);
+    const double q4 = fma(kExp[4], r, kExp[5]), q5 = fma(kExp[2], r, kExp[3]);
+    const double q6 = fma(kExp[0], r, kExp[1]);
+    const double u0 = fma(q1, r2, q0), u1 = fma(q3, r2, q2), u2 = fma(q5, r2, q4);
+    const double t0 = fma(u1, r4, u0), t1 = fma(q6, r4, u2);
+    double p = fma(t1, r8, t0);
     // scale by 2^k in two halves so that k in [-1010, 1010] never leaves the normal range midway
     const int k1 = k >> 1, k2 = k - k1;
     const double s1 = __hiloint2double((k1 + 1023) << 20, 0), s2 = __hiloint2double((k2 + 1023) << 20, 0);
