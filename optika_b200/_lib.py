@@ -9,6 +9,7 @@ Status codes map to the exceptions the reference raises for the same mistakes
 
 from __future__ import annotations
 import ctypes as C
+import os
 import pathlib
 
 __all__ = [
@@ -229,7 +230,8 @@ class OptkError(RuntimeError):
     pass
 
 
-_PATH = pathlib.Path(__file__).parent / "liboptk.so"
+# OPTK_LIBRARY points experiments at another build of the same ABI
+_PATH = pathlib.Path(os.environ.get("OPTK_LIBRARY") or pathlib.Path(__file__).parent / "liboptk.so")
 
 # every symbol include/optk.h declares
 SYMBOLS = (

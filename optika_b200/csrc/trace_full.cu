@@ -5,7 +5,7 @@ namespace optk {
 
 trace_kernel_t select_full_kernel(bool dense, bool vec, bool acc, bool image) {
 #define OPTK_PICK(D, V, A, I) \
-    if (dense == D && vec == V && acc == A && image == I) return (trace_kernel_t)trace_kernel<3, 2, true, D, V, A, I>;
+    if (dense == D && vec == V && acc == A && image == I) return (trace_kernel_t)trace_kernel<OPTK_FULL_MINB, 2, true, D, V, A, I>;
     OPTK_PICK(true, true, false, false)
     OPTK_PICK(true, true, true, false)
     OPTK_PICK(true, true, false, true)

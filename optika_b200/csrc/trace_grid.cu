@@ -8,7 +8,7 @@ namespace optk {
 trace_kernel_t select_grid_kernel(bool full, bool acc, bool image) {
 #define OPTK_PICK(A, I)                                                                             \
     if (acc == A && image == I)                                                                     \
-        return full ? (trace_kernel_t)trace_kernel<3, 2, true, false, false, A, I, true>            \
+        return full ? (trace_kernel_t)trace_kernel<OPTK_FULL_MINB, 2, true, false, false, A, I, true>            \
                     : (trace_kernel_t)trace_kernel<4, 1, false, false, false, A, I, true>;
     OPTK_PICK(false, false)
     OPTK_PICK(true, false)

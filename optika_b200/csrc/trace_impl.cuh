@@ -9,6 +9,11 @@
 // store per surface when accumulating), and optionally never leave the chip:
 // the final rays can be binned straight into the detector image.
 #pragma once
+// resident CTAs per SM the streamlined (two rays per thread) kernels are compiled for: 3 -> 80
+// registers with ~190 B of spills, 24 warps; 2 -> up to 128 registers, no spills, 16 warps
+#ifndef OPTK_FULL_MINB
+#define OPTK_FULL_MINB 3
+#endif
 #include "common.cuh"
 #include "bin.cuh"
 #include "params.cuh"
