@@ -339,12 +339,12 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
                 const double x1 = S.vertices_x[i], y1 = S.vertices_y[i];
                 const double ex = sub_rn(x1, x0), ey = sub_rn(y1, y0);
                 const double cross = sub_rn(mul_rn(ex, sub_rn(y, y0)), mul_rn(ey, sub_rn(x, x0)));
-                const bool within = (fmin(x0, x1) <= x) && (x <= fmax(x0, x1)) && (fmin(y0, y1) <= y) &&
-                                    (y <= fmax(y0, y1));
-                on_edge |= (cross == 0.0) && within;
+                if (cross == 0.0) {  // on the supporting line (rare): is it on the segment?
+                    on_edge |= (fmin(x0, x1) <= x) && (x <= fmax(x0, x1)) && (fmin(y0, y1) <= y) && (y <= fmax(y0, y1));
+                }
+                // left of a straddling edge  <=>  the cross product has the sign of the edge's dy
                 const bool straddles = (y0 > y) != (y1 > y);
-                const double x_cross = add_rn(x0, mul_rn(sub_rn(y, y0), ex) / ey);
-                inside ^= straddles && (x < x_cross);
+                inside ^= straddles && ((cross > 0.0) == (ey > 0.0));
                 x0 = x1;
                 y0 = y1;
             }
@@ -387,6 +387,10 @@ static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double q
         // gradient, iterated to convergence (the reference's secant stops at
         // |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
         const double c = S.sag[3], rr = S.sag[2];
+        // Newton converges quadratically: e' ~ |f'' / (2 f')| e^2 with |f''| bounded by a few
+        // times the larger curvature.  Once the step just taken predicts a next step below the
+        // tolerance, that next evaluation (two square roots, two divisions) is skipped.
+        const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));
         double tt = 0.0;
         for (int it = 0; it < 64; ++it) {
             double z, dzdx, dzdy;
@@ -396,7 +400,9 @@ static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double q
             const double step = fdiv(f, df);
             tt -= step;
             ++hit.iterations;
-            if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(tt)))) break;
+            const double tolerance = 1e-13 * fmax(1.0, fabs(tt));
+            if (!(fabs(step) > tolerance)) break;
+            if (step * step * curvature <= tolerance * fabs(df)) break;
         }
         hit.t = tt;
     } else {
@@ -833,6 +839,7 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
             // analytic gradient, iterated to convergence (the reference's secant
             // stops at |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
             const double c = S.sag[3], rr = S.sag[2];
+            const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));  // see sag_cold
             t = 0.0;
             for (int it = 0; it < 64; ++it) {
                 double z, dzdx, dzdy;
@@ -842,7 +849,9 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
                 const double step = fdiv(f, df);
                 t -= step;
                 ++newton_iterations;
-                if (!(fabs(step) > 1e-13 * fmax(1.0, fabs(t)))) break;
+                const double tolerance = 1e-13 * fmax(1.0, fabs(t));
+                if (!(fabs(step) > tolerance)) break;
+                if (step * step * curvature <= tolerance * fabs(df)) break;
             }
         } else {
             t = sag_intercept_closed(S, qx, qy, qz, vx, vy, vz);

@@ -832,10 +832,10 @@ def point_in_polygon(x, y, vx, vy):
                 & (np.minimum(y0, y1) <= y) & (y <= np.maximum(y0, y1))
             )
             on_edge |= (cross == 0) & within
-            # half-open crossing rule
+            # half-open crossing rule: the point is left of the edge, x < x0 + (y - y0) (x1 - x0) / (y1 - y0),
+            # written without the division: the sign of the same cross product, oriented by the edge
             straddles = (y0 > y) != (y1 > y)
-            x_cross = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
-            inside ^= straddles & (x < x_cross)
+            inside ^= straddles & ((cross > 0) == (y1 > y0))
     return inside | on_edge
 
 
