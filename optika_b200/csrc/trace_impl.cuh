@@ -391,7 +391,10 @@ static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double q
         // times the larger curvature.  Once the step just taken predicts a next step below the
         // tolerance, that next evaluation (two square roots, two divisions) is skipped.
         const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));
-        double tt = 0.0;
+        // The reference starts at t = 0, and its first step lands next to the vertex plane.  Start
+        // there directly (one division instead of a toroid evaluation); same root.
+        double tt = fdiv(-qz, vz);
+        if (!(fabs(tt) < OPTK_INF)) tt = 0.0;
         for (int it = 0; it < 64; ++it) {
             double z, dzdx, dzdy;
             toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
@@ -840,7 +843,8 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
             // stops at |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
             const double c = S.sag[3], rr = S.sag[2];
             const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));  // see sag_cold
-            t = 0.0;
+            t = fdiv(-r.pz, r.dz);
+            if (!(fabs(t) < OPTK_INF)) t = 0.0;
             for (int it = 0; it < 64; ++it) {
                 double z, dzdx, dzdy;
                 toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
