@@ -54,19 +54,21 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         const char* e = getenv("OPTK_TRACE_TMA");
         return e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }();
-    bool use_tma = tma_mode == 1;
-    if (tma_mode < 0) {
-        double cost = 0.0;
-        for (int s = 0; s < P.n_surf; ++s) {
-            const optk_surface_t& S = P.surf[s];
-            cost += S.sag_kind == OPTK_SAG_FLAT ? 1.0
-                    : (S.sag_kind == OPTK_SAG_SPHERICAL || S.sag_kind == OPTK_SAG_PARABOLIC) ? 1.3
-                    : S.sag_kind == OPTK_SAG_TOROIDAL ? 4.0 : 2.0;
-            if (S.ruling_kind > OPTK_RULING_CONSTANT) cost += 1.0;
-            if (S.material_kind == OPTK_MAT_GLASS) cost += 0.5;
-        }
-        use_tma = cost <= 4.5;
+    // rough per-ray cost of the surface list in units of a flat surface
+    double cost = 0.0;
+    bool out_of_line = false;  // a sag or ruling kind that is a call in the streamlined kernels
+    for (int s = 0; s < P.n_surf; ++s) {
+        const optk_surface_t& S = P.surf[s];
+        out_of_line = out_of_line || S.ruling_kind > OPTK_RULING_CONSTANT ||
+                      !(S.sag_kind == OPTK_SAG_FLAT || S.sag_kind == OPTK_SAG_SPHERICAL || S.sag_kind == OPTK_SAG_PARABOLIC);
+        cost += S.sag_kind == OPTK_SAG_FLAT ? 1.0
+                : (S.sag_kind == OPTK_SAG_SPHERICAL || S.sag_kind == OPTK_SAG_PARABOLIC) ? 1.3
+                : S.sag_kind == OPTK_SAG_TOROIDAL ? 4.0 : 2.0;
+        if (S.ruling_kind > OPTK_RULING_CONSTANT) cost += 1.0;
+        if (S.material_kind == OPTK_MAT_GLASS) cost += 0.5;
     }
+    const bool heavy = cost > 4.5;
+    const bool use_tma = tma_mode == 1 || (tma_mode < 0 && !heavy);
     if (use_tma && vec && !acc && !image && !from_grid && P.n_rays >= 64LL * tma_tile_rays()) {
         // bulk copies need 16-byte aligned sources (the fields are, `vec`; the mask may not be)
         bool all_out = P.out.unvignetted != nullptr && aligned16(P.in.unvignetted);
@@ -124,7 +126,15 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         return OPTK_ERR_INVALID;
     }
     trace_kernel_t kernel;
-    if (from_grid)
+    static const int heavy_mode = [] {
+        const char* e = getenv("OPTK_TRACE_HEAVY");
+        return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }();
+    // (with calls in the walk the extra registers do not pay: cfg 3 fused 9.8 -> 11.1 ms)
+    const bool use_heavy = full && from_grid && image && (heavy_mode == 1 || (heavy_mode < 0 && heavy && !out_of_line));
+    if (use_heavy)
+        kernel = select_heavy_kernel(from_grid, acc, image);
+    else if (from_grid)
         kernel = select_grid_kernel(full, acc, image);
     else if (full)
         kernel = select_full_kernel(dense, vec, acc, image);

@@ -1461,5 +1461,6 @@ typedef void (*trace_kernel_t)(const TraceParams);
 trace_kernel_t select_full_kernel(bool dense, bool vec, bool acc, bool image);
 trace_kernel_t select_generic_kernel(bool dense, bool acc, bool image);
 trace_kernel_t select_grid_kernel(bool full, bool acc, bool image);
+trace_kernel_t select_heavy_kernel(bool grid, bool acc, bool image);  // trace_heavy.cu
 
 }  // namespace optk
