@@ -31,11 +31,14 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     bool full = P.in.normal[0] == nullptr && P.out.cos_incidence == nullptr;
     for (int s = 0; s < P.n_surf; ++s)
         full = full && (P.surf[s].stages == OPTK_STAGE_ALL) && !(P.surf[s].flags & OPTK_F_SAG_TRANSFORM) &&
-               P.surf[s].material_kind <= OPTK_MAT_GLASS && P.surf[s].material_efficiency == OPTK_EFF_UNIT &&
-               P.surf[s].ruling_profile == OPTK_PROFILE_IDEAL;
+               P.surf[s].material_kind <= OPTK_MAT_GLASS;
+    bool efficiency = false;  // measured mirrors / rulings, groove profiles: the EFF instantiations
+    for (int s = 0; s < P.n_surf; ++s)
+        efficiency = efficiency || P.surf[s].material_efficiency != OPTK_EFF_UNIT ||
+                     P.surf[s].ruling_profile != OPTK_PROFILE_IDEAL;
     const bool dense = P.dense_in != 0 && !from_grid, acc = P.accumulate != 0, image = P.has_image != 0;
     // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
-    bool vec = full && dense && !from_grid && (P.accumulate_stride % 2 == 0);
+    bool vec = full && dense && !from_grid && !efficiency && (P.accumulate_stride % 2 == 0);
     for (int f = 0; f < OPTK_NUM_FIELDS && vec; ++f)
         vec = aligned16(P.in.field[f]) && aligned16(P.out.field[f]);
     if (vec && P.in.unvignetted) vec = (reinterpret_cast<uintptr_t>(P.in.unvignetted) & 1u) == 0;
@@ -132,7 +135,9 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     }();
     // (with calls in the walk the extra registers do not pay: cfg 3 fused 9.8 -> 11.1 ms)
     const bool use_heavy = full && from_grid && image && (heavy_mode == 1 || (heavy_mode < 0 && heavy && !out_of_line));
-    if (use_heavy)
+    if (full && efficiency)
+        kernel = select_efficiency_kernel(from_grid, dense, acc, image);
+    else if (use_heavy)
         kernel = select_heavy_kernel(from_grid, acc, image);
     else if (from_grid)
         kernel = select_grid_kernel(full, acc, image);

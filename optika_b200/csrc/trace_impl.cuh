@@ -441,6 +441,10 @@ static __device__ __noinline__ double glass_index(const optk_surface_t& S, doubl
                         S.material[2] * fdiv(w2, w2 - S.material[5])));
 }
 
+static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S, double w, double px, double py,
+                                                         double pz, double dx, double dy, double dz, double nx,
+                                                         double ny, double nz);
+
 // ---------------------------------------------------------------------------
 // one surface, FULL operator (every stage, sag normal, no sag transformation): the
 // streamlined path that SequentialSystem.raytrace / propagate_rays / accumulate_rays
@@ -450,7 +454,7 @@ static __device__ __noinline__ double glass_index(const optk_surface_t& S, doubl
 // parallelism for the long fp64 dependency chains).
 // AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
-template <int R>
+template <int R, bool EFF = false>
 __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations) {
     const int flags = S.flags;
 
@@ -571,6 +575,18 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             r[k].dy += f * ky;
             r[k].dz += f * kz;
         }
+    }
+
+    // efficiency = material.efficiency(rays_1, normal) [* rulings.efficiency(rays_1, normal)] on the
+    // effective direction and the incoming wavelength (surfaces.py:175-179); a call, and only for
+    // measured mirrors / rulings and groove profiles
+    // measured mirrors / rulings and groove profiles (kernels instantiated with EFF, trace_eff.cu:
+    // the call site costs the unit-efficiency kernels 2-3 % even when it is never taken)
+    if (EFF && (S.material_efficiency != OPTK_EFF_UNIT || S.ruling_profile != OPTK_PROFILE_IDEAL)) {
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            r[k].intensity *= surface_efficiency(S, r[k].w, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz,
+                                                 nx[k], ny[k], nz[k]);
     }
 
     // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
@@ -738,8 +754,11 @@ static __device__ __noinline__ double bessel_jn(int n, double x) {
 
 // material.efficiency(rays_1, normal) * rulings.efficiency(rays_1, normal): `r` carries the
 // effective direction (after incident_effective) and the wavelength before the rescale.
-static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S, const Ray& r, double nx, double ny,
-                                                         double nz) {
+static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S, double w_, double px_, double py_,
+                                                         double pz_, double dx_, double dy_, double dz_, double nx,
+                                                         double ny, double nz) {
+    // (arguments by value: a reference to the ray would pin the caller's state to local memory)
+    const struct { double w, px, py, pz, dx, dy, dz; } r = {w_, px_, py_, pz_, dx_, dy_, dz_};
     double eff = 1.0;
     if (S.material_efficiency == OPTK_EFF_LUT) eff = lut_interp(S.material_lut_x, S.material_lut_y, S.material_lut_n, r.w);
     const int profile = S.ruling_profile;
@@ -922,7 +941,7 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
     const bool has_efficiency = S.material_efficiency != OPTK_EFF_UNIT || S.ruling_profile != OPTK_PROFILE_IDEAL;
     double efficiency = 1.0;
     if (has_efficiency && (stages & (OPTK_STAGE_REFRACT | OPTK_STAGE_EFFICIENCY_OUT)))
-        efficiency = surface_efficiency(S, r, nx, ny, nz);
+        efficiency = surface_efficiency(S, r.w, r.px, r.py, r.pz, r.dx, r.dy, r.dz, nx, ny, nz);
     if (stages & OPTK_STAGE_EFFICIENCY_OUT) r.intensity = efficiency;
 
     // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
@@ -1263,7 +1282,7 @@ __device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long 
         *reinterpret_cast<uchar2*>(out.unvignetted + o) = make_uchar2(r[0].unv ? 1 : 0, r[1].unv ? 1 : 0);
 }
 
-template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID>
+template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID, bool EFF>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
     // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
@@ -1363,7 +1382,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     {
         for (int s = 0; s < P.n_surf; ++s) {
             if (FULL)
-                surface_full<R>(P.surf[s], r, newton_iterations);
+                surface_full<R, EFF>(P.surf[s], r, newton_iterations);
             else
                 surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz, cos_incidence);
             if (ACC && P.has_out) {
@@ -1450,9 +1469,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
 // One kernel per (FULL, DENSE, VEC, ACC, IMAGE): uniform decisions are made once on the host
 // instead of per ray per surface.  The streamlined kernels carry two rays per thread in
 // <= 80 registers (3 CTAs of 256 threads per SM: the measured best).
-template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID = false>
+template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID = false, bool EFF = false>
 __global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
-    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE, GRID>(P);
+    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE, GRID, EFF>(P);
 }
 
 typedef void (*trace_kernel_t)(const TraceParams);
@@ -1462,5 +1481,6 @@ trace_kernel_t select_full_kernel(bool dense, bool vec, bool acc, bool image);
 trace_kernel_t select_generic_kernel(bool dense, bool acc, bool image);
 trace_kernel_t select_grid_kernel(bool full, bool acc, bool image);
 trace_kernel_t select_heavy_kernel(bool grid, bool acc, bool image);  // trace_heavy.cu
+trace_kernel_t select_efficiency_kernel(bool grid, bool dense, bool acc, bool image);  // trace_eff.cu
 
 }  // namespace optk
