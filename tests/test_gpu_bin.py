@@ -183,3 +183,19 @@ def test_size_independent_properties_at_scale(cuda_device):
     inside = (x >= ex[0]) & (x <= ex[-1]) & (y >= ey[0]) & (y <= ey[-1]) & (mask != 0)
     assert int(image.counts.sum().item()) == int(inside.sum().item())
     assert np.isclose(float(image.flux.sum().item()), float(inten[inside].sum().item()), rtol=1e-10)
+
+
+def test_fused_image_of_more_rays_than_one_launch_holds(cuda_device):
+    """
+    A separable grid of 3 x 8.3e8 = 2.49e9 rays (> 2^31 - 1) through `image_rays`: the engine
+    splits the outermost axis into launches.  The Newtonian has no dispersion, so every
+    wavelength contributes the same hits: the counts are exactly three times a single one's.
+    """
+    system = configs.newtonian(num_field=900, num_pupil=32, num_pixel=64)
+    edges = na.ScalarArray(np.array([400.0, 600.0]) * u.nm, "wavelength")
+    one = system.image_rays(edges, wavelength=500 * u.nm, counts=True).counts.cpu().numpy()
+    three = system.image_rays(
+        edges, wavelength=na.ScalarArray(np.array([450.0, 500.0, 550.0]) * u.nm, "wavelength"), counts=True
+    ).counts.cpu().numpy()
+    assert 900 * 900 * 32 * 32 * 3 > 2**31 - 1
+    assert one.sum() > 0 and np.array_equal(three, 3 * one)

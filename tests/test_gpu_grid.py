@@ -233,3 +233,33 @@ def test_grid_argument_errors(cuda_device, newtonian):
     assert rc == -1
     with pytest.raises(ValueError):
         _lib.check(rc)
+
+
+def test_more_rays_than_one_launch_holds(cuda_device, newtonian):
+    """
+    2.36e9 rays (> 2^31 - 1, the launch limit) through the fused generate + trace + bin path:
+    the box is cut into launches; hit counts must equal the sum over two halves traced
+    separately and the number of unvignetted rays the kernel reports.
+    """
+    n = (1, 1200, 1200, 40, 41)
+    v = [
+        np.linspace(499e-6, 501e-6, n[0] + 1), np.linspace(-0.1, 0.1, n[1] + 1) * u.deg,
+        np.linspace(-0.1, 0.1, n[2] + 1) * u.deg, np.linspace(-40, 40, n[3] + 1), np.linspace(-40, 40, n[4] + 1),
+    ]
+    grid = _grid.RayGrid(v, seed=2)
+    assert grid.size == 2_361_600_000 > 2**31 - 1
+    compiled = newtonian._compiled_local
+    ex, ey = newtonian.sensor.pixel_edges()
+    ew = np.array([499e-6, 501e-6])
+    whole = _engine.DeviceImage.zeros(ew, ex, ey, cuda_device, moments=False, counts=True)
+    before = _grid.LAUNCHES
+    _, stats = _grid.trace_grid(compiled, grid, image=whole, write_rays=False, stats=True)
+    assert _grid.LAUNCHES - before >= 2
+    assert stats["n_rays"] == grid.size
+    halves = _engine.DeviceImage.zeros(ew, ex, ey, cuda_device, moments=False, counts=True)
+    for begin, count in (((0, 0, 0, 0, 0), (1, 500, 1200, 40, 41)), ((0, 500, 0, 0, 0), (1, 700, 1200, 40, 41))):
+        _grid.trace_grid(compiled, grid.sub(begin, count), image=halves, write_rays=False)
+    a, b = whole.counts.cpu().numpy(), halves.counts.cpu().numpy()
+    assert np.array_equal(a, b)
+    assert 0 < a.sum() <= stats["n_unvignetted"]  # binned rays are unvignetted rays on the sensor
+    assert a.sum() > 0.5 * stats["n_unvignetted"]
