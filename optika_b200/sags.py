@@ -5,7 +5,7 @@ Host-side descriptions with the field names of ``optika.sags`` (reference:
 ``optika/sags/_flat.py``, ``_spherical.py``, ``_cylindrical.py``, ``_conic.py``,
 ``_parabolic.py``, ``_toroidal.py``, ``_abc.py``).  These classes hold parameters
 only; the arithmetic (intercept, normal, Beer-Lambert attenuation) runs in the
-fused CUDA kernel ``optika_b200/csrc/trace.cu``.  The unit operations
+fused CUDA kernel ``optika_b200/csrc/trace_impl.cuh``.  The unit operations
 ``__call__``, ``normal``, ``intercept`` and ``propagate_rays`` keep the reference
 signatures (``optika/sags/_abc.py:48-122``) and are executed on the device by a
 one-surface trace restricted to the relevant stages.
