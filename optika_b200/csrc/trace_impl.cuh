@@ -606,6 +606,24 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             }
             same_medium = same_medium && (r[k].n == n2[k]);
         }
+        // A unit, undiffracted direction that stays in its medium leaves Snell's law unchanged:
+        // b = a + d n with d = -a.n + sign(a.n) sqrt(1 + (a.n)^2 - |a|^2) = O(|a|^2 - 1).  The
+        // plain surfaces of a system (object, stops, baffles, the sensor) are all of this kind;
+        // skipping the root there changes directions by < 1e-14 / |a.n|.  Directions that are not
+        // unit to 1e-14 (user input) take the full formula, which renormalises them as the
+        // reference does.
+        bool straight = same_medium && !mirror && S.ruling_kind == OPTK_RULING_NONE;
+        if (straight) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const double a2 = r[k].dx * r[k].dx + r[k].dy * r[k].dy + r[k].dz * r[k].dz;
+                straight = straight && (fabs(a2 - 1.0) <= 1e-14);
+            }
+        }
+        if (straight) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) r[k].att = 0.0;  // _materials.py:101-105, 440-444; index unchanged
+        } else {
         // n1 == n2: r = 1 and 1 / r^2 = 1 exactly (no divisions, wavelength unchanged)
         double ratio[R], inv_r2[R];
 #pragma unroll
@@ -631,6 +649,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             r[k].dz = ratio[k] * (r[k].dz + d * nz[k]);
             if (!mirror) r[k].att = 0.0;  // _materials.py:101-105, 141-145, 440-444
             r[k].n = n2[k];
+        }
         }
     }
 
