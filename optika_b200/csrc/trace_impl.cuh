@@ -454,8 +454,11 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
 // parallelism for the long fp64 dependency chains).
 // AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
+// `attenuating`: some ray of the thread still carries a non-zero attenuation (set when the rays
+// are loaded, cleared by every non-mirror material, which zeroes the attenuation).
 template <int R, bool EFF = false>
-__device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations) {
+__device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations,
+                                             bool& attenuating) {
     const int flags = S.flags;
 
     // 1. global -> surface-local (surfaces.py:141-142)
@@ -530,9 +533,6 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
         // optika/sags/_abc.py:116-120: intensity *= exp(-attenuation * |displacement|).
         // With attenuation == 0 the factor is exactly 1 unless the displacement is not finite
         // (exp(-0 * inf) = exp(-0 * nan) = nan in the reference).
-        bool attenuating = false;
-#pragma unroll
-        for (int k = 0; k < R; ++k) attenuating = attenuating || (r[k].att != 0.0);
         if (attenuating) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
@@ -620,6 +620,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                 straight = straight && (fabs(a2 - 1.0) <= 1e-14);
             }
         }
+        if (!mirror) attenuating = false;  // every non-mirror material zeroes the attenuation below
         if (straight) {
 #pragma unroll
             for (int k = 0; k < R; ++k) r[k].att = 0.0;  // _materials.py:101-105, 440-444; index unchanged
@@ -1395,13 +1396,20 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         load_rays<R, DENSE>(P, i0, j0, base, valid, r, normal_given, gnx, gny, gnz);
     }
 
+    // generated rays start with zero attenuation: the Beer-Lambert branch is dead code there
+    bool attenuating = false;
+    if (FULL && !GRID) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) attenuating = attenuating || (r[k].att != 0.0);
+    }
+
     // No `if (valid)` around the walk: threads past the end trace a harmless dummy ray, so the
     // surface loop stays warp-convergent and its per-surface decisions and parameter loads
     // can use the uniform datapath (only the stores are predicated).
     {
         for (int s = 0; s < P.n_surf; ++s) {
             if (FULL)
-                surface_full<R, EFF>(P.surf[s], r, newton_iterations);
+                surface_full<R, EFF>(P.surf[s], r, newton_iterations, attenuating);
             else
                 surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz, cos_incidence);
             if (ACC && P.has_out) {
