@@ -263,3 +263,41 @@ def test_more_rays_than_one_launch_holds(cuda_device, newtonian):
     assert np.array_equal(a, b)
     assert 0 < a.sum() <= stats["n_unvignetted"]  # binned rays are unvignetted rays on the sensor
     assert a.sum() > 0.5 * stats["n_unvignetted"]
+
+
+def test_image_with_normalized_field_and_pupil(cuda_device, newtonian):
+    """
+    Normalised scene and pupil vertices ([-1, 1], the reference's default units) are mapped to
+    physical ones by the stop solver (``_denormalize_grid``, ``_sequential.py:748-789``) before
+    the grid goes to the device; the oracle gets the same physical vertices.
+    """
+    nf, npup = 8, 12
+    field = na.Cartesian2dVectorLinearSpace(-0.25, 0.25, na.Cartesian2dVectorArray("field_x", "field_y"), nf + 1)
+    w = na.linspace(499 * u.nm, 501 * u.nm, "wavelength", 2)
+    rng = np.random.default_rng(9)
+    scene = na.FunctionArray(
+        inputs=optika.vectors.SpectralPositionalVectorArray(wavelength=w, position=field),
+        outputs=na.ScalarArray(rng.uniform(1e9, 2e9, (1, nf, nf)), ("wavelength", "field_x", "field_y")),
+    )
+    pupil = na.Cartesian2dVectorLinearSpace(-1, 1, na.Cartesian2dVectorArray("pupil_x", "pupil_y"), npup + 1)
+    image = newtonian.image(
+        scene, pupil=pupil, noise=False, normalized_field=True, normalized_pupil=True, seed=12
+    )
+    physical = newtonian.denormalize(
+        optika.vectors.ObjectVectorArray(wavelength=w, field=field, pupil=pupil), True, True
+    )
+    vert = lambda a, ax: newtonian._separable(a, ax, {}, (), ax)  # noqa: E731
+    v = [
+        w.ndarray, vert(physical.field.x, "field_x"), vert(physical.field.y, "field_y"),
+        vert(physical.pupil.x, "pupil_x"), vert(physical.pupil.y, "pupil_y"),
+    ]
+    assert np.isclose(v[3][0], -v[3][-1]) and 39 < v[3][-1] < 42  # the 40 mm primary is the pupil stop
+    aw, af, ap = og.cell_area(v, True, False)
+    rays0 = og.input_rays(v, weight_scene=scene.outputs.ndarray * aw[:, None, None] * af[None], weight_pupil=ap, seed=12)
+    out = ora.propagate_rays(newtonian.surfaces_all, rays0, extended=True)
+    local = ora._rays_transform(newtonian.sensor.transformation, out, inverse=True)
+    ex, ey = newtonian.sensor.pixel_edges()
+    want, _, _ = orb.collect(local, np.array([w.ndarray.min(), w.ndarray.max()]), ex, ey)
+    got = image.outputs.ndarray
+    assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
+    assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
