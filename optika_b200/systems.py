@@ -94,8 +94,9 @@ class SequentialSystem(AbstractSequentialSystem):
         return _engine.CompiledSystem(self.surfaces_all)
 
     def invalidate(self):
-        """Drop the cached device table after mutating a surface."""
-        self.__dict__.pop("_compiled", None)
+        """Drop the cached device tables (and the stop solution) after mutating a surface."""
+        for name in ("_compiled", "_compiled_local", "_stop_cache"):
+            self.__dict__.pop(name, None)
 
     # -- input rays --------------------------------------------------------
     def _calc_rayfunction_input(self, grid: ObjectVectorArray) -> RayFunctionArray:

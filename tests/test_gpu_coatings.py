@@ -177,3 +177,41 @@ def test_image_of_a_scene_through_a_coated_system(cuda_device):
     assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
     # the coating matters: far from unit efficiency
     assert got.sum() < 0.5 * rays0["intensity"].sum()
+
+
+def test_image_through_two_coated_surfaces(cuda_device):
+    """Filter film + multilayer grating: the grid chain applies two coatings (`trace_grid_coated`)."""
+    from oracle import grid as og
+
+    system = coated_grating(mo_si(num_periods=6))
+    film = optika.surfaces.Surface(
+        name="filter",
+        material=M.MultilayerFilm(layers=[M.Layer("Si", thickness=80 * u.nm)]),
+        transformation=optika.transformations.Cartesian3dTranslation(z=300 * u.mm),
+    )
+    system.surfaces = [film] + list(system.surfaces)
+    system.invalidate()
+    assert sorted(system._compiled_local.coatings) == [1, 2]
+    nf = 4
+    field = na.Cartesian2dVectorLinearSpace(
+        -0.05 * u.deg, 0.05 * u.deg, na.Cartesian2dVectorArray("field_x", "field_y"), nf + 1
+    )
+    w = na.linspace(13.0 * u.nm, 14.0 * u.nm, "wavelength", 3)
+    scene = na.FunctionArray(
+        inputs=optika.vectors.SpectralPositionalVectorArray(wavelength=w, position=field),
+        outputs=na.ScalarArray(np.full((2, nf, nf), 1e9), ("wavelength", "field_x", "field_y")),
+    )
+    pupil = na.Cartesian2dVectorLinearSpace(
+        -40 * u.mm, 40 * u.mm, na.Cartesian2dVectorArray("pupil_x", "pupil_y"), 13
+    )
+    image = system.image(scene, pupil=pupil, noise=False, normalized_pupil=False, seed=3)
+    v = [w.ndarray, field.x.ndarray, field.y.ndarray, pupil.x.ndarray, pupil.y.ndarray]
+    aw, af, ap = og.cell_area(v, True, False)
+    rays0 = og.input_rays(v, weight_scene=scene.outputs.ndarray * aw[:, None, None] * af[None], weight_pupil=ap, seed=3)
+    out = ora.propagate_rays(system.surfaces_all, rays0, extended=True)
+    local = ora._rays_transform(system.sensor.transformation, out, inverse=True)
+    ex, ey = system.sensor.pixel_edges()
+    want, _, _ = orb.collect(local, np.array([w.ndarray.min(), w.ndarray.max()]), ex, ey)
+    got = image.outputs.ndarray
+    assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
+    assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
