@@ -373,10 +373,17 @@ typedef struct optk_grid {
     int32_t jitter;
     int32_t has_frame;
     uint64_t seed;
-    const double* vertices[5];  /* device; n[a] + 1 values each                       */
+    const double* vertices[5];  /* device; n[a] + 1 values each (see field_2d / pupil_2d) */
     const double* weight_scene; /* device; [n0][n1][n2] or NULL                       */
     const double* weight_pupil; /* device; [n3][n4] or NULL                           */
     optk_affine_t frame;
+    /* Curvilinear (e.g. polar) field / pupil grids: with field_2d the x and y vertex arrays
+     * vertices[1] and vertices[2] are both 2-D, [n1 + 1][n2 + 1], and the sample of cell
+     * (i1, i2) is the bilinear combination of its four corner vertices with weights
+     * (t_1, t_2) (cell_centers applied along one axis after the other); likewise pupil_2d
+     * for vertices[3], vertices[4] with [n3 + 1][n4 + 1] and (t_3, t_4). */
+    int32_t field_2d;
+    int32_t pupil_2d;
 } optk_grid_t;
 
 /* As optk_trace, with the rays of `grid` as input.  surf_count = 0 returns the

@@ -47,9 +47,18 @@ class RayGrid:
     count: tuple | None = None
 
     def __post_init__(self):
-        self.vertices = tuple(np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in self.vertices)
+        self.vertices = tuple(np.ascontiguousarray(v, dtype=np.float64) for v in self.vertices)
         if len(self.vertices) != 5:
             raise ValueError("a ray grid has five axes: wavelength, field x/y, pupil x/y")
+        if self.vertices[0].ndim != 1:
+            raise ValueError("the wavelength vertices must be one-dimensional")
+        for name, (a, b) in (("field", (1, 2)), ("pupil", (3, 4))):
+            va, vb = self.vertices[a], self.vertices[b]
+            if not ((va.ndim == 1 and vb.ndim == 1) or (va.ndim == 2 and va.shape == vb.shape)):
+                raise ValueError(
+                    f"the {name} vertices are two 1-D arrays (separable grid) or two 2-D arrays of one shape "
+                    f"(curvilinear grid), got shapes {va.shape} and {vb.shape}"
+                )
         n = self.n
         if any(k < 1 for k in n):
             raise ValueError(f"every axis needs at least two vertices, got cells {n}")
@@ -64,8 +73,19 @@ class RayGrid:
         self._device = {}
 
     @property
+    def field_2d(self) -> bool:
+        return self.vertices[1].ndim == 2
+
+    @property
+    def pupil_2d(self) -> bool:
+        return self.vertices[3].ndim == 2
+
+    @property
     def n(self) -> tuple:
-        return tuple(len(v) - 1 for v in self.vertices)
+        v = self.vertices
+        nf = (v[1].shape[0] - 1, v[1].shape[1] - 1) if self.field_2d else (len(v[1]) - 1, len(v[2]) - 1)
+        npup = (v[3].shape[0] - 1, v[3].shape[1] - 1) if self.pupil_2d else (len(v[3]) - 1, len(v[4]) - 1)
+        return (len(v[0]) - 1,) + nf + npup
 
     @property
     def shape(self) -> dict[str, int]:
@@ -95,7 +115,7 @@ class RayGrid:
         torch = _engine._torch()
         key = str(device)
         if key not in self._device:
-            up = lambda a: None if a is None else torch.from_numpy(np.array(a, dtype=np.float64)).to(device)  # noqa: E731
+            up = lambda a: None if a is None else torch.from_numpy(np.array(a, dtype=np.float64).reshape(-1)).to(device)  # noqa: E731
             self._device[key] = dict(
                 vertices=[up(v) for v in self.vertices],
                 weight_scene=up(self.weight_scene),
@@ -116,6 +136,8 @@ class RayGrid:
             g.vertices[a] = dev["vertices"][a].data_ptr()
         g.weight_scene = None if dev["weight_scene"] is None else dev["weight_scene"].data_ptr()
         g.weight_pupil = None if dev["weight_pupil"] is None else dev["weight_pupil"].data_ptr()
+        g.field_2d = 1 if self.field_2d else 0
+        g.pupil_2d = 1 if self.pupil_2d else 0
         if self.frame is not None:
             g.has_frame = 1
             g.frame.r[:] = list(np.asarray(self.frame[0], dtype=float).reshape(9))

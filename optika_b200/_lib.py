@@ -173,6 +173,8 @@ class Grid(C.Structure):
         ("weight_scene", C.c_void_p),
         ("weight_pupil", C.c_void_p),
         ("frame", Affine),
+        ("field_2d", C.c_int32),
+        ("pupil_2d", C.c_int32),
     ]
 
 

@@ -1198,6 +1198,28 @@ __device__ __forceinline__ double grid_sample(const double* vertices, int i, boo
     return fma(t, hi - lo, lo);
 }
 
+// Curvilinear grids (field_2d / pupil_2d): bilinear sample of a cell of two 2-D vertex arrays
+// [n_a + 1][n_b + 1].  Out of line: the separable case stays the short one.
+static __device__ __noinline__ Vec3 grid_sample_2d(const double* vx, const double* vy, int ia, int ib, int row, bool jitter,
+                                                   uint32_t bits_a, uint32_t bits_b) {
+    const double ta = jitter ? ((double)bits_a + 0.5) * 2.98023223876953125e-08 : 0.5;
+    const double tb = jitter ? ((double)bits_b + 0.5) * 2.98023223876953125e-08 : 0.5;
+    const long long o = (long long)ia * row + ib;
+    Vec3 out;
+    {
+        const double v00 = __ldg(vx + o), v01 = __ldg(vx + o + 1), v10 = __ldg(vx + o + row), v11 = __ldg(vx + o + row + 1);
+        const double lo = fma(ta, v10 - v00, v00), hi = fma(ta, v11 - v01, v01);  // along axis a, then b
+        out.x = fma(tb, hi - lo, lo);
+    }
+    {
+        const double v00 = __ldg(vy + o), v01 = __ldg(vy + o + 1), v10 = __ldg(vy + o + row), v11 = __ldg(vy + o + row + 1);
+        const double lo = fma(ta, v10 - v00, v00), hi = fma(ta, v11 - v01, v01);
+        out.y = fma(tb, hi - lo, lo);
+    }
+    out.z = 0.0;
+    return out;
+}
+
 // SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
 // (optika/systems/_sequential.py:1055-1086, 791-828) for the R consecutive rays of a thread.
 // `j0` is the C-order index of the first ray in the sub-box of this launch (< 2^31).
@@ -1247,10 +1269,23 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         // low 7 bits of the four words side by side (include/optk.h)
         const uint32_t low = (x[0] & 127u) | ((x[1] & 127u) << 7) | ((x[2] & 127u) << 14) | ((x[3] & 15u) << 21);
         const double w = grid_sample(G.vertices[0], g[0], jitter, x[0] >> 7);
-        const double fx = grid_sample(G.vertices[1], g[1], jitter, x[1] >> 7);
-        const double fy = grid_sample(G.vertices[2], g[2], jitter, x[2] >> 7);
-        const double px = grid_sample(G.vertices[3], g[3], jitter, x[3] >> 7);
-        const double py = grid_sample(G.vertices[4], g[4], jitter, low);
+        double fx, fy, px, py;
+        if (G.field_2d) {
+            const Vec3 f = grid_sample_2d(G.vertices[1], G.vertices[2], g[1], g[2], G.n[2] + 1, jitter, x[1] >> 7, x[2] >> 7);
+            fx = f.x;
+            fy = f.y;
+        } else {
+            fx = grid_sample(G.vertices[1], g[1], jitter, x[1] >> 7);
+            fy = grid_sample(G.vertices[2], g[2], jitter, x[2] >> 7);
+        }
+        if (G.pupil_2d) {
+            const Vec3 p = grid_sample_2d(G.vertices[3], G.vertices[4], g[3], g[4], G.n[4] + 1, jitter, x[3] >> 7, low);
+            px = p.x;
+            py = p.y;
+        } else {
+            px = grid_sample(G.vertices[3], g[3], jitter, x[3] >> 7);
+            py = grid_sample(G.vertices[4], g[4], jitter, low);
+        }
         // position / angles by the location of the object (:797-802)
         const double ax = G.at_infinity ? fx : px, ay = G.at_infinity ? fy : py;
         double sx, cx, sy, cy;

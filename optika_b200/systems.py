@@ -314,6 +314,44 @@ class SequentialSystem(AbstractSequentialSystem):
             )
         return np.asarray(nd.mean(axis=0), dtype=np.float64)
 
+    def _curvilinear(self, vector, axes: tuple, config_shape: dict, cindex: tuple, convert, what: str):
+        """
+        The two 2-D vertex arrays ``[n_a + 1][n_b + 1]`` of a field / pupil grid whose components
+        both vary along both of its axes (e.g. a polar pupil grid); other axes as in `_separable`.
+        """
+        out = []
+        for c in (vector.x, vector.y):
+            v = na.as_named_array(convert(c))
+            shape_ = dict(config_shape)
+            for ax in axes:
+                n = na.shape(vector).get(ax)
+                if n is None:
+                    raise ValueError(f"the {what} vertices must vary along axes {axes}, got {na.shape(vector)}")
+                shape_[ax] = n
+            for ax, n in v.shape.items():
+                shape_.setdefault(ax, n)
+            nd = np.broadcast_to(na.aligned(v, shape_), tuple(shape_.values()))[cindex]
+            names = [ax for ax in shape_ if ax not in config_shape]
+            nd = np.moveaxis(nd, [names.index(axes[0]), names.index(axes[1])], [-2, -1])
+            nd = nd.reshape((-1,) + nd.shape[-2:])
+            extent = float(np.ptp(nd)) or 1.0
+            if float(np.ptp(nd, axis=0).max()) > 1e-9 * extent:
+                raise NotImplementedError(
+                    f"the {what} vertices vary along axes other than {axes}; trace explicit rays with `image_rays`"
+                )
+            out.append(np.ascontiguousarray(nd.mean(axis=0), dtype=np.float64))
+        return tuple(out)
+
+    def _grid_vertices(self, vector, axes: tuple, config_shape: dict, cindex: tuple, convert, what: str):
+        """1-D (separable) vertex arrays of a field / pupil grid when possible, else 2-D (curvilinear) ones."""
+        x, y = na.as_named_array(convert(vector.x)), na.as_named_array(convert(vector.y))
+        if axes[1] not in x.axes and axes[0] not in y.axes:
+            return (
+                self._separable(x, axes[0], config_shape, cindex, what + " x"),
+                self._separable(y, axes[1], config_shape, cindex, what + " y"),
+            )
+        return self._curvilinear(vector, axes, config_shape, cindex, convert, what)
+
     def _frame_input(self, config_shape: dict, cindex: tuple):
         """Object-local -> first-surface coordinates as ``(R, t)`` (``_sequential.py:823-826, 908-909``)."""
         t_obj = self.object.transformation if self.object is not None else None
@@ -360,28 +398,30 @@ class SequentialSystem(AbstractSequentialSystem):
         axes = (axis_wavelength,) + tuple(axis_field) + tuple(axis_pupil)
         grids = []
         for cindex in np.ndindex(*config_shape.values()) if config_shape else [()]:
-            get = lambda v, ax, what: self._separable(v, ax, config_shape, cindex, what)  # noqa: E731
             vertices = (
-                get(u.length(grid.wavelength), axis_wavelength, "wavelength"),
-                get(conv_field(grid.field.x), axis_field[0], "field x"),
-                get(conv_field(grid.field.y), axis_field[1], "field y"),
-                get(conv_pupil(grid.pupil.x), axis_pupil[0], "pupil x"),
-                get(conv_pupil(grid.pupil.y), axis_pupil[1], "pupil y"),
+                self._separable(u.length(grid.wavelength), axis_wavelength, config_shape, cindex, "wavelength"),
+                *self._grid_vertices(grid.field, axis_field, config_shape, cindex, conv_field, "field"),
+                *self._grid_vertices(grid.pupil, axis_pupil, config_shape, cindex, conv_pupil, "pupil"),
             )
+
+            def named(a, b, axes2):
+                if vertices[a].ndim == 2:
+                    return na.Cartesian2dVectorArray(na.ScalarArray(vertices[a], axes2), na.ScalarArray(vertices[b], axes2))
+                return na.Cartesian2dVectorArray(
+                    na.ScalarArray(vertices[a], axes2[0]), na.ScalarArray(vertices[b], axes2[1])
+                )
+
             cell = ObjectVectorArray(
                 wavelength=na.ScalarArray(vertices[0], axis_wavelength),
-                field=na.Cartesian2dVectorArray(
-                    na.ScalarArray(vertices[1], axis_field[0]), na.ScalarArray(vertices[2], axis_field[1])
-                ),
-                pupil=na.Cartesian2dVectorArray(
-                    na.ScalarArray(vertices[3], axis_pupil[0]), na.ScalarArray(vertices[4], axis_pupil[1])
-                ),
+                field=named(1, 2, tuple(axis_field)),
+                pupil=named(3, 4, tuple(axis_pupil)),
             )
             area_w, area_f, area_p = cell.cell_area(
                 axis_wavelength, axis_field, axis_pupil,
                 field_is_angular=at_infinity, pupil_is_angular=not at_infinity, factors=True,
             )
-            n = [len(v) - 1 for v in vertices]
+            n_field = [s_ - 1 for s_ in vertices[1].shape] if vertices[1].ndim == 2 else [len(vertices[1]) - 1, len(vertices[2]) - 1]
+            n = [len(vertices[0]) - 1] + n_field
             scene_shape = dict(zip(axes[:3], n[:3]))
             rad = na.as_named_array(radiance)
             extra = set(rad.axes) - set(scene_shape) - set(config_shape)

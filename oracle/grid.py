@@ -82,30 +82,46 @@ def jitter(cell: np.ndarray, seed: int) -> np.ndarray:
     return np.stack([(w.astype(np.float64) + 0.5) * 2.0**-25 for w in words])
 
 
+def _cells(vertices):
+    """Cells per axis of a grid whose field / pupil vertices are 1-D (separable) or 2-D (curvilinear)."""
+    v = [np.asarray(a, dtype=np.float64) for a in vertices]
+    nf = (v[1].shape[0] - 1, v[1].shape[1] - 1) if v[1].ndim == 2 else (len(v[1]) - 1, len(v[2]) - 1)
+    npup = (v[3].shape[0] - 1, v[3].shape[1] - 1) if v[3].ndim == 2 else (len(v[3]) - 1, len(v[4]) - 1)
+    return v, [len(v[0]) - 1, *nf, *npup]
+
+
 def cell_samples(vertices, begin=None, count=None, random: bool = True, seed: int = 0):
     """
-    One sample per cell of the sub-box ``[begin, begin + count)`` of a separable 5-axis
-    vertex grid (wavelength, field_x, field_y, pupil_x, pupil_y).  Returns 5 arrays of the
-    sub-box shape and the whole-grid cell indices.
+    One sample per cell of the sub-box ``[begin, begin + count)`` of a 5-axis vertex grid
+    (wavelength, field_x, field_y, pupil_x, pupil_y).  Field and pupil vertices are either
+    separable (two 1-D arrays) or curvilinear (two 2-D arrays ``[n_a + 1][n_b + 1]``, sampled
+    bilinearly: ``cell_centers`` applied along one axis after the other).  Returns 5 arrays
+    of the sub-box shape and the whole-grid cell indices.
     """
-    n = [len(v) - 1 for v in vertices]
+    v, n = _cells(vertices)
     begin = [0] * 5 if begin is None else list(begin)
     count = [n[a] - begin[a] for a in range(5)] if count is None else list(count)
     idx = np.meshgrid(*[np.arange(begin[a], begin[a] + count[a], dtype=np.int64) for a in range(5)], indexing="ij")
     cell = idx[0].astype(np.uint64)
     for a in range(1, 5):
         cell = cell * np.uint64(n[a]) + idx[a].astype(np.uint64)
-    t = jitter(cell, seed) if random else None
-    out = []
-    for a in range(5):
-        v = np.asarray(vertices[a], dtype=np.float64)
-        lo, hi = v[idx[a]], v[idx[a] + 1]
-        if random:
-            # the device uses one fused multiply-add here; the difference (<= 1 ulp of the
-            # sample) is far below the parity tolerance
-            out.append(lo + t[a] * (hi - lo))
+    t = jitter(cell, seed) if random else np.full((5,) + cell.shape, 0.5)
+
+    def lerp(lo, hi, ta):
+        # the device uses fused multiply-adds here; the difference (<= 1 ulp of the sample) is
+        # far below the parity tolerance
+        return lo + ta * (hi - lo) if random else 0.5 * (lo + hi)
+
+    out = [lerp(v[0][idx[0]], v[0][idx[0] + 1], t[0])]
+    for a, b in ((1, 2), (3, 4)):
+        if v[a].ndim == 2:
+            for comp in (v[a], v[b]):
+                lo = lerp(comp[idx[a], idx[b]], comp[idx[a] + 1, idx[b]], t[a])
+                hi = lerp(comp[idx[a], idx[b] + 1], comp[idx[a] + 1, idx[b] + 1], t[a])
+                out.append(lerp(lo, hi, t[b]))
         else:
-            out.append(0.5 * (lo + hi))
+            out.append(lerp(v[a][idx[a]], v[a][idx[a] + 1], t[a]))
+            out.append(lerp(v[b][idx[b]], v[b][idx[b] + 1], t[b]))
     return out, idx
 
 
@@ -204,8 +220,8 @@ def cell_area(vertices, field_is_angular: bool, pupil_is_angular: bool):
     the three factors of ``ObjectVectorArray.cell_area`` (``_vectors_object.py:98-133``).
     """
     w, fx, fy, px, py = [np.asarray(v, dtype=np.float64) for v in vertices]
-    FX, FY = np.meshgrid(fx, fy, indexing="ij")
-    PX, PY = np.meshgrid(px, py, indexing="ij")
+    FX, FY = (fx, fy) if fx.ndim == 2 else np.meshgrid(fx, fy, indexing="ij")
+    PX, PY = (px, py) if px.ndim == 2 else np.meshgrid(px, py, indexing="ij")
     area_field = solid_angle_cell(FX, FY) if field_is_angular else volume_cell_2d(FX, FY)
     area_pupil = solid_angle_cell(PX, PY) if pupil_is_angular else volume_cell_2d(PX, PY)
     return volume_cell_1d(w), np.abs(area_field), np.abs(area_pupil)

@@ -301,3 +301,49 @@ def test_image_with_normalized_field_and_pupil(cuda_device, newtonian):
     got = image.outputs.ndarray
     assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
     assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
+
+
+def polar_pupil(num_r=6, num_phi=12):
+    r = na.linspace(5 * u.mm, 40 * u.mm, "pupil_r", num_r + 1)
+    phi = na.linspace(0, 2 * np.pi, "pupil_phi", num_phi + 1)
+    return na.Cartesian2dVectorArray(r * np.cos(phi), r * np.sin(phi))
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+def test_curvilinear_grid_rays_match_oracle(cuda_device, newtonian, jitter):
+    """Field and pupil given as 2-D vertex arrays (a sheared field grid, a polar pupil grid)."""
+    fx, fy = np.meshgrid(np.linspace(-0.1, 0.1, 5) * u.deg, np.linspace(-0.08, 0.1, 4) * u.deg, indexing="ij")
+    fx = fx + 0.2 * fy  # sheared: not separable
+    p = polar_pupil()
+    px, py = p.x.numpy(("pupil_r", "pupil_phi")), p.y.numpy(("pupil_r", "pupil_phi"))
+    v = [np.linspace(499e-6, 501e-6, 3), fx, fy, px, py]
+    grid = _grid.RayGrid(v, jitter=jitter, seed=31)
+    assert grid.n == (2, 4, 3, 6, 12) and grid.field_2d and grid.pupil_2d
+    got = _grid.trace_grid(newtonian._compiled_local, grid, surf_count=0)
+    want = og.input_rays(v, random=jitter, seed=31)
+    parity.compare_states(device_dict(got), want)
+    # sub-boxes draw the same samples
+    sub = grid.sub((1, 1, 0, 2, 3), (1, 2, 3, 3, 5))
+    part = device_dict(_grid.trace_grid(newtonian._compiled_local, sub, surf_count=0))
+    full = device_dict(got)["px"].reshape(grid.n)[1:2, 1:3, :, 2:5, 3:8].reshape(-1)
+    assert np.array_equal(part["px"], full)
+
+
+def test_image_with_a_polar_pupil_grid(cuda_device, newtonian):
+    scene = scene_for(newtonian, num_field=(6, 6), num_wavelength=1)
+    pupil = polar_pupil(num_r=8, num_phi=24)
+    image = newtonian.image(
+        scene, pupil=pupil, axis_pupil=("pupil_r", "pupil_phi"), noise=False, normalized_pupil=False, seed=5
+    )
+    w, f = scene.inputs.wavelength.ndarray, scene.inputs.position
+    v = [w, f.x.ndarray, f.y.ndarray, pupil.x.numpy(("pupil_r", "pupil_phi")), pupil.y.numpy(("pupil_r", "pupil_phi"))]
+    aw, af, ap = og.cell_area(v, True, False)
+    assert np.isclose(ap.sum(), np.pi * (40**2 - 5**2) * np.sin(2 * np.pi / 24) / (2 * np.pi / 24), rtol=1e-12)
+    rays0 = og.input_rays(v, weight_scene=scene.outputs.ndarray * aw[:, None, None] * af[None], weight_pupil=ap, seed=5)
+    out = ora.propagate_rays(newtonian.surfaces_all, rays0, extended=True)
+    local = ora._rays_transform(newtonian.sensor.transformation, out, inverse=True)
+    ex, ey = newtonian.sensor.pixel_edges()
+    want, _, _ = orb.collect(local, np.array([w.min(), w.max()]), ex, ey)
+    got = image.outputs.ndarray
+    assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
+    assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
