@@ -36,6 +36,9 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     for (int s = 0; s < P.n_surf; ++s)
         efficiency = efficiency || P.surf[s].material_efficiency != OPTK_EFF_UNIT ||
                      P.surf[s].ruling_profile != OPTK_PROFILE_IDEAL;
+    // curvilinear grids with non-unit efficiencies are rare enough to share the generic kernels
+    const bool curvilinear = from_grid && (P.grid.field_2d || P.grid.pupil_2d);
+    if (curvilinear && efficiency) full = false;
     const bool dense = P.dense_in != 0 && !from_grid, acc = P.accumulate != 0, image = P.has_image != 0;
     // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
     bool vec = full && dense && !from_grid && !efficiency && (P.accumulate_stride % 2 == 0);
@@ -135,12 +138,14 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     }();
     // (with calls in the walk the extra registers do not pay: cfg 3 fused 9.8 -> 11.1 ms)
     const bool use_heavy = full && from_grid && image && (heavy_mode == 1 || (heavy_mode < 0 && heavy && !out_of_line));
-    if (full && efficiency)
+    if (curvilinear)
+        kernel = select_grid_kernel(full, acc, image, true);
+    else if (full && efficiency)
         kernel = select_efficiency_kernel(from_grid, dense, acc, image);
     else if (use_heavy)
         kernel = select_heavy_kernel(from_grid, acc, image);
     else if (from_grid)
-        kernel = select_grid_kernel(full, acc, image);
+        kernel = select_grid_kernel(full, acc, image, false);
     else if (full)
         kernel = select_full_kernel(dense, vec, acc, image);
     else

@@ -10,7 +10,7 @@ namespace optk {
 trace_kernel_t select_efficiency_kernel(bool grid, bool dense, bool acc, bool image) {
 #define OPTK_PICK(G, D, A, I)                                    \
     if (grid == G && dense == D && acc == A && image == I)       \
-        return (trace_kernel_t)trace_kernel<OPTK_FULL_MINB, 2, true, D, false, A, I, G, true>;
+        return (trace_kernel_t)trace_kernel<OPTK_FULL_MINB, 2, true, D, false, A, I, G ? 1 : 0, true>;
     OPTK_PICK(false, false, false, false)
     OPTK_PICK(false, false, true, false)
     OPTK_PICK(false, false, false, true)

@@ -5,15 +5,21 @@
 
 namespace optk {
 
-trace_kernel_t select_grid_kernel(bool full, bool acc, bool image) {
-#define OPTK_PICK(A, I)                                                                             \
-    if (acc == A && image == I)                                                                     \
-        return full ? (trace_kernel_t)trace_kernel<OPTK_FULL_MINB, 2, true, false, false, A, I, true>            \
-                    : (trace_kernel_t)trace_kernel<4, 1, false, false, false, A, I, true>;
-    OPTK_PICK(false, false)
-    OPTK_PICK(true, false)
-    OPTK_PICK(false, true)
-    OPTK_PICK(true, true)
+// curvilinear grids (2-D vertex arrays) have their own instantiations: the out-of-line bilinear
+// sampler's call sites cost the separable kernels 5 % even when never taken
+trace_kernel_t select_grid_kernel(bool full, bool acc, bool image, bool curvilinear) {
+#define OPTK_PICK(A, I, G)                                                                          \
+    if (acc == A && image == I && curvilinear == (G == 2))                                          \
+        return full ? (trace_kernel_t)trace_kernel<OPTK_FULL_MINB, 2, true, false, false, A, I, G>  \
+                    : (trace_kernel_t)trace_kernel<4, 1, false, false, false, A, I, G>;
+    OPTK_PICK(false, false, 1)
+    OPTK_PICK(true, false, 1)
+    OPTK_PICK(false, true, 1)
+    OPTK_PICK(true, true, 1)
+    OPTK_PICK(false, false, 2)
+    OPTK_PICK(true, false, 2)
+    OPTK_PICK(false, true, 2)
+    OPTK_PICK(true, true, 2)
 #undef OPTK_PICK
     return nullptr;
 }

@@ -10,7 +10,7 @@ namespace optk {
 
 trace_kernel_t select_heavy_kernel(bool grid, bool acc, bool image) {
 #define OPTK_PICK(G, A, I) \
-    if (grid == G && acc == A && image == I) return (trace_kernel_t)trace_kernel<2, 2, true, false, false, A, I, G>;
+    if (grid == G && acc == A && image == I) return (trace_kernel_t)trace_kernel<2, 2, true, false, false, A, I, G ? 1 : 0>;
     OPTK_PICK(true, false, true)
     OPTK_PICK(true, true, true)
 #undef OPTK_PICK

@@ -1223,7 +1223,7 @@ static __device__ __noinline__ Vec3 grid_sample_2d(const double* vx, const doubl
 // SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
 // (optika/systems/_sequential.py:1055-1086, 791-828) for the R consecutive rays of a thread.
 // `j0` is the C-order index of the first ray in the sub-box of this launch (< 2^31).
-template <int R>
+template <int R, bool CURVILINEAR>
 __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0, const bool (&valid)[R],
                                               Ray (&r)[R]) {
     const optk_grid_t& G = P.grid;
@@ -1270,7 +1270,7 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         const uint32_t low = (x[0] & 127u) | ((x[1] & 127u) << 7) | ((x[2] & 127u) << 14) | ((x[3] & 15u) << 21);
         const double w = grid_sample(G.vertices[0], g[0], jitter, x[0] >> 7);
         double fx, fy, px, py;
-        if (G.field_2d) {
+        if (CURVILINEAR && G.field_2d) {
             const Vec3 f = grid_sample_2d(G.vertices[1], G.vertices[2], g[1], g[2], G.n[2] + 1, jitter, x[1] >> 7, x[2] >> 7);
             fx = f.x;
             fy = f.y;
@@ -1278,7 +1278,7 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
             fx = grid_sample(G.vertices[1], g[1], jitter, x[1] >> 7);
             fy = grid_sample(G.vertices[2], g[2], jitter, x[2] >> 7);
         }
-        if (G.pupil_2d) {
+        if (CURVILINEAR && G.pupil_2d) {
             const Vec3 p = grid_sample_2d(G.vertices[3], G.vertices[4], g[3], g[4], G.n[4] + 1, jitter, x[3] >> 7, low);
             px = p.x;
             py = p.y;
@@ -1337,7 +1337,7 @@ __device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long 
         *reinterpret_cast<uchar2*>(out.unvignetted + o) = make_uchar2(r[0].unv ? 1 : 0, r[1].unv ? 1 : 0);
 }
 
-template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID, bool EFF>
+template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID, bool EFF>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
     // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
@@ -1426,7 +1426,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             r[0].unv = r[R - 1].unv = true;
         }
     } else if (GRID) {
-        generate_rays<R>(P, (uint32_t)i0, valid, r);
+        generate_rays<R, GRID == 2>(P, (uint32_t)i0, valid, r);
     } else {
         load_rays<R, DENSE>(P, i0, j0, base, valid, r, normal_given, gnx, gny, gnz);
     }
@@ -1531,7 +1531,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
 // One kernel per (FULL, DENSE, VEC, ACC, IMAGE): uniform decisions are made once on the host
 // instead of per ray per surface.  The streamlined kernels carry two rays per thread in
 // <= 80 registers (3 CTAs of 256 threads per SM: the measured best).
-template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, bool GRID = false, bool EFF = false>
+// GRID: 0 rays from memory, 1 on-device separable vertex grid, 2 curvilinear (2-D vertex arrays)
+template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID = 0, bool EFF = false>
 __global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
     trace_body<R, FULL, DENSE, VEC, ACC, IMAGE, GRID, EFF>(P);
 }
@@ -1541,7 +1542,7 @@ typedef void (*trace_kernel_t)(const TraceParams);
 // defined in trace_full.cu / trace_generic.cu (separate translation units: parallel compilation)
 trace_kernel_t select_full_kernel(bool dense, bool vec, bool acc, bool image);
 trace_kernel_t select_generic_kernel(bool dense, bool acc, bool image);
-trace_kernel_t select_grid_kernel(bool full, bool acc, bool image);
+trace_kernel_t select_grid_kernel(bool full, bool acc, bool image, bool curvilinear);
 trace_kernel_t select_heavy_kernel(bool grid, bool acc, bool image);  // trace_heavy.cu
 trace_kernel_t select_efficiency_kernel(bool grid, bool dense, bool acc, bool image);  // trace_eff.cu
 
