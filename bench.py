@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--num-field", type=int, default=100)
     ap.add_argument("--num-pupil", type=int, default=100)
     ap.add_argument("--num-wavelength", type=int, default=64)
-    ap.add_argument("--cpu-sample-rays", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample-rays", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--host-rays", type=int, default=20_000_000, help="rays of the host-array e2e sample")
