@@ -260,7 +260,8 @@ typedef struct optk_rays_out {
 } optk_rays_out_t;
 
 /* Detector binning target (optika/sensors/_sensors.py:139-161). Planes are
- * [n_wavelength][n_x][n_y], C order, caller-zeroed; contributions are ADDED. */
+ * [n_wavelength][n_x][n_y], C order, caller-zeroed; contributions are ADDED.
+ * n_wavelength * n_x * n_y < 2^31 (split the wavelength axis beyond that). */
 typedef struct optk_image {
     int32_t n_wavelength, n_x, n_y;
     const double* edges_wavelength; /* n_wavelength + 1, device or host like the rays */

@@ -203,6 +203,10 @@ int fill_image(const optk_image_t* image, ImageDev* dev) {
         set_error("image bin edges are NULL");
         return OPTK_ERR_INVALID;
     }
+    if ((long long)image->n_wavelength * image->n_x * image->n_y > 0x7fffffffLL) {
+        set_error("an image plane set holds at most 2^31 - 1 bins; split the wavelength axis");
+        return OPTK_ERR_INVALID;
+    }
     dev->n_w = image->n_wavelength;
     dev->n_x = image->n_x;
     dev->n_y = image->n_y;

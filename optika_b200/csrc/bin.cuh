@@ -105,14 +105,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // they land on a few adjacent pixels in runs and most lanes retire; whoever is left issues
 // its own global reductions (RED.ADD.F64 / RED.ADD.U64 at L2).  No loops, no match_any;
 // exact for the integer counts, order-independent up to rounding for the fp64 sums.
-__device__ __forceinline__ void image_add(const ImageDev& im, long long bin, double w_flux, double w_real,
+__device__ __forceinline__ void image_add(const ImageDev& im, int bin, double w_flux, double w_real,
                                           double w_imag, unsigned count) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     if (__all_sync(full, bin < 0)) return;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const long long pb = __shfl_xor_sync(full, bin, o);
+        const int pb = __shfl_xor_sync(full, bin, o);
         const double pf = __shfl_xor_sync(full, w_flux, o);
         const double pr = __shfl_xor_sync(full, w_real, o);
         const unsigned pc = __shfl_xor_sync(full, count, o);
@@ -140,21 +140,22 @@ __device__ __forceinline__ void image_add(const ImageDev& im, long long bin, dou
 // Bin index of one ray given in sensor-local coordinates, or -1 (dropped / vignetted).
 // flux = intensity * where (optika/sensors/_sensors.py:139): vignetted rays carry weight
 // zero and are not counted.
-__device__ __forceinline__ long long image_bin_index(const ImageDev& im, const ImageGuess& g, bool valid,
+// (an image has fewer than 2^31 bins, checked in fill_image: a 32-bit index halves the shuffles)
+__device__ __forceinline__ int image_bin_index(const ImageDev& im, const ImageGuess& g, bool valid,
                                                      double wavelength, double x, double y, bool unvignetted) {
     if (!valid || !unvignetted) return -1;
     const int iw = find_bin_search(im.e_w, im.n_w, wavelength, g.w0, g.w1);
     const int ix = find_bin_guess(im.e_x, im.n_x, x, g.x0, g.x1, g.inv_dx);
     const int iy = find_bin_guess(im.e_y, im.n_y, y, g.y0, g.y1, g.inv_dy);
     if (iw < 0 || ix < 0 || iy < 0) return -1;
-    return ((long long)iw * im.n_x + ix) * im.n_y + iy;
+    return (iw * im.n_x + ix) * im.n_y + iy;
 }
 
 // Bin one ray given in sensor-local coordinates.  All lanes of the warp call this.
 __device__ __forceinline__ void image_bin_ray(const ImageDev& im, const ImageGuess& g, bool valid, double wavelength, double x,
                                               double y, double cos_real, double cos_imag, double intensity,
                                               bool unvignetted) {
-    const long long bin = image_bin_index(im, g, valid, wavelength, x, y, unvignetted);
+    const int bin = image_bin_index(im, g, valid, wavelength, x, y, unvignetted);
     image_add(im, bin, intensity, intensity * cos_real, intensity * cos_imag, 1u);
 }
 

@@ -1485,7 +1485,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         // AbstractImagingSensor.collect on the final rays in sensor-local coordinates
         // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
         // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
-        long long bin[R];
+        int bin[R];
         double w_flux[R], w_real[R];
         unsigned count[R];
 #pragma unroll
