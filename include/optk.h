@@ -23,7 +23,9 @@
 #ifndef OPTK_H
 #define OPTK_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -477,6 +479,18 @@ OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp
 
 /* intensity[i] *= (e_s[i] + e_p[i]) / 2   (PolarizationVectorArray.average) */
 OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream);
+
+/* ---- run-time specialisation ---------------------------------------------------
+ * Long launches of the streamlined kernels (>= 2^25 rays, full operator, no accumulate) are
+ * served by a kernel compiled with NVRTC for exactly the traced surface list (every kind and
+ * flag a compile-time constant, the walk unrolled; ~1.5 s once per system and kernel
+ * variant, cached for the life of the process).  mode: -1 automatic (default; also the
+ * environment variable OPTK_JIT=-1), 0 never, 1 for every eligible launch.  Results are
+ * bit-identical to the table-driven kernels.  If libnvrtc / libcuda cannot be loaded or the
+ * compilation fails, the table-driven kernels run (a message goes to stderr). */
+OPTK_API int optk_jit_mode(int32_t mode);
+/* Number of kernels compiled so far in this process. */
+OPTK_API int64_t optk_jit_compiled(void);
 
 /* ---- measurement helpers ----------------------------------------------------
  * FP64 DFMA peak micro-benchmark (the roofline denominator that

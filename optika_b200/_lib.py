@@ -248,6 +248,8 @@ SYMBOLS = (
     "optk_trace_grid",
     "optk_bin",
     "optk_multilayer",
+    "optk_jit_mode",
+    "optk_jit_compiled",
     "optk_interp",
     "optk_apply_efficiency",
     "optk_measure_fp64_peak",
@@ -291,6 +293,7 @@ def lib() -> C.CDLL:
     L.optk_multilayer.argtypes = [
         C.POINTER(MlInput), i32, C.POINTER(MlLayer), i32, C.POINTER(MlSegment), vp, vp, vp, vp, vp,
     ]
+    L.optk_jit_mode.argtypes = [i32]
     L.optk_interp.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp, vp]
     L.optk_apply_efficiency.argtypes = [i64, vp, vp, vp, vp]
     L.optk_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
@@ -298,6 +301,7 @@ def lib() -> C.CDLL:
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int
+    L.optk_jit_compiled.restype = C.c_int64
     if L.optk_abi_version() != ABI_VERSION:
         raise OptkError("liboptk.so ABI version mismatch; rebuild it")
     _lib = L

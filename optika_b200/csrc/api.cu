@@ -468,6 +468,13 @@ OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const opt
     return rc;
 }
 
+OPTK_API int optk_jit_mode(int32_t mode) {
+    jit_set_mode(mode);
+    return OPTK_OK;
+}
+
+OPTK_API int64_t optk_jit_compiled(void) { return jit_compiled_count(); }
+
 OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp, const double* fp_re, const double* fp_im,
                 double* out_re, double* out_im, void* stream) {
     if (n < 0 || m < 1 || !x || !xp || !fp_re || !out_re || (fp_im && !out_im)) {

@@ -1,12 +1,26 @@
 // Shared device/host helpers for liboptk (sm_100a).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation of a kernel specialised for one system (jit.cu): no host headers
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long uintptr_t;
+#define NAN __longlong_as_double(0x7ff8000000000000LL)
+#define INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#endif
 #include "optk.h"
 
 namespace optk {
 
+#ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------------------
 // error handling (host)
 // ---------------------------------------------------------------------------
@@ -18,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* what);
         cudaError_t e__ = (call);                              \
         if (e__ != cudaSuccess) return ::optk::cuda_fail(e__, #call); \
     } while (0)
+#endif
 
 // ---------------------------------------------------------------------------
 // exact division of a 32-bit index by a runtime constant: q = umul64hi(n, M),

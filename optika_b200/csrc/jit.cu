@@ -1,0 +1,199 @@
+// Run-time specialisation of the streamlined trace kernels for one system.
+//
+// The table-driven kernels decide per surface and per ray pair which sag, material, ruling
+// and aperture code to run and read every surface parameter through an indexed constant load.
+// For a long job that is worth compiling away: NVRTC builds the same trace_body with the walk
+// written out as surface_full<2, EFF, FixedKinds<...>>(P.surf[k], ...) for compile-time k --
+// no kind or flag tests, parameters as direct constant-bank operands, no spills (measured on
+// cfg 2: fused image 7.8e10 -> 1.0e11 intercepts/s).  The device headers are embedded in the
+// library (embedded_sources.inc); libnvrtc and libcuda are loaded lazily with dlopen so that
+// the library still loads on a machine without a driver.  Any failure falls back to the
+// table-driven CUDA kernels (never to a CPU path).
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "params.cuh"
+#include "embedded_sources.inc"
+
+namespace optk {
+
+namespace {
+
+typedef int (*nvrtcCreateProgram_t)(void**, const char*, const char*, int, const char* const*, const char* const*);
+typedef int (*nvrtcCompileProgram_t)(void*, int, const char* const*);
+typedef int (*nvrtcGetSize_t)(void*, size_t*);
+typedef int (*nvrtcGetData_t)(void*, char*);
+typedef int (*nvrtcDestroyProgram_t)(void**);
+typedef int (*cuModuleLoadData_t)(void**, const void*);
+typedef int (*cuModuleGetFunction_t)(void**, void*, const char*);
+typedef int (*cuLaunchKernel_t)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*,
+                                void**, void**);
+
+struct Api {
+    bool tried = false, ok = false;
+    nvrtcCreateProgram_t create = nullptr;
+    nvrtcCompileProgram_t compile = nullptr;
+    nvrtcGetSize_t cubin_size = nullptr, log_size = nullptr;
+    nvrtcGetData_t cubin = nullptr, log = nullptr;
+    nvrtcDestroyProgram_t destroy = nullptr;
+    cuModuleLoadData_t module_load = nullptr;
+    cuModuleGetFunction_t get_function = nullptr;
+    cuLaunchKernel_t launch = nullptr;
+};
+
+Api g_api;
+std::mutex g_mutex;
+std::map<std::string, void*> g_kernels;  // signature -> CUfunction (nullptr: compilation failed, do not retry)
+int g_mode = -2;                         // -2: read OPTK_JIT on first use; -1 auto; 0 off; 1 always
+long long g_compiled = 0;
+
+void* open_first(const char* const* names) {
+    for (; *names; ++names)
+        if (void* h = dlopen(*names, RTLD_NOW | RTLD_GLOBAL)) return h;
+    return nullptr;
+}
+
+bool load_api() {
+    if (g_api.tried) return g_api.ok;
+    g_api.tried = true;
+    static const char* const rtc_names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so", nullptr};
+    static const char* const cuda_names[] = {"libcuda.so.1", "libcuda.so", nullptr};
+    void* rtc = open_first(rtc_names);
+    void* cu = open_first(cuda_names);
+    if (!rtc || !cu) return false;
+#define OPTK_SYM(handle, field, name)                   \
+    g_api.field = (decltype(g_api.field))dlsym(handle, name); \
+    if (!g_api.field) return false;
+    OPTK_SYM(rtc, create, "nvrtcCreateProgram")
+    OPTK_SYM(rtc, compile, "nvrtcCompileProgram")
+    OPTK_SYM(rtc, cubin_size, "nvrtcGetCUBINSize")
+    OPTK_SYM(rtc, cubin, "nvrtcGetCUBIN")
+    OPTK_SYM(rtc, log_size, "nvrtcGetProgramLogSize")
+    OPTK_SYM(rtc, log, "nvrtcGetProgramLog")
+    OPTK_SYM(rtc, destroy, "nvrtcDestroyProgram")
+    OPTK_SYM(cu, module_load, "cuModuleLoadData")
+    OPTK_SYM(cu, get_function, "cuModuleGetFunction")
+    OPTK_SYM(cu, launch, "cuLaunchKernel")
+#undef OPTK_SYM
+    g_api.ok = true;
+    return true;
+}
+
+bool verbose() {
+    static const bool v = getenv("OPTK_JIT_VERBOSE") != nullptr;
+    return v;
+}
+
+}  // namespace
+
+void jit_set_mode(int mode) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_mode = mode < -1 ? -1 : (mode > 1 ? 1 : mode);
+}
+
+long long jit_compiled_count() { return g_compiled; }
+
+// The generated translation unit for one (system signature, kernel variant).
+std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* key_out) {
+    char line[512];
+    std::string walk;
+    for (int k = 0; k < P.n_surf; ++k) {
+        const optk_surface_t& S = P.surf[k];
+        const bool eff = S.material_efficiency != OPTK_EFF_UNIT || S.ruling_profile != OPTK_PROFILE_IDEAL;
+        snprintf(line, sizeof(line),
+                 "    surface_full<2, %s, FixedKinds<%d, %d, %d, %d, %d>>(P.surf[%d], r, newton_iterations, attenuating);\n",
+                 eff ? "true" : "false", S.sag_kind, S.material_kind, S.ruling_kind, S.aperture_kind, S.flags, k);
+        walk += line;
+    }
+    snprintf(line, sizeof(line), "// variant: dense %d vec %d image %d grid %d minb %d\n", v.dense, v.vec, v.image, v.grid,
+             v.minb);
+    std::string src = line;
+    src +=
+        "#define OPTK_JIT_WALK 1\n"
+        "#include \"trace_impl.cuh\"\n"
+        "namespace optk {\n"
+        "__device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,\n"
+        "                                              bool& attenuating) {\n";
+    src += walk;
+    src += "}\n}  // namespace optk\n";
+    snprintf(line, sizeof(line),
+             "extern \"C\" __global__ void __launch_bounds__(256, %d) optk_jit_kernel(const __grid_constant__ optk::TraceParams P) {\n"
+             "    optk::trace_body<2, true, %s, %s, false, %s, %d, false, 1>(P);\n}\n",
+             v.minb, v.dense ? "true" : "false", v.vec ? "true" : "false", v.image ? "true" : "false", v.grid);
+    src += line;
+    if (key_out) *key_out = src;  // the source is its own cache key
+    return src;
+}
+
+// CUfunction for this launch, compiling it on first use; nullptr = use the table-driven kernel.
+void* jit_kernel(const TraceParams& P, const JitVariant& v) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_mode == -2) {
+        const char* e = getenv("OPTK_JIT");
+        g_mode = e ? (atoi(e) > 0 ? 1 : (atoi(e) == 0 ? 0 : -1)) : -1;
+    }
+    if (g_mode == 0) return nullptr;
+    // automatic: only launches long enough to amortise ~1.5 s of compilation over a few repeats
+    if (g_mode == -1 && P.n_rays < (1LL << 25)) return nullptr;
+    std::string key;
+    const std::string src = jit_source(P, v, &key);
+    auto it = g_kernels.find(key);
+    if (it != g_kernels.end()) return it->second;
+    void* function = nullptr;
+    g_kernels[key] = nullptr;
+    if (!load_api()) {
+        if (verbose()) fprintf(stderr, "optk jit: libnvrtc / libcuda not available, using the table-driven kernels\n");
+        return nullptr;
+    }
+    int device = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    if (major != 10 || minor != 0) return nullptr;  // this library is sm_100a only
+    void* prog = nullptr;
+    if (g_api.create(&prog, src.c_str(), "optk_jit.cu", kHeaderCount, kHeaderSources, kHeaderNames) != 0) return nullptr;
+    const char* options[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-lineinfo"};
+    const int rc = g_api.compile(prog, 4, options);
+    if (rc != 0) {
+        size_t n = 0;
+        g_api.log_size(prog, &n);
+        std::vector<char> log(n + 1, 0);
+        g_api.log(prog, log.data());
+        fprintf(stderr, "optk jit: compilation failed (%d), using the table-driven kernels\n%s\n", rc, log.data());
+        g_api.destroy(&prog);
+        return nullptr;
+    }
+    size_t n = 0;
+    g_api.cubin_size(prog, &n);
+    std::vector<char> cubin(n);
+    g_api.cubin(prog, cubin.data());
+    g_api.destroy(&prog);
+    cudaFree(nullptr);  // make sure the primary context is current for the driver API
+    void* module = nullptr;
+    if (g_api.module_load(&module, cubin.data()) != 0 || g_api.get_function(&function, module, "optk_jit_kernel") != 0) {
+        fprintf(stderr, "optk jit: loading the compiled kernel failed, using the table-driven kernels\n");
+        return nullptr;
+    }
+    ++g_compiled;
+    if (verbose()) fprintf(stderr, "optk jit: compiled a kernel for %d surfaces (%zu bytes)\n", P.n_surf, n);
+    g_kernels[key] = function;
+    return function;
+}
+
+int jit_launch(void* function, const TraceParams& P, unsigned grid, cudaStream_t stream) {
+    void* args[] = {(void*)&P};
+    const int rc = g_api.launch(function, grid, 1, 1, 256, 1, 1, 0, (void*)stream, args, nullptr);
+    if (rc != 0) {
+        set_error("optk jit: cuLaunchKernel failed (%d)", rc);
+        return OPTK_ERR_CUDA;
+    }
+    return OPTK_OK;
+}
+
+}  // namespace optk

@@ -45,11 +45,21 @@ struct TraceParams {
     optk_surface_t surf[OPTK_MAX_SURFACES];
 };
 
+#ifndef __CUDACC_RTC__
+// run-time specialised kernels (jit.cu)
+struct JitVariant {
+    int dense, vec, image, grid, minb;
+};
+void* jit_kernel(const TraceParams& P, const JitVariant& v);  // CUfunction or nullptr
+int jit_launch(void* function, const TraceParams& P, unsigned grid, cudaStream_t stream);
+void jit_set_mode(int mode);  // -1 automatic (long launches), 0 off, 1 always
+long long jit_compiled_count();
 int launch_trace(const TraceParams& P, cudaStream_t stream);
 int launch_trace_tma(const TraceParams& P, cudaStream_t stream);  // full tiles of tma_tile_rays() rays only
 int tma_tile_rays();
 int launch_bin(long long n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
                const double* intensity, const uint8_t* unvignetted, const ImageDev& im, cudaStream_t stream);
+#endif
 
 struct LayerDev {
     const double* n_re;
@@ -82,11 +92,14 @@ struct MultilayerParams {
     int32_t pad;
 };
 
+#ifndef __CUDACC_RTC__
 int launch_multilayer(const MultilayerParams& P, cudaStream_t stream);
 int launch_interp(long long n, const double* x, int m, const double* xp, const double* fp_re, const double* fp_im,
                   double* out_re, double* out_im, cudaStream_t stream);
 int launch_apply_efficiency(long long n, double* intensity, const double* e_s, const double* e_p, cudaStream_t stream);
 int measure_fp64_peak(double* flops, cudaStream_t stream);
 int measure_soa_copy(long long n_rays, double* gbytes_per_second, cudaStream_t stream);
+
+#endif
 
 }  // namespace optk

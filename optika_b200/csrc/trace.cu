@@ -177,6 +177,11 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         OPTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, (const void*)kernel, block, 0));
         Q.prefetch_distance = (long long)prefetch_waves * sms * ctas * block * rays_per_thread;
     }
+    // a kernel compiled for exactly this surface list, when the launch is long enough to pay for it
+    if (full && !acc && !curvilinear) {
+        const JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0, use_heavy ? 2 : 3};
+        if (void* function = jit_kernel(P, variant)) return jit_launch(function, P, (unsigned)grid, stream);
+    }
     void* args[] = {(void*)&P};
     OPTK_CUDA(cudaLaunchKernel((const void*)kernel, dim3((unsigned)grid), dim3(block), args, 0, stream));
     return OPTK_OK;

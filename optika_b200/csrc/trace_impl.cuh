@@ -17,7 +17,9 @@
 #include "common.cuh"
 #include "bin.cuh"
 #include "params.cuh"
+#ifndef __CUDACC_RTC__
 #include <cstdlib>
+#endif
 
 namespace optk {
 
@@ -454,12 +456,30 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
 // parallelism for the long fp64 dependency chains).
 // AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
+// Where the element kinds and flags of a surface come from: the table (run time) or template
+// arguments (a kernel specialised for one system: every kind test folds away at compile time).
+struct TableKinds {
+    static __device__ __forceinline__ int sag(const optk_surface_t& S) { return S.sag_kind; }
+    static __device__ __forceinline__ int material(const optk_surface_t& S) { return S.material_kind; }
+    static __device__ __forceinline__ int ruling(const optk_surface_t& S) { return S.ruling_kind; }
+    static __device__ __forceinline__ int aperture(const optk_surface_t& S) { return S.aperture_kind; }
+    static __device__ __forceinline__ int flags(const optk_surface_t& S) { return S.flags; }
+};
+template <int SAG, int MATERIAL, int RULING, int APERTURE, int FLAGS>
+struct FixedKinds {
+    static __device__ __forceinline__ constexpr int sag(const optk_surface_t&) { return SAG; }
+    static __device__ __forceinline__ constexpr int material(const optk_surface_t&) { return MATERIAL; }
+    static __device__ __forceinline__ constexpr int ruling(const optk_surface_t&) { return RULING; }
+    static __device__ __forceinline__ constexpr int aperture(const optk_surface_t&) { return APERTURE; }
+    static __device__ __forceinline__ constexpr int flags(const optk_surface_t&) { return FLAGS; }
+};
+
 // `attenuating`: some ray of the thread still carries a non-zero attenuation (set when the rays
 // are loaded, cleared by every non-mirror material, which zeroes the attenuation).
-template <int R, bool EFF = false>
+template <int R, bool EFF = false, class K = TableKinds>
 __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations,
                                              bool& attenuating) {
-    const int flags = S.flags;
+    const int flags = K::flags(S);
 
     // 1. global -> surface-local (surfaces.py:141-142)
     if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
@@ -479,7 +499,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 
     // 2 + 3. path length to the sag and the unit normal at the hit point (surfaces.py:144-148)
     double t[R], nx[R], ny[R], nz[R];
-    switch (S.sag_kind) {
+    switch (K::sag(S)) {
         case OPTK_SAG_FLAT:
 #pragma unroll
             for (int k = 0; k < R; ++k) {
@@ -550,11 +570,11 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
     }
 
     // 4. rulings.incident_effective  (surfaces.py:150-154, rulings/_rulings.py:107-128, 187-204)
-    if (S.ruling_kind != OPTK_RULING_NONE) {
+    if (K::ruling(S) != OPTK_RULING_NONE) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             double kx, ky, kz;
-            if (S.ruling_kind == OPTK_RULING_CONSTANT) {
+            if (K::ruling(S) == OPTK_RULING_CONSTANT) {
                 // optika/rulings/_spacing.py:69-74
                 const double c = S.ruling_coeff[0];
                 kx = c * S.ruling_normal[0];
@@ -591,8 +611,8 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 
     // 5-8. material: index, wavelength, Snell, attenuation  (surfaces.py:156-190)
     {
-        const bool mirror = S.material_kind == OPTK_MAT_MIRROR;
-        const bool glass = S.material_kind == OPTK_MAT_GLASS;
+        const bool mirror = K::material(S) == OPTK_MAT_MIRROR;
+        const bool glass = K::material(S) == OPTK_MAT_GLASS;
         double n2[R];
         bool same_medium = true;
 #pragma unroll
@@ -612,7 +632,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
         // skipping the root there changes directions by < 1e-14 / |a.n|.  Directions that are not
         // unit to 1e-14 (user input) take the full formula, which renormalises them as the
         // reference does.
-        bool straight = same_medium && !mirror && S.ruling_kind == OPTK_RULING_NONE;
+        bool straight = same_medium && !mirror && K::ruling(S) == OPTK_RULING_NONE;
         if (straight) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
@@ -655,8 +675,8 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
     }
 
     // 9. aperture.clip_rays on the outgoing ray, local coordinates  (surfaces.py:192-193)
-    if (S.aperture_kind != OPTK_APERTURE_NONE) {
-        if (S.aperture_kind == OPTK_APERTURE_RECTANGULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
+    if (K::aperture(S) != OPTK_APERTURE_NONE) {
+        if (K::aperture(S) == OPTK_APERTURE_RECTANGULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
             // optika/apertures/_apertures.py:962-963 (the common case, inlined)
             const double hx = S.aperture[0], hy = S.aperture[1];
             const bool inverted = flags & OPTK_F_APERTURE_INVERTED, active = flags & OPTK_F_APERTURE_ACTIVE;
@@ -666,7 +686,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                 m = (m != inverted) || !active;
                 r[k].unv = r[k].unv && m;
             }
-        } else if (S.aperture_kind == OPTK_APERTURE_CIRCULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
+        } else if (K::aperture(S) == OPTK_APERTURE_CIRCULAR && !(flags & (OPTK_F_APERTURE_TRANSFORM | OPTK_F_APERTURE_ANGULAR))) {
             // optika/apertures/_apertures.py:309 as "x^2 + y^2 <= T" (see aperture_test), inlined
             const double threshold = S.aperture[3];
             const bool inverted = flags & OPTK_F_APERTURE_INVERTED, active = flags & OPTK_F_APERTURE_ACTIVE;
@@ -1337,7 +1357,13 @@ __device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long 
         *reinterpret_cast<uchar2*>(out.unvignetted + o) = make_uchar2(r[0].unv ? 1 : 0, r[1].unv ? 1 : 0);
 }
 
-template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID, bool EFF>
+#ifdef OPTK_JIT_WALK
+__device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,
+                                              bool& attenuating);
+#endif
+
+// SPEC: 0 the surface list is walked from the table; 1 a run-time compiled walk (R = 2, no ACC)
+template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID, bool EFF, int SPEC = 0>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
     __shared__ ImageGuess guess;
     // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
@@ -1442,6 +1468,13 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     // surface loop stays warp-convergent and its per-surface decisions and parameter loads
     // can use the uniform datapath (only the stores are predicated).
     {
+        if constexpr (SPEC == 1) {
+            // a kernel compiled at run time for one system (jit.cu): the walk is a straight sequence of
+            // surface_full<2, EFF, FixedKinds<...>>(P.surf[k], ...) with compile-time k
+#ifdef OPTK_JIT_WALK
+            optk_jit_walk(P, r, newton_iterations, attenuating);
+#endif
+        } else
         for (int s = 0; s < P.n_surf; ++s) {
             if (FULL)
                 surface_full<R, EFF>(P.surf[s], r, newton_iterations, attenuating);
@@ -1532,9 +1565,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
 // instead of per ray per surface.  The streamlined kernels carry two rays per thread in
 // <= 80 registers (3 CTAs of 256 threads per SM: the measured best).
 // GRID: 0 rays from memory, 1 on-device separable vertex grid, 2 curvilinear (2-D vertex arrays)
-template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID = 0, bool EFF = false>
+template <int MINB, int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID = 0, bool EFF = false, int SPEC = 0>
 __global__ void __launch_bounds__(256, MINB) trace_kernel(const __grid_constant__ TraceParams P) {
-    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE, GRID, EFF>(P);
+    trace_body<R, FULL, DENSE, VEC, ACC, IMAGE, GRID, EFF, SPEC>(P);
 }
 
 typedef void (*trace_kernel_t)(const TraceParams);
