@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 3
+#define OPTK_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -479,6 +479,41 @@ OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp
 
 /* intensity[i] *= (e_s[i] + e_p[i]) / 2   (PolarizationVectorArray.average) */
 OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream);
+
+/* ---- stop solver -------------------------------------------
+ * SequentialSystem._calc_rayfunction_stops_only (optika/systems/_sequential.py:396-623) finds
+ * the rays that connect a grid of points on one stop surface with a grid of points on the other
+ * one by a 2-D Newton iteration with a finite-difference Jacobian (na.optimize.root_newton /
+ * na.jacobian, :586-606) around _ray_error (:363-394).  optk_solve_stops runs that iteration on
+ * the device, one thread per unknown ray, around the same surface walk optk_trace uses.
+ *
+ * The rays start in the GLOBAL frame on surface `surf_first` (they are not propagated through
+ * it) and are traced through surf_first + 1 ... surf_last.  `variable` says which vector of the
+ * ray is solved for -- its global x, y components are the unknowns, its z follows from them
+ * (direction: sqrt(1 - x^2 - y^2); position: the sag of surf_first at (x, y), which must not
+ * carry a sag transformation) -- the other vector is `fixed`.  `target` says which vector of the
+ * traced ray, in the local frame of surf_last, must equal (target_x, target_y).
+ * Per-ray device arrays of length n; x, y hold the initial guess on entry and the solution on
+ * exit, z receives the third component.  A ray stops iterating once both residual components
+ * are <= max_abs_error; *n_unconverged (device, caller-zeroed) counts rays that did not get
+ * there within max_iterations (the reference raises "Max iterations exceeded"). */
+#define OPTK_STOP_DIRECTION 0
+#define OPTK_STOP_POSITION 1
+typedef struct optk_stop_problem_t {
+    int32_t variable;       /* OPTK_STOP_DIRECTION / OPTK_STOP_POSITION */
+    int32_t target;         /* OPTK_STOP_DIRECTION / OPTK_STOP_POSITION */
+    int32_t surf_first;
+    int32_t surf_last;      /* > surf_first, at most OPTK_MAX_SURFACES - 1 surfaces apart */
+    int32_t max_iterations; /* the reference's default: 100 */
+    int32_t reserved;
+    double step;            /* forward-difference step of the Jacobian (:586-591) */
+    double max_abs_error;   /* :561-568 */
+} optk_stop_problem_t;
+
+OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const optk_stop_problem_t* problem, int64_t n,
+                     const double* wavelength, const double* fixed_x, const double* fixed_y, const double* fixed_z,
+                     const double* target_x, const double* target_y, double* x, double* y, double* z,
+                     uint32_t* n_unconverged, void* stream);
 
 /* ---- run-time specialisation ---------------------------------------------------
  * Long launches of the streamlined kernels (>= 2^25 rays, full operator, no accumulate) are

@@ -600,6 +600,87 @@ def _trace(
 
 
 # ---------------------------------------------------------------------------
+# stop solver on the device (optk_solve_stops)
+# ---------------------------------------------------------------------------
+def solve_stops(
+    surfaces,
+    rays: RayVectorArray,
+    variable: str,
+    x0,
+    y0,
+    target_xy: na.Cartesian2dVectorArray,
+    target: str,
+    step: float,
+    max_abs_error: float,
+    max_iterations: int = 100,
+    device=None,
+):
+    """
+    The Newton iteration of ``SequentialSystem._calc_rayfunction_stops_only``
+    (``optika/systems/_sequential.py:551-606``) in one launch per configuration.
+
+    `surfaces` is the sub-system between the two stops (both included); `rays` start on
+    ``surfaces[0]`` in global coordinates; `variable` ("direction" / "position") names the vector
+    whose global x, y components are solved for, starting from `x0`, `y0`; `target` names the
+    vector of the traced ray that must equal `target_xy` in the local frame of ``surfaces[-1]``.
+    Returns the three components of the solved vector as named arrays, or ``None`` when the
+    problem is outside what the kernel covers (the caller then iterates on the host).
+    """
+    if len(surfaces) < 2 or len(surfaces) > L.MAX_SURFACES:
+        return None
+    sag = getattr(surfaces[0], "sag", None)
+    if variable == "position" and sag is not None and getattr(sag, "transformation", None) is not None:
+        return None
+    torch = _torch()
+    device = require_cuda(device)
+    system = CompiledSystem(surfaces)
+    fixed = rays.position if variable == "direction" else rays.direction
+    named = [rays.wavelength, fixed.x, fixed.y, fixed.z, target_xy.x, target_xy.y, x0, y0]
+    named = [na.as_named_array(u.length(a) if k == 0 else a) for k, a in enumerate(named)]
+    total = na.broadcast_shapes(system.shape, *[a.shape for a in named])
+    full = {ax: total[ax] for ax in system.shape}
+    full.update({ax: n for ax, n in total.items() if ax not in full})
+    dims = tuple(full.values())
+    n_config = system.n_config
+    n = int(np.prod(dims, dtype=np.int64)) // max(n_config, 1) if dims else 1
+
+    def upload(a):
+        nd = np.broadcast_to(na.aligned(a, full), dims).astype(np.float64)
+        return torch.from_numpy(np.ascontiguousarray(nd).reshape(n_config, n)).to(device)
+
+    w, fx, fy, fz, tx, ty, x, y = [upload(a) for a in named]
+    z = torch.empty_like(x)
+    unconverged = torch.zeros(1, dtype=torch.int32, device=device)
+    problem = L.StopProblem(
+        variable=L.STOP_DIRECTION if variable == "direction" else L.STOP_POSITION,
+        target=L.STOP_DIRECTION if target == "direction" else L.STOP_POSITION,
+        surf_first=0,
+        surf_last=len(surfaces) - 1,
+        max_iterations=max_iterations,
+        reserved=0,
+        step=float(step),
+        max_abs_error=float(max_abs_error),
+    )
+    stream = _stream_ptr(device)
+    lib = L.lib()
+    for c in range(n_config):
+        if n == 0:
+            break
+        L.check(
+            lib.optk_solve_stops(
+                system.handle, c, C.byref(problem), n,
+                w[c].data_ptr(), fx[c].data_ptr(), fy[c].data_ptr(), fz[c].data_ptr(),
+                tx[c].data_ptr(), ty[c].data_ptr(), x[c].data_ptr(), y[c].data_ptr(), z[c].data_ptr(),
+                unconverged.data_ptr(), stream,
+            )
+        )
+    if int(unconverged.item()) > 0:
+        raise ValueError("Max iterations exceeded")
+    axes = tuple(full)
+    return tuple(na.ScalarArray(t.cpu().numpy().reshape(dims), axes) for t in (x, y, z))
+
+
+# ---------------------------------------------------------------------------
 # unit operations of the reference API, executed by one-surface traces that are
 # restricted to the relevant stages of the surface operator
 # ---------------------------------------------------------------------------

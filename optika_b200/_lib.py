@@ -178,6 +178,22 @@ class Grid(C.Structure):
     ]
 
 
+STOP_DIRECTION, STOP_POSITION = 0, 1
+
+
+class StopProblem(C.Structure):
+    _fields_ = [
+        ("variable", C.c_int32),
+        ("target", C.c_int32),
+        ("surf_first", C.c_int32),
+        ("surf_last", C.c_int32),
+        ("max_iterations", C.c_int32),
+        ("reserved", C.c_int32),
+        ("step", C.c_double),
+        ("max_abs_error", C.c_double),
+    ]
+
+
 class TraceStats(C.Structure):
     _fields_ = [
         ("n_rays", C.c_uint64),
@@ -225,7 +241,7 @@ class MlInput(C.Structure):
     ]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class OptkError(RuntimeError):
@@ -248,6 +264,7 @@ SYMBOLS = (
     "optk_trace_grid",
     "optk_bin",
     "optk_multilayer",
+    "optk_solve_stops",
     "optk_jit_mode",
     "optk_jit_compiled",
     "optk_interp",
@@ -294,6 +311,7 @@ def lib() -> C.CDLL:
         C.POINTER(MlInput), i32, C.POINTER(MlLayer), i32, C.POINTER(MlSegment), vp, vp, vp, vp, vp,
     ]
     L.optk_jit_mode.argtypes = [i32]
+    L.optk_solve_stops.argtypes = [vp, i32, C.POINTER(StopProblem), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.optk_interp.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp, vp]
     L.optk_apply_efficiency.argtypes = [i64, vp, vp, vp, vp]
     L.optk_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]

@@ -5,10 +5,12 @@ Mirrors ``SequentialSystem._calc_rayfunction_stops_only`` / ``_calc_rayfunction_
 / ``_denormalize_grid`` (``optika/systems/_sequential.py:396-678, 748-789``).  This is a
 host-side *caller* of the hot path: a 2-D Newton
 iteration with a finite-difference Jacobian whose residual function traces a
-small batch of rays through the sub-system between the two stop surfaces.  Every
-trace runs on the device through ``propagators.propagate_rays``; the Newton
-bookkeeping (a few hundred rays) is NumPy on the host, exactly where the
-reference keeps it.
+small batch of rays through the sub-system between the two stop surfaces.  With
+the device backend the whole iteration runs in one kernel launch per
+configuration (``optk_solve_stops``, one thread per unknown ray); the host
+iteration below (every trace on the device through ``propagators.propagate_rays``,
+Newton bookkeeping in NumPy, exactly where the reference keeps it) remains for
+injected backends and for the cases the kernel does not cover.
 
 The two primitives the solver needs -- ``propagate(surfaces, rays)`` and
 ``sag(surface, x, y)`` -- come from a small backend object (default: the device
@@ -43,6 +45,13 @@ class DeviceBackend:
     @staticmethod
     def sag(surface, x, y):
         return surface.sag(na.Cartesian3dVectorArray(x, y, 0.0 * (x + y)))
+
+    @staticmethod
+    def solve(surfaces, rays, variable, x0, y0, target_xy, target, step, max_abs_error):
+        """The whole Newton iteration on the device (``optk_solve_stops``); ``None`` = not covered."""
+        from . import _engine
+
+        return _engine.solve_stops(surfaces, rays, variable, x0, y0, target_xy, target, step, max_abs_error)
 
 
 def _is_angular(aperture) -> bool:
@@ -220,13 +229,22 @@ def _stops_only(system, wavelength, samples_pupil_stop, samples_field_stop, back
         x0 = na.broadcast_to(na.as_named_array(variables.x), shape_).copy()
         y0 = na.broadcast_to(na.as_named_array(variables.y), shape_).copy()
         try:
-            rx, ry = _newton(function, x0, y0, dx, max_abs_error)
+            # the device backend runs the whole iteration in one launch per configuration
+            # (SURVEY.md section 8f-1); other backends, and problems the kernel does not cover,
+            # iterate here with one batch of traces per residual evaluation
+            solve = getattr(backend, "solve", None)
+            solved = None
+            if solve is not None:
+                solved = solve(subsystem, rays, variable, x0, y0, grid_last, target, dx, max_abs_error)
+            if solved is None:
+                rx, ry = _newton(function, x0, y0, dx, max_abs_error)
+                solved = (rx, ry, zfunc(rx, ry))
         except ValueError as e:
             raise ValueError(
                 f"Could not solve for the rays connecting the stop surfaces "
                 f"{surface_first.name!r} and {surface_last.name!r}."
             ) from e
-        rays = dataclasses.replace(rays, **{variable: na.Cartesian3dVectorArray(rx, ry, zfunc(rx, ry))})
+        rays = dataclasses.replace(rays, **{variable: na.Cartesian3dVectorArray(*solved)})
     return inputs, rays, surfaces
 
 

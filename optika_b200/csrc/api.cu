@@ -468,6 +468,71 @@ OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const opt
     return rc;
 }
 
+OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const optk_stop_problem_t* problem, int64_t n,
+                     const double* wavelength, const double* fixed_x, const double* fixed_y, const double* fixed_z,
+                     const double* target_x, const double* target_y, double* x, double* y, double* z,
+                     uint32_t* n_unconverged, void* stream) {
+    static thread_local TraceParams P;
+    if (!problem || n < 0) {
+        set_error("optk_solve_stops: problem is NULL or n is negative");
+        return OPTK_ERR_INVALID;
+    }
+    if (n > 0 && (!wavelength || !fixed_x || !fixed_y || !fixed_z || !target_x || !target_y || !x || !y || !z ||
+                  !n_unconverged)) {
+        set_error("optk_solve_stops: NULL array");
+        return OPTK_ERR_INVALID;
+    }
+    if ((problem->variable != OPTK_STOP_DIRECTION && problem->variable != OPTK_STOP_POSITION) ||
+        (problem->target != OPTK_STOP_DIRECTION && problem->target != OPTK_STOP_POSITION)) {
+        set_error("optk_solve_stops: variable / target must be OPTK_STOP_DIRECTION or OPTK_STOP_POSITION");
+        return OPTK_ERR_INVALID;
+    }
+    const int count = problem->surf_last - problem->surf_first;
+    if (count < 1 || count > OPTK_MAX_SURFACES - 1) {
+        set_error("optk_solve_stops: surf_last - surf_first = %d out of range [1, %d]", count, OPTK_MAX_SURFACES - 1);
+        return OPTK_ERR_INVALID;
+    }
+    if (!(problem->step > 0.0) || !(problem->max_abs_error >= 0.0) || problem->max_iterations < 1) {
+        set_error("optk_solve_stops: step must be positive, max_abs_error non-negative, max_iterations >= 1");
+        return OPTK_ERR_INVALID;
+    }
+    // surfaces surf_first + 1 ... surf_last are walked; the first stop surface rides along in the
+    // next slot for its sag
+    int rc = pack_trace(sys, config, problem->surf_first + 1, count, 1, 0, &P);
+    if (rc) return rc;
+    if (problem->surf_first < 0) {
+        set_error("optk_solve_stops: surf_first is negative");
+        return OPTK_ERR_INVALID;
+    }
+    const optk_surface_t& first = sys->table[(size_t)config * sys->n_surface + problem->surf_first];
+    int sag_slot = -1;
+    if (problem->variable == OPTK_STOP_POSITION && first.sag_kind != OPTK_SAG_FLAT) {
+        if (first.flags & OPTK_F_SAG_TRANSFORM) {
+            set_error("optk_solve_stops: a first stop surface whose sag carries a transformation is not supported");
+            return OPTK_ERR_UNSUPPORTED;
+        }
+        sag_slot = count;
+        P.surf[sag_slot] = first;
+    }
+    for (int k = 0; k < count; ++k) {
+        if (P.surf[k].stages != OPTK_STAGE_ALL) {
+            set_error("optk_solve_stops: the system must be compiled with the full surface operator");
+            return OPTK_ERR_INVALID;
+        }
+    }
+    P.surf[count - 1].flags |= OPTK_F_LOCAL_OUT;  // residuals live in the last surface's local frame
+    memset(&P.in, 0, sizeof(P.in));
+    memset(&P.out, 0, sizeof(P.out));
+    P.n_rays = n;
+    P.stats = nullptr;
+    P.has_image = 0;
+    P.has_frame = 0;
+    const double* fixed[3] = {fixed_x, fixed_y, fixed_z};
+    const double* target[2] = {target_x, target_y};
+    return launch_stop_newton(P, *problem, sag_slot, n, wavelength, fixed, target, x, y, z, n_unconverged,
+                              (cudaStream_t)stream);
+}
+
 OPTK_API int optk_jit_mode(int32_t mode) {
     jit_set_mode(mode);
     return OPTK_OK;

@@ -106,9 +106,18 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
     for (int k = 0; k < P.n_surf; ++k) {
         const optk_surface_t& S = P.surf[k];
         const bool eff = S.material_efficiency != OPTK_EFF_UNIT || S.ruling_profile != OPTK_PROFILE_IDEAL;
+        // loop lengths and integer exponents that shape the code are compile-time constants as well:
+        // polygon vertices (the edge loop unrolls) and the polynomial ruling's powers (x^p by
+        // repeated multiplication folds to the few multiplications it is)
+        const int nv = S.aperture_kind == OPTK_APERTURE_POLYGON ? S.n_vertices : 0;
+        const int nc = S.ruling_kind == OPTK_RULING_POLYNOMIAL ? S.n_coeff : 0;
+        int pw[OPTK_MAX_COEFF] = {0};
+        for (int j = 0; j < nc && j < OPTK_MAX_COEFF; ++j) pw[j] = S.ruling_power[j];
         snprintf(line, sizeof(line),
-                 "    surface_full<2, %s, FixedKinds<%d, %d, %d, %d, %d>>(P.surf[%d], r, newton_iterations, attenuating);\n",
-                 eff ? "true" : "false", S.sag_kind, S.material_kind, S.ruling_kind, S.aperture_kind, S.flags, k);
+                 "    surface_full<2, %s, FixedKinds<%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d>>"
+                 "(P.surf[%d], r, newton_iterations, attenuating);\n",
+                 eff ? "true" : "false", S.sag_kind, S.material_kind, S.ruling_kind, S.aperture_kind, S.flags, nv, nc,
+                 pw[0], pw[1], pw[2], pw[3], pw[4], pw[5], pw[6], pw[7], k);
         walk += line;
     }
     snprintf(line, sizeof(line), "// variant: dense %d vec %d image %d grid %d minb %d\n", v.dense, v.vec, v.image, v.grid,

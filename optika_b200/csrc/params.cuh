@@ -55,6 +55,9 @@ int jit_launch(void* function, const TraceParams& P, unsigned grid, cudaStream_t
 void jit_set_mode(int mode);  // -1 automatic (long launches), 0 off, 1 always
 long long jit_compiled_count();
 int launch_trace(const TraceParams& P, cudaStream_t stream);
+int launch_stop_newton(const TraceParams& P, const optk_stop_problem_t& problem, int sag_slot, long long n,
+                       const double* wavelength, const double* const fixed[3], const double* const target[2], double* x,
+                       double* y, double* z, unsigned int* n_unconverged, cudaStream_t stream);
 int launch_trace_tma(const TraceParams& P, cudaStream_t stream);  // full tiles of tma_tile_rays() rays only
 int tma_tile_rays();
 int launch_bin(long long n_rays, const double* wavelength, const double* x, const double* y, const double* dz,

@@ -74,7 +74,19 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         if (S.material_kind == OPTK_MAT_GLASS) cost += 0.5;
     }
     const bool heavy = cost > 4.5;
-    const bool use_tma = tma_mode == 1 || (tma_mode < 0 && !heavy);
+    static const int jit_minb = [] {
+        const char* e = getenv("OPTK_JIT_MINB");  // experiments: resident CTAs per SM the compiled kernel is built for
+        return e ? atoi(e) : 0;
+    }();
+    // A kernel compiled for this surface list (jit.cu) streams faster than the pipeline: its walk is
+    // short enough for 24 resident warps to cover HBM latency (cfg 2: 2.41 ms per 1e8 rays against
+    // 2.74 for the pipeline and 3.18 for the table-driven direct-load kernel).
+    bool specialised = false;
+    if (tma_mode < 0 && !heavy && full && vec && !acc && !image && !from_grid) {
+        const JitVariant variant = {1, 1, 0, 0, jit_minb > 0 ? jit_minb : 3};
+        specialised = jit_kernel(P, variant) != nullptr;
+    }
+    const bool use_tma = tma_mode == 1 || (tma_mode < 0 && !heavy && !specialised);
     if (use_tma && vec && !acc && !image && !from_grid && P.n_rays >= 64LL * tma_tile_rays()) {
         // bulk copies need 16-byte aligned sources (the fields are, `vec`; the mask may not be)
         bool all_out = P.out.unvignetted != nullptr && aligned16(P.in.unvignetted);
@@ -179,7 +191,8 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     }
     // a kernel compiled for exactly this surface list, when the launch is long enough to pay for it
     if (full && !acc && !curvilinear) {
-        const JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0, use_heavy ? 2 : 3};
+        const JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0,
+                                    jit_minb > 0 ? jit_minb : (use_heavy ? 2 : 3)};
         if (void* function = jit_kernel(P, variant)) return jit_launch(function, P, (unsigned)grid, stream);
     }
     void* args[] = {(void*)&P};

@@ -28,6 +28,36 @@ struct Ray {
     bool unv;
 };
 
+// Where the element kinds and flags of a surface come from: the table (run time) or template
+// arguments (a kernel compiled at run time for one system, jit.cu: every kind test folds away,
+// polygon and polynomial loops unroll, and the rarer element kinds are inlined for both rays).
+struct TableKinds {
+    static constexpr bool fixed = false;
+    static __device__ __forceinline__ int sag(const optk_surface_t& S) { return S.sag_kind; }
+    static __device__ __forceinline__ int material(const optk_surface_t& S) { return S.material_kind; }
+    static __device__ __forceinline__ int ruling(const optk_surface_t& S) { return S.ruling_kind; }
+    static __device__ __forceinline__ int aperture(const optk_surface_t& S) { return S.aperture_kind; }
+    static __device__ __forceinline__ int flags(const optk_surface_t& S) { return S.flags; }
+    static __device__ __forceinline__ int n_vertices(const optk_surface_t& S) { return S.n_vertices; }
+    static __device__ __forceinline__ int n_coeff(const optk_surface_t& S) { return S.n_coeff; }
+    static __device__ __forceinline__ int power(const optk_surface_t& S, int k) { return S.ruling_power[k]; }
+};
+template <int SAG, int MATERIAL, int RULING, int APERTURE, int FLAGS, int NV = 0, int NC = 0, int P0 = 0, int P1 = 0,
+          int P2 = 0, int P3 = 0, int P4 = 0, int P5 = 0, int P6 = 0, int P7 = 0>
+struct FixedKinds {
+    static constexpr bool fixed = true;
+    static __device__ __forceinline__ constexpr int sag(const optk_surface_t&) { return SAG; }
+    static __device__ __forceinline__ constexpr int material(const optk_surface_t&) { return MATERIAL; }
+    static __device__ __forceinline__ constexpr int ruling(const optk_surface_t&) { return RULING; }
+    static __device__ __forceinline__ constexpr int aperture(const optk_surface_t&) { return APERTURE; }
+    static __device__ __forceinline__ constexpr int flags(const optk_surface_t&) { return FLAGS; }
+    static __device__ __forceinline__ constexpr int n_vertices(const optk_surface_t&) { return NV; }
+    static __device__ __forceinline__ constexpr int n_coeff(const optk_surface_t&) { return NC; }
+    static __device__ __forceinline__ constexpr int power(const optk_surface_t&, int k) {
+        return k == 0 ? P0 : k == 1 ? P1 : k == 2 ? P2 : k == 3 ? P3 : k == 4 ? P4 : k == 5 ? P5 : k == 6 ? P6 : P7;
+    }
+};
+
 // ---------------------------------------------------------------------------
 // sag profiles, evaluated in the sag's own frame
 // ---------------------------------------------------------------------------
@@ -59,9 +89,10 @@ __device__ __forceinline__ double parabola_intercept(double f, double ox, double
 }
 
 // Path length t to the surface for a ray o + t u (closed forms), or NaN/inf on a miss.
+template <class K = TableKinds>
 __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, double ox, double oy, double oz,
                                                        double ux, double uy, double uz) {
-    switch (S.sag_kind) {
+    switch (K::sag(S)) {
         case OPTK_SAG_FLAT:
             // optika/sags/_flat.py:58: d = -o.z / u.z
             return fdiv(-oz, uz);
@@ -130,21 +161,29 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
 // Toroid: z and its gradient (optika/sags/_toroidal.py:38-88).
 __device__ __forceinline__ void toroid_eval(double c, double r, double x, double y, double& z, double& dzdx,
                                             double& dzdy) {
+    // g = sqrt(a) and f = sqrt(b) are needed together with 1 / g and 1 / f: one reciprocal square
+    // root each (g = a / sqrt(a)) and one reciprocal for 1 / (1 + g), instead of two square roots,
+    // two divisions and a reciprocal.  Outside the domain (a < 0 or b < 0) everything is NaN as in
+    // the reference; exactly on its boundary (a = 0 or b = 0, a set of measure zero) the reference's
+    // infinite slope becomes NaN.
     const double y2 = y * y;
-    const double g = fsqrt(1.0 - c * c * y2);
-    const double zy = fdiv(c * y2, 1.0 + g);
+    const double a = 1.0 - c * c * y2;
+    const double inv_g = frsqrt(a);
+    const double g = a * inv_g;
+    const double zy = c * y2 * frcp(1.0 + g);
     const double rz = r - zy;
-    const double f = fsqrt(rz * rz - x * x);
-    z = r - f;
-    const double inv_f = frcp(f);
+    const double b = rz * rz - x * x;
+    const double inv_f = frsqrt(b);
+    z = r - b * inv_f;
     dzdx = x * inv_f;
-    dzdy = rz * fdiv(c * y, g) * inv_f;
+    dzdy = rz * (c * y * inv_g) * inv_f;
 }
 
 // Unit normal at a point of the sag frame (not rotated back, as in the reference).
+template <class K = TableKinds>
 __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, double y, double& nx, double& ny,
                                            double& nz) {
-    switch (S.sag_kind) {
+    switch (K::sag(S)) {
         case OPTK_SAG_FLAT:
             nx = 0.0; ny = 0.0; nz = -1.0;  // optika/sags/_flat.py:43-47
             return;
@@ -245,9 +284,10 @@ __device__ __forceinline__ double ipow(double x, int p) {
     return neg ? 1.0 / r : r;
 }
 
+template <class K = TableKinds>
 __device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px, double py, double pz, double nx,
                                               double ny, double nz, double& kx, double& ky, double& kz) {
-    switch (S.ruling_kind) {
+    switch (K::ruling(S)) {
         case OPTK_RULING_CONSTANT: {
             // optika/rulings/_spacing.py:69-74
             const double c = S.ruling_coeff[0];
@@ -258,10 +298,15 @@ __device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px
         }
         case OPTK_RULING_POLYNOMIAL: {
             // optika/rulings/_spacing.py:109-128
-            if (S.flags & OPTK_F_RULING_TRANSFORM) affine_forward(S.ruling_transform, px, py, pz, false);
+            if (K::flags(S) & OPTK_F_RULING_TRANSFORM) affine_forward(S.ruling_transform, px, py, pz, false);
             const double x = px * S.ruling_normal[0] + py * S.ruling_normal[1] + pz * S.ruling_normal[2];
             double d = 0.0;
-            for (int k = 0; k < S.n_coeff; ++k) d += S.ruling_coeff[k] * ipow(x, S.ruling_power[k]);
+            if (K::fixed) {
+#pragma unroll
+                for (int k = 0; k < K::n_coeff(S); ++k) d += S.ruling_coeff[k] * ipow(x, K::power(S, k));
+            } else {
+                for (int k = 0; k < K::n_coeff(S); ++k) d += S.ruling_coeff[k] * ipow(x, K::power(S, k));
+            }
             kx = d * S.ruling_normal[0];
             ky = d * S.ruling_normal[1];
             kz = d * S.ruling_normal[2];
@@ -269,8 +314,8 @@ __device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px
         }
         case OPTK_RULING_HOLOGRAPHIC: {
             // optika/rulings/_spacing.py:295-328
-            const double d1 = (S.flags & OPTK_F_HOLO_DIVERGING_1) ? 1.0 : -1.0;
-            const double d2 = (S.flags & OPTK_F_HOLO_DIVERGING_2) ? 1.0 : -1.0;
+            const double d1 = (K::flags(S) & OPTK_F_HOLO_DIVERGING_1) ? 1.0 : -1.0;
+            const double d2 = (K::flags(S) & OPTK_F_HOLO_DIVERGING_2) ? 1.0 : -1.0;
             double ax = px - S.holo_x1[0], ay = py - S.holo_x1[1], az = pz - S.holo_x1[2];
             double bx = px - S.holo_x2[0], by = py - S.holo_x2[1], bz = pz - S.holo_x2[2];
             const double ia = d1 * frsqrt(ax * ax + ay * ay + az * az);
@@ -299,10 +344,24 @@ __device__ __forceinline__ double py_mod(double a, double b) {
     return r;
 }
 
+// One edge (x0, y0) -> (x1, y1) of the even-odd crossing test (see aperture_test).
+__device__ __forceinline__ void polygon_edge(double x, double y, double x0, double y0, double x1, double y1,
+                                             bool& inside, bool& on_edge) {
+    const double ex = sub_rn(x1, x0), ey = sub_rn(y1, y0);
+    const double cross = sub_rn(mul_rn(ex, sub_rn(y, y0)), mul_rn(ey, sub_rn(x, x0)));
+    if (cross == 0.0) {  // on the supporting line (rare): is it on the segment?
+        on_edge |= (fmin(x0, x1) <= x) && (x <= fmax(x0, x1)) && (fmin(y0, y1) <= y) && (y <= fmax(y0, y1));
+    }
+    // left of a straddling edge  <=>  the cross product has the sign of the edge's dy
+    const bool straddles = (y0 > y) != (y1 > y);
+    inside ^= straddles && ((cross > 0.0) == (ey > 0.0));
+}
+
+template <class K = TableKinds>
 __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x, double y, double z) {
-    if (S.flags & OPTK_F_APERTURE_TRANSFORM) affine_inverse(S.aperture_transform, x, y, z, false);
+    if (K::flags(S) & OPTK_F_APERTURE_TRANSFORM) affine_inverse(S.aperture_transform, x, y, z, false);
     bool mask = false;
-    switch (S.aperture_kind) {
+    switch (K::aperture(S)) {
         case OPTK_APERTURE_CIRCULAR:
             // optika/apertures/_apertures.py:309: position.xy.length <= radius
             // sqrt is monotone and correctly rounded in the reference, so "sqrt(r2) <= radius" is
@@ -333,22 +392,24 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
         }
         case OPTK_APERTURE_POLYGON: {
             // na.geometry.point_in_polygon (third party): even-odd crossing, boundary inside
-            if (!(S.flags & OPTK_F_APERTURE_ACTIVE)) return true;  // _apertures.py:751, 775-776
+            if (!(K::flags(S) & OPTK_F_APERTURE_ACTIVE)) return true;  // _apertures.py:751, 775-776
             bool inside = false, on_edge = false;
-            const int nv = S.n_vertices;
+            const int nv = K::n_vertices(S);
             double x0 = S.vertices_x[nv - 1], y0 = S.vertices_y[nv - 1];
-            for (int i = 0; i < nv; ++i) {
-                const double x1 = S.vertices_x[i], y1 = S.vertices_y[i];
-                const double ex = sub_rn(x1, x0), ey = sub_rn(y1, y0);
-                const double cross = sub_rn(mul_rn(ex, sub_rn(y, y0)), mul_rn(ey, sub_rn(x, x0)));
-                if (cross == 0.0) {  // on the supporting line (rare): is it on the segment?
-                    on_edge |= (fmin(x0, x1) <= x) && (x <= fmax(x0, x1)) && (fmin(y0, y1) <= y) && (y <= fmax(y0, y1));
+            if constexpr (K::fixed) {
+#pragma unroll
+                for (int i = 0; i < nv; ++i) {
+                    polygon_edge(x, y, x0, y0, S.vertices_x[i], S.vertices_y[i], inside, on_edge);
+                    x0 = S.vertices_x[i];
+                    y0 = S.vertices_y[i];
                 }
-                // left of a straddling edge  <=>  the cross product has the sign of the edge's dy
-                const bool straddles = (y0 > y) != (y1 > y);
-                inside ^= straddles && ((cross > 0.0) == (ey > 0.0));
-                x0 = x1;
-                y0 = y1;
+            } else {
+                for (int i = 0; i < nv; ++i) {
+                    const double x1 = S.vertices_x[i], y1 = S.vertices_y[i];
+                    polygon_edge(x, y, x0, y0, x1, y1, inside, on_edge);
+                    x0 = x1;
+                    y0 = y1;
+                }
             }
             mask = inside || on_edge;
             break;
@@ -356,8 +417,8 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
         default:
             return true;
     }
-    if (S.flags & OPTK_F_APERTURE_INVERTED) mask = !mask;
-    if (!(S.flags & OPTK_F_APERTURE_ACTIVE)) mask = true;
+    if (K::flags(S) & OPTK_F_APERTURE_INVERTED) mask = !mask;
+    if (!(K::flags(S) & OPTK_F_APERTURE_ACTIVE)) mask = true;
     return mask;
 }
 
@@ -378,6 +439,43 @@ struct SagHit {
 struct Vec3 {
     double x, y, z;
 };
+
+// The toroid intercept of sag_cold below for the R rays of a thread at once (run-time compiled
+// kernels): the Newton chains of the rays interleave instead of running one after the other
+// behind a call.  Each ray takes exactly the steps it takes in sag_cold (a ray that has converged
+// keeps its value while the other one finishes), so the results are bit-identical.
+template <int R>
+__device__ __forceinline__ void toroid_intercept(const optk_surface_t& S, const Ray (&r)[R], double (&t)[R],
+                                                 unsigned& iterations) {
+    const double c = S.sag[3], rr = S.sag[2];
+    const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));
+    bool active[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        t[k] = fdiv(-r[k].pz, r[k].dz);
+        if (!(fabs(t[k]) < OPTK_INF)) t[k] = 0.0;
+        active[k] = true;
+    }
+    for (int it = 0; it < 64; ++it) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            double z, dzdx, dzdy;
+            toroid_eval(c, rr, r[k].px + r[k].dx * t[k], r[k].py + r[k].dy * t[k], z, dzdx, dzdy);
+            const double f = (r[k].pz + r[k].dz * t[k]) - z;
+            const double df = r[k].dz - (dzdx * r[k].dx + dzdy * r[k].dy);
+            const double step = fdiv(f, df);
+            const double tt = t[k] - step;
+            const double tolerance = 1e-13 * fmax(1.0, fabs(tt));
+            const bool done = !(fabs(step) > tolerance) || (step * step * curvature <= tolerance * fabs(df));
+            t[k] = active[k] ? tt : t[k];
+            iterations += active[k] ? 1u : 0u;
+            active[k] = active[k] && !done;
+            any = any || active[k];
+        }
+        if (!any) break;
+    }
+}
 
 static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double qx, double qy, double qz, double vx,
                                                double vy, double vz) {
@@ -436,12 +534,13 @@ static __device__ __noinline__ bool aperture_cold(const optk_surface_t& S, doubl
     return aperture_test(S, x, y, z);
 }
 
-static __device__ __noinline__ double glass_index(const optk_surface_t& S, double w) {
+__device__ __forceinline__ double glass_index_inline(const optk_surface_t& S, double w) {
     // optika/materials/_materials.py:428-438
     const double w2 = w * w;
     return fsqrt(1.0 + (S.material[0] * fdiv(w2, w2 - S.material[3]) + S.material[1] * fdiv(w2, w2 - S.material[4]) +
                         S.material[2] * fdiv(w2, w2 - S.material[5])));
 }
+static __device__ __noinline__ double glass_index(const optk_surface_t& S, double w) { return glass_index_inline(S, w); }
 
 static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S, double w, double px, double py,
                                                          double pz, double dx, double dy, double dz, double nx,
@@ -456,24 +555,6 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
 // parallelism for the long fp64 dependency chains).
 // AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
-// Where the element kinds and flags of a surface come from: the table (run time) or template
-// arguments (a kernel specialised for one system: every kind test folds away at compile time).
-struct TableKinds {
-    static __device__ __forceinline__ int sag(const optk_surface_t& S) { return S.sag_kind; }
-    static __device__ __forceinline__ int material(const optk_surface_t& S) { return S.material_kind; }
-    static __device__ __forceinline__ int ruling(const optk_surface_t& S) { return S.ruling_kind; }
-    static __device__ __forceinline__ int aperture(const optk_surface_t& S) { return S.aperture_kind; }
-    static __device__ __forceinline__ int flags(const optk_surface_t& S) { return S.flags; }
-};
-template <int SAG, int MATERIAL, int RULING, int APERTURE, int FLAGS>
-struct FixedKinds {
-    static __device__ __forceinline__ constexpr int sag(const optk_surface_t&) { return SAG; }
-    static __device__ __forceinline__ constexpr int material(const optk_surface_t&) { return MATERIAL; }
-    static __device__ __forceinline__ constexpr int ruling(const optk_surface_t&) { return RULING; }
-    static __device__ __forceinline__ constexpr int aperture(const optk_surface_t&) { return APERTURE; }
-    static __device__ __forceinline__ constexpr int flags(const optk_surface_t&) { return FLAGS; }
-};
-
 // `attenuating`: some ray of the thread still carries a non-zero attenuation (set when the rays
 // are loaded, cleared by every non-mirror material, which zeroes the attenuation).
 template <int R, bool EFF = false, class K = TableKinds>
@@ -538,14 +619,28 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             break;
         }
         default:
+            if constexpr (K::fixed) {
+                // a kernel compiled for this system: the rarer kinds inline, for all rays together
+                if (K::sag(S) == OPTK_SAG_TOROIDAL) {
+                    toroid_intercept<R>(S, r, t, newton_iterations);
+                } else {
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const SagHit hit = sag_cold(S, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
-                t[k] = hit.t;
-                nx[k] = hit.nx;
-                ny[k] = hit.ny;
-                nz[k] = hit.nz;
-                newton_iterations += hit.iterations;
+                    for (int k = 0; k < R; ++k)
+                        t[k] = sag_intercept_closed<K>(S, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
+                }
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    sag_normal<K>(S, r[k].px + r[k].dx * t[k], r[k].py + r[k].dy * t[k], nx[k], ny[k], nz[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const SagHit hit = sag_cold(S, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
+                    t[k] = hit.t;
+                    nx[k] = hit.nx;
+                    ny[k] = hit.ny;
+                    nz[k] = hit.nz;
+                    newton_iterations += hit.iterations;
+                }
             }
             break;
     }
@@ -580,6 +675,8 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                 kx = c * S.ruling_normal[0];
                 ky = c * S.ruling_normal[1];
                 kz = c * S.ruling_normal[2];
+            } else if constexpr (K::fixed) {
+                ruling_vector<K>(S, r[k].px, r[k].py, r[k].pz, nx[k], ny[k], nz[k], kx, ky, kz);
             } else {
                 const Vec3 kappa = ruling_cold(S, r[k].px, r[k].py, r[k].pz, nx[k], ny[k], nz[k]);
                 kx = kappa.x;
@@ -620,7 +717,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             if (mirror) {
                 n2[k] = r[k].n;  // _materials.py:135-139
             } else if (glass) {
-                n2[k] = glass_index(S, r[k].w);
+                n2[k] = K::fixed ? glass_index_inline(S, r[k].w) : glass_index(S, r[k].w);
             } else {
                 n2[k] = 1.0;  // _materials.py:95-99
             }
@@ -700,8 +797,14 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             const bool angular = flags & OPTK_F_APERTURE_ANGULAR;  // dimensionless aperture: test the direction
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const bool m = angular ? aperture_cold(S, r[k].dx, r[k].dy, r[k].dz)
-                                       : aperture_cold(S, r[k].px, r[k].py, r[k].pz);
+                bool m;
+                if constexpr (K::fixed) {
+                    m = angular ? aperture_test<K>(S, r[k].dx, r[k].dy, r[k].dz)
+                                : aperture_test<K>(S, r[k].px, r[k].py, r[k].pz);
+                } else {
+                    m = angular ? aperture_cold(S, r[k].dx, r[k].dy, r[k].dz)
+                                : aperture_cold(S, r[k].px, r[k].py, r[k].pz);
+                }
                 r[k].unv = r[k].unv && m;
             }
         }

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""
+Compile, with nvcc and WITHOUT a GPU, the translation unit that jit.cu would hand to NVRTC for
+one of the BASELINE systems, and print ptxas' register / spill report and the SASS size:
+
+    python tools/jit_offline.py cfg3 [dense|image|grid]
+
+The walk is generated here from the lowered surface table the same way jit.cu::jit_source does
+(keep the two in step); flags that only the library computes (OPTK_F_TRANSLATION_ONLY is set by
+optk_system_create) are reproduced below.
+"""
+import pathlib
+import subprocess
+import sys
+import tempfile
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+from optika_b200 import _lib as L, _lowering
+import configs
+
+POLYGON, POLYNOMIAL = L.APERTURE_POLYGON, L.RULING_POLYNOMIAL
+
+
+def walk_source(table, n_surface):
+    lines = []
+    for k in range(n_surface):
+        S = table[k]
+        flags = S.flags
+        r = np.array(list(S.transform.r)).reshape(3, 3)
+        if (flags & L.F_TRANSFORM) and np.array_equal(r, np.eye(3)):
+            flags |= 0x400  # OPTK_F_TRANSLATION_ONLY
+        eff = S.material_efficiency != 0 or S.ruling_profile != 0
+        nv = S.n_vertices if S.aperture_kind == POLYGON else 0
+        nc = S.n_coeff if S.ruling_kind == POLYNOMIAL else 0
+        pw = [S.ruling_power[j] if j < nc else 0 for j in range(8)]
+        args = [S.sag_kind, S.material_kind, S.ruling_kind, S.aperture_kind, flags, nv, nc, *pw]
+        lines.append(
+            f"    surface_full<2, {'true' if eff else 'false'}, FixedKinds<{', '.join(map(str, args))}>>"
+            f"(P.surf[{k}], r, newton_iterations, attenuating);"
+        )
+    return "\n".join(lines)
+
+
+def main():
+    name = sys.argv[1]
+    mode = sys.argv[2] if len(sys.argv) > 2 else "dense"
+    system = {
+        "cfg1": lambda: configs.newtonian(100, 100, 128),
+        "cfg2": lambda: configs.spherical_grating(100, 100, 1, 2048),
+        "cfg3": lambda: configs.toroidal_vls(100, 100, 1),
+    }[name]()
+    surfaces = system.surfaces_all
+    table, _ = _lowering.lower_system(surfaces, stages=L.STAGE_ALL)
+    dense, vec, image, grid = {"dense": (1, 1, 0, 0), "image": (0, 0, 1, 0), "grid": (0, 0, 1, 1)}[mode]
+    minb = 3
+    b = lambda v: "true" if v else "false"  # noqa: E731
+    src = f"""#define OPTK_JIT_WALK 1
+#include "trace_impl.cuh"
+namespace optk {{
+__device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,
+                                              bool& attenuating) {{
+{walk_source(table, len(surfaces))}
+}}
+}}  // namespace optk
+extern "C" __global__ void __launch_bounds__(256, {minb}) optk_jit_kernel(const __grid_constant__ optk::TraceParams P) {{
+    optk::trace_body<2, true, {b(dense)}, {b(vec)}, false, {b(image)}, {grid}, false, 1>(P);
+}}
+"""
+    print(src)
+    with tempfile.TemporaryDirectory() as d:
+        cu = pathlib.Path(d) / "optk_jit.cu"
+        cu.write_text(src)
+        out = pathlib.Path(d) / "optk_jit.cubin"
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-cubin", "-lineinfo",
+               "-Xptxas", "-v", "--expt-relaxed-constexpr", f"-I{ROOT / 'optika_b200' / 'csrc'}", f"-I{ROOT / 'include'}",
+               str(cu), "-o", str(out)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        print(r.stdout, r.stderr)
+        if r.returncode == 0:
+            sass = subprocess.run(["cuobjdump", "-sass", str(out)], capture_output=True, text=True).stdout
+            ops = [ln.split()[1].rstrip(";") for ln in sass.splitlines() if ln.strip().startswith("/*") and len(ln.split()) > 2 and ln.split()[1][0].isalpha()]
+            import collections
+            c = collections.Counter(o.split(".")[0] for o in ops)
+            print("SASS instructions:", len(ops), dict(c.most_common(14)))
+
+
+if __name__ == "__main__":
+    main()
