@@ -518,13 +518,14 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
 /* ---- run-time specialisation ---------------------------------------------------
  * Long launches of the streamlined kernels (>= 2^25 rays, full operator, no accumulate) are
  * served by a kernel compiled with NVRTC for exactly the traced surface list (every kind and
- * flag a compile-time constant, the walk unrolled; ~1.5 s once per system and kernel
- * variant, cached for the life of the process).  mode: -1 automatic (default; also the
+ * flag a compile-time constant, the walk unrolled; ~1.5 s once per system shape and kernel
+ * variant, cached for the life of the process and, as a cubin, on disk across processes).  mode: -1 automatic (default; also the
  * environment variable OPTK_JIT=-1), 0 never, 1 for every eligible launch.  Results are
  * bit-identical to the table-driven kernels.  If libnvrtc / libcuda cannot be loaded or the
  * compilation fails, the table-driven kernels run (a message goes to stderr). */
 OPTK_API int optk_jit_mode(int32_t mode);
-/* Number of kernels compiled so far in this process. */
+/* Number of specialised kernels made available so far in this process (compiled, or loaded
+ * from the disk cache $OPTK_JIT_CACHE, default ~/.cache/optika_b200/jit; empty string = no cache). */
 OPTK_API int64_t optk_jit_compiled(void);
 
 /* ---- measurement helpers ----------------------------------------------------

@@ -10,9 +10,12 @@
 // the library still loads on a machine without a driver.  Any failure falls back to the
 // table-driven CUDA kernels (never to a CPU path).
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
@@ -51,7 +54,7 @@ Api g_api;
 std::mutex g_mutex;
 std::map<std::string, void*> g_kernels;  // signature -> CUfunction (nullptr: compilation failed, do not retry)
 int g_mode = -2;                         // -2: read OPTK_JIT on first use; -1 auto; 0 off; 1 always
-long long g_compiled = 0;
+long long g_compiled = 0, g_loaded = 0;  // kernels compiled / loaded from the disk cache
 
 void* open_first(const char* const* names) {
     for (; *names; ++names)
@@ -90,6 +93,66 @@ bool verbose() {
     return v;
 }
 
+
+// ---- disk cache of compiled kernels: compilation costs ~1.5 s, more than a 1e10-ray job saves, so
+// the cubin is kept across processes in $OPTK_JIT_CACHE (default ~/.cache/optika_b200/jit; set it
+// to the empty string to switch the cache off), keyed by a hash of the generated source AND of
+// the embedded device headers.
+uint64_t fnv1a(const char* data, size_t n, uint64_t h = 1469598103934665603ULL) {
+    for (size_t i = 0; i < n; ++i) {
+        h ^= (unsigned char)data[i];
+        h *= 1099511628211ULL;
+    }
+    return h;
+}
+
+std::string cache_path(const std::string& src) {
+    const char* dir = getenv("OPTK_JIT_CACHE");
+    std::string base;
+    if (dir) {
+        if (!*dir) return std::string();
+        base = dir;
+    } else {
+        const char* home = getenv("HOME");
+        if (!home || !*home) return std::string();
+        base = std::string(home) + "/.cache/optika_b200/jit";
+    }
+    uint64_t h = fnv1a(src.data(), src.size());
+    for (int k = 0; k < kHeaderCount; ++k) h = fnv1a(kHeaderSources[k], strlen(kHeaderSources[k]), h);
+    char name[64];
+    snprintf(name, sizeof(name), "/optk_sm100a_abi%d_%016llx.cubin", OPTK_ABI_VERSION, (unsigned long long)h);
+    // mkdir -p
+    for (size_t i = 1; i <= base.size(); ++i)
+        if (i == base.size() || base[i] == '/') mkdir(base.substr(0, i).c_str(), 0755);
+    return base + name;
+}
+
+bool read_file(const std::string& path, std::vector<char>& data) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = n > 0;
+    if (ok) {
+        data.resize((size_t)n);
+        ok = fread(data.data(), 1, (size_t)n, f) == (size_t)n;
+    }
+    fclose(f);
+    return ok;
+}
+
+void write_file_atomically(const std::string& path, const std::vector<char>& data) {
+    char tmp[32];
+    snprintf(tmp, sizeof(tmp), ".%d.tmp", (int)getpid());
+    const std::string partial = path + tmp;
+    FILE* f = fopen(partial.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    if (!ok || rename(partial.c_str(), path.c_str()) != 0) remove(partial.c_str());
+}
+
 }  // namespace
 
 void jit_set_mode(int mode) {
@@ -97,7 +160,7 @@ void jit_set_mode(int mode) {
     g_mode = mode < -1 ? -1 : (mode > 1 ? 1 : mode);
 }
 
-long long jit_compiled_count() { return g_compiled; }
+long long jit_compiled_count() { return g_compiled + g_loaded; }
 
 // The generated translation unit for one (system signature, kernel variant).
 std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* key_out) {
@@ -165,6 +228,20 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
     cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
     if (major != 10 || minor != 0) return nullptr;  // this library is sm_100a only
+    cudaFree(nullptr);  // make sure the primary context is current for the driver API
+    const std::string cached = cache_path(src);
+    if (!cached.empty()) {
+        std::vector<char> cubin;
+        void* module = nullptr;
+        if (read_file(cached, cubin) && g_api.module_load(&module, cubin.data()) == 0 &&
+            g_api.get_function(&function, module, "optk_jit_kernel") == 0) {
+            if (verbose()) fprintf(stderr, "optk jit: loaded %s\n", cached.c_str());
+            ++g_loaded;
+            g_kernels[key] = function;
+            return function;
+        }
+        function = nullptr;
+    }
     void* prog = nullptr;
     if (g_api.create(&prog, src.c_str(), "optk_jit.cu", kHeaderCount, kHeaderSources, kHeaderNames) != 0) return nullptr;
     const char* options[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-lineinfo"};
@@ -190,6 +267,7 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
         return nullptr;
     }
     ++g_compiled;
+    if (!cached.empty()) write_file_atomically(cached, cubin);
     if (verbose()) fprintf(stderr, "optk jit: compiled a kernel for %d surfaces (%zu bytes)\n", P.n_surf, n);
     g_kernels[key] = function;
     return function;

@@ -127,7 +127,8 @@ int launch_stop_newton(const TraceParams& P, const optk_stop_problem_t& problem,
     const int block = 128;
     const long long grid = (n + block - 1) / block;
     stop_newton_kernel<<<(unsigned)grid, block, 0, stream>>>(P, Q);
-    return cuda_fail(cudaGetLastError(), "stop_newton_kernel launch") ;
+    OPTK_CUDA(cudaGetLastError());
+    return OPTK_OK;
 }
 
 }  // namespace optk

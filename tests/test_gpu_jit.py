@@ -106,3 +106,53 @@ def test_specialised_grid_kernel_and_efficiencies(cuda_device, jit):
     assert torch.equal(results[1][1].counts, results[0][1].counts)
     assert results[0][1].counts.sum().item() > 0
     assert float(results[0][0].fields["intensity"].max()) < 1.0  # the efficiencies were applied
+
+
+def _element_surfaces():
+    """One surface per element kind that the specialised kernels inline (test_gpu_trace's zoo)."""
+    import test_gpu_trace as zoo
+
+    S = optika.surfaces.Surface
+    surfaces = []
+    for sag in zoo.SAGS:
+        if getattr(sag, "transformation", None) is None:  # sag transformations take the generic kernel
+            surfaces.append((f"sag-{type(sag).__name__}-mirror", S(sag=sag, material=optika.materials.Mirror(), transformation=zoo.T_LIST)))
+            surfaces.append((f"sag-{type(sag).__name__}-glass", S(sag=sag, material=optika.materials.Glass.n_bk7())))
+    for k, aperture in enumerate(zoo.APERTURES):
+        surfaces.append((f"aperture-{k}-{type(aperture).__name__}", S(aperture=aperture, transformation=zoo.T_LIST)))
+    for k, rulings in enumerate(zoo.RULINGS):
+        surfaces.append(
+            (
+                f"rulings-{k}-{type(rulings.spacing_).__name__}",
+                S(sag=optika.sags.ToroidalSag(400.0, 450.0), rulings=rulings, material=optika.materials.Mirror(), transformation=zoo.T_LIST),
+            )
+        )
+    return surfaces
+
+
+@pytest.mark.parametrize("name,surface", _element_surfaces(), ids=[n for n, _ in _element_surfaces()])
+def test_every_element_kind_is_bit_identical_when_specialised(cuda_device, jit, name, surface):
+    """
+    The specialised kernels inline the element kinds that the table-driven kernels call out of
+    line (conic, cylinder, toroid with the paired Newton loop, polynomial and holographic
+    rulings, polygon / sector / elliptical apertures, Sellmeier glass) and fold loop lengths and
+    exponents: every one of them must reproduce the table-driven result bit for bit, rays that
+    miss the surface (NaN / inf) included.
+    """
+    import test_gpu_trace as zoo
+
+    rays = zoo.random_rays(n=6001, spread=60.0, wavelength=300 * u.nm)  # odd count: the last thread holds one ray
+    system = _engine.CompiledSystem([surface])
+    dense_in = _engine.trace(system, rays, surf_count=0)
+    broadcast = name.startswith("rulings")  # strided-input variant too (one more compilation) for a few
+    jit(0)
+    want = _engine.trace(system, dense_in)
+    want_broadcast = _engine.trace(system, rays) if broadcast else None
+    before = jit.compiled
+    jit(1)
+    got = _engine.trace(system, dense_in)
+    got_broadcast = _engine.trace(system, rays) if broadcast else None
+    assert jit.compiled > before
+    same(got, want)
+    if broadcast:
+        same(got_broadcast, want_broadcast)
