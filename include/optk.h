@@ -520,8 +520,9 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
  * served by a kernel compiled with NVRTC for exactly the traced surface list (every kind and
  * flag a compile-time constant, the walk unrolled; ~1.5 s once per system shape and kernel
  * variant, cached for the life of the process and, as a cubin, on disk across processes).  mode: -1 automatic (default; also the
- * environment variable OPTK_JIT=-1), 0 never, 1 for every eligible launch.  Results are
- * bit-identical to the table-driven kernels.  If libnvrtc / libcuda cannot be loaded or the
+ * environment variable OPTK_JIT=-1), 0 never, 1 for every eligible launch.  Results equal
+ * those of the table-driven kernels to rounding (the same expressions; the compiler may contract
+ * different multiply-add pairs into FMAs), masks and NaN / inf patterns exactly.  If libnvrtc / libcuda cannot be loaded or the
  * compilation fails, the table-driven kernels run (a message goes to stderr). */
 OPTK_API int optk_jit_mode(int32_t mode);
 /* Number of specialised kernels made available so far in this process (compiled, or loaded

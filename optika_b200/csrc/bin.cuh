@@ -109,7 +109,25 @@ __device__ __forceinline__ void image_add(const ImageDev& im, int bin, double w_
                                           double w_imag, unsigned count) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    if (__all_sync(full, bin < 0)) return;
+    // Every ray of the warp that is kept lands on ONE pixel (a focused system: the rays of a warp
+    // are the pupil samples of one field point): plain butterfly sums, no bin compares or selects,
+    // one lane issues the reductions.  REDUX gives the largest bin; dropped rays carry weight zero.
+    const int top = __reduce_max_sync(full, bin);
+    if (top < 0) return;
+    if (__all_sync(full, bin == top || bin < 0)) {
+        const bool keep = bin >= 0;
+        w_flux = warp_sum(keep ? w_flux : 0.0);
+        w_real = warp_sum(keep ? w_real : 0.0);
+        if (im.moment_imag) w_imag = warp_sum(keep ? w_imag : 0.0);
+        count = __reduce_add_sync(full, keep ? count : 0u);
+        if (lane == 0) {
+            if (im.flux) atomicAdd(im.flux + top, w_flux);
+            if (im.moment_real) atomicAdd(im.moment_real + top, w_real);
+            if (im.moment_imag) atomicAdd(im.moment_imag + top, w_imag);
+            if (im.counts) atomicAdd(im.counts + top, (unsigned long long)count);
+        }
+        return;
+    }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int pb = __shfl_xor_sync(full, bin, o);

@@ -90,6 +90,12 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 #define OPTK_INF __longlong_as_double(0x7ff0000000000000LL)
 #define OPTK_NAN __longlong_as_double(0x7ff8000000000000LL)
 
+// inf or NaN?  Decided on the exponent bits with two integer instructions (ALU pipe) instead of a
+// DSETP: the trace kernels are bound by the FP64 pipe, where every compare costs an issue slot.
+__device__ __forceinline__ bool not_finite(double y) {
+    return ((unsigned)__double2hiint(y) & 0x7ff00000u) == 0x7ff00000u;
+}
+
 __device__ __forceinline__ double rcp_seed(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -108,7 +114,7 @@ __device__ __forceinline__ double frcp(double x) {
     double y = fma(y0, e, y0);
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
-    return (fabs(y) < OPTK_INF) ? y : y0;  // x = 0, inf, NaN: the seed is the answer
+    return not_finite(y) ? y0 : y;  // x = 0, inf, NaN: the seed is the answer
 }
 
 __device__ __forceinline__ double fdiv(double a, double b) {
@@ -123,10 +129,11 @@ __device__ __forceinline__ double fdiv(double a, double b) {
     // instead of a multiply and a two-word select.
     asm("{\n"
         ".reg .pred p;\n"
-        ".reg .f64 t;\n"
-        "abs.f64 t, %0;\n"
-        "setp.lt.f64 p, t, 0d7FF0000000000000;\n"
-        "@!p mul.f64 %0, %1, %2;\n"
+        ".reg .b32 lo, hi;\n"
+        "mov.b64 {lo, hi}, %0;\n"
+        "and.b32 hi, hi, 0x7ff00000;\n"
+        "setp.eq.u32 p, hi, 0x7ff00000;\n"
+        "@p mul.f64 %0, %1, %2;\n"
         "}"
         : "+d"(q)
         : "d"(a), "d"(y0));
@@ -147,7 +154,9 @@ __device__ __forceinline__ double fsqrt(double x) {
     // first two have sqrt(x) = x and are exactly the non-negative fixed points of x + x = x;
     // for the others NaN is the answer.  (A subnormal radicand is flushed by the seed and also
     // yields NaN; radicands here are sums of squares of millimetre-scale quantities.)
-    return ((x + x == x) && (x >= 0.0)) ? x : g;
+    // (decided on the bit patterns, off the FP64 pipe: g is NaN in exactly those cases, and
+    // "x >= 0 or x is NaN with a clear sign" is one unsigned compare of the high word, -0 included)
+    return (not_finite(g) && (unsigned)__double2hiint(x) <= 0x80000000u) ? x : g;
 }
 
 // 1 / sqrt(x)
@@ -157,7 +166,7 @@ __device__ __forceinline__ double frsqrt(double x) {
     double y = fma(0.5 * y0, e, y0);
     e = fma(-x * y, y, 1.0);
     y = fma(y * fma(0.375, e, 0.5), e, y);  // second step with the e^2 term
-    return (fabs(y) < OPTK_INF) ? y : y0;
+    return not_finite(y) ? y0 : y;
 }
 
 // ---------------------------------------------------------------------------

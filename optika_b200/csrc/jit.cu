@@ -164,7 +164,7 @@ long long jit_compiled_count() { return g_compiled + g_loaded; }
 
 // The generated translation unit for one (system signature, kernel variant).
 std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* key_out) {
-    char line[512];
+    char line[1024];
     std::string walk;
     for (int k = 0; k < P.n_surf; ++k) {
         const optk_surface_t& S = P.surf[k];
@@ -186,6 +186,29 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
     snprintf(line, sizeof(line), "// variant: dense %d vec %d image %d grid %d minb %d\n", v.dense, v.vec, v.image, v.grid,
              v.minb);
     std::string src = line;
+    // strided ("broadcast") input: the layout is part of the kernel -- see load_rays
+    if (!v.dense && !v.grid && P.offsets32 && !P.in.normal[0]) {
+        unsigned long long lo = 0, hi = 0;
+        unsigned outer = 0;
+        const int n_axes = P.in.n_axes, first = n_axes - P.n_inner_axes;
+        const bool has_mask = P.in.unvignetted != nullptr;
+        for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) {
+            if (f == OPTK_NUM_FIELDS && !has_mask) continue;
+            for (int a = 0; a < n_axes && a < OPTK_MAX_AXES; ++a) {
+                if (P.stride32[f][a] == 0) continue;
+                if (a < first) outer |= 1u << f;
+                if (f < 8) lo |= 1ULL << (f * 8 + a);
+                else hi |= 1ULL << ((f - 8) * 8 + a);
+            }
+        }
+        snprintf(line, sizeof(line),
+                 "#define OPTK_JIT_LAYOUT 1\n#define OPTK_JIT_N_AXES %d\n#define OPTK_JIT_FIRST %d\n"
+                 "#define OPTK_JIT_HAS_MASK %d\n"
+                 "#define OPTK_JIT_VARIES(f, a) ((((f) < 8 ? 0x%llxULL >> (((f) & 7) * 8 + (a)) : 0x%llxULL >> (((f) & 7) * 8 + (a))) & 1) != 0)\n"
+                 "#define OPTK_JIT_VARIES_OUTER(f) (((0x%xu >> (f)) & 1) != 0)\n",
+                 n_axes, first, has_mask ? 1 : 0, lo, hi, outer);
+        src += line;
+    }
     src +=
         "#define OPTK_JIT_WALK 1\n"
         "#include \"trace_impl.cuh\"\n"

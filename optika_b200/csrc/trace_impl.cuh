@@ -1215,6 +1215,56 @@ __device__ __forceinline__ void load_rays(const TraceParams& P, long long i0, lo
             // the trailing axes of its own ray.  `off`, `offn` and `last_index` live across the
             // rays of the thread: the second ray is the first one's neighbour along the last axis
             // and only adds that axis' strides unless it wraps.
+#ifdef OPTK_JIT_LAYOUT
+            // A kernel compiled for this input layout (jit.cu): the number of axes, which of them
+            // the thread resolves itself, and WHICH FIELD VARIES ALONG WHICH AXIS are compile-time
+            // constants, so only the strides that are not zero cost a multiply-add (a separable
+            // grid: two or three out of sixty) and an absent mask costs nothing.
+            {
+                constexpr int n_axes = OPTK_JIT_N_AXES, first = OPTK_JIT_FIRST, last = n_axes - 1;
+                if (k > 0 && have_offsets && last_index + 1u < P.div[last].divisor) {
+                    ++last_index;
+#pragma unroll
+                    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f)
+                        if (OPTK_JIT_VARIES(f, last)) off[f] += P.stride32[f][last];
+                } else {
+                    uint32_t rem = (uint32_t)(j0 + k + P.index_offset);
+                    int o32[OPTK_NUM_FIELDS + 1];
+#pragma unroll
+                    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f) o32[f] = 0;
+#pragma unroll
+                    for (int a = n_axes - 1; a >= first; --a) {
+                        uint32_t q, idx;
+                        if (a == first) {
+                            idx = rem;
+                        } else {
+                            divmod(rem, P.div[a], q, idx);
+                            rem = q;
+                        }
+                        if (a == last) last_index = idx;
+#pragma unroll
+                        for (int f = 0; f <= OPTK_NUM_FIELDS; ++f)
+                            if (OPTK_JIT_VARIES(f, a)) o32[f] += (int)idx * P.stride32[f][a];
+                    }
+#pragma unroll
+                    for (int f = 0; f <= OPTK_NUM_FIELDS; ++f)
+                        off[f] = (OPTK_JIT_VARIES_OUTER(f) ? base[f] : 0) + o32[f];
+                    have_offsets = first < n_axes;
+                }
+            }
+            r[k].w = __ldg(P.in.field[OPTK_WAVELENGTH] + off[OPTK_WAVELENGTH]);
+            r[k].px = __ldg(P.in.field[OPTK_PX] + off[OPTK_PX]);
+            r[k].py = __ldg(P.in.field[OPTK_PY] + off[OPTK_PY]);
+            r[k].pz = __ldg(P.in.field[OPTK_PZ] + off[OPTK_PZ]);
+            r[k].dx = __ldg(P.in.field[OPTK_DX] + off[OPTK_DX]);
+            r[k].dy = __ldg(P.in.field[OPTK_DY] + off[OPTK_DY]);
+            r[k].dz = __ldg(P.in.field[OPTK_DZ] + off[OPTK_DZ]);
+            r[k].intensity = __ldg(P.in.field[OPTK_INTENSITY] + off[OPTK_INTENSITY]);
+            r[k].att = __ldg(P.in.field[OPTK_ATTENUATION] + off[OPTK_ATTENUATION]);
+            r[k].n = __ldg(P.in.field[OPTK_INDEX_REFRACTION] + off[OPTK_INDEX_REFRACTION]);
+            r[k].unv = OPTK_JIT_HAS_MASK ? (__ldg(P.in.unvignetted + off[OPTK_NUM_FIELDS]) != 0) : true;
+            continue;
+#endif
             const int last = P.in.n_axes - 1;
             if (k > 0 && have_offsets && !normal_given && last_index + 1u < P.div[last].divisor) {
                 ++last_index;

@@ -60,7 +60,18 @@ def main():
     dense, vec, image, grid = {"dense": (1, 1, 0, 0), "image": (0, 0, 1, 0), "grid": (0, 0, 1, 1)}[mode]
     minb = 3
     b = lambda v: "true" if v else "false"  # noqa: E731
-    src = f"""#define OPTK_JIT_WALK 1
+    layout = ""
+    if mode == "image":
+        # a separable grid as image_rays passes it: axes (field_x, field_y | pupil_x, pupil_y); wavelength and
+        # direction vary along the leading (per-CTA) axes, position x / y along one trailing axis each, no mask
+        lo = (1 << (1 * 8 + 2)) | (1 << (2 * 8 + 3)) | (1 << (4 * 8 + 0)) | (1 << (4 * 8 + 1)) | (1 << (5 * 8 + 0)) \
+            | (1 << (5 * 8 + 1)) | (1 << (6 * 8 + 0)) | (1 << (6 * 8 + 1))
+        layout = (
+            "#define OPTK_JIT_LAYOUT 1\n#define OPTK_JIT_N_AXES 4\n#define OPTK_JIT_FIRST 2\n#define OPTK_JIT_HAS_MASK 0\n"
+            f"#define OPTK_JIT_VARIES(f, a) ((((f) < 8 ? {hex(lo)}ULL >> (((f) & 7) * 8 + (a)) : 0x0ULL >> (((f) & 7) * 8 + (a))) & 1) != 0)\n"
+            "#define OPTK_JIT_VARIES_OUTER(f) (((0x70u >> (f)) & 1) != 0)\n"
+        )
+    src = layout + f"""#define OPTK_JIT_WALK 1
 #include "trace_impl.cuh"
 namespace optk {{
 __device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,

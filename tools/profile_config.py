@@ -34,6 +34,24 @@ def main():
         dense = _engine.trace(system._compiled_local, rays, surf_count=1, ray_axes_order=order, device=device)
         for _ in range(4):
             _engine.trace(system._compiled, dense, device=device)
+    elif mode == "grid":
+        # generate (Philox) + trace + bin: optk_trace_grid on a 1 x 100 x 100 x 100 x 100 vertex grid
+        from optika_b200 import _grid, units as u
+
+        deg = u.deg
+        lin = lambda lo, hi, n: np.linspace(lo, hi, n + 1)  # noqa: E731
+        vertices = {
+            "cfg1": [lin(499 * u.nm, 501 * u.nm, 1), lin(-0.1 * deg, 0.1 * deg, 100), lin(-0.1 * deg, 0.1 * deg, 100), lin(-40, 40, 100), lin(-40, 40, 100)],
+            "cfg2": [lin(17 * u.nm, 63 * u.nm, 1), lin(-0.05 * deg, 0.05 * deg, 100), lin(-0.05 * deg, 0.05 * deg, 100), lin(-45, 45, 100), lin(-45, 45, 100)],
+            "cfg3": [lin(25 * u.nm, 35 * u.nm, 1), lin(-0.2 * deg, 0.2 * deg, 100), lin(-0.2 * deg, 0.2 * deg, 100), lin(-22, 22, 100), lin(-22, 22, 100)],
+        }[name]
+        compiled = system._compiled_local
+        ex, ey = system.sensor.pixel_edges()
+        ew = np.array([vertices[0][0], vertices[0][-1]])
+        image = _engine.DeviceImage.zeros(ew, ex, ey, device, leading=tuple(compiled.shape.values()), moments=True, counts=True)
+        grid = _grid.RayGrid(vertices, jitter=True, seed=0)
+        for _ in range(4):
+            _grid.trace_grid(compiled, grid, config=0, image=image, write_rays=False, device=device)
     else:
         edges = na.ScalarArray(np.array([1e-6, 1e-2]), "wavelength")
         ex, ey = system.sensor.pixel_edges()
