@@ -516,7 +516,8 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
                      uint32_t* n_unconverged, void* stream);
 
 /* ---- run-time specialisation ---------------------------------------------------
- * Long launches of the streamlined kernels (>= 2^25 rays, full operator, no accumulate) are
+ * Long launches of the streamlined kernels (>= 2^25 rays -- >= 2^20 when the kernel is already in
+ * the disk cache -- full operator, no accumulate) are
  * served by a kernel compiled with NVRTC for exactly the traced surface list (every kind and
  * flag a compile-time constant, the walk unrolled; ~1.5 s once per system shape and kernel
  * variant, cached for the life of the process and, as a cubin, on disk across processes).  mode: -1 automatic (default; also the

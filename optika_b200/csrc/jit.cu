@@ -53,6 +53,8 @@ struct Api {
 Api g_api;
 std::mutex g_mutex;
 std::map<std::string, void*> g_kernels;  // signature -> CUfunction (nullptr: compilation failed, do not retry)
+int g_not_on_disk_tag;
+void* const kNotOnDisk = &g_not_on_disk_tag;  // looked in the disk cache, nothing there; not compiled yet
 int g_mode = -2;                         // -2: read OPTK_JIT on first use; -1 auto; 0 off; 1 always
 long long g_compiled = 0, g_loaded = 0;  // kernels compiled / loaded from the disk cache
 
@@ -234,12 +236,17 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
         g_mode = e ? (atoi(e) > 0 ? 1 : (atoi(e) == 0 ? 0 : -1)) : -1;
     }
     if (g_mode == 0) return nullptr;
-    // automatic: only launches long enough to amortise ~1.5 s of compilation over a few repeats
-    if (g_mode == -1 && P.n_rays < (1LL << 25)) return nullptr;
+    // automatic: compile (~1.5 s) only for launches long enough that a production run of them
+    // pays for it; a kernel that is already in the disk cache costs a file read and is taken for
+    // mid-sized launches too
+    const bool may_compile = g_mode == 1 || P.n_rays >= (1LL << 25);
+    if (!may_compile && P.n_rays < (1LL << 20)) return nullptr;
     std::string key;
     const std::string src = jit_source(P, v, &key);
     auto it = g_kernels.find(key);
-    if (it != g_kernels.end()) return it->second;
+    if (it != g_kernels.end() && it->second != kNotOnDisk) return it->second;
+    if (it != g_kernels.end() && !may_compile) return nullptr;  // looked before: not cached, too short to compile
+    const bool looked_on_disk = it != g_kernels.end();
     void* function = nullptr;
     g_kernels[key] = nullptr;
     if (!load_api()) {
@@ -253,7 +260,7 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
     if (major != 10 || minor != 0) return nullptr;  // this library is sm_100a only
     cudaFree(nullptr);  // make sure the primary context is current for the driver API
     const std::string cached = cache_path(src);
-    if (!cached.empty()) {
+    if (!cached.empty() && !looked_on_disk) {
         std::vector<char> cubin;
         void* module = nullptr;
         if (read_file(cached, cubin) && g_api.module_load(&module, cubin.data()) == 0 &&
@@ -264,6 +271,10 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
             return function;
         }
         function = nullptr;
+    }
+    if (!may_compile) {
+        g_kernels[key] = kNotOnDisk;
+        return nullptr;
     }
     void* prog = nullptr;
     if (g_api.create(&prog, src.c_str(), "optk_jit.cu", kHeaderCount, kHeaderSources, kHeaderNames) != 0) return nullptr;
