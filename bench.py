@@ -387,14 +387,26 @@ def run_b200(args):
         h2d = 8 * (nw + 2 * npup + 3 * nf * nf + 5)  # the separable axes the engine uploads
         image_host = {}
 
+        breakdown = os.environ.get("OPTK_BENCH_BREAKDOWN") is not None  # per-stage wall times to stderr
+
         def e2e_step():
+            t_a = time.perf_counter()
             image = system.image_rays(edges, device=device, counts=True)
+            if breakdown:
+                torch.cuda.synchronize()
+                t_b = time.perf_counter()
             if world > 1:
                 dist.all_reduce(image.flux)
                 dist.all_reduce(image.moment_real)
                 dist.all_reduce(image.counts)
+            if breakdown:
+                torch.cuda.synchronize()
+                t_c = time.perf_counter()
             if rank == 0 or world == 1:
                 image_host.update(image.to_host(pinned=True))
+            if breakdown:
+                print(f"[rank {rank}] e2e step: trace+bin {t_b - t_a:.4f} s, all_reduce {t_c - t_b:.4f} s, "
+                      f"read-back {time.perf_counter() - t_c:.4f} s", file=sys.stderr, flush=True)
             return image
 
         e2e_step()

@@ -24,14 +24,18 @@ struct TraceParams {
     // broadcast views whose offsets fit 32 bits (the usual case: small separable arrays):
     // element strides of the fields (and the mask, index OPTK_NUM_FIELDS) as int32
     int32_t offsets32;
-    int32_t pad3;
+    int32_t cta_count;  // CTAs that hold rays (see cta_rows)
     int32_t stride32[OPTK_NUM_FIELDS + 1][OPTK_MAX_AXES];
     int32_t n_surf;
     int32_t accumulate;
     int32_t dense_in;  // every input is a dense array indexed by the thread index
     int32_t has_image;
     int32_t has_frame;
-    int32_t pad;
+    // Fused image launches visit the ray grid in a strided order: CTA b works on tile
+    // (b mod 512) * cta_rows + b / 512, so the ~450 CTAs resident at any time are spread over the
+    // whole grid instead of sitting on ~20 neighbouring field points whose rays all add to the same
+    // few pixels (same-address reductions serialise in L2).  0 = identity order.
+    int32_t cta_rows;
     ImageDev image;
     optk_affine_t frame;
     optk_trace_stats_t* stats;

@@ -189,6 +189,20 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         OPTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, (const void*)kernel, block, 0));
         Q.prefetch_distance = (long long)prefetch_waves * sms * ctas * block * rays_per_thread;
     }
+    // fused image launches without a dense input stream: strided visiting order (params.cuh)
+    Q.cta_rows = 0;
+    Q.cta_count = (int32_t)grid;
+    static const int spread_mode = [] {
+        const char* e = getenv("OPTK_TRACE_SPREAD");
+        return e ? atoi(e) : 1;
+    }();
+    if (image && !dense && spread_mode && grid > 512) {
+        const long long rows = (grid + 511) / 512;
+        if (rows * 512 <= 0x7fffffffLL) {
+            Q.cta_rows = (int32_t)rows;
+            grid = rows * 512;
+        }
+    }
     // a kernel compiled for exactly this surface list, when the launch is long enough to pay for it
     if (full && !acc && !curvilinear) {
         const JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0,

@@ -1518,6 +1518,11 @@ __device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2],
 // SPEC: 0 the surface list is walked from the table; 1 a run-time compiled walk (R = 2, no ACC)
 template <int R, bool FULL, bool DENSE, bool VEC, bool ACC, bool IMAGE, int GRID, bool EFF, int SPEC = 0>
 __device__ __forceinline__ void trace_body(const TraceParams& P) {
+    uint32_t block = blockIdx.x;
+    if (IMAGE && !DENSE && P.cta_rows) {
+        block = (block & 511u) * (uint32_t)P.cta_rows + (block >> 9);  // strided visiting order, params.cuh
+        if (block >= (uint32_t)P.cta_count) return;                     // padding of the last row
+    }
     __shared__ ImageGuess guess;
     // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
     // second warp while the first warp computes the outer offsets
@@ -1530,10 +1535,10 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     long long i0, j0 = 0;
     long long limit = P.n_rays;
     if (DENSE || GRID) {
-        i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * R;
+        i0 = ((long long)block * blockDim.x + threadIdx.x) * R;
     } else {
         uint32_t outer32, tile32;
-        divmod(blockIdx.x, P.div_tiles, outer32, tile32);  // blockIdx.x / tiles_per_outer without a 64-bit division
+        divmod(block, P.div_tiles, outer32, tile32);  // block / tiles_per_outer without a 64-bit division
         const long long outer = outer32, tile = tile32;
         j0 = (tile * blockDim.x + threadIdx.x) * R;
         i0 = outer * P.inner_size + j0;
