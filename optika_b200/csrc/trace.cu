@@ -220,10 +220,17 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
 __global__ void __launch_bounds__(256)
 bin_kernel(long long n_rays, const double* __restrict__ wavelength, const double* __restrict__ x,
            const double* __restrict__ y, const double* __restrict__ dz, const double* __restrict__ intensity,
-           const uint8_t* __restrict__ unvignetted, const __grid_constant__ ImageDev im) {
+           const uint8_t* __restrict__ unvignetted, const __grid_constant__ ImageDev im, int cta_rows, int cta_count) {
+    // strided visiting order (TraceParams::cta_rows): rays arrive field by field, and the CTAs resident
+    // at one time would otherwise all add to the same few pixels
+    unsigned block = blockIdx.x;
+    if (cta_rows) {
+        block = (block & 511u) * (unsigned)cta_rows + (block >> 9);
+        if (block >= (unsigned)cta_count) return;
+    }
     __shared__ ImageGuess guess;
     image_guess_init(im, &guess);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)block * blockDim.x + threadIdx.x;
     const bool valid = i < n_rays;
     double w = 0, px = 0, py = 0, c = 1.0, in = 0;
     bool unv = false;
@@ -242,12 +249,20 @@ int launch_bin(long long n_rays, const double* wavelength, const double* x, cons
                const double* intensity, const uint8_t* unvignetted, const ImageDev& im, cudaStream_t stream) {
     if (n_rays <= 0) return OPTK_OK;
     const int block = 256;
-    const long long grid = (n_rays + block - 1) / block;
-    if (grid > 0x7fffffffLL) {
+    long long grid = (n_rays + block - 1) / block;
+    const long long rows = (grid + 511) / 512;
+    if (rows * 512 > 0x7fffffffLL) {
         set_error("optk_bin: too many rays for one launch (%lld)", n_rays);
         return OPTK_ERR_INVALID;
     }
-    bin_kernel<<<(unsigned)grid, block, 0, stream>>>(n_rays, wavelength, x, y, dz, intensity, unvignetted, im);
+    int cta_rows = 0;
+    const int cta_count = (int)grid;
+    if (grid > 512) {
+        cta_rows = (int)rows;
+        grid = rows * 512;
+    }
+    bin_kernel<<<(unsigned)grid, block, 0, stream>>>(n_rays, wavelength, x, y, dz, intensity, unvignetted, im, cta_rows,
+                                                      cta_count);
     OPTK_CUDA(cudaGetLastError());
     return OPTK_OK;
 }
