@@ -567,6 +567,11 @@ def run_b200(args):
                 traffic=traffic,
                 kernel=kernel_name,
                 copy_same_pattern_gbs=soa_copy.value,
+                note=(
+                    "peak is the copy bandwidth MEASURED_PEAKS.json records (torch copy_, two streams); a fraction "
+                    "slightly above 1 means this kernel's 22-stream pattern sustains more than that copy does "
+                    "(copy_same_pattern_gbs: a pure copy with this kernel's pattern, same run; nominal HBM3e 8 TB/s)"
+                ),
                 algorithmic_bytes_per_launch=BYTES_PER_RAY * n_slab,
                 ms_per_launch=ms_per_launch,
                 peak_source=peak_source,

@@ -199,3 +199,31 @@ def test_fused_image_of_more_rays_than_one_launch_holds(cuda_device):
     ).counts.cpu().numpy()
     assert 900 * 900 * 32 * 32 * 3 > 2**31 - 1
     assert one.sum() > 0 and np.array_equal(three, 3 * one)
+
+
+def test_fused_image_in_strided_cta_order_matches_oracle(cuda_device):
+    """
+    More than 512 CTAs: fused image launches visit the ray grid in a strided CTA order
+    (``TraceParams::cta_rows``: CTA b works on tile (b mod 512) * rows + b / 512, the last row is
+    padded with CTAs that exit).  692 224 rays = 1352 tiles = 3 rows, 184 padding CTAs: every ray
+    must still be traced and counted exactly once, on the fused path and in ``optk_bin``.
+    """
+    system = configs.newtonian(num_field=26, num_pupil=32, num_pixel=128)
+    edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
+    fused = system.image_rays(edges, counts=True)
+    _, rays_in = system._input(None, None, None, None, False, False)
+    r0, _ = configs.flatten_rays(rays_in)
+    out = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
+    assert out["px"].size == 26 * 26 * 32 * 32 > 512 * 512
+    local = ora._rays_transform(system.sensor.transformation, out, inverse=True)
+    ex, ey = system.sensor.pixel_edges()
+    want = orb.counts(local, edges.ndarray, ex, ey)
+    got = fused.counts.cpu().numpy().reshape(want.shape)
+    assert got.sum() == want.sum() > 0
+    mism = got != want
+    near = (orb.bin_margin(local["px"], ex) < 1e-9 * abs(ex[0])) | (orb.bin_margin(local["py"], ey) < 1e-9 * abs(ey[0]))
+    assert mism.sum() <= 2 * near.sum()
+    # the standalone kernel on the traced rays (> 512 CTAs of 256 rays as well)
+    rays = system.rayfunction(on_device=True).outputs
+    image, _ = system.sensor.collect(rays, wavelength=edges)
+    assert np.allclose(fused.flux.cpu().numpy().reshape(image.outputs.ndarray.shape), image.outputs.ndarray, rtol=1e-12)
