@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 4
+#define OPTK_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -479,6 +479,24 @@ OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp
 
 /* intensity[i] *= (e_s[i] + e_p[i]) / 2   (PolarizationVectorArray.average) */
 OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream);
+
+/* ---- reductions over the pupil -----------------------------
+ * SequentialSystem.distortion / vignetting / area_effective reduce the traced rays over the pupil
+ * axes for every (configuration, wavelength, field point): unvignetted.any(axis_pupil),
+ * mean(position.xy, axis_pupil, where=unvignetted | ~where), unvignetted.mean(axis_pupil),
+ * intensity.sum(axis_pupil, where=unvignetted) (optika/systems/_sequential.py:1266-1285,
+ * 1351-1368, 1501-1506).  optk_reduce_groups computes the sums those are made of from dense
+ * device arrays of n_groups * n_inner rays, group g = rays [g n_inner, (g + 1) n_inner):
+ *   count[g]         number of unvignetted rays            (the caller zeroes every output first)
+ *   sum_intensity[g] sum of intensity over them            (intensity NULL = 1)
+ *   sum_x[g], sum_y[g]          sums of x, y over them
+ *   sum_x_all[g], sum_y_all[g]  sums of x, y over ALL rays of the group (the reference's
+ *                               fallback where no ray of a field point survives); may be NULL
+ * unvignetted NULL = every ray counts.  Integer counts are exact, fp64 sums are independent of
+ * the order up to rounding. */
+OPTK_API int optk_reduce_groups(int64_t n_groups, int64_t n_inner, const double* x, const double* y,
+                       const double* intensity, const uint8_t* unvignetted, double* sum_intensity, double* sum_x,
+                       double* sum_y, uint64_t* count, double* sum_x_all, double* sum_y_all, void* stream);
 
 /* ---- stop solver -------------------------------------------
  * SequentialSystem._calc_rayfunction_stops_only (optika/systems/_sequential.py:396-623) finds

@@ -15,6 +15,7 @@ import ctypes as C
 import dataclasses
 import math
 import numpy as np
+from typing import Sequence
 from . import named as na
 from . import units as u
 from . import _lib as L
@@ -596,6 +597,57 @@ def _trace(
         return result, dict(
             n_rays=int(s[0]), n_unvignetted=int(s[1]), n_newton_iterations=int(s[2]), n_binned=int(s[3])
         )
+    return result
+
+
+# ---------------------------------------------------------------------------
+# reductions over the pupil of traced rays (optk_reduce_groups)
+# ---------------------------------------------------------------------------
+def reduce_groups(rays: DeviceRays, axes: Sequence[str], device=None) -> dict:
+    """
+    Sums over the named `axes` of device-resident rays, for every index of the other axes, without
+    the rays leaving the GPU (``optk_reduce_groups``; the reductions ``SequentialSystem.distortion``
+    / ``vignetting`` / ``area_effective`` take over the pupil, ``optika/systems/_sequential.py:
+    1266-1285, 1351-1368, 1501-1506``).  `axes` must be the innermost axes of ``rays.shape`` (the
+    engine keeps the pupil axes innermost).  Returns host named arrays over the remaining axes:
+    ``count`` (unvignetted rays), ``sum_intensity``, ``sum_x``, ``sum_y`` (over the unvignetted
+    rays) and ``sum_x_all``, ``sum_y_all`` (over all rays).
+    """
+    torch = _torch()
+    device = require_cuda(device)
+    names = list(rays.shape)
+    axes = [ax for ax in names if ax in set(axes)]
+    if not axes or names[len(names) - len(axes):] != axes:
+        raise ValueError(f"the reduced axes {axes} must be the innermost axes of the rays {names}")
+    outer = {ax: rays.shape[ax] for ax in names[: len(names) - len(axes)]}
+    n_inner = int(np.prod([rays.shape[ax] for ax in axes], dtype=np.int64))
+    n_groups = int(np.prod(list(outer.values()), dtype=np.int64)) if outer else 1
+    out = {
+        k: torch.zeros(n_groups, dtype=torch.float64, device=device)
+        for k in ("sum_intensity", "sum_x", "sum_y", "sum_x_all", "sum_y_all")
+    }
+    count = torch.zeros(n_groups, dtype=torch.int64, device=device)
+    f = rays.fields
+    # one launch holds 2^31 - 1 rays: whole groups per launch
+    step = max(1, (2**31 - 1) // max(n_inner, 1))
+    if n_inner > 2**31 - 1:
+        raise ValueError("more than 2^31 - 1 rays per group")
+    for g0 in range(0, n_groups, step):
+        m = min(step, n_groups - g0)
+        o = 8 * g0 * n_inner
+        L.check(
+            L.lib().optk_reduce_groups(
+                m, n_inner, f["px"].data_ptr() + o, f["py"].data_ptr() + o, f["intensity"].data_ptr() + o,
+                rays.unvignetted.data_ptr() + g0 * n_inner,
+                out["sum_intensity"].data_ptr() + 8 * g0, out["sum_x"].data_ptr() + 8 * g0, out["sum_y"].data_ptr() + 8 * g0,
+                count.data_ptr() + 8 * g0, out["sum_x_all"].data_ptr() + 8 * g0, out["sum_y_all"].data_ptr() + 8 * g0,
+                _stream_ptr(device),
+            )
+        )
+    dims, ax_out = tuple(outer.values()), tuple(outer)
+    result = {k: na.ScalarArray(v.cpu().numpy().reshape(dims), ax_out) for k, v in out.items()}
+    result["count"] = na.ScalarArray(count.cpu().numpy().reshape(dims), ax_out)
+    result["n_inner"] = n_inner
     return result
 
 

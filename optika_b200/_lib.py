@@ -241,7 +241,7 @@ class MlInput(C.Structure):
     ]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class OptkError(RuntimeError):
@@ -265,6 +265,7 @@ SYMBOLS = (
     "optk_bin",
     "optk_multilayer",
     "optk_solve_stops",
+    "optk_reduce_groups",
     "optk_jit_mode",
     "optk_jit_compiled",
     "optk_interp",
@@ -311,6 +312,7 @@ def lib() -> C.CDLL:
         C.POINTER(MlInput), i32, C.POINTER(MlLayer), i32, C.POINTER(MlSegment), vp, vp, vp, vp, vp,
     ]
     L.optk_jit_mode.argtypes = [i32]
+    L.optk_reduce_groups.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.optk_solve_stops.argtypes = [vp, i32, C.POINTER(StopProblem), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.optk_interp.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp, vp]
     L.optk_apply_efficiency.argtypes = [i64, vp, vp, vp, vp]

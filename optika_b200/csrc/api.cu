@@ -533,6 +533,22 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
                               (cudaStream_t)stream);
 }
 
+OPTK_API int optk_reduce_groups(int64_t n_groups, int64_t n_inner, const double* x, const double* y,
+                       const double* intensity, const uint8_t* unvignetted, double* sum_intensity, double* sum_x,
+                       double* sum_y, uint64_t* count, double* sum_x_all, double* sum_y_all, void* stream) {
+    if (n_groups < 0 || n_inner < 1 || n_groups > 0x7fffffffLL || n_inner > 0x7fffffffLL ||
+        n_groups * n_inner > 0x7fffffffLL) {
+        set_error("optk_reduce_groups: n_groups >= 0, n_inner >= 1 and n_groups * n_inner <= 2^31 - 1 are required");
+        return OPTK_ERR_INVALID;
+    }
+    if (n_groups > 0 && (!x || !y)) {
+        set_error("optk_reduce_groups: x or y is NULL");
+        return OPTK_ERR_INVALID;
+    }
+    return launch_reduce_groups(n_groups, n_inner, x, y, intensity, unvignetted, sum_intensity, sum_x, sum_y,
+                                (unsigned long long*)count, sum_x_all, sum_y_all, (cudaStream_t)stream);
+}
+
 OPTK_API int optk_jit_mode(int32_t mode) {
     jit_set_mode(mode);
     return OPTK_OK;

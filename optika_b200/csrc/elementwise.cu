@@ -1,6 +1,8 @@
 // Small per-ray kernels of the multilayer-coated-surface chain (include/optk.h, "per-ray
 // multilayer efficiency"): table interpolation of optical constants at the ray wavelengths
 // and the polarisation-averaged efficiency applied to the intensity.  HBM-bound streams.
+#include "common.cuh"
+#include "bin.cuh"
 #include "params.cuh"
 
 namespace optk {
@@ -74,6 +76,72 @@ int launch_apply_efficiency(long long n, double* intensity, const double* e_s, c
     int rc = grid_for(n, &grid);
     if (rc) return rc;
     apply_efficiency_kernel<<<grid, 256, 0, stream>>>(n, intensity, e_s, e_p);
+    OPTK_CUDA(cudaGetLastError());
+    return OPTK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Reductions over the pupil of traced rays, per field point: what
+// SequentialSystem.distortion / vignetting / area_effective take from the ray arrays
+// (optika/systems/_sequential.py:1266-1285, 1351-1368, 1501-1506) -- `unvignetted.any(axis_pupil)`,
+// `mean(position.xy, axis_pupil, where=unvignetted | ~where)`, `unvignetted.mean(axis_pupil)`,
+// `intensity.sum(axis_pupil, where=unvignetted)` -- computed where the rays are.
+// Rays are dense arrays with the pupil axes innermost: group g = rays [g n_inner, (g + 1) n_inner).
+// One thread per ray; the warp network of bin.cuh merges the rays of a warp by group before the
+// reductions go to L2; CTAs visit the rays in the strided order of the fused image kernels.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reduce_groups_kernel(long long n, FastDiv div_inner, const double* __restrict__ x, const double* __restrict__ y,
+                     const double* __restrict__ intensity, const uint8_t* __restrict__ unvignetted,
+                     double* sum_intensity, double* sum_x, double* sum_y, unsigned long long* count, double* sum_x_all,
+                     double* sum_y_all, int cta_rows, int cta_count) {
+    unsigned block = blockIdx.x;
+    if (cta_rows) {
+        block = (block & 511u) * (unsigned)cta_rows + (block >> 9);
+        if (block >= (unsigned)cta_count) return;
+    }
+    const long long i = (long long)block * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    double px = 0.0, py = 0.0, in = 0.0;
+    bool unv = false;
+    int group = -1;
+    if (valid) {
+        uint32_t q, r;
+        divmod((uint32_t)i, div_inner, q, r);
+        group = (int)q;
+        px = __ldg(x + i);
+        py = __ldg(y + i);
+        in = intensity ? __ldg(intensity + i) : 1.0;
+        unv = unvignetted ? (__ldg(unvignetted + i) != 0) : true;
+    }
+    ImageDev kept = {}, all = {};
+    kept.flux = sum_intensity;
+    kept.moment_real = sum_x;
+    kept.moment_imag = sum_y;
+    kept.counts = count;
+    all.moment_real = sum_x_all;
+    all.moment_imag = sum_y_all;
+    image_add(kept, unv ? group : -1, in, px, py, 1u);
+    if (sum_x_all || sum_y_all) image_add(all, group, 0.0, px, py, 0u);
+}
+
+int launch_reduce_groups(long long n_groups, long long n_inner, const double* x, const double* y, const double* intensity,
+                         const uint8_t* unvignetted, double* sum_intensity, double* sum_x, double* sum_y,
+                         unsigned long long* count, double* sum_x_all, double* sum_y_all, cudaStream_t stream) {
+    const long long n = n_groups * n_inner;
+    if (n <= 0) return OPTK_OK;
+    const int block = 256;
+    long long grid = (n + block - 1) / block;
+    const long long rows = (grid + 511) / 512;
+    int cta_rows = 0;
+    const int cta_count = (int)grid;
+    if (grid > 512) {
+        cta_rows = (int)rows;
+        grid = rows * 512;
+    }
+    reduce_groups_kernel<<<(unsigned)grid, block, 0, stream>>>(n, make_fastdiv((uint32_t)n_inner), x, y, intensity,
+                                                               unvignetted, sum_intensity, sum_x, sum_y, count, sum_x_all,
+                                                               sum_y_all, cta_rows, cta_count);
     OPTK_CUDA(cudaGetLastError());
     return OPTK_OK;
 }

@@ -242,6 +242,52 @@ class SequentialSystem(AbstractSequentialSystem):
         result.outputs = out if on_device else out.to_host()
         return result
 
+    def pupil_moments(
+        self,
+        intensity=None,
+        wavelength=None,
+        field=None,
+        pupil=None,
+        normalized_field: bool = False,
+        normalized_pupil: bool = False,
+        device=None,
+    ) -> dict:
+        """
+        What ``distortion``, ``vignetting`` and ``area_effective`` reduce from the rays at the
+        sensor (``_sequential.py:1266-1285, 1351-1368, 1501-1506``), computed on the device: the
+        rays are traced to the sensor (local coordinates, as ``rayfunction``) and reduced over the
+        pupil axes for every configuration, wavelength and field point without leaving the GPU.
+
+        Returns named arrays over the remaining axes:
+
+        * ``where``: ``unvignetted.any(axis_pupil)``;
+        * ``position``: ``mean(position.xy, axis_pupil, where=unvignetted | ~where)`` -- the mean
+          over the unvignetted rays, or over all rays where none survives (``:1272-1279``);
+        * ``illumination``: ``unvignetted.mean(axis_pupil)`` (``:1354``, before its normalisation);
+        * ``intensity``: ``intensity.sum(axis_pupil, where=unvignetted)`` (``:1501-1504``).
+        """
+        result, rays = self._input(intensity, wavelength, field, pupil, normalized_field, normalized_pupil)
+        axis_pupil = tuple(na.shape(result.inputs.pupil))
+        out = _engine.trace(self._compiled_local, rays, device=device, ray_axes_order=self._ray_axes_order)
+        missing = [ax for ax in axis_pupil if ax not in out.shape]
+        if missing:
+            raise ValueError(f"the pupil axes {missing} are not axes of the traced rays")
+        sums = _engine.reduce_groups(out, axis_pupil, device=device)
+        count = sums["count"]
+        where = count > 0
+        n_inner = sums["n_inner"]
+        denominator = np.where(where.ndarray, count.ndarray, n_inner)
+        x = np.where(where.ndarray, sums["sum_x"].ndarray, sums["sum_x_all"].ndarray) / denominator
+        y = np.where(where.ndarray, sums["sum_y"].ndarray, sums["sum_y_all"].ndarray) / denominator
+        axes = count.axes
+        return dict(
+            inputs=result.inputs,
+            where=where,
+            position=na.Cartesian2dVectorArray(na.ScalarArray(x, axes), na.ScalarArray(y, axes)),
+            illumination=count / n_inner,
+            intensity=sums["sum_intensity"],
+        )
+
     @functools.cached_property
     def _compiled_local(self) -> _engine.CompiledSystem:
         """

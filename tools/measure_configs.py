@@ -97,6 +97,19 @@ def bin_config():
     )
 
 
+def reduce_config():
+    """optk_reduce_groups: 1e8 cfg-1 rays at the sensor reduced over the pupil (25 B read per ray)."""
+    device = torch.device("cuda", 0)
+    system = configs.newtonian(100, 100, 128)
+    _, rays = system._input(None, None, None, None, False, False)
+    out = _engine.trace(system._compiled_local, rays, ray_axes_order=system._ray_axes_order, device=device)
+    ms = time_ms(lambda: _engine.reduce_groups(out, ("pupil_x", "pupil_y"), device=device))
+    return dict(
+        config="optk_reduce_groups, cfg1 rays at the sensor, 1e4 field points x 1e4 pupil samples", rays=out.size, ms=ms,
+        rays_per_s=out.size / (ms * 1e-3), hbm_gbs=25.0 * out.size / (ms * 1e-3) / 1e9,
+    )
+
+
 def multilayer_config(n_w=4096, n_t=1024, n_c=256, bilayers=30):
     """cfg 4: 60-layer Mo/Si stack on SiO2, erf interfaces, thickness scaled per configuration."""
     device = torch.device("cuda", 0)
@@ -133,6 +146,7 @@ def main():
                      configs.misaligned_telescope(64, 100, 4096, 8), 6, 791)
     )
     results.append(bin_config())
+    results.append(reduce_config())
     results.append(multilayer_config())
     fp64 = C.c_double()
     _lib.check(_lib.lib().optk_measure_fp64_peak(C.byref(fp64), None))
