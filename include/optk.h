@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 5
+#define OPTK_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -278,6 +278,14 @@ typedef struct optk_image {
      * device memory at the start of every CTA.  Must equal the array values exactly. */
     int32_t has_range;
     double range[6];
+    /* 0: a detector image as described above.  > 0 (optk_trace / optk_trace_grid only): not a
+     * detector but one accumulator per GROUP of `group_size` consecutive rays of the launch (C order
+     * of the ray axes; the engine keeps the pupil axes innermost, so a group is the pupil of one
+     * field point) -- the reductions over the pupil of SURVEY.md section 8f-4 fused into the trace,
+     * no ray is written: flux[g] = sum of intensity, moment_real[g] = sum of x, moment_imag[g] =
+     * sum of y (final frame of the trace), counts[g] = number, all over the UNVIGNETTED rays of
+     * group g.  n_x = number of groups, n_wavelength = n_y = 1; the edge arrays are not used. */
+    int64_t group_size;
 } optk_image_t;
 
 /* Counters returned by the trace (device-side reductions, optional). */

@@ -222,6 +222,44 @@ class DeviceImage:
         return im
 
 
+@dataclasses.dataclass(eq=False)
+class DeviceGroups:
+    """
+    Per-group accumulators in HBM for the reductions fused into the trace (``optk_image_t.group_size``):
+    one entry per group of `group_size` consecutive rays of a configuration -- with the pupil axes
+    innermost, the pupil of one field point.  ``flux`` = sum of intensity, ``moment_real`` / ``moment_imag``
+    = sums of x / y, ``counts`` = number, over the unvignetted rays; shape ``[n_config][n_groups]``.
+    """
+
+    group_size: int
+    n_groups: int
+    flux: object
+    moment_real: object
+    moment_imag: object
+    counts: object
+
+    @classmethod
+    def zeros(cls, n_config: int, n_groups: int, group_size: int, device):
+        torch = _torch()
+        z = lambda dt: torch.zeros((n_config, n_groups), dtype=dt, device=device)  # noqa: E731
+        return cls(group_size, n_groups, z(torch.float64), z(torch.float64), z(torch.float64), z(torch.int64))
+
+    def struct(self, plane_index: int = 0, first_ray: int = 0) -> L.Image:
+        """The accumulators of configuration `plane_index` for a launch that starts at ray `first_ray`."""
+        if first_ray % self.group_size:
+            raise ValueError("a launch must start at a group boundary")
+        first = first_ray // self.group_size
+        im = L.Image()
+        im.n_wavelength, im.n_x, im.n_y = 1, self.n_groups - first, 1
+        im.group_size = self.group_size
+        offset = 8 * (plane_index * self.n_groups + first)
+        im.flux = self.flux.data_ptr() + offset
+        im.moment_real = self.moment_real.data_ptr() + offset
+        im.moment_imag = self.moment_imag.data_ptr() + offset
+        im.counts = self.counts.data_ptr() + offset
+        return im
+
+
 class CompiledSystem:
     """
     A surface list lowered to the device table (``optk_system_create``): the
@@ -571,7 +609,10 @@ def _trace(
                 rout.unvignetted = out_mask.data_ptr() + o
             if capture_cos:
                 rout.cos_incidence = out_cos.data_ptr() + 8 * (c * n_ray + i0 * inner)
-            im = image.struct(c) if image is not None else None
+            if isinstance(image, DeviceGroups):
+                im = image.struct(c, first_ray=i0 * inner)  # launches start at multiples of `inner` rays
+            else:
+                im = image.struct(c) if image is not None else None
             L.check(
                 lib.optk_trace(
                     system.handle, c, C.byref(rin), C.byref(rout) if write_rays else None,

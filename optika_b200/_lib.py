@@ -157,6 +157,7 @@ class Image(C.Structure):
         ("counts", C.c_void_p),
         ("has_range", C.c_int32),
         ("range", C.c_double * 6),
+        ("group_size", C.c_int64),
     ]
 
 
@@ -241,7 +242,7 @@ class MlInput(C.Structure):
     ]
 
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class OptkError(RuntimeError):

@@ -194,7 +194,29 @@ long long view_extent(const int64_t* stride, const int64_t* dims, int n_axes) {
     return e + 1;
 }
 
-int fill_image(const optk_image_t* image, ImageDev* dev) {
+int fill_image(const optk_image_t* image, ImageDev* dev, bool groups_allowed = true) {
+    if (image->group_size != 0) {
+        // per-group accumulators instead of a detector (optk_image_t::group_size)
+        if (!groups_allowed || image->group_size < 0 || image->group_size > 0x7fffffffLL || image->n_x < 1 ||
+            image->n_wavelength != 1 || image->n_y != 1) {
+            set_error("image.group_size needs optk_trace / optk_trace_grid, 0 < group_size < 2^31, n_x >= 1 groups and "
+                      "n_wavelength = n_y = 1");
+            return OPTK_ERR_INVALID;
+        }
+        memset(dev, 0, sizeof(*dev));
+        dev->n_w = 1;
+        dev->n_x = image->n_x;
+        dev->n_y = 1;
+        dev->group = 1;
+        dev->flux = image->flux;
+        dev->moment_real = image->moment_real;
+        dev->moment_imag = image->moment_imag;
+        dev->counts = image->counts;
+        dev->has_range = 1;  // nothing to fetch: the edges are not used
+        dev->range[1] = dev->range[3] = dev->range[5] = 1.0;
+        dev->div_group = make_fastdiv((uint32_t)image->group_size);
+        return OPTK_OK;
+    }
     if (image->n_wavelength < 1 || image->n_x < 1 || image->n_y < 1) {
         set_error("image needs at least one bin along every axis");
         return OPTK_ERR_INVALID;
@@ -210,7 +232,8 @@ int fill_image(const optk_image_t* image, ImageDev* dev) {
     dev->n_w = image->n_wavelength;
     dev->n_x = image->n_x;
     dev->n_y = image->n_y;
-    dev->pad = 0;
+    dev->group = 0;
+    dev->div_group = make_fastdiv(1u);
     dev->e_w = image->edges_wavelength;
     dev->e_x = image->edges_x;
     dev->e_y = image->edges_y;
@@ -580,7 +603,7 @@ OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x,
         return OPTK_ERR_INVALID;
     }
     ImageDev dev;
-    int rc = fill_image(image, &dev);
+    int rc = fill_image(image, &dev, false);
     if (rc) return rc;
     return launch_bin(n_rays, wavelength, x, y, dz, intensity, unvignetted, dev, (cudaStream_t)stream);
 }
@@ -700,7 +723,7 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const opt
         image_dev.moment_real = (double*)dev_planes[1];
         image_dev.moment_imag = (double*)dev_planes[2];
         image_dev.counts = (unsigned long long*)dev_planes[3];
-        rc = fill_image(&image_dev, &P.image);
+        rc = fill_image(&image_dev, &P.image, false);
         if (rc) return rc;
     }
     optk_trace_stats_t* stats_dev = nullptr;

@@ -13,7 +13,7 @@ namespace optk {
 
 struct ImageDev {
     int32_t n_w, n_x, n_y;
-    int32_t pad;
+    int32_t group;  // optk_image_t::group_size > 0: bins are groups of consecutive rays, see div_group
     const double* e_w;
     const double* e_x;
     const double* e_y;
@@ -24,6 +24,7 @@ struct ImageDev {
     int32_t has_range;  // range[] below is valid: no loads needed for the guess
     int32_t pad2;
     double range[6];    // first / last edge of wavelength, x, y
+    FastDiv div_group;  // divisor group_size
 };
 
 // first / last edge and 1 / mean bin width of the pixel axes: range test and first guess

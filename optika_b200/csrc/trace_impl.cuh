@@ -1677,7 +1677,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
         // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
         int bin[R];
-        double w_flux[R], w_real[R];
+        double w_flux[R], w_real[R], w_imag[R];
         unsigned count[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
@@ -1686,20 +1686,33 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                 affine_inverse(P.frame, x, y, z, false);
                 affine_inverse(P.frame, cx, cy, cz, true);
             }
-            bin[k] = image_bin_index(P.image, guess, valid[k], r[k].w, x, y, r[k].unv);
             w_flux[k] = r[k].intensity;
-            w_real[k] = r[k].intensity * cz;
             count[k] = 1u;
+            if (P.image.group) {
+                // not a detector: one accumulator per group of consecutive rays (the pupil of a field
+                // point), optk_image_t::group_size -- sums of intensity, x, y and the number of the
+                // unvignetted rays (SequentialSystem.distortion / vignetting / area_effective)
+                uint32_t q, rem;
+                divmod((uint32_t)(i0 + k), P.image.div_group, q, rem);
+                bin[k] = (valid[k] && r[k].unv) ? (int)q : -1;
+                w_real[k] = x;
+                w_imag[k] = y;
+            } else {
+                bin[k] = image_bin_index(P.image, guess, valid[k], r[k].w, x, y, r[k].unv);
+                w_real[k] = r[k].intensity * cz;
+                w_imag[k] = 0.0;
+            }
         }
         // the two rays of a thread are pupil neighbours: usually the same pixel, merged here
         if (R == 2 && bin[0] == bin[R - 1] && bin[0] >= 0) {
             w_flux[0] += w_flux[R - 1];
             w_real[0] += w_real[R - 1];
+            w_imag[0] += w_imag[R - 1];
             count[0] += count[R - 1];
             bin[R - 1] = -1;
         }
 #pragma unroll
-        for (int k = 0; k < R; ++k) image_add(P.image, bin[k], w_flux[k], w_real[k], 0.0, count[k]);
+        for (int k = 0; k < R; ++k) image_add(P.image, bin[k], w_flux[k], w_real[k], w_imag[k], count[k]);
     }
 
     if (P.stats) {

@@ -256,7 +256,9 @@ class SequentialSystem(AbstractSequentialSystem):
         What ``distortion``, ``vignetting`` and ``area_effective`` reduce from the rays at the
         sensor (``_sequential.py:1266-1285, 1351-1368, 1501-1506``), computed on the device: the
         rays are traced to the sensor (local coordinates, as ``rayfunction``) and reduced over the
-        pupil axes for every configuration, wavelength and field point without leaving the GPU.
+        pupil axes for every configuration, wavelength and field point inside the same kernel launch
+        (``optk_image_t.group_size``): no ray is written to HBM, so the grid may be as large as an
+        ``image`` grid.
 
         Returns named arrays over the remaining axes:
 
@@ -266,26 +268,60 @@ class SequentialSystem(AbstractSequentialSystem):
         * ``illumination``: ``unvignetted.mean(axis_pupil)`` (``:1354``, before its normalisation);
         * ``intensity``: ``intensity.sum(axis_pupil, where=unvignetted)`` (``:1501-1504``).
         """
+        device = _engine.require_cuda(device)
         result, rays = self._input(intensity, wavelength, field, pupil, normalized_field, normalized_pupil)
-        axis_pupil = tuple(na.shape(result.inputs.pupil))
-        out = _engine.trace(self._compiled_local, rays, device=device, ray_axes_order=self._ray_axes_order)
-        missing = [ax for ax in axis_pupil if ax not in out.shape]
-        if missing:
+        axis_pupil = [ax for ax in self._ray_axes_order if ax in na.shape(result.inputs.pupil)]
+        compiled = self._compiled_local
+        config, ray = _engine._grid_shape(rays, compiled.shape)
+        missing = [ax for ax in na.shape(result.inputs.pupil) if ax not in ray]
+        if missing or not axis_pupil:
             raise ValueError(f"the pupil axes {missing} are not axes of the traced rays")
-        sums = _engine.reduce_groups(out, axis_pupil, device=device)
-        count = sums["count"]
+        # device order of the ray axes (see _engine._trace): the requested order last, pupil innermost
+        order = [ax for ax in ray if ax not in self._ray_axes_order] + [ax for ax in self._ray_axes_order if ax in ray]
+        if order[len(order) - len(axis_pupil):] != axis_pupil:
+            raise ValueError("the pupil axes must be the innermost ray axes")
+        outer = {ax: ray[ax] for ax in order[: len(order) - len(axis_pupil)]}
+        n_inner = int(np.prod([ray[ax] for ax in axis_pupil], dtype=np.int64))
+        n_groups = int(np.prod(list(outer.values()), dtype=np.int64)) if outer else 1
+        n_config = int(np.prod(list(config.values()), dtype=np.int64)) if config else 1
+        shape_ = dict(config)
+        shape_.update(outer)
+        axes, dims = tuple(shape_), tuple(shape_.values())
+        if compiled.coatings:
+            # multilayer-coated surfaces are traced in chained launches with the rays in HBM between the
+            # links (DESIGN.md 4.5): reduce the dense result
+            out = _engine.trace(compiled, rays, device=device, ray_axes_order=self._ray_axes_order)
+            sums = _engine.reduce_groups(out, axis_pupil, device=device)
+            count, sum_i = sums["count"].ndarray.reshape(dims), sums["sum_intensity"].ndarray.reshape(dims)
+            sum_x, sum_y = sums["sum_x"].ndarray.reshape(dims), sums["sum_y"].ndarray.reshape(dims)
+            all_x, all_y = sums["sum_x_all"].ndarray.reshape(dims), sums["sum_y_all"].ndarray.reshape(dims)
+        else:
+            # fused: the kernel that traces the rays also reduces them; no ray is written to HBM
+            groups = _engine.DeviceGroups.zeros(n_config, n_groups, n_inner, device)
+            _engine.trace(
+                compiled, rays, image=groups, write_rays=False, device=device, ray_axes_order=self._ray_axes_order
+            )
+            count = groups.counts.cpu().numpy().reshape(dims)
+            sum_i = groups.flux.cpu().numpy().reshape(dims)
+            sum_x = groups.moment_real.cpu().numpy().reshape(dims)
+            sum_y = groups.moment_imag.cpu().numpy().reshape(dims)
+            all_x = all_y = None
         where = count > 0
-        n_inner = sums["n_inner"]
-        denominator = np.where(where.ndarray, count.ndarray, n_inner)
-        x = np.where(where.ndarray, sums["sum_x"].ndarray, sums["sum_x_all"].ndarray) / denominator
-        y = np.where(where.ndarray, sums["sum_y"].ndarray, sums["sum_y_all"].ndarray) / denominator
-        axes = count.axes
+        if not where.all() and all_x is None:
+            # field points without a surviving ray: the reference averages over ALL their rays there
+            # (:1272-1279, a placeholder that its fits mask out); rare, so taken from a plain trace
+            out = _engine.trace(compiled, rays, device=device, ray_axes_order=self._ray_axes_order)
+            sums = _engine.reduce_groups(out, axis_pupil, device=device)
+            all_x, all_y = sums["sum_x_all"].ndarray.reshape(dims), sums["sum_y_all"].ndarray.reshape(dims)
+        denominator = np.where(where, count, n_inner)
+        x = np.where(where, sum_x, all_x if all_x is not None else 0.0) / denominator
+        y = np.where(where, sum_y, all_y if all_y is not None else 0.0) / denominator
         return dict(
             inputs=result.inputs,
-            where=where,
+            where=na.ScalarArray(where, axes),
             position=na.Cartesian2dVectorArray(na.ScalarArray(x, axes), na.ScalarArray(y, axes)),
-            illumination=count / n_inner,
-            intensity=sums["sum_intensity"],
+            illumination=na.ScalarArray(count / n_inner, axes),
+            intensity=na.ScalarArray(sum_i, axes),
         )
 
     @functools.cached_property

@@ -104,7 +104,12 @@ def reduce_config():
     _, rays = system._input(None, None, None, None, False, False)
     out = _engine.trace(system._compiled_local, rays, ray_axes_order=system._ray_axes_order, device=device)
     ms = time_ms(lambda: _engine.reduce_groups(out, ("pupil_x", "pupil_y"), device=device))
+    # fused: trace + reduce in one launch, no ray written (optk_image_t.group_size)
+    groups = _engine.DeviceGroups.zeros(1, 100 * 100, 100 * 100, device)
+    ms_fused = time_ms(lambda: _engine.trace(system._compiled_local, rays, image=groups, write_rays=False,
+                                             ray_axes_order=system._ray_axes_order, device=device))
     return dict(
+        ms_fused_trace_reduce=ms_fused, intercepts_per_s_fused_trace_reduce=out.size * 6 / (ms_fused * 1e-3),
         config="optk_reduce_groups, cfg1 rays at the sensor, 1e4 field points x 1e4 pupil samples", rays=out.size, ms=ms,
         rays_per_s=out.size / (ms * 1e-3), hbm_gbs=25.0 * out.size / (ms * 1e-3) / 1e9,
     )
