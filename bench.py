@@ -155,18 +155,59 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """
+    SM clock, power and throttle reasons DURING the timed region.  NVML is polled from a thread
+    every 10 ms (the timed region of three steps is under half a second: `nvidia-smi -lms` often
+    has not produced its first line by then); `nvidia-smi` remains the fallback.
+    """
+
     QUERY = (
         "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     )
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index: int):
         self.rows = []
+        self.samples = []  # (sm MHz, power W, reasons bitmask) from NVML
         self.proc = None
+        self.thread = None
         self.gpu_index = gpu_index
+        self.nvml = None
+        self.handle = None
+        self.sm_max = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons"
+        )
+        while True:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                power = float(nv.nvmlDeviceGetPowerUsage(self.handle)) / 1e3
+                self.samples.append((sm, power, int(reasons(self.handle))))
+            except Exception:
+                pass
+            if self._stop.wait(0.01):
+                break
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -183,6 +224,23 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            if not self.samples:
+                return dict(sm_mhz=None, sm_max_mhz=self.sm_max, reasons=["no samples"])
+            mask = 0
+            for _, _, bits in self.samples:
+                mask |= bits
+            return dict(
+                sm_mhz=float(np.median([s[0] for s in self.samples])),
+                sm_max_mhz=self.sm_max,
+                power_w_max=float(np.max([s[1] for s in self.samples])),
+                samples=len(self.samples),
+                reasons=sorted(name for name, bit in self.REASON_BITS.items() if mask & bit),
+                source="NVML, 10 ms polling during the timed region",
+            )
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -213,6 +271,7 @@ class ClockSampler:
             power_w_max=float(np.max(power)),
             samples=len(sm),
             reasons=sorted(reasons),
+            source="nvidia-smi -lms 100 during the timed region",
         )
 
 

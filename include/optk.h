@@ -284,7 +284,10 @@ typedef struct optk_image {
      * field point) -- the reductions over the pupil of SURVEY.md section 8f-4 fused into the trace,
      * no ray is written: flux[g] = sum of intensity, moment_real[g] = sum of x, moment_imag[g] =
      * sum of y (final frame of the trace), counts[g] = number, all over the UNVIGNETTED rays of
-     * group g.  n_x = number of groups, n_wavelength = n_y = 1; the edge arrays are not used. */
+     * group g.  n_x = number of groups, n_wavelength = n_y = 1; the edge arrays are not used.
+     * Served by the run-time compiled kernels only (full surface operator, no accumulate; a launch
+     * they cannot serve returns OPTK_ERR_UNSUPPORTED: reduce the traced rays with
+     * optk_reduce_groups instead), so that the detector path carries no code for it. */
     int64_t group_size;
 } optk_image_t;
 

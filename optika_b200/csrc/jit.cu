@@ -188,6 +188,7 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
     snprintf(line, sizeof(line), "// variant: dense %d vec %d image %d grid %d minb %d\n", v.dense, v.vec, v.image, v.grid,
              v.minb);
     std::string src = line;
+    if (v.groups) src += "#define OPTK_JIT_GROUPS 1\n";
     // strided ("broadcast") input: the layout is part of the kernel -- see load_rays
     if (!v.dense && !v.grid && P.offsets32 && !P.in.normal[0]) {
         unsigned long long lo = 0, hi = 0;
@@ -239,7 +240,7 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
     // automatic: compile (~1.5 s) only for launches long enough that a production run of them
     // pays for it; a kernel that is already in the disk cache costs a file read and is taken for
     // mid-sized launches too
-    const bool may_compile = g_mode == 1 || P.n_rays >= (1LL << 25);
+    const bool may_compile = g_mode == 1 || P.n_rays >= (1LL << 25) || v.groups;  // group launches have no other kernel
     if (!may_compile && P.n_rays < (1LL << 20)) return nullptr;
     std::string key;
     const std::string src = jit_source(P, v, &key);

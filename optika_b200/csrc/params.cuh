@@ -53,6 +53,7 @@ struct TraceParams {
 // run-time specialised kernels (jit.cu)
 struct JitVariant {
     int dense, vec, image, grid, minb;
+    int groups = 0;  // optk_image_t::group_size: accumulate per group of rays instead of per pixel
 };
 void* jit_kernel(const TraceParams& P, const JitVariant& v);  // CUfunction or nullptr
 int jit_launch(void* function, const TraceParams& P, unsigned grid, cudaStream_t stream);

@@ -205,9 +205,15 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     }
     // a kernel compiled for exactly this surface list, when the launch is long enough to pay for it
     if (full && !acc && !curvilinear) {
-        const JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0,
-                                    jit_minb > 0 ? jit_minb : (use_heavy ? 2 : 3)};
+        JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0,
+                              jit_minb > 0 ? jit_minb : (use_heavy ? 2 : 3)};
+        variant.groups = (image && P.image.group) ? 1 : 0;
         if (void* function = jit_kernel(P, variant)) return jit_launch(function, P, (unsigned)grid, stream);
+    }
+    if (image && P.image.group) {
+        set_error("group accumulators (optk_image_t.group_size) are served by the run-time compiled kernels only "
+                  "(full operator, no accumulate, NVRTC available, OPTK_JIT != 0); use optk_reduce_groups on the traced rays");
+        return OPTK_ERR_UNSUPPORTED;
     }
     void* args[] = {(void*)&P};
     OPTK_CUDA(cudaLaunchKernel((const void*)kernel, dim3((unsigned)grid), dim3(block), args, 0, stream));

@@ -1677,8 +1677,42 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         // (optika/systems/_sequential.py:983-986, optika/sensors/_sensors.py:125-161);
         // IdealSensorMaterial: cos = -direction . (0, 0, -1) = d_z.
         int bin[R];
-        double w_flux[R], w_real[R], w_imag[R];
+        double w_flux[R], w_real[R];
         unsigned count[R];
+        // Group accumulators exist only in kernels compiled at run time with OPTK_JIT_GROUPS (jit.cu):
+        // as a run-time branch they cost the detector path 4 % (measured), and launch_trace refuses
+        // group launches that no such kernel serves.
+#ifdef OPTK_JIT_GROUPS
+        constexpr bool groups = true;
+#else
+        constexpr bool groups = false;
+#endif
+        if constexpr (groups) {
+            // Not a detector: one accumulator per group of consecutive rays (the pupil of a field
+            // point), optk_image_t::group_size -- sums of intensity, x, y and the number of the
+            // unvignetted rays (SequentialSystem.distortion / vignetting / area_effective).  The sum
+            // of y goes first, in a pass of its own, so that the detector path below carries no third
+            // weight (two more live doubles cost the fused image kernels 3-4 %, measured).
+            int gb[R];
+            double wy[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                double x = r[k].px, y = r[k].py, z = r[k].pz;
+                if (P.has_frame) affine_inverse(P.frame, x, y, z, false);
+                uint32_t q, rem;
+                divmod((uint32_t)(i0 + k), P.image.div_group, q, rem);
+                gb[k] = (valid[k] && r[k].unv) ? (int)q : -1;
+                wy[k] = y;
+            }
+            if (R == 2 && gb[0] == gb[R - 1] && gb[0] >= 0) {
+                wy[0] += wy[R - 1];
+                gb[R - 1] = -1;
+            }
+            ImageDev sum_y = {};
+            sum_y.flux = P.image.moment_imag;
+#pragma unroll
+            for (int k = 0; k < R; ++k) image_add(sum_y, gb[k], wy[k], 0.0, 0.0, 0u);
+        }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             double x = r[k].px, y = r[k].py, z = r[k].pz, cx = r[k].dx, cy = r[k].dy, cz = r[k].dz;
@@ -1686,33 +1720,34 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                 affine_inverse(P.frame, x, y, z, false);
                 affine_inverse(P.frame, cx, cy, cz, true);
             }
-            w_flux[k] = r[k].intensity;
-            count[k] = 1u;
-            if (P.image.group) {
-                // not a detector: one accumulator per group of consecutive rays (the pupil of a field
-                // point), optk_image_t::group_size -- sums of intensity, x, y and the number of the
-                // unvignetted rays (SequentialSystem.distortion / vignetting / area_effective)
+            if constexpr (groups) {
                 uint32_t q, rem;
                 divmod((uint32_t)(i0 + k), P.image.div_group, q, rem);
                 bin[k] = (valid[k] && r[k].unv) ? (int)q : -1;
-                w_real[k] = x;
-                w_imag[k] = y;
             } else {
                 bin[k] = image_bin_index(P.image, guess, valid[k], r[k].w, x, y, r[k].unv);
-                w_real[k] = r[k].intensity * cz;
-                w_imag[k] = 0.0;
             }
+            w_flux[k] = r[k].intensity;
+            w_real[k] = groups ? x : r[k].intensity * cz;
+            count[k] = 1u;
         }
         // the two rays of a thread are pupil neighbours: usually the same pixel, merged here
         if (R == 2 && bin[0] == bin[R - 1] && bin[0] >= 0) {
             w_flux[0] += w_flux[R - 1];
             w_real[0] += w_real[R - 1];
-            w_imag[0] += w_imag[R - 1];
             count[0] += count[R - 1];
             bin[R - 1] = -1;
         }
+        // (with groups the imaginary-moment plane holds the sum of y added above: leave it alone)
+        if constexpr (groups) {
+            ImageDev planes = P.image;
+            planes.moment_imag = nullptr;
 #pragma unroll
-        for (int k = 0; k < R; ++k) image_add(P.image, bin[k], w_flux[k], w_real[k], w_imag[k], count[k]);
+            for (int k = 0; k < R; ++k) image_add(planes, bin[k], w_flux[k], w_real[k], 0.0, count[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) image_add(P.image, bin[k], w_flux[k], w_real[k], 0.0, count[k]);
+        }
     }
 
     if (P.stats) {

@@ -287,20 +287,25 @@ class SequentialSystem(AbstractSequentialSystem):
         shape_ = dict(config)
         shape_.update(outer)
         axes, dims = tuple(shape_), tuple(shape_.values())
-        if compiled.coatings:
+        fused = not compiled.coatings
+        if fused:
+            # the kernel that traces the rays also reduces them; no ray is written to HBM
+            groups = _engine.DeviceGroups.zeros(n_config, n_groups, n_inner, device)
+            try:
+                _engine.trace(
+                    compiled, rays, image=groups, write_rays=False, device=device, ray_axes_order=self._ray_axes_order
+                )
+            except NotImplementedError:
+                fused = False  # no run-time compiled kernel for this launch (generic operator, OPTK_JIT=0, no NVRTC)
+        if not fused:
             # multilayer-coated surfaces are traced in chained launches with the rays in HBM between the
-            # links: reduce the dense result
+            # links, and launches without a run-time compiled kernel: reduce the dense result
             out = _engine.trace(compiled, rays, device=device, ray_axes_order=self._ray_axes_order)
             sums = _engine.reduce_groups(out, axis_pupil, device=device)
             count, sum_i = sums["count"].ndarray.reshape(dims), sums["sum_intensity"].ndarray.reshape(dims)
             sum_x, sum_y = sums["sum_x"].ndarray.reshape(dims), sums["sum_y"].ndarray.reshape(dims)
             all_x, all_y = sums["sum_x_all"].ndarray.reshape(dims), sums["sum_y_all"].ndarray.reshape(dims)
         else:
-            # fused: the kernel that traces the rays also reduces them; no ray is written to HBM
-            groups = _engine.DeviceGroups.zeros(n_config, n_groups, n_inner, device)
-            _engine.trace(
-                compiled, rays, image=groups, write_rays=False, device=device, ray_axes_order=self._ray_axes_order
-            )
             count = groups.counts.cpu().numpy().reshape(dims)
             sum_i = groups.flux.cpu().numpy().reshape(dims)
             sum_x = groups.moment_real.cpu().numpy().reshape(dims)
