@@ -203,3 +203,28 @@ def test_input_rays_match_reference_construction():
     assert np.allclose(rays.direction.z.numpy(("field_x", "field_y")), want[2])
     assert float(rays.position.z) == 0.0
     assert system._ray_axes_order == ["field_x", "field_y", "pupil_x", "pupil_y"]
+
+
+def test_device_groups_struct_addresses_whole_groups():
+    """``DeviceGroups.struct``: plane pointers of one configuration, offset to the first group of a launch."""
+    import torch
+
+    groups = _engine.DeviceGroups.zeros(n_config=3, n_groups=10, group_size=64, device=torch.device("cpu"))
+    im = groups.struct(0)
+    assert (im.n_wavelength, im.n_x, im.n_y, im.group_size) == (1, 10, 1, 64)
+    assert im.flux == groups.flux.data_ptr() and im.counts == groups.counts.data_ptr()
+    im = groups.struct(2, first_ray=4 * 64)  # third configuration, launch starting at the fifth group
+    assert im.n_x == 6
+    assert im.moment_imag == groups.moment_imag.data_ptr() + 8 * (2 * 10 + 4)
+    with pytest.raises(ValueError):
+        groups.struct(0, first_ray=65)  # not a group boundary
+
+
+def test_reductions_have_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    system = configs.newtonian(num_field=2, num_pupil=4)
+    with pytest.raises(RuntimeError):
+        system.pupil_moments()
