@@ -3,7 +3,7 @@
 Compile, with nvcc and WITHOUT a GPU, the translation unit that jit.cu would hand to NVRTC for
 one of the BASELINE systems, and print ptxas' register / spill report and the SASS size:
 
-    python tools/jit_offline.py cfg3 [dense|image|grid]
+    python tools/jit_offline.py cfg3 [dense|image|grid|groups]
 
 The walk is generated here from the lowered surface table the same way jit.cu::jit_source does
 (keep the two in step); flags that only the library computes (OPTK_F_TRANSLATION_ONLY is set by
@@ -57,11 +57,13 @@ def main():
     }[name]()
     surfaces = system.surfaces_all
     table, _ = _lowering.lower_system(surfaces, stages=L.STAGE_ALL)
-    dense, vec, image, grid = {"dense": (1, 1, 0, 0), "image": (0, 0, 1, 0), "grid": (0, 0, 1, 1)}[mode]
+    dense, vec, image, grid = {
+        "dense": (1, 1, 0, 0), "image": (0, 0, 1, 0), "grid": (0, 0, 1, 1), "groups": (0, 0, 1, 0),
+    }[mode]
     minb = 3
     b = lambda v: "true" if v else "false"  # noqa: E731
     layout = ""
-    if mode == "image":
+    if mode in ("image", "groups"):
         # a separable grid as image_rays passes it: axes (field_x, field_y | pupil_x, pupil_y); wavelength and
         # direction vary along the leading (per-CTA) axes, position x / y along one trailing axis each, no mask
         lo = (1 << (1 * 8 + 2)) | (1 << (2 * 8 + 3)) | (1 << (4 * 8 + 0)) | (1 << (4 * 8 + 1)) | (1 << (5 * 8 + 0)) \
@@ -71,6 +73,8 @@ def main():
             f"#define OPTK_JIT_VARIES(f, a) ((((f) < 8 ? {hex(lo)}ULL >> (((f) & 7) * 8 + (a)) : 0x0ULL >> (((f) & 7) * 8 + (a))) & 1) != 0)\n"
             "#define OPTK_JIT_VARIES_OUTER(f) (((0x70u >> (f)) & 1) != 0)\n"
         )
+    if mode == "groups":  # per-group accumulators instead of detector pixels (optk_image_t.group_size)
+        layout = "#define OPTK_JIT_GROUPS 1\n" + layout
     src = layout + f"""#define OPTK_JIT_WALK 1
 #include "trace_impl.cuh"
 namespace optk {{
