@@ -59,6 +59,7 @@ def test_struct_layout_matches_c(tmp_path, lib):
         "optk_ml_layer_t": _lib.MlLayer,
         "optk_ml_segment_t": _lib.MlSegment,
         "optk_ml_input_t": _lib.MlInput,
+        "optk_stop_problem_t": _lib.StopProblem,
     }
     probes = [
         ("optk_surface_t", "transform"), ("optk_surface_t", "sag"), ("optk_surface_t", "ruling_power"),
@@ -68,6 +69,8 @@ def test_struct_layout_matches_c(tmp_path, lib):
         ("optk_grid_t", "seed"), ("optk_grid_t", "vertices"), ("optk_grid_t", "frame"),
         ("optk_ml_layer_t", "width_stride"), ("optk_ml_layer_t", "profile_kind"),
         ("optk_ml_input_t", "direction_stride"), ("optk_ml_input_t", "n_stride"),
+        ("optk_image_t", "group_size"), ("optk_stop_problem_t", "max_iterations"), ("optk_stop_problem_t", "step"),
+        ("optk_stop_problem_t", "max_abs_error"),
     ]
     src = ["#include <stdio.h>", "#include <stddef.h>", '#include "optk.h"', "int main(void) {"]
     for name in structs:
@@ -125,6 +128,50 @@ def test_system_create_validates_without_a_gpu(lib):
     _lib.check(lib.optk_system_size(handle, C.byref(n_s), C.byref(n_c)))
     assert (n_s.value, n_c.value) == (1, 1)
     _lib.check(lib.optk_system_destroy(handle))
+
+
+def test_stop_solver_and_reductions_validate_their_arguments_without_a_gpu(lib):
+    """Argument checks of optk_solve_stops / optk_reduce_groups come before any CUDA call."""
+    from optika_b200 import _lib
+
+    table = (_lib.Surface * 3)()
+    for k in range(3):
+        table[k].sag_kind = _lib.SAG_FLAT
+        table[k].stages = _lib.STAGE_ALL
+    handle = C.c_void_p()
+    _lib.check(lib.optk_system_create(table, 3, 1, C.byref(handle)))
+    one = (C.c_double * 1)(0.0)
+    counter = (C.c_uint32 * 1)(0)
+    ptr = C.cast(one, C.c_void_p)
+
+    def solve(problem, n=1):
+        return lib.optk_solve_stops(
+            handle, 0, C.byref(problem) if problem is not None else None, n, ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr,
+            C.cast(counter, C.c_void_p), None,
+        )
+
+    good = dict(variable=_lib.STOP_DIRECTION, target=_lib.STOP_POSITION, surf_first=0, surf_last=2, max_iterations=100,
+                reserved=0, step=1e-6, max_abs_error=1e-9)
+    with pytest.raises(ValueError):
+        _lib.check(solve(None))
+    for bad in (dict(variable=7), dict(surf_last=0), dict(surf_last=40), dict(step=0.0), dict(max_iterations=0),
+                dict(max_abs_error=-1.0)):
+        with pytest.raises(ValueError):
+            _lib.check(solve(_lib.StopProblem(**{**good, **bad})))
+    with pytest.raises(ValueError):
+        _lib.check(solve(_lib.StopProblem(**{**good, "surf_first": 1, "surf_last": 3})))  # past the last surface
+    assert solve(_lib.StopProblem(**good), n=0) == 0  # nothing to do: no launch
+    _lib.check(lib.optk_system_destroy(handle))
+
+    def reduce(n_groups, n_inner, x=ptr):
+        return lib.optk_reduce_groups(n_groups, n_inner, x, ptr, None, None, None, None, None, None, None, None, None)
+
+    for n_groups, n_inner in ((1, 0), (-1, 4), (2**20, 2**20)):
+        with pytest.raises(ValueError):
+            _lib.check(reduce(n_groups, n_inner))
+    with pytest.raises(ValueError):
+        _lib.check(reduce(1, 1, x=None))
+    assert reduce(0, 5) == 0
 
 
 def test_no_cpu_fallback():
