@@ -182,7 +182,25 @@ class ClockSampler:
             import pynvml
 
             pynvml.nvmlInit()
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.handle = None
+            try:
+                # the CUDA device by its UUID: NVML numbers the GPUs of the box, CUDA the visible ones
+                import torch
+
+                uuid = getattr(torch.cuda.get_device_properties(gpu_index), "uuid", None)
+                if uuid is not None:
+                    name = str(uuid)
+                    name = name if name.startswith("GPU-") else "GPU-" + name
+                    for candidate in (name, name.encode()):
+                        try:
+                            self.handle = pynvml.nvmlDeviceGetHandleByUUID(candidate)
+                            break
+                        except Exception:
+                            continue
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
         except Exception:
