@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--host-rays", type=int, default=20_000_000, help="rays of the host-array e2e sample")
+    ap.add_argument("--strong", default="cfg3,cfg5", help="strong-scaling image simulations to run (cfg3,cfg5 or none)")
+    ap.add_argument("--strong-steps", type=int, default=2)
+    ap.add_argument("--only-strong", action="store_true", help="skip the cfg 2 sections (development)")
     return ap.parse_args()
 
 
@@ -293,6 +296,195 @@ class ClockSampler:
         )
 
 
+
+# ---------------------------------------------------------------------------
+# strong scaling of the image simulations north_star names (cfg 3: 1e9 rays; cfg 5: 1e10 rays into
+# eight 4096 x 4096 images): the WHOLE job is fixed, every rank draws, traces and bins a slab of the ray
+# grid on chip, and the planes are summed over the ranks and read back to the host while the next
+# configuration is traced (optika_b200.distributed.ImagePipeline).  Collective and read-back are
+# inside the timed region.
+# ---------------------------------------------------------------------------
+def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, rank, world, steps, warmup):
+    import torch
+    import torch.distributed as dist
+    from optika_b200 import _engine, distributed, named as na
+
+    wavelength, field, pupil, axes = grid_spec
+    t_setup = time.perf_counter()
+    grids = system.ray_grids(
+        1.0, wavelength, field, pupil, axes[0], axes[1:3], axes[3:5],
+        normalized_field=False, normalized_pupil=False, random=True, seed=0,
+    )
+    w = np.asarray(wavelength.ndarray, dtype=float)
+    w_edges = np.array([w.min(), w.max()])  # integrate=True: one spectral bin (_sequential.py:1189-1196)
+    compiled = system._compiled_local
+    ex, ey = system.sensor.pixel_edges()
+    leading = tuple(compiled.shape.values())
+    n_rays = sum(g.size for g in grids)
+    stream = torch.cuda.current_stream(device)
+
+    def make(local):
+        image = _engine.DeviceImage.zeros(
+            w_edges, ex, ey, device, leading=leading, moments=True, counts=True, fused=True, pad_to=1 if local else world
+        )
+        return distributed.ImagePipeline(image, device, local=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def run(pipeline, shard, n_steps, n_warm, collective=True):
+        """ms per exposure (device, this rank), stage times, host planes of the last exposure."""
+        marks = []
+
+        def on_launch(c, phase):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            marks.append(e)
+
+        totals, stages, planes, wall = [], [], None, []
+        for k in range(n_warm + n_steps):
+            timed = k >= n_warm
+            pipeline.timing = timed
+            marks.clear()
+            if collective:
+                barrier()
+            else:
+                torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            pipeline.image.zero_()
+            planes = system.collect_grids(
+                grids, w_edges, device=device, pipeline=pipeline, shard=shard, on_launch=on_launch if timed else None
+            )
+            # collect_grids returned after pipeline.finish(): side stream drained, all ranks done
+            stream.wait_stream(pipeline.side)
+            e1.record(stream)
+            torch.cuda.synchronize(device)
+            wall.append(time.perf_counter() - t0)
+            if timed:
+                totals.append(e0.elapsed_time(e1))
+                st = pipeline.stage_ms()
+                st["ms_trace"] = sum(marks[i].elapsed_time(marks[i + 1]) for i in range(0, len(marks), 2))
+                stages.append(st)
+        mean = lambda key: float(np.mean([st[key] for st in stages]))  # noqa: E731
+        return (
+            float(np.mean(totals)), dict(ms_trace=mean("ms_trace"), ms_reduce=mean("ms_reduce"), ms_d2h=mean("ms_d2h")),
+            planes, float(np.mean(wall[n_warm:])),
+        )
+
+    pipeline = make(local=(world == 1))
+    setup_s = time.perf_counter() - t_setup
+    ms, stages, planes, wall = run(pipeline, shard=True, n_steps=steps, n_warm=warmup)
+    counts_sharded = np.array(planes["counts"]) if rank == 0 and world > 1 else None
+    binned = int(planes["counts"].sum()) if rank == 0 else 0
+    flux_total = float(planes["flux"].sum()) if rank == 0 else 0.0
+    d2h_total = sum(int(v.nbytes) for v in planes.values())
+    t = torch.tensor([ms, stages["ms_trace"], stages["ms_reduce"], stages["ms_d2h"], wall * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_trace, ms_reduce, ms_d2h, ms_wall = [float(v) for v in t.tolist()]
+    out = dict(
+        workload=name,
+        rays=n_rays,
+        surfaces=n_surfaces,
+        n_gpus=world,
+        scaling="strong",
+        ms_total=ms_total,
+        ms_wall=ms_wall,
+        ms_trace=ms_trace,
+        ms_reduce=ms_reduce,
+        ms_d2h=ms_d2h,
+        stage_note="ms_total: CUDA events on the launch stream around zeroing, all launches, the reduce-scatter and "
+                   "the device -> host copies (max over ranks); ms_trace / ms_reduce / ms_d2h: busy time of each stage "
+                   "(max over ranks); reduce and copy of configuration k run on a side stream under the trace of k + 1",
+        intercepts_per_s=n_rays * n_surfaces / (ms_total * 1e-3),
+        fp64_tflops_algorithmic=flop_per_ray * n_rays / (ms_total * 1e-3) / 1e12,
+        images=f"{int(np.prod(leading)) if leading else 1} x {len(ex) - 1} x {len(ey) - 1} pixels, planes flux / flux cos / counts",
+        d2h_bytes=d2h_total,
+        d2h_bytes_per_rank=d2h_total // world,
+        collective=("reduce_scatter (NCCL), one per dtype and configuration; every rank copies its 1/N slice to a "
+                    "shared page-locked host buffer over its own PCIe link") if world > 1 else "none (one GPU)",
+        shard_axis=(["wavelength", "field_x", "field_y", "pupil_x", "pupil_y"][distributed.best_shard_axis(grids[0].count, world)]
+                    if world > 1 else None),
+        rays_binned=binned,
+        binned_fraction=binned / n_rays if rank == 0 else None,
+        flux_total=flux_total,
+        setup_s=setup_s,
+        steps=steps,
+        warmup=warmup,
+    )
+    if world > 1:
+        # the same job on rank 0 ALONE, same run (no collective; the other ranks wait): the denominator of
+        # the strong-scaling efficiency, and the image the sharded + reduced one must equal count for count
+        n1 = None
+        if rank == 0:
+            single = make(local=True)
+            ms1, st1, planes1, wall1 = run(single, shard=False, n_steps=max(1, min(steps, 2)), n_warm=1, collective=False)
+            n1 = dict(ms_total=ms1, ms_wall=wall1 * 1e3, **st1)
+            n1["counts_equal"] = bool(np.array_equal(planes1["counts"], counts_sharded))
+            n1["flux_max_rel_diff"] = float(
+                np.max(np.abs(planes1["flux"] - planes["flux"])) / max(float(np.max(np.abs(planes1["flux"]))), 1e-300)
+            )
+            del planes1
+            single.close()
+            del single
+        dist.barrier()
+        if rank == 0:
+            out["n1_same_run"] = n1
+            out["efficiency_vs_n1"] = n1["ms_total"] / (world * ms_total)
+            out["counts_equal_n1"] = n1["counts_equal"]
+    del planes
+    pipeline.close()
+    del pipeline
+    torch.cuda.empty_cache()
+    return out
+
+
+def strong_scaling_configs(device, rank, world, steps, warmup, which):
+    import configs
+    from optika_b200 import named as na, units as u
+
+    axes = ("wavelength", "field_x", "field_y", "pupil_x", "pupil_y")
+
+    def grid(w_lo, w_hi, n_w, half_field, n_field, half_pupil, n_pupil):
+        wavelength = na.ScalarArray(np.linspace(w_lo, w_hi, n_w + 1), axes[0])
+        field = na.Cartesian2dVectorArray(
+            na.ScalarArray(np.linspace(-half_field[0], half_field[0], n_field[0] + 1), axes[1]),
+            na.ScalarArray(np.linspace(-half_field[1], half_field[1], n_field[1] + 1), axes[2]),
+        )
+        pupil = na.Cartesian2dVectorArray(
+            na.ScalarArray(np.linspace(-half_pupil[0], half_pupil[0], n_pupil[0] + 1), axes[3]),
+            na.ScalarArray(np.linspace(-half_pupil[1], half_pupil[1], n_pupil[1] + 1), axes[4]),
+        )
+        return wavelength, field, pupil, axes
+
+    out = {}
+    if "cfg3" in which:
+        # cfg 3: EUV slitless spectrograph (octagonal field stop, toroidal VLS grating), 1e9 rays, 8 wavelength cells
+        deg = u.deg
+        out["cfg3_strong"] = strong_scaling(
+            "cfg3 toroidal VLS spectrograph: 8 wavelength x 100x100 field x 112x112 pupil cells = 1.0e9 stratified "
+            "random rays, 4 surfaces, 2048x1024 sensor",
+            configs.toroidal_vls(6, 12, 3),
+            grid(25 * u.nm, 35 * u.nm, 8, (0.2 * deg, 0.2 * deg), (100, 100), (22.0, 22.0), (112, 112)),
+            4, 771, device, rank, world, steps, warmup,
+        )
+    if "cfg5" in which:
+        # cfg 5: full detector image simulation: one field cell per pixel, 10 x 8 pupil cells each, 8 tilts
+        system = configs.telescope_4k(num_tilt=8, num_pixel=4096)
+        half = float(np.arctan(0.5 * 4096 * 15e-3 / 3200.0))
+        out["cfg5_strong"] = strong_scaling(
+            "cfg5 misaligned telescope, full detector image: 8 tilts x 4096x4096 field cells (one per pixel) x 10x8 "
+            "pupil cells = 1.07e10 stratified random rays, 6 surfaces, 4096x4096 sensor",
+            system,
+            grid(499 * u.nm, 501 * u.nm, 1, (half, half), (4096, 4096), (160.0, 160.0), (10, 8)),
+            6, 791, device, rank, world, steps, warmup,
+        )
+    return out
+
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
@@ -316,6 +508,15 @@ def run_b200(args):
 
     lib = _lib.lib()
     stream = torch.cuda.current_stream(device)
+
+    which_strong = [w for w in args.strong.split(",") if w in ("cfg3", "cfg5")]
+    if args.only_strong:
+        strong = strong_scaling_configs(device, rank, world, args.strong_steps, 1, which_strong)
+        if rank == 0:
+            print(json.dumps(dict(metric=METRIC, unit=UNIT, n_gpus=world, config=strong)), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- the system and its separable grid; rank r traces its own pupil slab (weak scaling)
     nf, npup, nw = args.num_field, args.num_pupil, args.num_wavelength
@@ -468,7 +669,7 @@ def run_b200(args):
 
         def e2e_step():
             t_a = time.perf_counter()
-            image = system.image_rays(edges, device=device, counts=True)
+            image = system.image_rays(edges, device=device, counts=True, **configs.PHYSICAL)
             if breakdown:
                 torch.cuda.synchronize()
                 t_b = time.perf_counter()
@@ -606,6 +807,13 @@ def run_b200(args):
             rays_binned_fraction=float(chip_image.counts.sum().item()) / (2.0 * ray_grid.size),
         )
 
+    # ---- strong scaling of the cfg 3 / cfg 5 image simulations (collective + read-back timed)
+    strong = {}
+    if which_strong and not args.no_e2e:
+        del fields_in, mask_in, mask_out
+        torch.cuda.empty_cache()
+        strong = strong_scaling_configs(device, rank, world, args.strong_steps, 1, which_strong)
+
     # ---- CPU baseline beside it (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -633,6 +841,7 @@ def run_b200(args):
                 l2="inputs exceed L2: every launch streams 16.2 GB of dense rays through HBM",
                 unvignetted_fraction=unv_frac,
                 generated_on_chip=on_chip,
+                **strong,
                 sharding="pupil slab per rank, no data-path collective" if world > 1 else "single GPU",
             ),
             roofline=dict(

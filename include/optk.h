@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 6
+#define OPTK_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -566,6 +566,14 @@ OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream);
 /* Bandwidth (GB/s, 162 B per ray) of the trace kernel's access pattern with no arithmetic:
  * ten fp64 arrays + a byte mask in, the same out.  Allocates 162 * n_rays bytes. */
 OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, void* stream);
+
+/* ---- host memory ---------------------------------------------------------------
+ * Page-lock (cudaHostRegister, portable) / release a host range the caller owns, e.g. a POSIX
+ * shared-memory mapping that several single-GPU processes read detector planes back into
+ * (optika_b200/distributed.py): copies into registered memory run at PCIe speed and are
+ * asynchronous.  The range must stay mapped until it is unregistered. */
+OPTK_API int optk_host_register(void* data, int64_t n_bytes);
+OPTK_API int optk_host_unregister(void* data);
 
 #ifdef __cplusplus
 }

@@ -151,15 +151,39 @@ class DeviceImage:
     counts: object = None
     range: object = None  # first / last edge of (wavelength, x, y) as host floats, when known
 
+    buffer_f64: object = None  # fused layout: [n_config][row] with flux | moment_real of one configuration side by side
+    buffer_i64: object = None  # fused layout: [n_config][row] counts
+
     @classmethod
-    def zeros(cls, edges_wavelength, edges_x, edges_y, device, leading=(), moments=True, counts=True):
+    def zeros(cls, edges_wavelength, edges_x, edges_y, device, leading=(), moments=True, counts=True,
+              fused: bool = False, pad_to: int = 1):
+        """
+        Zeroed planes.  ``fused``: the fp64 planes of one configuration are adjacent in ONE buffer
+        (``buffer_f64[c] = flux[c] | moment_real[c]``, rows padded to a multiple of `pad_to` elements;
+        ``buffer_i64[c] = counts[c]``), so a configuration is reduced over the ranks with one collective
+        per dtype and read back with one copy (:class:`optika_b200.distributed.ImagePipeline`).
+        """
         torch = _torch()
 
         def dev(e):
             return torch.from_numpy(np.array(e, dtype=np.float64)).to(device)
 
         ew, ex, ey = dev(edges_wavelength), dev(edges_x), dev(edges_y)
-        dims = tuple(leading) + (len(ew) - 1, len(ex) - 1, len(ey) - 1)
+        dims3 = (len(ew) - 1, len(ex) - 1, len(ey) - 1)
+        dims = tuple(leading) + dims3
+        rng = [float(v) for e in (edges_wavelength, edges_x, edges_y) for v in (np.asarray(e)[0], np.asarray(e)[-1])]
+        if fused:
+            n = int(np.prod(dims3, dtype=np.int64))
+            n_config = int(np.prod(tuple(leading), dtype=np.int64)) if leading else 1
+            n_planes = 2 if moments else 1
+            pad = lambda m: -(-m // pad_to) * pad_to  # noqa: E731
+            buf_f = torch.zeros((n_config, pad(n_planes * n)), dtype=torch.float64, device=device)
+            buf_i = torch.zeros((n_config, pad(n)), dtype=torch.int64, device=device) if counts else None
+            plane = lambda b, k: b[:, k * n:(k + 1) * n].view(dims)  # noqa: E731
+            return cls(
+                ew, ex, ey, flux=plane(buf_f, 0), moment_real=plane(buf_f, 1) if moments else None, moment_imag=None,
+                counts=plane(buf_i, 0) if counts else None, range=rng, buffer_f64=buf_f, buffer_i64=buf_i,
+            )
         z = lambda dt: torch.zeros(dims, dtype=dt, device=device)  # noqa: E731
         return cls(
             ew, ex, ey,
@@ -167,17 +191,30 @@ class DeviceImage:
             moment_real=z(torch.float64) if moments else None,
             moment_imag=None,
             counts=z(torch.int64) if counts else None,
-            range=[float(v) for e in (edges_wavelength, edges_x, edges_y) for v in (np.asarray(e)[0], np.asarray(e)[-1])],
+            range=rng,
         )
+
+    def zero_(self):
+        """Clear every plane (re-use of the buffers between exposures)."""
+        if self.buffer_f64 is not None:
+            self.buffer_f64.zero_()
+            if self.buffer_i64 is not None:
+                self.buffer_i64.zero_()
+        else:
+            for t in (self.flux, self.moment_real, self.moment_imag, self.counts):
+                if t is not None:
+                    t.zero_()
+        return self
 
     _pinned = {}
 
-    def to_host(self, pinned: bool = True) -> dict:
+    def to_host(self, pinned: bool = False) -> dict:
         """
-        Copy the planes to host memory.  With ``pinned`` the destination buffers are
-        page-locked and cached per (name, shape): the copy then runs at PCIe speed instead of
-        being staged through pageable memory.  Returns ``{name: torch tensor}``; the buffers are
-        reused by the next call with the same shapes.
+        Copy the planes to host memory; returns ``{name: torch tensor}``.  With ``pinned`` the
+        destination buffers are page-locked and cached per (name, shape) -- the copy then runs at
+        PCIe speed instead of being staged through pageable memory, but the SAME buffers are handed
+        out again by the next call with equal shapes (callers that keep two images must copy);
+        :meth:`release_pinned` frees the cache.  The default returns fresh pageable tensors.
         """
         torch = _torch()
         out = {}
@@ -199,6 +236,11 @@ class DeviceImage:
             torch.cuda.current_stream(self.flux.device).synchronize()
         return out
 
+    @classmethod
+    def release_pinned(cls):
+        """Free the page-locked read-back buffers cached by ``to_host(pinned=True)``."""
+        cls._pinned.clear()
+
     def struct(self, plane_index: int = 0) -> L.Image:
         im = L.Image()
         im.n_wavelength = len(self.edges_wavelength) - 1
@@ -207,10 +249,13 @@ class DeviceImage:
         im.edges_wavelength = self.edges_wavelength.data_ptr()
         im.edges_x = self.edges_x.data_ptr()
         im.edges_y = self.edges_y.data_ptr()
-        n = im.n_wavelength * im.n_x * im.n_y
 
         def ptr(t):
-            return None if t is None else t.data_ptr() + plane_index * n * 8
+            # planes are [config axes...][n_w][n_x][n_y]; the configuration axes are contiguous among
+            # themselves in both layouts, so the last of them carries the stride of one configuration
+            if t is None:
+                return None
+            return t.data_ptr() + (plane_index * t.stride(t.dim() - 4) * 8 if t.dim() > 3 else 0)
 
         if self.range is not None:
             im.has_range = 1
@@ -267,9 +312,9 @@ class CompiledSystem:
     (``optika/propagators.py:38-39, 67-71``).
     """
 
-    def __init__(self, surfaces, stages: int = L.STAGE_ALL, local_last: bool = False):
+    def __init__(self, surfaces, stages: int = L.STAGE_ALL, local_last: bool = False, lowered=None):
         self.surfaces = list(surfaces)
-        table, shape_ = _lowering.lower_system(self.surfaces, stages=stages)
+        table, shape_ = lowered if lowered is not None else _lowering.lower_system(self.surfaces, stages=stages)
         # surfaces whose efficiency is a per-ray multilayer evaluation (MultilayerMirror /
         # MultilayerFilm): the trace is chained around them, see `trace`
         self.coatings = {
@@ -285,17 +330,53 @@ class CompiledSystem:
         self.shape = shape_
         self.n_surface = len(self.surfaces)
         self.n_config = len(table) // max(self.n_surface, 1)
-        handle = C.c_void_p()
-        L.check(L.lib().optk_system_create(table, self.n_surface, self.n_config, C.byref(handle)))
-        self.handle = handle
+        self._handles = {}  # device ordinal -> optk_system_t*: efficiency tables live on ONE device
+        self.handle  # validate the table now (unsupported kinds raise here, as before)
+
+    def handle_for(self, device=None):
+        """The ``optk_system_t*`` whose device-side tables live on `device` (default: the current one)."""
+        torch = _torch()
+        if not torch.cuda.is_available():
+            ordinal = -1
+        elif device is None:
+            ordinal = torch.cuda.current_device()
+        else:
+            ordinal = torch.device(device).index
+            ordinal = torch.cuda.current_device() if ordinal is None else ordinal
+        handle = self._handles.get(ordinal)
+        if handle is None:
+            handle = C.c_void_p()
+            with device_guard(ordinal):
+                L.check(L.lib().optk_system_create(self.table, self.n_surface, self.n_config, C.byref(handle)))
+            self._handles[ordinal] = handle
+        return handle
+
+    @property
+    def handle(self):
+        return self.handle_for(None)
 
     def __del__(self):
         try:
-            if getattr(self, "handle", None):
-                L.lib().optk_system_destroy(self.handle)
-                self.handle = None
+            for handle in getattr(self, "_handles", {}).values():
+                L.lib().optk_system_destroy(handle)
+            self._handles = {}
         except Exception:  # pragma: no cover
             pass
+
+
+def device_guard(device):
+    """
+    Context manager that makes `device` the current CUDA device (no-op without CUDA or for ``-1``).
+    Launches themselves follow the stream they are given (``DeviceScope`` in ``csrc/api.cu``); the
+    guard is for what has no stream argument: allocations made by ``optk_system_create`` and
+    torch's own current-stream lookups.
+    """
+    import contextlib
+
+    torch = _torch()
+    if not torch.cuda.is_available() or device is None or device == -1:
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
 
 
 # ---------------------------------------------------------------------------
@@ -615,7 +696,7 @@ def _trace(
                 im = image.struct(c) if image is not None else None
             L.check(
                 lib.optk_trace(
-                    system.handle, c, C.byref(rin), C.byref(rout) if write_rays else None,
+                    system.handle_for(device), c, C.byref(rin), C.byref(rout) if write_rays else None,
                     surf_begin, surf_count, surf_step, 1 if accumulate else 0, n_ray,
                     C.byref(im) if im is not None else None,
                     C.byref(frame) if frame is not None else None,
@@ -761,7 +842,7 @@ def solve_stops(
             break
         L.check(
             lib.optk_solve_stops(
-                system.handle, c, C.byref(problem), n,
+                system.handle_for(device), c, C.byref(problem), n,
                 w[c].data_ptr(), fx[c].data_ptr(), fy[c].data_ptr(), fz[c].data_ptr(),
                 tx[c].data_ptr(), ty[c].data_ptr(), x[c].data_ptr(), y[c].data_ptr(), z[c].data_ptr(),
                 unconverged.data_ptr(), stream,

@@ -232,7 +232,7 @@ def trace_grid(
         LAUNCHES += 1
         L.check(
             lib.optk_trace_grid(
-                system.handle, config, C.byref(g), C.byref(rout) if write_rays else None,
+                system.handle_for(device), config, C.byref(g), C.byref(rout) if write_rays else None,
                 surf_begin, surf_count, surf_step, 1 if accumulate else 0, n_ray,
                 C.byref(im) if im is not None else None,
                 C.byref(frame) if frame is not None else None,
@@ -287,7 +287,7 @@ def _trace_dense(system, config: int, rays, surf_begin: int, surf_count: int, im
     LAUNCHES += 1
     L.check(
         L.lib().optk_trace(
-            system.handle, config, C.byref(rin), C.byref(rout) if write_rays else None, surf_begin, surf_count, 1,
+            system.handle_for(device), config, C.byref(rin), C.byref(rout) if write_rays else None, surf_begin, surf_count, 1,
             0, 0, C.byref(im) if im is not None else None, None, None, _engine._stream_ptr(device),
         )
     )
@@ -302,6 +302,8 @@ def trace_grid_coated(system, grid: RayGrid, config: int, image, device=None, ma
     (:func:`optika_b200._engine.apply_coating`), and so on; the last link bins into `image`.
     """
     device = _engine.require_cuda(device)
+    if grid.size == 0:
+        return  # an empty slab (more ranks than cells): nothing to trace, the caller still reduces
     coated = sorted(system.coatings)
     n_surface = system.n_surface
     for begin, count in _boxes(grid.begin, grid.count, max_rays):

@@ -242,7 +242,7 @@ class MlInput(C.Structure):
     ]
 
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class OptkError(RuntimeError):
@@ -273,6 +273,8 @@ SYMBOLS = (
     "optk_apply_efficiency",
     "optk_measure_fp64_peak",
     "optk_measure_soa_copy",
+    "optk_host_register",
+    "optk_host_unregister",
 )
 
 _lib = None
@@ -319,6 +321,8 @@ def lib() -> C.CDLL:
     L.optk_apply_efficiency.argtypes = [i64, vp, vp, vp, vp]
     L.optk_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
     L.optk_measure_soa_copy.argtypes = [i64, C.POINTER(C.c_double), vp]
+    L.optk_host_register.argtypes = [vp, i64]
+    L.optk_host_unregister.argtypes = [vp]
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int

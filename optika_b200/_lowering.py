@@ -11,6 +11,7 @@ time; transformations are composed into one affine per element.
 """
 
 from __future__ import annotations
+import ctypes as C
 import numpy as np
 from . import named as na
 from . import units as u
@@ -280,12 +281,33 @@ def lower_system(surfaces, shape_: dict[str, int] | None = None, stages: int = L
     n_config = int(np.prod(list(shape_.values()), dtype=np.int64)) if shape_ else 1
     table = _table_type(n_config * len(surfaces))()
     table.keep = []
+    # a surface without named axes is the same record in every configuration: lowered once
+    # (a tolerance sweep varies one or two surfaces out of many)
+    fixed = [None if na.shape(s) else lower_surface(s, {}, (), stages, table.keep) for s in surfaces]
     k = 0
     for index in np.ndindex(*shape_.values()):
-        for s in surfaces:
-            table[k] = lower_surface(s, shape_, index, stages, table.keep)
+        for s, record in zip(surfaces, fixed):
+            table[k] = record if record is not None else lower_surface(s, shape_, index, stages, table.keep)
             k += 1
     return table, shape_
+
+
+_POINTER_FIELDS = ("material_lut_x", "material_lut_y", "ruling_lut_x", "ruling_lut_y")
+
+
+def table_key(table) -> bytes:
+    """
+    The content of a lowered table as a hashable key: the packed records with their host pointers
+    blanked, followed by the arrays those pointers refer to.  Two lowerings of an unchanged system
+    give the same key; any edit of a surface that matters to the trace changes it.
+    """
+    raw = bytearray(table)
+    size = C.sizeof(L.Surface)
+    for k in range(len(table)):
+        for name in _POINTER_FIELDS:
+            field = getattr(L.Surface, name)
+            raw[k * size + field.offset: k * size + field.offset + field.size] = bytes(field.size)
+    return bytes(raw) + b"".join(np.ascontiguousarray(a).tobytes() for a in getattr(table, "keep", ()))
 
 
 def _table_type(n: int):

@@ -280,13 +280,12 @@ def rayfunction_stops(system, wavelength, samples_pupil_stop=101, samples_field_
     return inputs, rays
 
 
-def denormalize_grid(system, grid: ObjectVectorArray, normalized_field=True, normalized_pupil=True, backend=None):
-    """``_denormalize_grid`` (``_sequential.py:748-789``): normalised [-1, 1] -> physical coordinates."""
-    if (not normalized_field) and (not normalized_pupil):
-        return grid
-    _, rays = rayfunction_stops(
-        system, grid.wavelength, samples_pupil_stop=21, samples_field_stop=21, backend=backend
-    )
+def stop_extents(system, wavelength, backend=None) -> tuple:
+    """
+    ``(field_min, field_ptp, pupil_min, pupil_ptp)`` of the rays through the edges of both stops
+    (21 x 21 samples), the quantities ``_denormalize_grid`` scales with (``_sequential.py:761-787``).
+    """
+    _, rays = rayfunction_stops(system, wavelength, samples_pupil_stop=21, samples_field_stop=21, backend=backend)
     axes = (AXIS_FIELD_STOP, AXIS_PUPIL_STOP)
     if system.object_is_at_infinity:
         field = _util.angles(rays.direction)
@@ -294,11 +293,20 @@ def denormalize_grid(system, grid: ObjectVectorArray, normalized_field=True, nor
     else:
         field = na.Cartesian2dVectorArray(rays.position.x, rays.position.y)
         pupil = _util.angles(rays.direction)
+    return field.min(axis=axes), field.ptp(axis=axes), pupil.min(axis=axes), pupil.ptp(axis=axes)
+
+
+def denormalize_grid(system, grid: ObjectVectorArray, normalized_field=True, normalized_pupil=True, backend=None,
+                     extents=None):
+    """``_denormalize_grid`` (``_sequential.py:748-789``): normalised [-1, 1] -> physical coordinates."""
+    if (not normalized_field) and (not normalized_pupil):
+        return grid
+    if extents is None:
+        extents = stop_extents(system, grid.wavelength, backend)
+    field_lo, field_ptp, pupil_lo, pupil_ptp = extents
     result = grid.copy_shallow()
     if normalized_field:
-        lo, ptp = field.min(axis=axes), field.ptp(axis=axes)
-        result.field = ptp * (result.field + 1) / 2 + lo
+        result.field = field_ptp * (result.field + 1) / 2 + field_lo
     if normalized_pupil:
-        lo, ptp = pupil.min(axis=axes), pupil.ptp(axis=axes)
-        result.pupil = ptp * (result.pupil + 1) / 2 + lo
+        result.pupil = pupil_ptp * (result.pupil + 1) / 2 + pupil_lo
     return result

@@ -38,6 +38,30 @@ struct optk_system {
     int32_t n_config;
     std::vector<optk_surface_t> table;
     double* lut_device = nullptr;  // every efficiency table of the system, one allocation
+    int lut_ordinal = -1;          // the device that allocation lives on
+};
+
+// Launches go to the device that owns the caller's stream, whatever device happens to be current in
+// the calling thread (a process that drives several GPUs passes `device=` per call): the current
+// device is switched for the duration of the entry point and restored.  NULL (the legacy default
+// stream) keeps the current device.
+struct DeviceScope {
+    int previous = -1;
+    bool switched = false;
+    explicit DeviceScope(void* stream) {
+        int wanted = -1;
+        if (!stream) return;
+        if (cudaStreamGetDevice((cudaStream_t)stream, &wanted) != cudaSuccess || cudaGetDevice(&previous) != cudaSuccess) {
+            cudaGetLastError();  // not a stream of this process: let the launch report it
+            return;
+        }
+        if (wanted != previous && cudaSetDevice(wanted) == cudaSuccess) switched = true;
+    }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(previous);
+    }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
 };
 
 // ---- scratch cache for the host-pointer path ------------------------------------
@@ -266,6 +290,15 @@ int pack_trace(const optk_system_t* sys, int32_t config, int32_t surf_begin, int
         set_error("surf_step must be +1 or -1");
         return OPTK_ERR_INVALID;
     }
+    if (sys->lut_device) {
+        int current = -1;
+        cudaGetDevice(&current);
+        if (current != sys->lut_ordinal) {
+            set_error("this system handle owns efficiency tables on device %d but the launch is on device %d; "
+                      "create one handle per device", sys->lut_ordinal, current);
+            return OPTK_ERR_INVALID;
+        }
+    }
     const optk_surface_t* row = sys->table.data() + (size_t)config * sys->n_surface;
     for (int k = 0; k < surf_count; ++k) {
         const int s = surf_begin + k * surf_step;
@@ -341,6 +374,7 @@ OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, 
     if (lut_total) {
         std::vector<double> host;
         host.reserve(lut_total);
+        cudaGetDevice(&sys->lut_ordinal);
         cudaError_t e = cudaMalloc((void**)&sys->lut_device, lut_total * sizeof(double));
         if (e != cudaSuccess) {
             delete sys;
@@ -391,6 +425,7 @@ OPTK_API int optk_trace(const optk_system_t* sys, int32_t config, const optk_ray
                int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
                int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
                optk_trace_stats_t* stats_device, void* stream) {
+    DeviceScope device_scope(stream);
     static thread_local TraceParams P;
     long long n = 0;
     int rc = grid_size(in, &n);
@@ -429,6 +464,7 @@ OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const opt
                     int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
                     int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
                     optk_trace_stats_t* stats_device, void* stream) {
+    DeviceScope device_scope(stream);
     static thread_local TraceParams P;
     if (!grid) {
         set_error("optk_trace_grid: grid is NULL");
@@ -495,6 +531,7 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
                      const double* wavelength, const double* fixed_x, const double* fixed_y, const double* fixed_z,
                      const double* target_x, const double* target_y, double* x, double* y, double* z,
                      uint32_t* n_unconverged, void* stream) {
+    DeviceScope device_scope(stream);
     static thread_local TraceParams P;
     if (!problem || n < 0) {
         set_error("optk_solve_stops: problem is NULL or n is negative");
@@ -559,6 +596,7 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
 OPTK_API int optk_reduce_groups(int64_t n_groups, int64_t n_inner, const double* x, const double* y,
                        const double* intensity, const uint8_t* unvignetted, double* sum_intensity, double* sum_x,
                        double* sum_y, uint64_t* count, double* sum_x_all, double* sum_y_all, void* stream) {
+    DeviceScope device_scope(stream);
     if (n_groups < 0 || n_inner < 1 || n_groups > 0x7fffffffLL || n_inner > 0x7fffffffLL ||
         n_groups * n_inner > 0x7fffffffLL) {
         set_error("optk_reduce_groups: n_groups >= 0, n_inner >= 1 and n_groups * n_inner <= 2^31 - 1 are required");
@@ -581,6 +619,7 @@ OPTK_API int64_t optk_jit_compiled(void) { return jit_compiled_count(); }
 
 OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp, const double* fp_re, const double* fp_im,
                 double* out_re, double* out_im, void* stream) {
+    DeviceScope device_scope(stream);
     if (n < 0 || m < 1 || !x || !xp || !fp_re || !out_re || (fp_im && !out_im)) {
         set_error("optk_interp: bad arguments");
         return OPTK_ERR_INVALID;
@@ -589,6 +628,7 @@ OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp
 }
 
 OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream) {
+    DeviceScope device_scope(stream);
     if (n < 0 || !intensity || !e_s || !e_p) {
         set_error("optk_apply_efficiency: bad arguments");
         return OPTK_ERR_INVALID;
@@ -598,6 +638,7 @@ OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e
 
 OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
              const double* intensity, const uint8_t* unvignetted, const optk_image_t* image, void* stream) {
+    DeviceScope device_scope(stream);
     if (!wavelength || !x || !y || !image) {
         set_error("optk_bin: NULL argument");
         return OPTK_ERR_INVALID;
@@ -835,6 +876,7 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const opt
 OPTK_API int optk_multilayer(const optk_ml_input_t* input, int32_t n_layers, const optk_ml_layer_t* layers,
                     int32_t n_segments, const optk_ml_segment_t* segments, double* reflectivity_s,
                     double* reflectivity_p, double* transmissivity_s, double* transmissivity_p, void* stream) {
+    DeviceScope device_scope(stream);
     if (!input || !layers || n_layers < 1 || n_layers > OPTK_ML_MAX_LAYERS) {
         set_error("optk_multilayer: need 1..%d layers (the last one is the substrate)", OPTK_ML_MAX_LAYERS);
         return OPTK_ERR_INVALID;
@@ -944,6 +986,7 @@ OPTK_API int optk_multilayer(const optk_ml_input_t* input, int32_t n_layers, con
 }
 
 OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream) {
+    DeviceScope device_scope(stream);
     if (!flops_per_second) {
         set_error("optk_measure_fp64_peak: NULL argument");
         return OPTK_ERR_INVALID;
@@ -952,11 +995,30 @@ OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream) {
 }
 
 OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, void* stream) {
+    DeviceScope device_scope(stream);
     if (!gbytes_per_second || n_rays < 2) {
         set_error("optk_measure_soa_copy: bad arguments");
         return OPTK_ERR_INVALID;
     }
     return measure_soa_copy(n_rays, gbytes_per_second, (cudaStream_t)stream);
+}
+
+OPTK_API int optk_host_register(void* data, int64_t n_bytes) {
+    if (!data || n_bytes <= 0) {
+        set_error("optk_host_register: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    OPTK_CUDA(cudaHostRegister(data, (size_t)n_bytes, cudaHostRegisterPortable));
+    return OPTK_OK;
+}
+
+OPTK_API int optk_host_unregister(void* data) {
+    if (!data) {
+        set_error("optk_host_unregister: NULL argument");
+        return OPTK_ERR_INVALID;
+    }
+    OPTK_CUDA(cudaHostUnregister(data));
+    return OPTK_OK;
 }
 
 }  // extern "C"

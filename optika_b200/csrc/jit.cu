@@ -244,6 +244,11 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
     if (!may_compile && P.n_rays < (1LL << 20)) return nullptr;
     std::string key;
     const std::string src = jit_source(P, v, &key);
+    // a CUfunction belongs to the context of ONE device: the in-process cache is per device ordinal
+    // (the cubin on disk is not)
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    key = "device " + std::to_string(device) + "\n" + key;
     auto it = g_kernels.find(key);
     if (it != g_kernels.end() && it->second != kNotOnDisk) return it->second;
     if (it != g_kernels.end() && !may_compile) return nullptr;  // looked before: not cached, too short to compile
@@ -254,8 +259,7 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
         if (verbose()) fprintf(stderr, "optk jit: libnvrtc / libcuda not available, using the table-driven kernels\n");
         return nullptr;
     }
-    int device = 0, major = 0, minor = 0;
-    if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    int major = 0, minor = 0;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
     cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
     if (major != 10 || minor != 0) return nullptr;  // this library is sm_100a only

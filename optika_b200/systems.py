@@ -9,10 +9,11 @@ the device engine in one call.  ``image_rays`` is the fused
 trace-and-bin path used for detector image simulation
 (``image`` -> ``sensor.measure``, ``:1088-1206``): rays never leave the chip.
 
-Grid coordinates are PHYSICAL by default here (``normalized_field=False``):
-the stop solver that maps normalised coordinates (``:396-678``) is a host-side
-caller of the hot path and is provided separately by
-:meth:`SequentialSystem.denormalize`.
+Grid coordinates are NORMALISED by default, as in the reference (``:843-844, 936-937``): they
+are mapped to physical ones through the stop solver (``:396-678``, on the device:
+``optk_solve_stops``), solved once per wavelength grid and cached.  Floats carry no unit here, so a
+grid in degrees / millimetres must be announced with ``normalized_field=False,
+normalized_pupil=False`` (the reference would raise a unit error instead).
 """
 
 from __future__ import annotations
@@ -88,15 +89,37 @@ class SequentialSystem(AbstractSequentialSystem):
             result += [self.sensor]
         return result
 
-    @functools.cached_property
+    def _compile(self, local_last: bool) -> _engine.CompiledSystem:
+        """
+        The surface list lowered to the device table.  The reference re-reads ``surfaces_all`` on every
+        ``raytrace`` (``_sequential.py:913-923``), so the list is lowered on every call (cheap host work)
+        and the device handle of the previous call is reused only when the lowered bytes are the same:
+        editing a radius, a transformation or the sensor takes effect on the next trace.
+        """
+        from . import _lowering
+
+        surfaces = self.surfaces_all
+        lowered = _lowering.lower_system(surfaces)
+        key = _lowering.table_key(lowered[0])
+        cache = self.__dict__.setdefault("_compiled_cache", {})
+        entry = cache.get(local_last)
+        if entry is None or entry[0] != key or len(entry[1].surfaces) != len(surfaces):
+            entry = (key, _engine.CompiledSystem(surfaces, local_last=local_last, lowered=lowered))
+            cache[local_last] = entry
+        compiled = entry[1]
+        # objects that are read again at trace time (coating stacks) always come from the current list
+        compiled.surfaces = surfaces
+        compiled.coatings = {k: s.material for k, s in enumerate(surfaces) if hasattr(s.material, "efficiency_device")}
+        return compiled
+
+    @property
     def _compiled(self) -> _engine.CompiledSystem:
-        """The lowered surface table; cached like ``rayfunction_default`` (``:990-1000``)."""
-        return _engine.CompiledSystem(self.surfaces_all)
+        return self._compile(local_last=False)
 
     def invalidate(self):
-        """Drop the cached device tables (and the stop solution) after mutating a surface."""
-        for name in ("_compiled", "_compiled_local", "_stop_cache"):
-            self.__dict__.pop(name, None)
+        """Kept for callers of round 1: the device tables now follow the surfaces by themselves."""
+        self.__dict__.pop("_compiled_cache", None)
+        self.__dict__.pop("_stop_cache", None)
 
     # -- input rays --------------------------------------------------------
     def _calc_rayfunction_input(self, grid: ObjectVectorArray) -> RayFunctionArray:
@@ -146,9 +169,31 @@ class SequentialSystem(AbstractSequentialSystem):
 
     def denormalize(self, grid: ObjectVectorArray, normalized_field=True, normalized_pupil=True, backend=None):
         """Map normalised field / pupil coordinates to physical ones (``:748-789``)."""
-        from . import _stops
+        from . import _stops, _lowering
 
-        return _stops.denormalize_grid(self, grid, normalized_field, normalized_pupil, backend=backend)
+        if (not normalized_field) and (not normalized_pupil):
+            return grid
+        # The stop solution depends on the surfaces and on the wavelength grid only: solved once and
+        # kept (the reference caches it for its default grid, ``_rayfunction_input``, :830-834), keyed
+        # on the lowered surface table so that an edited surface is solved again.
+        w = na.as_named_array(u.length(grid.wavelength))
+        frame = self.transformation.affine.numpy({}) if self.transformation is not None and not na.shape(self.transformation) else None
+        key = (
+            _lowering.table_key(_lowering.lower_system(self.surfaces_all)[0]),
+            tuple(w.axes), np.ascontiguousarray(w.ndarray, dtype=float).tobytes(),
+            None if frame is None else (frame[0].tobytes(), frame[1].tobytes()),
+            self.object_is_at_infinity, backend,
+        )
+        cache = self.__dict__.setdefault("_stop_cache", {})
+        cacheable = self.transformation is None or frame is not None
+        extents = cache.get(key) if cacheable else None
+        if extents is None:
+            extents = _stops.stop_extents(self, grid.wavelength, backend)
+            if cacheable:
+                if len(cache) >= 8:
+                    cache.pop(next(iter(cache)))
+                cache[key] = extents
+        return _stops.denormalize_grid(self, grid, normalized_field, normalized_pupil, backend=backend, extents=extents)
 
     def rayfunction_stops(self, wavelength=None, samples_pupil_stop=101, samples_field_stop=101, backend=None):
         """Rays through the edges of both stops, at the object (``:625-678``): ``(inputs, rays)``."""
@@ -198,8 +243,8 @@ class SequentialSystem(AbstractSequentialSystem):
         field=None,
         pupil=None,
         axis: None | str = None,
-        normalized_field: bool = False,
-        normalized_pupil: bool = False,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
         accumulate: bool = True,
         device=None,
         on_device: bool = False,
@@ -225,8 +270,8 @@ class SequentialSystem(AbstractSequentialSystem):
         wavelength=None,
         field=None,
         pupil=None,
-        normalized_field: bool = False,
-        normalized_pupil: bool = False,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
         device=None,
         on_device: bool = False,
     ) -> RayFunctionArray:
@@ -248,8 +293,8 @@ class SequentialSystem(AbstractSequentialSystem):
         wavelength=None,
         field=None,
         pupil=None,
-        normalized_field: bool = False,
-        normalized_pupil: bool = False,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
         device=None,
     ) -> dict:
         """
@@ -329,13 +374,13 @@ class SequentialSystem(AbstractSequentialSystem):
             intensity=na.ScalarArray(sum_i, axes),
         )
 
-    @functools.cached_property
+    @property
     def _compiled_local(self) -> _engine.CompiledSystem:
         """
         The system with the final local->global step of the sensor removed, so the
         trace ends in sensor-local coordinates (``_sequential.py:983-986``).
         """
-        return _engine.CompiledSystem(self.surfaces_all, local_last=True)
+        return self._compile(local_last=True)
 
     def image_rays(
         self,
@@ -344,8 +389,8 @@ class SequentialSystem(AbstractSequentialSystem):
         wavelength=None,
         field=None,
         pupil=None,
-        normalized_field: bool = False,
-        normalized_pupil: bool = False,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
         device=None,
         counts: bool = True,
         image: None | _engine.DeviceImage = None,
@@ -483,12 +528,23 @@ class SequentialSystem(AbstractSequentialSystem):
         at_infinity = self.object_is_at_infinity
         conv_field, conv_pupil = (u.angle, u.length) if at_infinity else (u.length, u.angle)
         axes = (axis_wavelength,) + tuple(axis_field) + tuple(axis_pupil)
+        # Vertices and weights that do not depend on the configuration (the usual case: a tolerance sweep
+        # moves surfaces, not the scene) are computed and uploaded once and shared by every configuration.
+        parts = (grid.wavelength, grid.field.x, grid.field.y, grid.pupil.x, grid.pupil.y, radiance)
+        shared = not any(set(na.shape(part)) & set(config_shape) for part in parts)
         grids = []
+        base = None
         for cindex in np.ndindex(*config_shape.values()) if config_shape else [()]:
+            if shared and base is not None:
+                g = dataclasses.replace(base, frame=self._frame_input(config_shape, cindex))
+                g._device = base._device
+                grids.append(g)
+                continue
+            shape_c, index_c = ({}, ()) if shared else (config_shape, cindex)
             vertices = (
-                self._separable(u.length(grid.wavelength), axis_wavelength, config_shape, cindex, "wavelength"),
-                *self._grid_vertices(grid.field, axis_field, config_shape, cindex, conv_field, "field"),
-                *self._grid_vertices(grid.pupil, axis_pupil, config_shape, cindex, conv_pupil, "pupil"),
+                self._separable(u.length(grid.wavelength), axis_wavelength, shape_c, index_c, "wavelength"),
+                *self._grid_vertices(grid.field, axis_field, shape_c, index_c, conv_field, "field"),
+                *self._grid_vertices(grid.pupil, axis_pupil, shape_c, index_c, conv_pupil, "pupil"),
             )
 
             def named(a, b, axes2):
@@ -514,22 +570,75 @@ class SequentialSystem(AbstractSequentialSystem):
             extra = set(rad.axes) - set(scene_shape) - set(config_shape)
             if extra:
                 raise ValueError(f"the radiance has axes {sorted(extra)} that are not scene or configuration axes")
-            full = dict(config_shape, **scene_shape)
-            rad = np.broadcast_to(na.aligned(rad, full), tuple(full.values()))[cindex]
+            full = dict(shape_c, **scene_shape)
+            rad = np.broadcast_to(na.aligned(rad, full), tuple(full.values()))[index_c]
             weight_scene = rad * area_w.numpy(axes[:1])[:, None, None] * area_f.numpy(axes[1:3])[None]
-            grids.append(
-                RayGrid(
-                    vertices=vertices,
-                    at_infinity=at_infinity,
-                    weight_scene=weight_scene,
-                    weight_pupil=area_p.numpy(axes[3:]),
-                    jitter=random,
-                    seed=seed,
-                    frame=self._frame_input(config_shape, cindex),
-                    axes=axes,
-                )
+            base = RayGrid(
+                vertices=vertices,
+                at_infinity=at_infinity,
+                weight_scene=weight_scene,
+                weight_pupil=area_p.numpy(axes[3:]),
+                jitter=random,
+                seed=seed,
+                frame=self._frame_input(config_shape, cindex),
+                axes=axes,
             )
+            grids.append(base)
         return grids
+
+    def collect_grids(self, grids: list, wavelength_edges, device=None, reduce: bool = True, counts: bool = False,
+                      pipeline=None, image=None, shard: bool = True, on_launch=None) -> dict:
+        """
+        The device part of :meth:`image`: every ray of `grids` (one :class:`~optika_b200._grid.RayGrid`
+        per configuration, from :meth:`ray_grids`) is drawn, traced and binned on the device
+        (``optk_trace_grid``: fused, no ray touches HBM) and the detector planes come back as host
+        arrays ``{"flux", "moment_real"[, "counts"]}`` of shape ``[config axes..., n_w, n_x, n_y]``.
+
+        Under ``torch.distributed`` every rank traces a slab of the grid (the axis that balances best,
+        :func:`optika_b200.distributed.best_shard_axis`); while configuration k + 1 is traced, the planes
+        of configuration k are summed over the ranks (``reduce_scatter``, NCCL) and each rank copies its
+        slice to a shared page-locked host buffer over its own PCIe link
+        (:class:`optika_b200.distributed.ImagePipeline`).  `pipeline` / `image` let a caller that
+        simulates many exposures keep the buffers; ``shard=False`` traces the whole grid in this process
+        (with a ``local`` pipeline: no collective); `on_launch(c, phase)` is called before (``0``) and after
+        (``1``) the launches of configuration `c` are queued (the bench records CUDA events there).
+        """
+        from . import _grid, distributed
+
+        device = _engine.require_cuda(device)
+        compiled = self._compiled_local
+        ex, ey = self.sensor.pixel_edges()
+        rank, world = distributed.rank_world() if shard else (0, 1)
+        own = pipeline is None
+        with _engine.device_guard(device):
+            if image is None:
+                image = _engine.DeviceImage.zeros(
+                    np.asarray(wavelength_edges, dtype=float), ex, ey, device, leading=tuple(compiled.shape.values()),
+                    moments=True, counts=counts, fused=True, pad_to=world if reduce else 1,
+                ) if pipeline is None else pipeline.image
+            if pipeline is None:
+                pipeline = distributed.ImagePipeline(image, device, local=(world == 1)) if (reduce or world == 1) else None
+            try:
+                for c, grid in enumerate(grids):
+                    if world > 1:
+                        grid = grid.shard(rank, world, axis=distributed.best_shard_axis(grid.count, world))
+                    if on_launch is not None:
+                        on_launch(c, 0)
+                    if compiled.coatings:
+                        _grid.trace_grid_coated(compiled, grid, c, image, device=device)
+                    else:
+                        _grid.trace_grid(compiled, grid, config=c, image=image, write_rays=False, device=device)
+                    if on_launch is not None:
+                        on_launch(c, 1)
+                    if pipeline is not None:
+                        pipeline.submit(c)
+                if pipeline is None:
+                    return {k: v.numpy() for k, v in image.to_host(pinned=False).items()}
+                planes = pipeline.finish()
+                return {k: np.array(v) for k, v in planes.items()} if own else planes
+            finally:
+                if own and pipeline is not None:
+                    pipeline.close()
 
     def image(
         self,
@@ -603,23 +712,8 @@ class SequentialSystem(AbstractSequentialSystem):
             w_edges = np.array([w_edges.min(), w_edges.max()])  # :1189-1196
         compiled = self._compiled_local
         ex, ey = self.sensor.pixel_edges()
-        image = _engine.DeviceImage.zeros(
-            w_edges, ex, ey, device, leading=tuple(compiled.shape.values()), moments=True, counts=False
-        )
-        rank, world = distributed.rank_world()
-        for c, grid in enumerate(grids):
-            if world > 1:
-                axis = 3 if grid.count[3] >= world else (1 if grid.count[1] >= world else 4)
-                grid = grid.shard(rank, world, axis=axis)
-            if compiled.coatings:
-                _grid.trace_grid_coated(compiled, grid, c, image, device=device)
-            else:
-                _grid.trace_grid(compiled, grid, config=c, image=image, write_rays=False, device=device)
-        if reduce and world > 1:
-            distributed.reduce_image(image)
-        planes = image.to_host(pinned=False)
-        flux = planes["flux"].numpy()
-        moment = planes["moment_real"].numpy()
+        planes = self.collect_grids(grids, w_edges, device=device, reduce=reduce)
+        flux, moment = planes["flux"], planes["moment_real"]
         with np.errstate(invalid="ignore", divide="ignore"):
             direction = np.where(flux > 0, moment / flux, 1) + 0j  # sensors/_sensors.py:163-169
         sensor = self.sensor

@@ -11,6 +11,11 @@ from optika_b200 import named as na
 from optika_b200 import units as u
 from optika_b200 import transformations as tf
 
+# The grids of these configurations are PHYSICAL (degrees, millimetres).  Floats carry no unit here,
+# so -- unlike the reference, which tells normalised from physical coordinates by their unit -- a call
+# must say so: ``system.raytrace(**PHYSICAL)``.  The defaults are the reference's (normalised).
+PHYSICAL = dict(normalized_field=False, normalized_pupil=False)
+
 
 def newtonian(num_field: int = 10, num_pupil: int = 32, num_pixel: int = 128):
     """
@@ -212,6 +217,71 @@ def misaligned_telescope(num_field: int = 6, num_pupil: int = 12, num_pixel: int
         [tf.Cartesian3dRotationX(tilt), tf.Cartesian3dTranslation(z=200 * u.mm)]
     )
     return system
+
+
+def telescope_4k(num_tilt: int = 8, num_pixel: int = 4096):
+    """
+    cfg 5 at full size: the Newtonian layout of cfg 1 scaled to a 4096 x 4096, 15 um sensor (61.4 mm)
+    so that the scene FILLS the detector -- a 320 mm f/10 parabola (f = 3200 mm), field of view
+    +-0.55 deg, flat fold 250 mm in front of the focus, the obscuration the fold casts on the way in;
+    named configuration axis ``misalign`` = `num_tilt` tilts of the primary about x within +-30 arcsec
+    (each shifts the image by up to 62 pixels).  Coma at the corner of the field is ~5 pixels, so the
+    pupil samples of one field cell spread over a handful of pixels, as in a real instrument.
+    """
+    focal = 3200 * u.mm
+    sensor_x = 250 * u.mm
+    fold_z = 200 * u.mm
+    primary_z = fold_z + (focal - sensor_x)
+    front = optika.surfaces.Surface(name="front")
+    tilt = na.linspace(-30 * u.arcsec, 30 * u.arcsec, axis="misalign", num=num_tilt) if num_tilt > 1 else 0.0
+    primary = optika.surfaces.Surface(
+        name="mirror",
+        sag=optika.sags.ParabolicSag(focal_length=-focal),
+        aperture=optika.apertures.RectangularAperture(160 * u.mm),
+        material=optika.materials.Mirror(),
+        is_pupil_stop=True,
+        transformation=tf.TransformationList(
+            [tf.Cartesian3dRotationX(tilt), tf.Cartesian3dTranslation(z=primary_z)]
+        ),
+    )
+    fold = optika.surfaces.Surface(
+        name="fold_mirror",
+        aperture=optika.apertures.RectangularAperture(na.Cartesian2dVectorArray(62 * u.mm, 45 * u.mm)),
+        material=optika.materials.Mirror(),
+        transformation=tf.TransformationList(
+            [tf.Cartesian3dRotationY((90 + 45) * u.deg), tf.Cartesian3dTranslation(z=fold_z)]
+        ),
+    )
+    obscuration = optika.surfaces.Surface(
+        name="obscuration",
+        aperture=optika.apertures.RectangularAperture(
+            na.Cartesian2dVectorArray(62 * u.mm, 45 * u.mm), inverted=True
+        ),
+        transformation=fold.transformation,
+    )
+    sensor = optika.sensors.ImagingSensor(
+        name="sensor",
+        width_pixel=15 * u.um,
+        axis_pixel=na.Cartesian2dVectorArray("detector_x", "detector_y"),
+        num_pixel=na.Cartesian2dVectorArray(num_pixel, num_pixel),
+        timedelta_exposure=1 * u.s,
+        transformation=tf.TransformationList(
+            [tf.Cartesian3dRotationY(-90 * u.deg), tf.Cartesian3dTranslation(x=-sensor_x, z=fold_z)]
+        ),
+        is_field_stop=True,
+    )
+    half = np.arctan(0.5 * num_pixel * 15e-3 / 3200.0)
+    field = na.Cartesian2dVectorLinearSpace(
+        start=-half, stop=half, axis=na.Cartesian2dVectorArray("field_x", "field_y"), num=8, centers=True,
+    )
+    pupil = na.Cartesian2dVectorLinearSpace(
+        start=-160 * u.mm, stop=160 * u.mm, axis=na.Cartesian2dVectorArray("pupil_x", "pupil_y"), num=8, centers=True,
+    )
+    return optika.systems.SequentialSystem(
+        surfaces=[front, obscuration, primary, fold],
+        sensor=sensor,
+        grid_input=optika.vectors.ObjectVectorArray(wavelength=500 * u.nm, field=field, pupil=pupil),
+    )
 
 
 def flatten_rays(rays) -> dict:

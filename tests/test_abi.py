@@ -186,7 +186,7 @@ def test_no_cpu_fallback():
 
     system = configs.newtonian(num_field=1, num_pupil=2)
     with pytest.raises(_lib.OptkError):
-        system.raytrace()
+        system.raytrace(**configs.PHYSICAL)
     with pytest.raises(_lib.OptkError):
         optika.materials.multilayer_efficiency(1e-5, 1, 1, [optika.materials.Layer("Si", thickness=1e-5)])
     # the product package must not import the oracle

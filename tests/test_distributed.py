@@ -138,3 +138,94 @@ def test_sharded_ray_grid_equals_whole_grid_gloo():
     assert np.array_equal(counts, want_counts) and counts.sum() > 0
     assert np.allclose(flux, want_flux, rtol=1e-12)
     assert distributed.rank_world() == (0, 1)
+
+
+# ---------------------------------------------------------------------------
+# ImagePipeline: per-configuration reduce + read-back into a shared host buffer
+# ---------------------------------------------------------------------------
+def _pipeline_worker(rank, world, port, queue):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from optika_b200 import _engine
+
+    ew, ex, ey = np.array([0.0, 1.0, 2.0]), np.linspace(-1, 1, 6), np.linspace(-1, 1, 4)  # 2 x 5 x 3 = 30 bins
+    image = _engine.DeviceImage.zeros(ew, ex, ey, "cpu", leading=(3,), moments=True, counts=True, fused=True, pad_to=world)
+    assert image.buffer_f64.shape == (3, 60) and image.buffer_i64.shape == (3, 30)
+    pipeline = distributed.ImagePipeline(image, "cpu")
+    results = []
+    for exposure in range(2):  # the buffers are reused
+        image.zero_()
+        for c in range(3):
+            image.flux[c] += (rank + 1) * (c + 1) * torch.arange(30.0, dtype=torch.float64).reshape(2, 5, 3)
+            image.moment_real[c] += 0.5 * (rank + 1)
+            image.counts[c] += (rank + 1) * (exposure + 1)
+            pipeline.submit(c)
+        planes = pipeline.finish()
+        results.append({k: np.array(v) for k, v in planes.items()})
+        dist.barrier()
+    if rank == 0:
+        queue.put(results)
+    dist.barrier()
+    pipeline.close()
+    dist.destroy_process_group()
+
+
+def test_image_pipeline_reduces_into_a_shared_host_buffer_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = queue.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    base = np.arange(30.0).reshape(2, 5, 3)
+    for exposure, planes in enumerate(results):
+        assert planes["flux"].shape == (3, 2, 5, 3)
+        for c in range(3):
+            assert np.array_equal(planes["flux"][c], 3 * (c + 1) * base)  # ranks contribute 1x and 2x
+            assert np.array_equal(planes["moment_real"][c], np.full((2, 5, 3), 1.5))
+            assert np.array_equal(planes["counts"][c], np.full((2, 5, 3), 3 * (exposure + 1)))
+
+
+def test_image_pipeline_single_process_is_a_plain_read_back():
+    from optika_b200 import _engine
+
+    image = _engine.DeviceImage.zeros(np.array([0.0, 1.0]), np.linspace(0, 1, 4), np.linspace(0, 1, 3), "cpu",
+                                      moments=True, counts=False, fused=True)
+    image.flux += 2.0
+    image.moment_real += 3.0
+    pipeline = distributed.ImagePipeline(image, "cpu")
+    pipeline.submit(0)
+    planes = pipeline.finish()
+    assert planes["flux"].shape == (1, 3, 2) and np.all(planes["flux"] == 2.0) and np.all(planes["moment_real"] == 3.0)
+    assert "counts" not in planes
+    pipeline.close()
+
+
+def test_fused_image_planes_are_addressed_through_their_strides():
+    from optika_b200 import _engine
+
+    image = _engine.DeviceImage.zeros(np.array([0.0, 1.0]), np.linspace(0, 1, 5), np.linspace(0, 1, 3), "cpu",
+                                      leading=(2, 3), moments=True, counts=True, fused=True, pad_to=8)
+    n = 4 * 2
+    assert image.buffer_f64.shape == (6, 16) and image.buffer_i64.shape == (6, 8)
+    for c in range(6):
+        im = image.struct(c)
+        assert im.flux == image.buffer_f64[c].data_ptr()
+        assert im.moment_real == image.buffer_f64[c].data_ptr() + 8 * n
+        assert im.counts == image.buffer_i64[c].data_ptr()
+    plain = _engine.DeviceImage.zeros(np.array([0.0, 1.0]), np.linspace(0, 1, 5), np.linspace(0, 1, 3), "cpu", leading=(2, 3))
+    assert plain.struct(4).flux == plain.flux.data_ptr() + 4 * n * 8
+
+
+def test_best_shard_axis_balances_the_slabs():
+    assert distributed.best_shard_axis((1, 354, 354, 100, 100), 8) == 1  # 354 / 8: 1.7 % imbalance, 100 / 8: 4 %
+    assert distributed.best_shard_axis((1, 100, 100, 112, 112), 8) == 3  # 112 = 8 x 14 exactly: pupil x
+    assert distributed.best_shard_axis((1, 4096, 4096, 10, 8), 8) == 1   # 10 pupil cells do not split into 8
+    assert distributed.best_shard_axis((1, 4, 4, 100, 100), 1) == 3
+    assert distributed.best_shard_axis((1, 3, 3, 2, 64), 8) == 4         # the only axis with enough cells

@@ -98,8 +98,8 @@ def test_fused_trace_bin_equals_trace_then_collect(cuda_device):
     """image_rays (no ray ever written to HBM) == rayfunction + collect == oracle."""
     system = configs.newtonian(num_field=6, num_pupil=24, num_pixel=128)
     edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
-    fused = system.image_rays(edges)
-    rays = system.rayfunction(on_device=True).outputs
+    fused = system.image_rays(edges, **configs.PHYSICAL)
+    rays = system.rayfunction(on_device=True, **configs.PHYSICAL).outputs
     image, _ = system.sensor.collect(rays, wavelength=edges)
     assert np.allclose(fused.flux.cpu().numpy().reshape(image.outputs.ndarray.shape), image.outputs.ndarray, rtol=1e-12)
     # oracle
@@ -125,7 +125,7 @@ def test_fused_image_with_explicit_frame_equals_local_trace(cuda_device):
     """optk_trace(image, image_frame = sensor.transformation) on the GLOBAL trace == binning the local trace."""
     system = configs.newtonian(num_field=4, num_pupil=20, num_pixel=64)
     edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
-    local = system.image_rays(edges)
+    local = system.image_rays(edges, **configs.PHYSICAL)
     _, rays = system._input(None, None, None, None, False, False)
     ex, ey = system.sensor.pixel_edges()
     image = _engine.DeviceImage.zeros(edges.ndarray, ex, ey, cuda_device, moments=True, counts=True)
@@ -142,7 +142,7 @@ def test_fused_image_with_explicit_frame_equals_local_trace(cuda_device):
 def test_fused_image_with_configuration_axis(cuda_device):
     system = configs.misaligned_telescope(num_field=3, num_pupil=12, num_pixel=64, num_tilt=3)
     edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
-    image = system.image_rays(edges)
+    image = system.image_rays(edges, **configs.PHYSICAL)
     counts = image.counts.cpu().numpy()
     assert counts.shape == (3, 1, 64, 64)
     _, rays_in = system._input(None, None, None, None, False, False)
@@ -193,9 +193,9 @@ def test_fused_image_of_more_rays_than_one_launch_holds(cuda_device):
     """
     system = configs.newtonian(num_field=900, num_pupil=32, num_pixel=64)
     edges = na.ScalarArray(np.array([400.0, 600.0]) * u.nm, "wavelength")
-    one = system.image_rays(edges, wavelength=500 * u.nm, counts=True).counts.cpu().numpy()
+    one = system.image_rays(edges, wavelength=500 * u.nm, counts=True, **configs.PHYSICAL).counts.cpu().numpy()
     three = system.image_rays(
-        edges, wavelength=na.ScalarArray(np.array([450.0, 500.0, 550.0]) * u.nm, "wavelength"), counts=True
+        edges, wavelength=na.ScalarArray(np.array([450.0, 500.0, 550.0]) * u.nm, "wavelength"), counts=True, **configs.PHYSICAL
     ).counts.cpu().numpy()
     assert 900 * 900 * 32 * 32 * 3 > 2**31 - 1
     assert one.sum() > 0 and np.array_equal(three, 3 * one)
@@ -210,7 +210,7 @@ def test_fused_image_in_strided_cta_order_matches_oracle(cuda_device):
     """
     system = configs.newtonian(num_field=26, num_pupil=32, num_pixel=128)
     edges = na.ScalarArray(np.array([499.0, 501.0]) * u.nm, "wavelength")
-    fused = system.image_rays(edges, counts=True)
+    fused = system.image_rays(edges, counts=True, **configs.PHYSICAL)
     _, rays_in = system._input(None, None, None, None, False, False)
     r0, _ = configs.flatten_rays(rays_in)
     out = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
@@ -224,6 +224,6 @@ def test_fused_image_in_strided_cta_order_matches_oracle(cuda_device):
     near = (orb.bin_margin(local["px"], ex) < 1e-9 * abs(ex[0])) | (orb.bin_margin(local["py"], ey) < 1e-9 * abs(ey[0]))
     assert mism.sum() <= 2 * near.sum()
     # the standalone kernel on the traced rays (> 512 CTAs of 256 rays as well)
-    rays = system.rayfunction(on_device=True).outputs
+    rays = system.rayfunction(on_device=True, **configs.PHYSICAL).outputs
     image, _ = system.sensor.collect(rays, wavelength=edges)
     assert np.allclose(fused.flux.cpu().numpy().reshape(image.outputs.ndarray.shape), image.outputs.ndarray, rtol=1e-12)

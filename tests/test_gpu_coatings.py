@@ -81,7 +81,7 @@ def test_coated_grating_trace(cuda_device, with_profile):
     if with_profile:
         rulings = lambda spacing: optika.rulings.SawtoothRulings(spacing=spacing, depth=4 * u.nm, diffraction_order=1)  # noqa: E731
     system = coated_grating(mo_si(), rulings)
-    result = system.raytrace(accumulate=True)
+    result = system.raytrace(accumulate=True, **configs.PHYSICAL)
     _, rays0 = system._input(None, None, None, None, False, False)
     r0, _ = configs.flatten_rays(rays0)
     states = ora.accumulate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
@@ -90,7 +90,7 @@ def test_coated_grating_trace(cuda_device, with_profile):
     final = states["intensity"][-1]
     assert 0 < final.max() < 1 and np.ptp(final) > 1e-4
     # without accumulate: the same final state
-    last = system.raytrace(accumulate=False).outputs
+    last = system.raytrace(accumulate=False, **configs.PHYSICAL).outputs
     assert np.allclose(
         na.as_named_array(last.intensity).numpy(tuple(rays0.shape)).reshape(-1), final, rtol=1e-9, atol=1e-15
     )
@@ -107,7 +107,7 @@ def test_film_and_mirror_in_one_system_with_a_configuration_axis(cuda_device):
     system.surfaces = [film] + list(system.surfaces)
     system.invalidate()
     assert system.shape == {"period": 3}
-    result = system.raytrace(accumulate=True)
+    result = system.raytrace(accumulate=True, **configs.PHYSICAL)
     _, rays0 = system._input(None, None, None, None, False, False)
     r0, _ = configs.flatten_rays(rays0)
     flat0 = {k: v.reshape(-1) for k, v in r0.items()}
@@ -134,7 +134,7 @@ def test_film_and_mirror_in_one_system_with_a_configuration_axis(cuda_device):
 def test_fused_image_of_a_coated_system(cuda_device):
     system = coated_grating(mo_si())
     edges = na.ScalarArray(np.array([12 * u.nm, 13.5 * u.nm, 15 * u.nm]), "wavelength")
-    image = system.image_rays(edges, counts=True)
+    image = system.image_rays(edges, counts=True, **configs.PHYSICAL)
     _, rays0 = system._input(None, None, None, None, False, False)
     r0, _ = configs.flatten_rays(rays0)
     out = ora.propagate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)

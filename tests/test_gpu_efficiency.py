@@ -113,7 +113,7 @@ def test_system_trace_with_efficiencies(cuda_device):
     mirror = optika.materials.MeasuredMirror(measured(np.exp(-np.square((w - 400 * u.AA) / (150 * u.AA))), w))
     rulings = optika.rulings.SawtoothRulings(spacing=(1 / 1200) * u.mm, depth=12 * u.nm, diffraction_order=1)
     system = grating_system(rulings, mirror)
-    result = system.raytrace(accumulate=True)
+    result = system.raytrace(accumulate=True, **configs.PHYSICAL)
     _, rays0 = system._input(None, None, None, None, False, False)
     r0, _ = configs.flatten_rays(rays0)
     states = ora.accumulate_rays(system.surfaces_all, {k: v.reshape(-1) for k, v in r0.items()}, extended=True)
@@ -143,7 +143,7 @@ def test_fused_image_with_efficiencies_and_a_configuration_axis(cuda_device):
     rulings = optika.rulings.SquareRulings(spacing=(1 / 1200) * u.mm, depth=9 * u.nm, diffraction_order=1)
     system = grating_system(rulings, mirror)
     edges = na.ScalarArray(np.array([100 * u.AA, 400 * u.AA, 700 * u.AA]), "wavelength")
-    image = system.image_rays(edges, counts=True)
+    image = system.image_rays(edges, counts=True, **configs.PHYSICAL)
     flux = image.flux.cpu().numpy()
     assert flux.shape == (2, 2, 256, 256)
     _, rays0 = system._input(None, None, None, None, False, False)

@@ -80,12 +80,12 @@ def test_specialised_kernels_are_bit_identical(cuda_device, jit, name):
     want = _engine.trace(system._compiled, rays, ray_axes_order=order)
     dense_in = _engine.trace(system._compiled, rays, ray_axes_order=order, surf_count=0)
     want_dense = _engine.trace(system._compiled, dense_in)
-    want_image = system.image_rays(edges, counts=True)
+    want_image = system.image_rays(edges, counts=True, **configs.PHYSICAL)
     before = jit.compiled
     jit(1)
     got = _engine.trace(system._compiled, rays, ray_axes_order=order)
     got_dense = _engine.trace(system._compiled, dense_in)
-    got_image = system.image_rays(edges, counts=True)
+    got_image = system.image_rays(edges, counts=True, **configs.PHYSICAL)
     assert jit.compiled > before, "nothing was compiled: NVRTC unavailable?"
     same(got, want)
     same(got_dense, want_dense)

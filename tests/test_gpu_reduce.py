@@ -29,7 +29,7 @@ def coated_system():
 
 def host_moments(system, **kwargs):
     """The reference's expressions on host arrays (NumPy, named axes resolved by hand)."""
-    result = system.rayfunction(**kwargs)
+    result = system.rayfunction(**configs.PHYSICAL, **kwargs)
     rays = result.outputs
     axis_pupil = tuple(na.shape(result.inputs.pupil))
     shape_ = rays.shape
@@ -70,7 +70,7 @@ def host_moments(system, **kwargs):
 )
 def test_pupil_moments_match_host_reductions(cuda_device, make, kwargs):
     system = make()
-    got = system.pupil_moments(**kwargs)
+    got = system.pupil_moments(**configs.PHYSICAL, **kwargs)
     outer, where, x, y, illumination, intensity = host_moments(system, **kwargs)
     shape_ = {ax: n for ax, n in zip(outer, where.shape)}
 

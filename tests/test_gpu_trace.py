@@ -92,14 +92,14 @@ def test_cfg1_float64_noise_of_the_reference_formula_is_enumerated(cuda_device):
 
 def test_cfg1_raytrace_api_matches_propagators(cuda_device):
     system = configs.newtonian(num_field=3, num_pupil=8)
-    a = system.raytrace(accumulate=True).outputs
+    a = system.raytrace(accumulate=True, **configs.PHYSICAL).outputs
     b = optika.propagators.accumulate_rays(system.surfaces_all, system._input(None, None, None, None, False, False)[1], axis="surface")
     for x, y in ((a.position.x, b.position.x), (a.direction.z, b.direction.z)):
         # named axes: raytrace() orders the device grid (field outer, pupil inner), values are identical
         assert np.array_equal(x.numpy(tuple(y.shape)), y.ndarray)
     assert "surface" in a.shape and a.shape["surface"] == 6
     # rayfunction: last surface, sensor-local coordinates (optika/systems/_sequential.py:970-986)
-    local = system.rayfunction().outputs
+    local = system.rayfunction(**configs.PHYSICAL).outputs
     last = {k: v[-1] for k, v in host_states(a, axis="surface").items()}
     want = ora._rays_transform(system.sensor.transformation, last, inverse=True)
     got = host_states(local)

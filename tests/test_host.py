@@ -227,4 +227,4 @@ def test_reductions_have_no_cpu_fallback():
         pytest.skip("a GPU is present")
     system = configs.newtonian(num_field=2, num_pupil=4)
     with pytest.raises(RuntimeError):
-        system.pupil_moments()
+        system.pupil_moments(**configs.PHYSICAL)

@@ -51,7 +51,7 @@ def trace_config(name, system, n_surfaces, flop_per_ray):
     image = _engine.DeviceImage.zeros(
         edges.ndarray, ex, ey, device, leading=tuple(system._compiled.shape.values()), moments=True, counts=True
     )
-    ms_image = time_ms(lambda: system.image_rays(edges, image=image, device=device))
+    ms_image = time_ms(lambda: system.image_rays(edges, image=image, device=device, **configs.PHYSICAL))
     _, stats = _engine.trace(system._compiled, rays, ray_axes_order=order, device=device, stats=True)
     return dict(
         config=name,

@@ -40,7 +40,7 @@ def main():
         system = strip_system(lo, hi)
         ex, ey = system.sensor.pixel_edges()
         image = _engine.DeviceImage.zeros(edges.ndarray, ex, ey, device, moments=True, counts=True)
-        ms = time_ms(lambda: system.image_rays(edges, image=image, device=device))
+        ms = time_ms(lambda: system.image_rays(edges, image=image, device=device, **configs.PHYSICAL))
         counts = image.counts
         results.append(dict(strip=[lo, hi], ms_per_1e8_rays=ms, pixels_hit=int((counts > 0).sum().item()),
                             rays_binned_per_pass=int(counts.sum().item()) // 8, max_per_pixel=int(counts.max().item()) // 8))

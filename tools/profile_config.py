@@ -58,7 +58,7 @@ def main():
         image = _engine.DeviceImage.zeros(edges.ndarray, ex, ey, device, leading=tuple(system._compiled.shape.values()),
                                           moments=True, counts=True)
         for _ in range(4):
-            system.image_rays(edges, image=image, device=device)
+            system.image_rays(edges, image=image, device=device, **configs.PHYSICAL)
     torch.cuda.synchronize()
 
 
