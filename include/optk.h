@@ -277,6 +277,13 @@ typedef struct optk_image {
      * (wavelength, x, y).  With has_range != 0 the kernels do not have to fetch them from
      * device memory at the start of every CTA.  Must equal the array values exactly. */
     int32_t has_range;
+    /* Optional promise about the pixel edges (needs has_range): bit 0 -- edges_x, bit 1 -- edges_y are
+     * UNIFORM: every edge lies within 1e-9 of a bin width of first + i (last - first) / n, which is what
+     * numpy.linspace produces (optika/sensors/_sensors.py:141-149).  The bin of a sample is then
+     * floor((v - first) n / (last - first)) and the edge arrays are consulted only for samples within
+     * 1e-6 of a bin width of an edge -- identical results, no loads on the common path.  Without the
+     * promise the exact search runs for every sample. */
+    int32_t uniform_edges;
     double range[6];
     /* 0: a detector image as described above.  > 0 (optk_trace / optk_trace_grid only): not a
      * detector but one accumulator per GROUP of `group_size` consecutive rays of the launch (C order
@@ -398,6 +405,13 @@ typedef struct optk_grid {
      * for vertices[3], vertices[4] with [n3 + 1][n4 + 1] and (t_3, t_4). */
     int32_t field_2d;
     int32_t pupil_2d;
+    /* Optional, separable grids only: for the two ANGULAR axes (field x, y for an object at infinity,
+     * else pupil x, y) one packed record per CELL i, {sin v_i, cos v_i, v_{i+1} - v_i, 0} (device,
+     * 32-byte records, 16-byte aligned), every cell at most 0.01 rad wide.  The kernel then forms the
+     * sine and cosine of the sampled angle v_i + t (v_{i+1} - v_i) by the addition theorems and a short
+     * series in the offset (truncation < 3e-21) instead of a full-range sincos per ray and angle; the
+     * vertex arrays of those two axes are not read.  Both NULL: sincos of the sampled angle. */
+    const double* angular_cells[2];
 } optk_grid_t;
 
 /* As optk_trace, with the rays of `grid` as input.  surf_count = 0 returns the

@@ -138,6 +138,16 @@ class DeviceRays:
         return DeviceRays(fields, mask, shape_)
 
 
+def _is_linspace(edges) -> bool:
+    """Every edge within 1e-9 of a bin width of ``first + i (last - first) / n`` (``optk_image_t.uniform_edges``)."""
+    e = np.asarray(edges, dtype=np.float64)
+    n = len(e) - 1
+    if n < 1 or not np.all(np.isfinite(e)) or not e[-1] > e[0]:
+        return False
+    width = (e[-1] - e[0]) / n
+    return bool(np.max(np.abs(e - (e[0] + np.arange(n + 1) * width))) <= 1e-9 * width)
+
+
 @dataclasses.dataclass(eq=False)
 class DeviceImage:
     """Detector planes in HBM, ``[n_wavelength][n_x][n_y]`` (optionally with leading config axes)."""
@@ -150,6 +160,7 @@ class DeviceImage:
     moment_imag: object = None
     counts: object = None
     range: object = None  # first / last edge of (wavelength, x, y) as host floats, when known
+    uniform_edges: int = 0  # optk_image_t.uniform_edges: bit 0 / 1 -- the x / y edges are a linspace
 
     buffer_f64: object = None  # fused layout: [n_config][row] with flux | moment_real of one configuration side by side
     buffer_i64: object = None  # fused layout: [n_config][row] counts
@@ -172,6 +183,7 @@ class DeviceImage:
         dims3 = (len(ew) - 1, len(ex) - 1, len(ey) - 1)
         dims = tuple(leading) + dims3
         rng = [float(v) for e in (edges_wavelength, edges_x, edges_y) for v in (np.asarray(e)[0], np.asarray(e)[-1])]
+        uniform = (1 if _is_linspace(edges_x) else 0) | (2 if _is_linspace(edges_y) else 0)
         if fused:
             n = int(np.prod(dims3, dtype=np.int64))
             n_config = int(np.prod(tuple(leading), dtype=np.int64)) if leading else 1
@@ -183,6 +195,7 @@ class DeviceImage:
             return cls(
                 ew, ex, ey, flux=plane(buf_f, 0), moment_real=plane(buf_f, 1) if moments else None, moment_imag=None,
                 counts=plane(buf_i, 0) if counts else None, range=rng, buffer_f64=buf_f, buffer_i64=buf_i,
+                uniform_edges=uniform,
             )
         z = lambda dt: torch.zeros(dims, dtype=dt, device=device)  # noqa: E731
         return cls(
@@ -192,6 +205,7 @@ class DeviceImage:
             moment_imag=None,
             counts=z(torch.int64) if counts else None,
             range=rng,
+            uniform_edges=uniform,
         )
 
     def zero_(self):
@@ -260,6 +274,7 @@ class DeviceImage:
         if self.range is not None:
             im.has_range = 1
             im.range[:] = self.range
+            im.uniform_edges = self.uniform_edges
         im.flux = ptr(self.flux)
         im.moment_real = ptr(self.moment_real)
         im.moment_imag = ptr(self.moment_imag)

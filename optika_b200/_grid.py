@@ -120,8 +120,31 @@ class RayGrid:
                 vertices=[up(v) for v in self.vertices],
                 weight_scene=up(self.weight_scene),
                 weight_pupil=up(self.weight_pupil),
+                angular_cells=[up(c) for c in self.angular_cells()],
             )
         return self._device[key]
+
+    def angular_cells(self) -> list:
+        """
+        ``optk_grid_t.angular_cells``: for the two angular axes (field for an object at infinity, else
+        pupil) one record ``{sin v_i, cos v_i, v_{i+1} - v_i, 0}`` per cell, when the grid is separable
+        along them and no cell is wider than 0.01 rad; else ``[None, None]`` (full sincos per ray).
+        """
+        a, b = (1, 2) if self.at_infinity else (3, 4)
+        va, vb = self.vertices[a], self.vertices[b]
+        if va.ndim != 1 or vb.ndim != 1:
+            return [None, None]
+        if max(np.max(np.abs(np.diff(va))), np.max(np.abs(np.diff(vb)))) > 0.01:
+            return [None, None]
+        if not (np.all(np.isfinite(va)) and np.all(np.isfinite(vb))):
+            return [None, None]
+
+        def pack(v):
+            out = np.zeros((len(v) - 1, 4))
+            out[:, 0], out[:, 1], out[:, 2] = np.sin(v[:-1]), np.cos(v[:-1]), np.diff(v)
+            return out
+
+        return [pack(va), pack(vb)]
 
     def struct(self, device, begin=None, count=None) -> L.Grid:
         dev = self.on_device(device)
@@ -138,6 +161,9 @@ class RayGrid:
         g.weight_pupil = None if dev["weight_pupil"] is None else dev["weight_pupil"].data_ptr()
         g.field_2d = 1 if self.field_2d else 0
         g.pupil_2d = 1 if self.pupil_2d else 0
+        for k in range(2):
+            cells = dev["angular_cells"][k]
+            g.angular_cells[k] = None if cells is None else cells.data_ptr()
         if self.frame is not None:
             g.has_frame = 1
             g.frame.r[:] = list(np.asarray(self.frame[0], dtype=float).reshape(9))

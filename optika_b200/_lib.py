@@ -156,6 +156,7 @@ class Image(C.Structure):
         ("moment_imag", C.c_void_p),
         ("counts", C.c_void_p),
         ("has_range", C.c_int32),
+        ("uniform_edges", C.c_int32),
         ("range", C.c_double * 6),
         ("group_size", C.c_int64),
     ]
@@ -176,6 +177,7 @@ class Grid(C.Structure):
         ("frame", Affine),
         ("field_2d", C.c_int32),
         ("pupil_2d", C.c_int32),
+        ("angular_cells", C.c_void_p * 2),
     ]
 
 

@@ -266,8 +266,11 @@ int fill_image(const optk_image_t* image, ImageDev* dev, bool groups_allowed = t
     dev->moment_imag = image->moment_imag;
     dev->counts = image->counts;
     dev->has_range = image->has_range ? 1 : 0;
-    dev->pad2 = 0;
+    dev->uniform = image->has_range ? (image->uniform_edges & 3) : 0;
     for (int k = 0; k < 6; ++k) dev->range[k] = image->range[k];
+    // the same expression the kernels evaluate when they have to fetch the range themselves (image_guess_fill)
+    dev->inv_dx = image->has_range ? (double)image->n_x / (image->range[3] - image->range[2]) : 0.0;
+    dev->inv_dy = image->has_range ? (double)image->n_y / (image->range[5] - image->range[4]) : 0.0;
     return OPTK_OK;
 }
 

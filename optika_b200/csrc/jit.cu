@@ -189,6 +189,14 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
              v.minb);
     std::string src = line;
     if (v.groups) src += "#define OPTK_JIT_GROUPS 1\n";
+    if (v.image_flags & 0x100) {
+        snprintf(line, sizeof(line), "#define OPTK_JIT_IMAGE_FLAGS 0x%x\n", v.image_flags & 0xff);
+        src += line;
+    }
+    if (v.grid_flags & 0x100) {
+        snprintf(line, sizeof(line), "#define OPTK_JIT_GRID_FLAGS 0x%x\n", v.grid_flags & 0xff);
+        src += line;
+    }
     // strided ("broadcast") input: the layout is part of the kernel -- see load_rays
     if (!v.dense && !v.grid && P.offsets32 && !P.in.normal[0]) {
         unsigned long long lo = 0, hi = 0;

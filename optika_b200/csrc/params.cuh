@@ -54,6 +54,9 @@ struct TraceParams {
 struct JitVariant {
     int dense, vec, image, grid, minb;
     int groups = 0;  // optk_image_t::group_size: accumulate per group of rays instead of per pixel
+    // launch-wide facts compiled into the kernel (bit 8 = "defined"): OPTK_IMAGE_* bits of bin.cuh,
+    // OPTK_GRID_* bits of trace_impl.cuh
+    int image_flags = 0, grid_flags = 0;
 };
 void* jit_kernel(const TraceParams& P, const JitVariant& v);  // CUfunction or nullptr
 int jit_launch(void* function, const TraceParams& P, unsigned grid, cudaStream_t stream);

@@ -208,6 +208,22 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0,
                               jit_minb > 0 ? jit_minb : (use_heavy ? 2 : 3)};
         variant.groups = (image && P.image.group) ? 1 : 0;
+        if (image && !P.image.group)
+            variant.image_flags = 0x100 | (P.image.has_range ? 1 << OPTK_IMAGE_HAS_RANGE : 0) |
+                                  ((P.image.uniform & 1) ? 1 << OPTK_IMAGE_UNIFORM_X : 0) |
+                                  ((P.image.uniform & 2) ? 1 << OPTK_IMAGE_UNIFORM_Y : 0) |
+                                  (P.image.n_w == 1 ? 1 << OPTK_IMAGE_ONE_WAVELENGTH : 0) |
+                                  (P.image.counts ? 1 << OPTK_IMAGE_COUNTS : 0) |
+                                  (P.image.moment_real ? 1 << OPTK_IMAGE_MOMENT_REAL : 0) |
+                                  (P.image.flux ? 1 << OPTK_IMAGE_FLUX : 0) |
+                                  (P.image.moment_imag ? 1 << OPTK_IMAGE_MOMENT_IMAG : 0);
+        if (from_grid)
+            variant.grid_flags = 0x100 | (P.grid.at_infinity ? 1 << OPTK_GRID_AT_INFINITY : 0) |
+                                 (P.grid.angular_cells[0] ? 1 << OPTK_GRID_PACKED : 0) |
+                                 (P.grid.jitter ? 1 << OPTK_GRID_JITTER : 0) |
+                                 (P.grid.has_frame ? 1 << OPTK_GRID_FRAME : 0) |
+                                 (P.grid.weight_scene ? 1 << OPTK_GRID_WEIGHT_SCENE : 0) |
+                                 (P.grid.weight_pupil ? 1 << OPTK_GRID_WEIGHT_PUPIL : 0);
         if (void* function = jit_kernel(P, variant)) return jit_launch(function, P, (unsigned)grid, stream);
     }
     if (image && P.image.group) {

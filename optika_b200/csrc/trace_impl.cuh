@@ -1371,6 +1371,23 @@ __device__ __forceinline__ double grid_sample(const double* vertices, int i, boo
     return fma(t, hi - lo, lo);
 }
 
+// sin and cos of the stratified sample of an ANGULAR cell from the host's packed record
+// {sin v_i, cos v_i, v_{i+1} - v_i, 0} (optk_grid_t::angular_cells): the addition theorems with a
+// seven-term series in the offset d = t (v_{i+1} - v_i), |d| <= 0.01 rad (checked by the caller):
+// truncation < 3e-21, so the result is sin / cos of the sampled angle to rounding -- 16 fp64
+// instructions instead of the ~35 of a full-range sincos, for each of the two angles of every ray.
+__device__ __forceinline__ void cell_sincos(const double* __restrict__ cells, int i, bool jitter, uint32_t bits25,
+                                            double& s, double& c) {
+    const double2 sc = __ldg(reinterpret_cast<const double2*>(cells) + 2 * i);
+    const double w = __ldg(cells + 4 * i + 2);
+    const double t = jitter ? ((double)bits25 + 0.5) * 2.98023223876953125e-08 : 0.5;
+    const double d = t * w, d2 = d * d;
+    const double sd = fma(d * d2, fma(d2, fma(d2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), d);   // sin d
+    const double cm = d2 * fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5);                      // cos d - 1
+    s = fma(sc.x, cm, fma(sc.y, sd, sc.x));
+    c = fma(sc.y, cm, fma(-sc.x, sd, sc.y));
+}
+
 // Curvilinear grids (field_2d / pupil_2d): bilinear sample of a cell of two 2-D vertex arrays
 // [n_a + 1][n_b + 1].  Out of line: the separable case stays the short one.
 static __device__ __noinline__ Vec3 grid_sample_2d(const double* vx, const double* vy, int ia, int ib, int row, bool jitter,
@@ -1393,6 +1410,20 @@ static __device__ __noinline__ Vec3 grid_sample_2d(const double* vx, const doubl
     return out;
 }
 
+// Launch-wide facts about the grid: run-time tests in the table-driven kernels, compile-time constants
+// in the run-time specialised ones (jit.cu defines OPTK_JIT_GRID_FLAGS for the variant).
+#define OPTK_GRID_AT_INFINITY 0
+#define OPTK_GRID_PACKED 1
+#define OPTK_GRID_JITTER 2
+#define OPTK_GRID_FRAME 3
+#define OPTK_GRID_WEIGHT_SCENE 4
+#define OPTK_GRID_WEIGHT_PUPIL 5
+#ifdef OPTK_JIT_GRID_FLAGS
+#define OPTK_GRID_FLAG(bit, runtime) ((((OPTK_JIT_GRID_FLAGS) >> (bit)) & 1) != 0)
+#else
+#define OPTK_GRID_FLAG(bit, runtime) (runtime)
+#endif
+
 // SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
 // (optika/systems/_sequential.py:1055-1086, 791-828) for the R consecutive rays of a thread.
 // `j0` is the C-order index of the first ray in the sub-box of this launch (< 2^31).
@@ -1412,7 +1443,8 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         }
         idx[0] = (int)rem;
     }
-    const bool jitter = G.jitter != 0;
+    const bool jitter = OPTK_GRID_FLAG(OPTK_GRID_JITTER, G.jitter != 0);
+    const bool at_infinity = OPTK_GRID_FLAG(OPTK_GRID_AT_INFINITY, G.at_infinity != 0);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         if (k > 0) {
@@ -1442,8 +1474,16 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         // low 7 bits of the four words side by side (include/optk.h)
         const uint32_t low = (x[0] & 127u) | ((x[1] & 127u) << 7) | ((x[2] & 127u) << 14) | ((x[3] & 15u) << 21);
         const double w = grid_sample(G.vertices[0], g[0], jitter, x[0] >> 7);
-        double fx, fy, px, py;
-        if (CURVILINEAR && G.field_2d) {
+        double fx = 0.0, fy = 0.0, px = 0.0, py = 0.0;
+        // the angular pair (field for an object at infinity, else pupil) enters only through its sines
+        // and cosines: with the host's packed cell records they come from the addition theorems
+        const bool packed = !CURVILINEAR && OPTK_GRID_FLAG(OPTK_GRID_PACKED, G.angular_cells[0] != nullptr);
+        const bool field_angular = at_infinity;
+        double sx, cx, sy, cy;
+        if (packed && field_angular) {
+            cell_sincos(G.angular_cells[0], g[1], jitter, x[1] >> 7, sx, cx);
+            cell_sincos(G.angular_cells[1], g[2], jitter, x[2] >> 7, sy, cy);
+        } else if (CURVILINEAR && G.field_2d) {
             const Vec3 f = grid_sample_2d(G.vertices[1], G.vertices[2], g[1], g[2], G.n[2] + 1, jitter, x[1] >> 7, x[2] >> 7);
             fx = f.x;
             fy = f.y;
@@ -1451,7 +1491,10 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
             fx = grid_sample(G.vertices[1], g[1], jitter, x[1] >> 7);
             fy = grid_sample(G.vertices[2], g[2], jitter, x[2] >> 7);
         }
-        if (CURVILINEAR && G.pupil_2d) {
+        if (packed && !field_angular) {
+            cell_sincos(G.angular_cells[0], g[3], jitter, x[3] >> 7, sx, cx);
+            cell_sincos(G.angular_cells[1], g[4], jitter, low, sy, cy);
+        } else if (CURVILINEAR && G.pupil_2d) {
             const Vec3 p = grid_sample_2d(G.vertices[3], G.vertices[4], g[3], g[4], G.n[4] + 1, jitter, x[3] >> 7, low);
             px = p.x;
             py = p.y;
@@ -1460,25 +1503,28 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
             py = grid_sample(G.vertices[4], g[4], jitter, low);
         }
         // position / angles by the location of the object (:797-802)
-        const double ax = G.at_infinity ? fx : px, ay = G.at_infinity ? fy : py;
-        double sx, cx, sy, cy;
-        fsincos(ax, &sx, &cx);
-        fsincos(ay, &sy, &cy);
+        if (!packed) {
+            const double ax = at_infinity ? fx : px, ay = at_infinity ? fy : py;
+            fsincos(ax, &sx, &cx);
+            fsincos(ay, &sy, &cy);
+        }
         r[k].w = w;
-        r[k].px = G.at_infinity ? px : fx;
-        r[k].py = G.at_infinity ? py : fy;
+        r[k].px = at_infinity ? px : fx;
+        r[k].py = at_infinity ? py : fy;
         r[k].pz = 0.0;
         r[k].dx = -cy * sx;  // optika.direction, optika/_util.py:64-73
         r[k].dy = -sy;
         r[k].dz = cy * cx;
         double weight = 1.0;
-        if (G.weight_scene) weight = __ldg(G.weight_scene + (g[0] * G.n[1] + g[1]) * (long long)G.n[2] + g[2]);
-        if (G.weight_pupil) weight *= __ldg(G.weight_pupil + g[3] * (long long)G.n[4] + g[4]);
+        if (OPTK_GRID_FLAG(OPTK_GRID_WEIGHT_SCENE, G.weight_scene != nullptr))
+            weight = __ldg(G.weight_scene + (g[0] * G.n[1] + g[1]) * (long long)G.n[2] + g[2]);
+        if (OPTK_GRID_FLAG(OPTK_GRID_WEIGHT_PUPIL, G.weight_pupil != nullptr))
+            weight *= __ldg(G.weight_pupil + g[3] * (long long)G.n[4] + g[4]);
         r[k].intensity = weight;
         r[k].att = 0.0;
         r[k].n = 1.0;
         r[k].unv = true;
-        if (G.has_frame) {
+        if (OPTK_GRID_FLAG(OPTK_GRID_FRAME, G.has_frame != 0)) {
             affine_forward(G.frame, r[k].px, r[k].py, r[k].pz, false);
             affine_forward(G.frame, r[k].dx, r[k].dy, r[k].dz, true);
         }
@@ -1523,10 +1569,17 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         block = (block & 511u) * (uint32_t)P.cta_rows + (block >> 9);  // strided visiting order, params.cuh
         if (block >= (uint32_t)P.cta_count) return;                     // padding of the last row
     }
-    __shared__ ImageGuess guess;
+    __shared__ ImageGuess guess_shared;
     // one barrier for all per-CTA set-up: the image guess is filled by the first thread of the
-    // second warp while the first warp computes the outer offsets
-    if (IMAGE && threadIdx.x == 32) image_guess_fill(P.image, &guess);
+    // second warp while the first warp computes the outer offsets.  With the caller's range hint
+    // (optk_image_t::has_range; compiled in for the run-time specialised kernels) the guess is a set of
+    // constant-bank operands: nothing to fill, and launches without per-CTA offsets need no barrier.
+#if defined(OPTK_JIT_IMAGE_FLAGS) && ((OPTK_JIT_IMAGE_FLAGS) & 1)
+    constexpr bool guess_const = true;
+#else
+    const bool guess_const = IMAGE && P.image.has_range;
+#endif
+    if (IMAGE && !guess_const && threadIdx.x == 32) image_guess_fill(P.image, &guess_shared);
 
     // Dense input: ray index = thread index.  Broadcast input: the CTA owns one index of the
     // leading ("outer") axes and a tile of the trailing ("inner") axes; its outer offsets are
@@ -1563,7 +1616,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             base[f] = o;
         }
     }
-    if (IMAGE || !(DENSE || GRID)) __syncthreads();
+    if ((IMAGE && !guess_const) || !(DENSE || GRID)) __syncthreads();
     bool valid[R];
     Ray r[R];
 #pragma unroll
@@ -1679,6 +1732,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
         int bin[R];
         double w_flux[R], w_real[R];
         unsigned count[R];
+        const ImageGuess guess = guess_const ? image_guess_const(P.image) : guess_shared;
         // Group accumulators exist only in kernels compiled at run time with OPTK_JIT_GROUPS (jit.cu):
         // as a run-time branch they cost the detector path 4 % (measured), and launch_trace refuses
         // group launches that no such kernel serves.

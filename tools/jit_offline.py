@@ -75,6 +75,13 @@ def main():
         )
     if mode == "groups":  # per-group accumulators instead of detector pixels (optk_image_t.group_size)
         layout = "#define OPTK_JIT_GROUPS 1\n" + layout
+    if mode in ("image", "grid") and "--no-flags" not in sys.argv:
+        # what launch_trace compiles in for a sensor image with a known range, linspace pixel edges, one spectral
+        # bin and the planes flux / moment_real / counts; for the grid: object at infinity, packed angular cells,
+        # jitter, both weights, no frame
+        layout = "#define OPTK_JIT_IMAGE_FLAGS 0x7f\n" + layout
+        if mode == "grid":
+            layout = "#define OPTK_JIT_GRID_FLAGS 0x37\n" + layout
     src = layout + f"""#define OPTK_JIT_WALK 1
 #include "trace_impl.cuh"
 namespace optk {{
