@@ -374,6 +374,166 @@ class SequentialSystem(AbstractSequentialSystem):
             intensity=na.ScalarArray(sum_i, axes),
         )
 
+    # -- consumers of ray output ----------------------------------
+    def _scene_axes(self, grid: ObjectVectorArray, what: str):
+        """``(axis_wavelength, axis_field)`` of a grid, as ``_rayfunction_and_axes`` finds them (``:1514-1582``)."""
+        config_axes = set(self.shape)
+        axis_wavelength = tuple(ax for ax in na.shape(grid.wavelength) if ax not in config_axes)
+        if len(axis_wavelength) != 1:
+            raise ValueError(
+                f"fitting a {what} model requires the wavelength grid to vary along its own logical axis."
+            )  # :1254-1258, :1339-1343
+        skip = config_axes | set(axis_wavelength)
+        axis_field = tuple(ax for ax in na.shape(grid.field) if ax not in skip)
+        return axis_wavelength[0], axis_field
+
+    def distortion(
+        self,
+        wavelength=None,
+        field=None,
+        pupil=None,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
+        degree: int = 2,
+        device=None,
+    ):
+        """
+        Fit a polynomial distortion model to the rays traced through this system
+        (``optika/systems/_sequential.py:1208-1285``).  The per-field-point mean sensor position over
+        the unvignetted rays of the pupil (over all of them where none survives, ``:1269-1276``) comes
+        out of the trace kernel itself (:meth:`pupil_moments`: no ray is written to HBM); the
+        least-squares fit of the few hundred field points is host work.
+        """
+        from .distortion import PolynomialDistortionModel
+        from .vectors import SpectralPositionalVectorArray
+
+        moments = self.pupil_moments(None, wavelength, field, pupil, normalized_field, normalized_pupil, device=device)
+        grid = moments["inputs"]
+        axis_wavelength, axis_field = self._scene_axes(grid, "distortion")
+        return PolynomialDistortionModel(
+            coordinates_scene=SpectralPositionalVectorArray(wavelength=grid.wavelength, position=grid.field),
+            coordinates_sensor=moments["position"],
+            axis_wavelength=axis_wavelength,
+            axis_field=axis_field,
+            degree=degree,
+            where=moments["where"],
+        )
+
+    def vignetting(
+        self,
+        wavelength=None,
+        field=None,
+        pupil=None,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
+        degree: int = 2,
+        device=None,
+    ):
+        """
+        Fit a polynomial vignetting model (``optika/systems/_sequential.py:1287-1368``): the relative
+        illumination of a scene coordinate is the unvignetted fraction of its pupil, normalised to a
+        unit mean over the field points that keep at least one ray (``:1351-1358``).
+        """
+        from .radiometry import PolynomialVignettingModel
+        from .vectors import SpectralPositionalVectorArray
+
+        moments = self.pupil_moments(None, wavelength, field, pupil, normalized_field, normalized_pupil, device=device)
+        grid = moments["inputs"]
+        axis_wavelength, axis_field = self._scene_axes(grid, "vignetting")
+        where, illumination = moments["where"], moments["illumination"]
+        axes = illumination.axes
+        keep = tuple(k for k, ax in enumerate(axes) if ax in axis_field)
+        w = where.ndarray
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = (illumination.ndarray * w).sum(axis=keep, keepdims=True) / w.sum(axis=keep, keepdims=True)
+            illumination = na.ScalarArray(illumination.ndarray / mean, axes)
+        return PolynomialVignettingModel(
+            coordinates_scene=SpectralPositionalVectorArray(wavelength=grid.wavelength, position=grid.field),
+            illumination=illumination,
+            axis_wavelength=axis_wavelength,
+            axis_field=axis_field,
+            degree=degree,
+            where=where,
+        )
+
+    def area_effective(
+        self,
+        wavelength=None,
+        field=None,
+        pupil=None,
+        normalized_field: bool = True,
+        normalized_pupil: bool = True,
+        seed: int = 0,
+        device=None,
+    ):
+        """
+        The wavelength-dependent effective area (``optika/systems/_sequential.py:1370-1512``): `pupil`
+        holds the VERTICES of a grid of pupil cells (default 11 x 11 over the normalised pupil, ``:1440-1444``);
+        one stratified random ray per cell, wavelength and field point carries the area of its cell as
+        intensity (``:1490-1499``), the traced intensities of the unvignetted rays are summed over the
+        pupil (inside the trace kernel) and averaged over the field (``:1501-1506``).  `seed` selects
+        the jitter (the reference draws from NumPy's global generator).
+        """
+        from .radiometry import InterpolatedEffectiveAreaModel
+
+        if wavelength is None:
+            wavelength = self.grid_input.wavelength
+        if field is None:
+            field = self.grid_input.field
+        if pupil is None:
+            pupil = na.Cartesian2dVectorArray(
+                x=na.linspace(-1, 1, axis="_pupil_x", num=11), y=na.linspace(-1, 1, axis="_pupil_y", num=11)
+            )
+        grid = self.denormalize(ObjectVectorArray(wavelength=wavelength, field=field, pupil=pupil),
+                                normalized_field, normalized_pupil)
+        wavelength, field, pupil = grid.wavelength, grid.field, grid.pupil
+        config_axes = set(self.shape)
+        axis_wavelength = tuple(ax for ax in na.shape(wavelength) if ax not in config_axes)
+        if len(axis_wavelength) != 1:
+            raise ValueError(
+                f"Computing the effective area requires that there be only one wavelength axis, got {axis_wavelength}"
+            )  # :1477-1481
+        (axis_wavelength,) = axis_wavelength
+        skip = config_axes | {axis_wavelength}
+        axis_field = tuple(ax for ax in na.shape(field) if ax not in skip)
+        skip |= set(axis_field)
+        axis_pupil = tuple(ax for ax in na.shape(pupil) if ax not in skip)
+        if len(axis_pupil) != 2:
+            raise ValueError(f"the pupil vertices must vary along two axes of their own, got {axis_pupil}")
+        px, py = na.as_named_array(pupil.x), na.as_named_array(pupil.y)
+        area = np.abs(na.Cartesian2dVectorArray(
+            na.broadcast_to(px, na.broadcast_shapes(px.shape, py.shape)),
+            na.broadcast_to(py, na.broadcast_shapes(px.shape, py.shape)),
+        ).volume_cell(axis_pupil))  # :1485
+        # cell_centers(axis_pupil, random=True) over the FULL grid shape (:1486): one uniform sample per
+        # cell for every wavelength and field point
+        full = na.broadcast_shapes(na.shape(wavelength), na.shape(field), na.shape(pupil))
+        rng = np.random.default_rng(seed)
+        axes_full = tuple(full)
+        ka, kb = axes_full.index(axis_pupil[0]), axes_full.index(axis_pupil[1])
+        cells = tuple(n - 1 if ax in axis_pupil else n for ax, n in full.items())
+        ta, tb = rng.uniform(size=cells), rng.uniform(size=cells)
+        centres = []
+        for c in (pupil.x, pupil.y):
+            nd = na.broadcast_to(na.as_named_array(c), full).ndarray
+
+            def corner(da, db):
+                index = [slice(None)] * nd.ndim
+                index[ka] = slice(da, nd.shape[ka] - 1 + da)
+                index[kb] = slice(db, nd.shape[kb] - 1 + db)
+                return nd[tuple(index)]
+
+            lo = corner(0, 0) + ta * (corner(1, 0) - corner(0, 0))  # along the first pupil axis, then the second
+            hi = corner(0, 1) + ta * (corner(1, 1) - corner(0, 1))
+            centres.append(na.ScalarArray(lo + tb * (hi - lo), axes_full))
+        moments = self.pupil_moments(
+            area, wavelength, field, na.Cartesian2dVectorArray(*centres), False, False, device=device
+        )
+        area_eff = moments["intensity"]
+        keep = tuple(ax for ax in area_eff.axes if ax in axis_field)
+        area_eff = area_eff.mean(keep) if keep else area_eff  # :1506
+        return InterpolatedEffectiveAreaModel(wavelength=wavelength, area=area_eff, axis_wavelength=axis_wavelength)
+
     @property
     def _compiled_local(self) -> _engine.CompiledSystem:
         """
