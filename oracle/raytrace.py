@@ -787,12 +787,38 @@ def rulings_efficiency(rulings, rays: dict, normal):
     raise NotImplementedError(f"oracle: rulings {name}")
 
 
+# How the surface operator evaluates Snell's law: None -- the NumPy expression below; "parallel" /
+# "serial" -- its numba ``guvectorize`` twin (oracle/snell_numba.py), which is how the reference itself
+# runs this one step (``_snells_law.py:294-302``: ``target="parallel"``).  Bit-identical results; set by
+# the CPU arm of bench.py through :func:`use_numba_snell`.
+_SNELL_MODE = None
+
+
+def use_numba_snell(mode: str | None) -> str | None:
+    """Select the Snell implementation of :func:`surface_propagate`; returns the mode in effect (None without numba)."""
+    global _SNELL_MODE
+    if mode is not None:
+        try:
+            from . import snell_numba  # noqa: F401
+        except Exception:
+            mode = None
+    _SNELL_MODE = mode
+    return mode
+
+
 def snells_law(ax, ay, az, n1, n2, ux, uy, uz, mirror: bool):
     """
     Vector Snell's law, ``optika/materials/_snells_law.py:341-366``
     (the numba kernel body; ``|a|^2`` is NOT assumed to be 1, which matters after
     ``incident_effective``).
     """
+    if _SNELL_MODE is not None:
+        from . import snell_numba
+
+        kernel = snell_numba.snells_law_parallel if _SNELL_MODE == "parallel" else snell_numba.snells_law_serial
+        args = np.broadcast_arrays(*[np.asarray(v, dtype=np.float64) for v in (ax, ay, az, n1, n2, ux, uy, uz)])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return kernel(*args, bool(mirror))
     with np.errstate(invalid="ignore", divide="ignore"):
         a2 = ax * ax + ay * ay + az * az
         r = n1 / n2

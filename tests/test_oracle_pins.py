@@ -290,3 +290,35 @@ def test_newtonian_focus_and_conventions():
     assert np.max(np.abs(local["pz"])) < 1e-9
     # rays arrive travelling along +z of the sensor frame
     assert np.all(local["dz"][m] > 0.9)
+
+
+def test_numba_snell_twin_is_bit_identical_to_the_numpy_expression():
+    """
+    The CPU arm runs Snell's law as the reference does, through a numba ``guvectorize`` kernel
+    (``optika/materials/_snells_law.py:294-366``); the oracle's NumPy expression and its numba twin
+    (parallel and serial targets) must agree to the last bit, NaN patterns included.
+    """
+    pytest.importorskip("numba")
+    from oracle import snell_numba
+
+    rng = np.random.default_rng(5)
+    n = 20000
+    a = rng.normal(size=(3, n))
+    a /= np.linalg.norm(a, axis=0) * rng.uniform(0.8, 1.2, n)  # not unit: |a|^2 enters the formula
+    normal = rng.normal(size=(3, n))
+    normal /= np.linalg.norm(normal, axis=0)
+    n1, n2 = rng.uniform(1, 1.7, n), rng.uniform(1, 1.7, n)
+    for mirror in (False, True):
+        want = ora.snells_law(*a, n1, n2, *normal, mirror)
+        assert np.isnan(want[0]).any() or mirror  # total internal reflection occurs in the sample
+        for kernel in (snell_numba.snells_law_parallel, snell_numba.snells_law_serial):
+            with np.errstate(invalid="ignore"):
+                got = kernel(*a, n1, n2, *normal, mirror)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w, equal_nan=True)
+    try:
+        assert ora.use_numba_snell("parallel") == "parallel"
+        through_switch = ora.snells_law(*a, n1, n2, *normal, True)
+    finally:
+        ora.use_numba_snell(None)
+    assert all(np.array_equal(g, w, equal_nan=True) for g, w in zip(through_switch, ora.snells_law(*a, n1, n2, *normal, True)))
