@@ -296,6 +296,7 @@ class SequentialSystem(AbstractSequentialSystem):
         normalized_field: bool = True,
         normalized_pupil: bool = True,
         device=None,
+        axis_pupil: None | tuple = None,
     ) -> dict:
         """
         What ``distortion``, ``vignetting`` and ``area_effective`` reduce from the rays at the
@@ -315,10 +316,13 @@ class SequentialSystem(AbstractSequentialSystem):
         """
         device = _engine.require_cuda(device)
         result, rays = self._input(intensity, wavelength, field, pupil, normalized_field, normalized_pupil)
-        axis_pupil = [ax for ax in self._ray_axes_order if ax in na.shape(result.inputs.pupil)]
+        # the axes reduced over: those of the pupil grid, or the ones the caller names (a pupil sampled
+        # independently for every wavelength and field point carries all the axes of the grid)
+        pupil_axes = na.shape(result.inputs.pupil) if axis_pupil is None else axis_pupil
+        axis_pupil = [ax for ax in self._ray_axes_order if ax in pupil_axes]
         compiled = self._compiled_local
         config, ray = _engine._grid_shape(rays, compiled.shape)
-        missing = [ax for ax in na.shape(result.inputs.pupil) if ax not in ray]
+        missing = [ax for ax in pupil_axes if ax not in ray]
         if missing or not axis_pupil:
             raise ValueError(f"the pupil axes {missing} are not axes of the traced rays")
         # device order of the ray axes (see _engine._trace): the requested order last, pupil innermost
@@ -527,7 +531,8 @@ class SequentialSystem(AbstractSequentialSystem):
             hi = corner(0, 1) + ta * (corner(1, 1) - corner(0, 1))
             centres.append(na.ScalarArray(lo + tb * (hi - lo), axes_full))
         moments = self.pupil_moments(
-            area, wavelength, field, na.Cartesian2dVectorArray(*centres), False, False, device=device
+            area, wavelength, field, na.Cartesian2dVectorArray(*centres), False, False, device=device,
+            axis_pupil=axis_pupil,
         )
         area_eff = moments["intensity"]
         keep = tuple(ax for ax in area_eff.axes if ax in axis_field)
