@@ -819,7 +819,10 @@ def run_b200(args):
         def chip_step():
             nonlocal chip_launches
             before = _grid.LAUNCHES
-            _grid.trace_grid(local, ray_grid, image=chip_image, write_rays=False, device=device, max_launch=n_slab)
+            # as few launches as the 2^31 - 1 ray limit allows: every launch then spans many wavelength cells and
+            # the strided CTA order spreads the resident CTAs over all of them (one 1e8-ray launch per cell piles
+            # the reductions of a whole launch onto the ~2000 pixels of one 0.7 nm band)
+            _grid.trace_grid(local, ray_grid, image=chip_image, write_rays=False, device=device)
             chip_launches = _grid.LAUNCHES - before
 
         chip_step()

@@ -87,7 +87,12 @@ typedef enum optk_material_kind {
 
 typedef enum optk_efficiency_kind {
     OPTK_EFF_UNIT = 0,
-    OPTK_EFF_LUT = 1
+    OPTK_EFF_LUT = 1,
+    /* efficiency(wavelength, cos(incidence)) from a table in DEVICE memory: multilayer coatings
+     * (MultilayerMirror / MultilayerFilm .efficiency, optika/materials/_multilayers.py:839-866, 908-935)
+     * tabulated once with optk_multilayer instead of one stack evaluation per ray; see
+     * optk_surface_t.material_efficiency */
+    OPTK_EFF_TABLE2D = 2
 } optk_efficiency_kind_t;
 
 typedef enum optk_ruling_profile {
@@ -211,7 +216,23 @@ typedef struct optk_surface {
      *   per-profile amplitude normalisation is applied by the kernel;
      *   MEASURED: MeasuredRulings (:287-313), numpy.interp like the mirror.
      * LUT arrays are HOST pointers when the table is given to optk_system_create, which
-     * copies them to the current device; they must be ascending in x.                  */
+     * copies them to the current device; they must be ascending in x.
+     * material_efficiency OPTK_EFF_TABLE2D (materials OPTK_MAT_MIRROR / OPTK_MAT_PASS only, whose
+     *   material[] is otherwise unused): the efficiency is a function of the ray's wavelength w and of
+     *   c = -(a . n), the cosine of incidence on the effective direction -- what the reference passes to
+     *   multilayer_efficiency (_multilayers.py:858, 927) for a ray in vacuum.  All pointers are DEVICE
+     *   pointers owned by the caller (nothing is copied):
+     *     material_lut_x  wavelength nodes, strictly ascending, material_lut_n >= 2 of them (they may be
+     *                     non-uniform: the distinct wavelengths of a ray grid, or a refinement that has
+     *                     a node on every kink of the optical constants);
+     *     material_lut_y  values [material_lut_n][n_c], n_c = (int) material[2] >= 4 uniform cosine
+     *                     nodes c_k = material[0] + k / material[1]  (material[1] = 1 / spacing);
+     *     ruling_lut_x    when the surface has no measured ruling profile: a uint64 counter in device
+     *                     memory (or NULL) that the kernels increment for every ray outside the table.
+     *   Lookup: linear between the two wavelength nodes around w (exact AT a node), cubic Lagrange
+     *   through the four cosine nodes around c; valid for material_lut_x[0] <= w <= last node and
+     *   c_1 <= c <= c_{n_c - 2}.  A ray outside takes the nearest edge value and is counted; NaN
+     *   inputs give NaN.                                                                     */
     int32_t material_efficiency;
     int32_t ruling_profile;
     int32_t material_lut_n;

@@ -130,9 +130,25 @@ int validate_surface(const optk_surface_t& s, int index) {
                   s.n_coeff);
         return OPTK_ERR_INVALID;
     }
-    if (s.material_efficiency < OPTK_EFF_UNIT || s.material_efficiency > OPTK_EFF_LUT) {
+    if (s.material_efficiency < OPTK_EFF_UNIT || s.material_efficiency > OPTK_EFF_TABLE2D) {
         set_error("surface %d: unsupported material efficiency kind %d", index, s.material_efficiency);
         return OPTK_ERR_UNSUPPORTED;
+    }
+    if (s.material_efficiency == OPTK_EFF_TABLE2D) {
+        if (s.material_kind != OPTK_MAT_MIRROR && s.material_kind != OPTK_MAT_PASS) {
+            set_error("surface %d: a 2-D efficiency table needs a mirror or pass-through material", index);
+            return OPTK_ERR_INVALID;
+        }
+        if (s.material_lut_n < 2 || !s.material_lut_x || !s.material_lut_y || !(s.material[1] > 0.0) ||
+            !(s.material[2] >= 4.0) || s.material[2] != (double)(int)s.material[2]) {
+            set_error("surface %d: a 2-D efficiency table needs >= 2 wavelength nodes, >= 4 cosine nodes with a "
+                      "positive spacing, and device pointers to both arrays", index);
+            return OPTK_ERR_INVALID;
+        }
+        if (s.ruling_profile == OPTK_PROFILE_MEASURED) {
+            set_error("surface %d: a 2-D efficiency table cannot be combined with measured rulings", index);
+            return OPTK_ERR_UNSUPPORTED;
+        }
     }
     if (s.ruling_profile < OPTK_PROFILE_IDEAL || s.ruling_profile > OPTK_PROFILE_MEASURED) {
         set_error("surface %d: unsupported ruling profile %d", index, s.ruling_profile);

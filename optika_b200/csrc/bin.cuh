@@ -188,6 +188,9 @@ __device__ __forceinline__ void image_add(const ImageDev& im, int bin, double w_
     // with the neighbouring lane (stratified random samples of a cell that spans several pixels),
     // the five compare-and-merge rounds (~100 instructions) would retire almost nobody -- every kept
     // lane issues its own reductions instead.  The sums are the same either way.
+    // (OPTK_BIN_DIRECT=0 in the environment of a process compiles this test out of its run-time
+    // specialised kernels: A/B measurements)
+#if !defined(OPTK_JIT_BIN_DIRECT) || OPTK_JIT_BIN_DIRECT
     {
         const int nb = __shfl_xor_sync(full, bin, 1);
         const unsigned paired = __ballot_sync(full, keep_lane && nb == bin);
@@ -202,6 +205,7 @@ __device__ __forceinline__ void image_add(const ImageDev& im, int bin, double w_
             return;
         }
     }
+#endif
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int pb = __shfl_xor_sync(full, bin, o);

@@ -189,6 +189,11 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
              v.minb);
     std::string src = line;
     if (v.groups) src += "#define OPTK_JIT_GROUPS 1\n";
+    static const int bin_direct = [] {
+        const char* e = getenv("OPTK_BIN_DIRECT");
+        return e ? atoi(e) : 1;
+    }();
+    if (!bin_direct) src += "#define OPTK_JIT_BIN_DIRECT 0\n";
     if (v.image_flags & 0x100) {
         snprintf(line, sizeof(line), "#define OPTK_JIT_IMAGE_FLAGS 0x%x\n", v.image_flags & 0xff);
         src += line;

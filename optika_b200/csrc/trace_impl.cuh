@@ -851,6 +851,56 @@ static __device__ __noinline__ double lut_interp(const double* __restrict__ xp, 
     return slope * (x - x0) + f0;
 }
 
+// OPTK_EFF_TABLE2D: efficiency(wavelength, cosine of incidence) of a multilayer coating from a table that
+// optk_multilayer filled once (include/optk.h, optk_surface_t.material_efficiency).  Wavelength nodes are
+// explicit (the distinct wavelengths of a ray grid: exact there; or a refinement with a node on every
+// kink of the optical constants): located with a guess from the mean spacing corrected against the node
+// values, linear in between.  Cosine nodes are uniform: cubic Lagrange through the four around c.
+static __device__ __noinline__ double table2d_lookup(const optk_surface_t& S, double w, double c) {
+    const double* __restrict__ xw = S.material_lut_x;
+    const double* __restrict__ table = S.material_lut_y;
+    const int n_w = S.material_lut_n, n_c = (int)S.material[2];
+    if (w != w || c != c) return OPTK_NAN;
+    const double w_first = __ldg(xw), w_last = __ldg(xw + n_w - 1);
+    bool outside = !(w >= w_first && w <= w_last);
+    w = fmin(fmax(w, w_first), w_last);
+    // interval i with xw[i] <= w <= xw[i + 1]
+    int i = (int)((w - w_first) * ((double)(n_w - 1) / (w_last - w_first)));
+    i = i < 0 ? 0 : (i > n_w - 2 ? n_w - 2 : i);
+    double lo = __ldg(xw + i), hi = __ldg(xw + i + 1);
+    while (w < lo) {
+        --i;
+        hi = lo;
+        lo = __ldg(xw + i);
+    }
+    while (w > hi && i < n_w - 2) {
+        ++i;
+        lo = hi;
+        hi = __ldg(xw + i + 1);
+    }
+    const double tw = (w - lo) / (hi - lo);
+    // cosine: u in node units, stencil k - 1 .. k + 2 around the cell [k, k + 1]
+    double u = (c - S.material[0]) * S.material[1];
+    outside = outside || !(u >= 1.0 && u <= (double)(n_c - 2));
+    u = fmin(fmax(u, 1.0), (double)(n_c - 2));
+    int k = (int)u;
+    k = k > n_c - 3 ? n_c - 3 : k;
+    const double t = u - (double)k;
+    const double tm = t - 1.0, tp = t + 1.0, t2 = t - 2.0;
+    const double l0 = -t * tm * t2 * (1.0 / 6.0), l1 = tp * tm * t2 * 0.5, l2 = -tp * t * t2 * 0.5, l3 = tp * t * tm * (1.0 / 6.0);
+    const double* row = table + (long long)i * n_c + (k - 1);
+    const double a = l0 * __ldg(row) + l1 * __ldg(row + 1) + l2 * __ldg(row + 2) + l3 * __ldg(row + 3);
+    double value = a;
+    if (tw != 0.0) {  // exactly on a wavelength node (a ray grid's own wavelengths): that row alone
+        row += n_c;
+        const double b = l0 * __ldg(row) + l1 * __ldg(row + 1) + l2 * __ldg(row + 2) + l3 * __ldg(row + 3);
+        value = fma(tw, b - a, a);
+    }
+    if (outside && S.ruling_lut_x && S.ruling_profile != OPTK_PROFILE_MEASURED)
+        atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<double*>(S.ruling_lut_x)), 1ULL);
+    return value;
+}
+
 // Bessel function of the first kind of integer order (scipy.special.jv in
 // SinusoidalRulings.efficiency, optika/rulings/_rulings.py:455): Miller's backward recurrence
 // J_{k-1} = (2 k / x) J_k - J_{k+1} from far above max(n, x), normalised with
@@ -904,6 +954,8 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
     const struct { double w, px, py, pz, dx, dy, dz; } r = {w_, px_, py_, pz_, dx_, dy_, dz_};
     double eff = 1.0;
     if (S.material_efficiency == OPTK_EFF_LUT) eff = lut_interp(S.material_lut_x, S.material_lut_y, S.material_lut_n, r.w);
+    if (S.material_efficiency == OPTK_EFF_TABLE2D)
+        eff = table2d_lookup(S, r.w, -(r.dx * nx + r.dy * ny + r.dz * nz));  // -direction @ normal, _multilayers.py:858, 927
     const int profile = S.ruling_profile;
     if (profile == OPTK_PROFILE_IDEAL) return eff;
     if (profile == OPTK_PROFILE_MEASURED)
