@@ -410,6 +410,7 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
         )
 
     pipeline = make(local=(world == 1))
+    transport = pipeline.transport
     setup_s = time.perf_counter() - t_setup
     ms, stages, planes, wall = run(pipeline, shard=True, n_steps=steps, n_warm=warmup)
     counts_sharded = np.array(planes["counts"]) if rank == 0 and world > 1 else None
@@ -439,8 +440,14 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
         images=f"{int(np.prod(leading)) if leading else 1} x {len(ex) - 1} x {len(ey) - 1} pixels, planes flux / flux cos / counts",
         d2h_bytes=d2h_total,
         d2h_bytes_per_rank=d2h_total // world,
-        collective=("reduce_scatter (NCCL), one per dtype and configuration; every rank copies its 1/N slice to a "
-                    "shared page-locked host buffer over its own PCIe link") if world > 1 else "none (one GPU)",
+        collective=({
+            "peer": "every rank pulls its 1/N slice of every other rank's planes over NVLink with the copy engines "
+                    "(CUDA IPC peer memory, interprocess events), adds the N pieces, and copies the sum to a shared "
+                    "page-locked host buffer over its own PCIe link",
+            "nccl": "reduce_scatter (NCCL), one per dtype and configuration; every rank copies its 1/N slice to a "
+                    "shared page-locked host buffer over its own PCIe link",
+        }.get(transport, transport)) if world > 1 else "none (one GPU)",
+        transport=transport,
         shard_axis=(["wavelength", "field_x", "field_y", "pupil_x", "pupil_y"][distributed.best_shard_axis(grids[0].count, world)]
                     if world > 1 else None),
         rays_binned=binned,

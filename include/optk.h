@@ -609,6 +609,10 @@ OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, vo
  * asynchronous.  The range must stay mapped until it is unregistered. */
 OPTK_API int optk_host_register(void* data, int64_t n_bytes);
 OPTK_API int optk_host_unregister(void* data);
+/* cudaMemcpyAsync(dst, src, n_bytes, cudaMemcpyDefault) on `stream`: device, registered-host or PEER
+ * pointers (memory of another GPU opened through CUDA IPC, optika_b200/distributed.py): the copy
+ * engines move detector planes over NVLink without occupying an SM. */
+OPTK_API int optk_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,7 +78,7 @@ STAGE_SAG_OUT = 0x40
 STAGE_KAPPA_OUT = 0x80
 STAGE_EFFICIENCY_OUT = 0x100
 STAGE_ALL = 0x1F
-EFF_UNIT, EFF_LUT = range(2)
+EFF_UNIT, EFF_LUT, EFF_TABLE2D = range(3)
 (PROFILE_IDEAL, PROFILE_SINUSOIDAL, PROFILE_SQUARE, PROFILE_SAWTOOTH, PROFILE_TRIANGULAR, PROFILE_RECTANGULAR,
  PROFILE_MEASURED) = range(7)
 
@@ -277,6 +277,7 @@ SYMBOLS = (
     "optk_measure_soa_copy",
     "optk_host_register",
     "optk_host_unregister",
+    "optk_memcpy_async",
 )
 
 _lib = None
@@ -325,6 +326,7 @@ def lib() -> C.CDLL:
     L.optk_measure_soa_copy.argtypes = [i64, C.POINTER(C.c_double), vp]
     L.optk_host_register.argtypes = [vp, i64]
     L.optk_host_unregister.argtypes = [vp]
+    L.optk_memcpy_async.argtypes = [vp, vp, i64, vp]
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int

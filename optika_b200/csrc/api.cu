@@ -1040,4 +1040,15 @@ OPTK_API int optk_host_unregister(void* data) {
     return OPTK_OK;
 }
 
+OPTK_API int optk_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream) {
+    DeviceScope device_scope(stream);
+    if (!dst || !src || n_bytes < 0) {
+        set_error("optk_memcpy_async: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    if (n_bytes == 0) return OPTK_OK;
+    OPTK_CUDA(cudaMemcpyAsync(dst, src, (size_t)n_bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return OPTK_OK;
+}
+
 }  // extern "C"

@@ -183,19 +183,31 @@ class ImagePipeline:
 
     `image` is a FUSED :class:`~optika_b200._engine.DeviceImage` (``zeros(..., fused=True,
     pad_to=world)``): the fp64 planes of a configuration are one row of ``buffer_f64``, the counts one
-    row of ``buffer_i64``.  :meth:`submit` (called right after the launches of configuration `c` were
-    queued on the current stream) makes the side stream wait for them and then
+    row of ``buffer_i64``.  :meth:`submit` is called right after the launches of configuration `c` were
+    queued on the current stream.  Every rank ends up owning the SUM of one 1 / world slice of every row
+    and copies it to the shared page-locked host buffer over its own PCIe link; :meth:`finish` waits for
+    all ranks and returns the host planes (complete on every rank: the buffer is shared).
 
-    * ``reduce_scatter`` s the row over the ranks (one collective per dtype; NCCL over NVLink) --
-      every rank ends up with the SUM of one 1 / world slice, which is all it needs because
-    * each rank copies its slice to the shared page-locked host buffer over its own PCIe link.
+    How the slices are summed (`transport`):
 
-    :meth:`finish` waits for the side stream and for the other ranks and returns the host planes
-    (complete on every rank: the buffer is shared).  With one rank it is just an overlapped read-back.
-    Gloo (the CPU tests) has no reduce-scatter: ``all_reduce`` and a slice take its place there.
+    * ``"peer"`` (default on one node): every rank opens the other ranks' plane buffers through CUDA
+      IPC and PULLS its slice of each with the copy engines over NVLink (``optk_memcpy_async`` into a
+      staging buffer), then adds the ``world`` pieces with a small elementwise kernel.  Ordering between
+      processes comes from interprocess CUDA events (recorded after the trace of a configuration,
+      waited on by the pulling streams) plus one host-side barrier per exposure.  No SM is needed for
+      the transfer, which matters here: the trace kernel keeps every SM full (3 CTAs x 256 threads x 80
+      registers), and a NCCL kernel that wants 40 k registers per CTA only gets onto an SM when the
+      trace grid drains -- measured at N = 2 on cfg 5: 18 ms per 400 MB configuration under the trace
+      against 0.3 ms on an idle GPU;
+    * ``"nccl"``: ``reduce_scatter`` (one collective per dtype and configuration) on the side stream;
+    * gloo (the CPU tests) has neither: ``all_reduce`` and a slice.
+
+    With one rank the pipeline is just an overlapped read-back.
     """
 
-    def __init__(self, image, device=None, group=None, to_host: bool = True, local: bool = False):
+    def __init__(self, image, device=None, group=None, to_host: bool = True, local: bool = False,
+                 transport: str | None = None):
+        import os
         import torch
 
         if image.buffer_f64 is None:
@@ -210,7 +222,11 @@ class ImagePipeline:
         if row_f % self.world or row_i % self.world:
             raise ValueError(f"fused rows must be padded to a multiple of the world size (pad_to={self.world})")
         self.n_config, self.row_f, self.row_i = n_config, row_f, row_i
-        self.side = torch.cuda.Stream(self.device) if self.cuda else None
+        # copies, adds and read-back must not queue behind the trace grid: highest priority
+        self.side = torch.cuda.Stream(self.device, priority=-1) if self.cuda else None
+        if transport is None:
+            transport = os.environ.get("OPTK_REDUCE_TRANSPORT", "peer")
+        self.transport = transport if (self.world > 1 and self.cuda) else "none"
         self.shard_f = torch.empty((n_config, row_f // self.world), dtype=torch.float64, device=self.device) \
             if self.world > 1 else None
         self.shard_i = torch.empty((n_config, row_i // self.world), dtype=torch.int64, device=self.device) \
@@ -223,6 +239,115 @@ class ImagePipeline:
                 if row_i else None
         self.events = []  # (config, start, reduced, copied) CUDA events of the side stream
         self.timing = False
+        self._pending = []
+        self._host_group = None
+        if self.transport == "peer":
+            try:
+                self._open_peers()
+            except Exception as e:  # no peer access / IPC: NCCL carries the planes instead
+                import warnings
+
+                warnings.warn(f"peer-memory reduction unavailable ({e}); using NCCL reduce_scatter")
+                self.transport = "nccl"
+            # every rank must take the same route
+            import torch.distributed as dist
+
+            flag = [self.transport]
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, flag[0], group=group)
+            if any(t != "peer" for t in gathered):
+                self.transport = "nccl"
+
+    # -- peer-memory transport ---------------------------------------------------------------
+    def _open_peers(self):
+        """Exchange CUDA IPC handles of the plane buffers and of one interprocess event per configuration."""
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        for peer in range(torch.cuda.device_count()):
+            if peer != self.device.index and not torch.cuda.can_device_access_peer(self.device.index, peer):
+                raise RuntimeError(f"device {self.device.index} has no peer access to device {peer}")
+        self._host_group = dist.new_group(backend="gloo")  # host-side barriers that do not touch the GPU queues
+        self._done = [torch.cuda.Event(enable_timing=False, interprocess=True) for _ in range(self.n_config)]
+        for e in self._done:
+            e.record(torch.cuda.current_stream(self.device))  # an IPC handle needs a recorded event
+        mine = dict(
+            f64=reduce_tensor(self.image.buffer_f64),
+            i64=reduce_tensor(self.image.buffer_i64) if self.row_i else None,
+            events=[e.ipc_handle() for e in self._done],
+            device=self.device.index,
+        )
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self._peer_f, self._peer_i, self._peer_done = {}, {}, {}
+        for r, other in enumerate(everyone):
+            if r == self.rank:
+                continue
+            rebuild, args = other["f64"]
+            self._peer_f[r] = rebuild(*args)
+            if self.row_i:
+                rebuild, args = other["i64"]
+                self._peer_i[r] = rebuild(*args)
+            self._peer_done[r] = [torch.cuda.Event.from_ipc_handle(self.device, h) for h in other["events"]]
+        n_f, n_i = self.row_f // self.world, self.row_i // self.world
+        self._stage_f = torch.empty((self.world - 1, n_f), dtype=torch.float64, device=self.device)
+        self._stage_i = torch.empty((self.world - 1, n_i), dtype=torch.int64, device=self.device) if self.row_i else None
+        dist.barrier(group=self._host_group)
+
+    def _pull(self, c: int):
+        """Side stream: sum this rank's slice of configuration `c` over all ranks into ``shard_*[c]``."""
+        import torch
+        from . import _lib as L
+
+        lib, stream = L.lib(), self.side.cuda_stream
+        rows = [(self.image.buffer_f64, self._peer_f, self._stage_f, self.shard_f)]
+        if self.row_i:
+            rows.append((self.image.buffer_i64, self._peer_i, self._stage_i, self.shard_i))
+        peers = sorted(self._peer_f)
+        self.side.wait_event(self._done[c])
+        for r in peers:
+            self.side.wait_event(self._peer_done[r][c])
+        for local, remote, stage, shard in rows:
+            n = shard.shape[1]
+            lo = self.rank * n
+            for j, r in enumerate(peers):
+                src = remote[r][c, lo:lo + n]
+                L.check(lib.optk_memcpy_async(stage[j].data_ptr(), src.data_ptr(), 8 * n, stream))
+            torch.sum(stage, dim=0, out=shard[c])
+            shard[c] += local[c, lo:lo + n]
+
+    def _flush(self):
+        """All configurations of this exposure are queued on every rank: start pulling."""
+        import torch
+        import torch.distributed as dist
+
+        dist.barrier(group=self._host_group)  # every rank has RECORDED its events: waits now see this exposure
+        with torch.cuda.stream(self.side):
+            for c in self._pending:
+                marks = None
+                if self.timing:
+                    marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    self.side.wait_event(self._done[c])
+                    marks[0].record(self.side)
+                self._pull(c)
+                if marks:
+                    marks[1].record(self.side)
+                self._read_back(c, dict(f=self.shard_f[c], i=self.shard_i[c] if self.row_i else None))
+                if marks:
+                    marks[2].record(self.side)
+                    self.events.append((c, *marks))
+        self._pending = []
+
+    def _read_back(self, c: int, sources: dict):
+        if not self.to_host:
+            return
+        for kind, host in (("f", self.host_f), ("i", self.host_i if self.row_i else None)):
+            if host is None or sources.get(kind) is None:
+                continue
+            src = sources[kind]
+            n = src.numel()
+            host[c, self.rank * n:(self.rank + 1) * n].copy_(src, non_blocking=True)
 
     def _side(self):
         import contextlib
@@ -234,6 +359,13 @@ class ImagePipeline:
         import torch
         import torch.distributed as dist
 
+        if self.transport == "peer":
+            # the planes of configuration c are complete once everything queued so far has run
+            self._done[c].record(torch.cuda.current_stream(self.device))
+            self._pending.append(c)
+            if len(self._pending) == self.n_config:
+                self._flush()
+            return
         if self.cuda:
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(self.device))
@@ -259,13 +391,7 @@ class ImagePipeline:
                     sources[kind] = buf[c, self.rank * n:(self.rank + 1) * n]
             if marks:
                 marks[1].record(self.side)
-            if self.to_host:
-                for kind, host in (("f", self.host_f), ("i", self.host_i if self.row_i else None)):
-                    if host is None:
-                        continue
-                    src = sources[kind]
-                    n = src.numel()
-                    host[c, self.rank * n:(self.rank + 1) * n].copy_(src, non_blocking=True)
+            self._read_back(c, sources)
             if marks:
                 marks[2].record(self.side)
                 self.events.append((c, *marks))
@@ -274,10 +400,13 @@ class ImagePipeline:
         """Wait for the queued reductions and copies (all ranks); the host planes as NumPy views."""
         import torch.distributed as dist
 
+        if self.transport == "peer" and self._pending:
+            self._flush()
         if self.cuda:
             self.side.synchronize()
         if self.world > 1:
-            dist.barrier(group=self.group)
+            # nobody may reuse (zero) its planes, or read the host buffer, before every rank is done
+            dist.barrier(group=self._host_group if self._host_group is not None else self.group)
         if not self.to_host:
             return {}
         im = self.image
@@ -299,6 +428,14 @@ class ImagePipeline:
         return dict(ms_reduce=reduce_ms, ms_d2h=copy_ms)
 
     def close(self):
+        if self.transport == "peer":
+            import torch.distributed as dist
+
+            if self.cuda:
+                self.side.synchronize()
+            dist.barrier(group=self._host_group)  # nobody unmaps while a peer may still read
+            self._peer_f = self._peer_i = self._peer_done = None
+            self.transport = "closed"
         if self.host is not None:
             self.host_f = self.host_i = None
             self.host.close()
