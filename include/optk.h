@@ -613,6 +613,9 @@ OPTK_API int optk_host_unregister(void* data);
  * pointers (memory of another GPU opened through CUDA IPC, optika_b200/distributed.py): the copy
  * engines move detector planes over NVLink without occupying an SM. */
 OPTK_API int optk_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream);
+/* cudaDeviceEnablePeerAccess(peer_device) for the CURRENT device (already enabled is not an error):
+ * without it a copy from peer memory is staged through the host (20 GB/s instead of NVLink). */
+OPTK_API int optk_enable_peer_access(int32_t peer_device);
 
 #ifdef __cplusplus
 }

@@ -475,6 +475,8 @@ def trace(
     stats: bool = False,
     normal: na.Cartesian3dVectorArray | None = None,
     ray_axes_order: list[str] | None = None,
+    _cos_log: dict | None = None,
+    _exact: bool = False,
 ):
     """
     Trace `rays` through `system` on the device (see :func:`_trace`).  Systems with
@@ -484,10 +486,24 @@ def trace(
     incidence captured, the stack evaluated per ray by ``optk_multilayer`` and multiplied into
     the intensity, then onwards.  Reverse traces (the stop solver) skip the coatings: they
     only use positions and directions.
+
+    With ``system.coating == "table"`` the coatings are tabulated instead (:mod:`optika_b200._coatings`):
+    efficiency(wavelength, cosine of incidence) to ``system.coating_tolerance``, looked up inside ONE
+    fused launch; rays that do not reach the coating in vacuum, or a table that cannot meet the
+    tolerance, take the exact chain.
     """
     if surf_count is None:
         surf_count = system.n_surface if surf_step > 0 else surf_begin + 1
     coated = [k for k in system.coatings if surf_begin <= k < surf_begin + surf_count] if surf_step > 0 else []
+    if coated and not _exact and normal is None and getattr(system, "coating", "exact") == "table":
+        tabled = _tabled_for_rays(system, rays, coated, surf_begin, surf_count, require_cuda(device), ray_axes_order)
+        if tabled is not None:
+            out = _trace(
+                tabled.compiled, rays, accumulate, axis, surf_begin, surf_count, surf_step, image, image_frame,
+                write_rays, device, stats, normal, ray_axes_order,
+            )
+            tabled.check()
+            return out
     if not coated:
         return _trace(
             system, rays, accumulate, axis, surf_begin, surf_count, surf_step, image, image_frame, write_rays,
@@ -519,6 +535,12 @@ def trace(
             if out is not None:
                 states.append(out)
             break
+        if _cos_log is not None:  # the range of cosines this surface sees (pilot of the efficiency tables)
+            finite = out.cos_incidence[torch.isfinite(out.cos_incidence)]
+            if finite.numel():
+                lo, hi = float(finite.min().item()), float(finite.max().item())
+                old = _cos_log.get(k)
+                _cos_log[k] = (lo, hi) if old is None else (min(lo, old[0]), max(hi, old[1]))
         apply_coating(system, k, out, device)
         states.append(out)
         current = out.last_state() if accumulate else out
@@ -531,6 +553,126 @@ def trace(
     if write_rays and states:
         result = states[-1] if not accumulate else DeviceRays.concatenate(states, axis if axis is not None else "surface")
     return (result, totals) if stats else result
+
+
+def _pilot_indices(n: int, count: int = 5) -> np.ndarray:
+    return np.unique(np.round(np.linspace(0, n - 1, min(n, count))).astype(np.int64))
+
+
+def _subsample_rays(rays: RayVectorArray) -> RayVectorArray:
+    """At most five samples (both ends included) along every axis of a host ray grid."""
+    picks = {ax: _pilot_indices(n) for ax, n in rays.shape.items()}
+
+    def take(a):
+        if isinstance(a, (na.Cartesian2dVectorArray, na.Cartesian3dVectorArray)):
+            return a._map(take)
+        if not isinstance(a, na.ScalarArray):
+            return a
+        nd = a.ndarray
+        for k, ax in enumerate(a.axes):
+            if nd.shape[k] > 1:
+                nd = np.take(nd, picks[ax], axis=k)
+        return na.ScalarArray(nd, a.axes)
+
+    return dataclasses.replace(
+        rays, wavelength=take(rays.wavelength), position=take(rays.position), direction=take(rays.direction),
+        intensity=take(rays.intensity), attenuation=take(rays.attenuation), index_refraction=take(rays.index_refraction),
+        unvignetted=take(rays.unvignetted),
+    )
+
+
+def coating_cos_ranges(log: dict, coated, override=None) -> dict:
+    """Tabulated cosine range per coated surface: what the pilot rays saw, widened by a quarter of the span."""
+    ranges = {}
+    for k in coated:
+        if override is not None:
+            ranges[k] = tuple(override[k] if isinstance(override, dict) else override)
+            continue
+        if k not in log:
+            return None
+        lo, hi = log[k]
+        margin = 0.25 * (hi - lo) + 2e-3
+        ranges[k] = (max(lo - margin, 1e-4), hi + margin)
+    return ranges
+
+
+def tabled_system_for(system: CompiledSystem, wavelengths, continuous: bool, ranges: dict, device):
+    """The cached :class:`~optika_b200._coatings.TabledSystem` that covers `wavelengths` and `ranges`, or a new one."""
+    from . import _coatings
+
+    wavelengths = np.unique(np.asarray(wavelengths, dtype=float))
+    tolerance = float(getattr(system, "coating_tolerance", 1e-6))
+    key = (wavelengths.tobytes(), bool(continuous), str(device), tolerance)
+    cache = system.__dict__.setdefault("_tabled", {})
+    hit = cache.get(key)
+    if hit is not None:
+        if hit == "exact":
+            return None
+        covered = all(
+            hit.tables[(k, 0)].cos_range[0] <= lo and hi <= hit.tables[(k, 0)].cos_range[1] for k, (lo, hi) in ranges.items()
+        )
+        if covered:
+            return hit
+        ranges = {k: (min(lo, hit.tables[(k, 0)].cos_range[0]), max(hi, hit.tables[(k, 0)].cos_range[1]))
+                  for k, (lo, hi) in ranges.items()}
+    with device_guard(device):
+        tabled = _coatings.tabled_system(
+            system, wavelengths, continuous, ranges, device, tolerance, int(getattr(system, "coating_max_bytes", 1 << 28))
+        )
+    cache[key] = tabled if tabled is not None else "exact"
+    return tabled
+
+
+def _vacuum_only(system: CompiledSystem, surf_begin: int, surf_count: int) -> bool:
+    """No surface of the range changes the index of refraction: rays that start in vacuum stay there."""
+    kinds = {system.table[c * system.n_surface + s].material_kind
+             for c in range(system.n_config) for s in range(surf_begin, surf_begin + surf_count)}
+    return kinds <= {L.MAT_VACUUM, L.MAT_MIRROR, L.MAT_PASS}
+
+
+def _tabled_for_rays(system, rays, coated, surf_begin, surf_count, device, ray_axes_order):
+    """Efficiency tables for this call, or ``None`` when the exact chain has to run."""
+    from . import _coatings
+
+    torch = _torch()
+    if not _vacuum_only(system, surf_begin, surf_count):
+        return None
+    if isinstance(rays, DeviceRays):
+        if system.n_config > 1:
+            return None
+        f = rays.fields
+        if bool((f["index_refraction"] != 1).any().item()) or bool((f["attenuation"] != 0).any().item()):
+            return None
+        n = rays.size
+        pick = torch.from_numpy(_pilot_indices(n, 4096)).to(f["wavelength"].device)
+        pilot = DeviceRays({name: t.reshape(-1)[pick].contiguous() for name, t in f.items()},
+                           rays.unvignetted.reshape(-1)[pick].contiguous(), {"_pilot": int(pick.numel())})
+        finite = f["wavelength"][torch.isfinite(f["wavelength"])]
+        if not finite.numel():
+            return None
+        wavelengths, continuous = [float(finite.min().item()), float(finite.max().item())], True
+        if wavelengths[0] == wavelengths[1]:
+            continuous = False
+        order = None
+    else:
+        if np.any(np.asarray(na.as_named_array(rays.index_refraction).ndarray) != 1):
+            return None
+        if np.any(np.asarray(na.as_named_array(rays.attenuation).ndarray) != 0):
+            return None
+        w = np.unique(np.asarray(na.as_named_array(u.length(rays.wavelength)).ndarray, dtype=float))
+        if not np.all(np.isfinite(w)):
+            return None
+        continuous = len(w) > _coatings.MAX_DISCRETE
+        wavelengths = [w[0], w[-1]] if continuous else w
+        pilot = _subsample_rays(rays)
+        order = ray_axes_order
+    log = {}
+    trace(system, pilot, False, None, surf_begin, surf_count, 1, None, None, True, device, False, None, order,
+          _cos_log=log, _exact=True)
+    ranges = coating_cos_ranges(log, coated, getattr(system, "coating_cos_range", None))
+    if ranges is None:
+        return None
+    return tabled_system_for(system, wavelengths, continuous, ranges, device)
 
 
 def apply_coating(system: CompiledSystem, k: int, out: "DeviceRays", device, config: int | None = None) -> None:

@@ -320,27 +320,95 @@ def _trace_dense(system, config: int, rays, surf_begin: int, surf_count: int, im
     return result
 
 
+def _chain(system, sub: RayGrid, config: int, image, device, cos_log: dict | None = None) -> None:
+    """
+    The exact route for one box of a grid: generated and traced to the first coated surface, the coating
+    evaluated per ray (:func:`optika_b200._engine.apply_coating`), and so on; the last link bins into
+    `image` (skipped without one).  `cos_log` collects the range of cosines every coated surface sees.
+    """
+    torch = _engine._torch()
+    coated = sorted(system.coatings)
+    n_surface = system.n_surface
+
+    def log(k, rays):
+        if cos_log is None:
+            return
+        finite = rays.cos_incidence[torch.isfinite(rays.cos_incidence)]
+        if finite.numel():
+            lo, hi = float(finite.min().item()), float(finite.max().item())
+            old = cos_log.get(k)
+            cos_log[k] = (lo, hi) if old is None else (min(lo, old[0]), max(hi, old[1]))
+
+    rays = trace_grid(system, sub, config=config, surf_count=coated[0] + 1, device=device, capture_cos=True)
+    log(coated[0], rays)
+    _engine.apply_coating(system, coated[0], rays, device, config=config)
+    at = coated[0] + 1
+    for k in coated[1:] + [None]:
+        stop = n_surface if k is None else k + 1
+        final = k is None
+        if final and image is None:
+            break
+        rays = _trace_dense(system, config, rays, at, stop - at, image if final else None, not final, not final, device)
+        if not final:
+            log(k, rays)
+            _engine.apply_coating(system, k, rays, device, config=config)
+        at = stop
+
+
+def _tabled_for_grid(system, grid: RayGrid, device):
+    """Efficiency tables that cover `grid` in every configuration, or ``None`` (exact chain)."""
+    coated = sorted(system.coatings)
+    if not _engine._vacuum_only(system, 0, system.n_surface):
+        return None
+    w = grid.vertices[0]
+    if grid.jitter:
+        wavelengths, continuous = [float(w.min()), float(w.max())], True
+    else:
+        wavelengths, continuous = 0.5 * (w[:-1] + w[1:]), False
+    cache = system.__dict__.setdefault("_grid_cos_ranges", {})
+    key = (grid.vertices[0].tobytes(), tuple(v.tobytes() for v in grid.vertices[1:]), grid.jitter, grid.seed)
+    ranges = cache.get(key)
+    if ranges is None:
+        # pilot: at most five vertices (both ends included) along every axis, every configuration
+        def pick(v):
+            if v.ndim == 1:
+                return v[_engine._pilot_indices(len(v))]
+            return v[np.ix_(_engine._pilot_indices(v.shape[0]), _engine._pilot_indices(v.shape[1]))]
+
+        pilot = RayGrid(
+            vertices=tuple(pick(v) for v in grid.vertices), at_infinity=grid.at_infinity, jitter=grid.jitter,
+            seed=grid.seed, frame=grid.frame, axes=grid.axes,
+        )
+        log = {}
+        for c in range(system.n_config):
+            _chain(system, pilot, c, None, device, cos_log=log)
+        ranges = _engine.coating_cos_ranges(log, coated, getattr(system, "coating_cos_range", None))
+        if ranges is None:
+            return None
+        cache[key] = ranges
+    return _engine.tabled_system_for(system, wavelengths, continuous, ranges, device)
+
+
 def trace_grid_coated(system, grid: RayGrid, config: int, image, device=None, max_rays: int = 1 << 25) -> None:
     """
-    Fused image of a system with multilayer-coated surfaces: the grid is cut into boxes of
-    at most `max_rays` rays (they do live in HBM between the links of the chain); each box is
-    generated and traced to the first coated surface, the coating evaluated per ray
-    (:func:`optika_b200._engine.apply_coating`), and so on; the last link bins into `image`.
+    Fused image of a system with multilayer-coated surfaces.
+
+    ``system.coating == "table"``: the coatings are efficiency tables (:mod:`optika_b200._coatings`) and the
+    whole grid is ONE fused launch like an uncoated system; the caller checks ``system._tabled_pending``
+    (rays outside a table) once its launches are done.  Otherwise -- or when the rays do not reach the
+    coating in vacuum, or no table meets the tolerance -- the exact route: the grid is cut into boxes of
+    at most `max_rays` rays (they do live in HBM between the links of the chain), see :func:`_chain`.
     """
     device = _engine.require_cuda(device)
     if grid.size == 0:
         return  # an empty slab (more ranks than cells): nothing to trace, the caller still reduces
-    coated = sorted(system.coatings)
-    n_surface = system.n_surface
+    if getattr(system, "coating", "exact") == "table":
+        tabled = _tabled_for_grid(system, grid, device)
+        if tabled is not None:
+            trace_grid(tabled.compiled, grid, config=config, image=image, write_rays=False, device=device)
+            pending = system.__dict__.setdefault("_tabled_pending", [])
+            if tabled not in pending:
+                pending.append(tabled)
+            return
     for begin, count in _boxes(grid.begin, grid.count, max_rays):
-        sub = grid.sub(begin, count)
-        rays = trace_grid(system, sub, config=config, surf_count=coated[0] + 1, device=device, capture_cos=True)
-        _engine.apply_coating(system, coated[0], rays, device, config=config)
-        at = coated[0] + 1
-        for k in coated[1:] + [None]:
-            stop = n_surface if k is None else k + 1
-            final = k is None
-            rays = _trace_dense(system, config, rays, at, stop - at, image if final else None, not final, not final, device)
-            if not final:
-                _engine.apply_coating(system, k, rays, device, config=config)
-            at = stop
+        _chain(system, grid.sub(begin, count), config, image, device)

@@ -278,6 +278,7 @@ SYMBOLS = (
     "optk_host_register",
     "optk_host_unregister",
     "optk_memcpy_async",
+    "optk_enable_peer_access",
 )
 
 _lib = None
@@ -327,6 +328,7 @@ def lib() -> C.CDLL:
     L.optk_host_register.argtypes = [vp, i64]
     L.optk_host_unregister.argtypes = [vp]
     L.optk_memcpy_async.argtypes = [vp, vp, i64, vp]
+    L.optk_enable_peer_access.argtypes = [i32]
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int

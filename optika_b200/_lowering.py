@@ -315,3 +315,53 @@ def _table_type(n: int):
         pass
 
     return SurfaceTable
+
+
+def fingerprint(obj) -> bytes:
+    """
+    A digest of everything a surface list is made of: dataclass fields, named arrays (axes and bytes),
+    NumPy arrays, scalars, containers -- walked recursively.  Two calls on an unchanged system give the
+    same digest at a fraction of the cost of lowering it (which evaluates every parameter at every
+    configuration), so ``SequentialSystem`` lowers again only when the digest moves.
+    """
+    import dataclasses
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+
+    def walk(o, depth=0):
+        if depth > 32:
+            raise RecursionError("fingerprint: structure too deep")
+        if o is None or isinstance(o, (bool, int, float, complex, str, bytes)):
+            h.update(repr(o).encode())
+        elif isinstance(o, np.ndarray):
+            h.update(o.dtype.str.encode())
+            h.update(repr(o.shape).encode())
+            h.update(np.ascontiguousarray(o).tobytes())
+        elif isinstance(o, np.generic):
+            h.update(repr(o.item()).encode())
+        elif isinstance(o, na.ScalarArray):
+            h.update(repr(o.axes).encode())
+            walk(np.asarray(o.ndarray), depth + 1)
+        elif dataclasses.is_dataclass(o) and not isinstance(o, type):
+            h.update(type(o).__qualname__.encode())
+            for f in dataclasses.fields(o):
+                h.update(f.name.encode())
+                walk(getattr(o, f.name), depth + 1)
+        elif isinstance(o, dict):
+            for k, v in o.items():
+                walk(k, depth + 1)
+                walk(v, depth + 1)
+        elif isinstance(o, (list, tuple)):
+            h.update(b"[")
+            for v in o:
+                walk(v, depth + 1)
+            h.update(b"]")
+        elif hasattr(o, "__dict__"):
+            h.update(type(o).__qualname__.encode())
+            walk({k: v for k, v in vars(o).items() if not k.startswith("_")}, depth + 1)
+        else:
+            h.update(repr(o).encode())
+
+    walk(obj)
+    return h.digest()

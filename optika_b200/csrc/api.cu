@@ -1051,4 +1051,23 @@ OPTK_API int optk_memcpy_async(void* dst, const void* src, int64_t n_bytes, void
     return OPTK_OK;
 }
 
+OPTK_API int optk_enable_peer_access(int32_t peer_device) {
+    int current = -1;
+    OPTK_CUDA(cudaGetDevice(&current));
+    if (peer_device == current) return OPTK_OK;
+    int can = 0;
+    OPTK_CUDA(cudaDeviceCanAccessPeer(&can, current, peer_device));
+    if (!can) {
+        set_error("device %d cannot access device %d as a peer", current, peer_device);
+        return OPTK_ERR_UNSUPPORTED;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return OPTK_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return OPTK_OK;
+}
+
 }  // extern "C"

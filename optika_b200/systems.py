@@ -49,6 +49,15 @@ class SequentialSystem(AbstractSequentialSystem):
     grid_input: None | ObjectVectorArray = None
     axis_surface: str = "surface"
     transformation: None | AbstractTransformation = None
+    coating: str = "exact"
+    """
+    How multilayer-coated surfaces are evaluated: ``"exact"`` -- ``multilayer_efficiency`` for every ray, as the
+    reference does (``optika/materials/_multilayers.py:908-935``; the trace is chained through HBM around
+    the coated surface); ``"table"`` -- efficiency(wavelength, cosine of incidence) tabulated once to
+    `coating_tolerance` and looked up inside one fused launch (:mod:`optika_b200._coatings`).
+    """
+    coating_tolerance: float = 1e-6
+    """Largest interpolation error of a coating table, relative to the largest efficiency in it."""
     object_at_infinity: None | bool = None
     """
     Stand-in for the unit test of ``object_is_at_infinity`` (``:44-62``): ``None``
@@ -99,14 +108,21 @@ class SequentialSystem(AbstractSequentialSystem):
         from . import _lowering
 
         surfaces = self.surfaces_all
-        lowered = _lowering.lower_system(surfaces)
-        key = _lowering.table_key(lowered[0])
         cache = self.__dict__.setdefault("_compiled_cache", {})
         entry = cache.get(local_last)
-        if entry is None or entry[0] != key or len(entry[1].surfaces) != len(surfaces):
-            entry = (key, _engine.CompiledSystem(surfaces, local_last=local_last, lowered=lowered))
+        # cheap change detection first: a digest of every field of every surface (0.2 ms against the
+        # 2-20 ms of lowering a system with a configuration axis)
+        digest = _lowering.fingerprint(surfaces)
+        if entry is None or entry[2] != digest:
+            lowered = _lowering.lower_system(surfaces)
+            key = _lowering.table_key(lowered[0])
+            if entry is None or entry[0] != key or len(entry[1].surfaces) != len(surfaces):
+                entry = (key, _engine.CompiledSystem(surfaces, local_last=local_last, lowered=lowered), digest)
+            else:
+                entry = (entry[0], entry[1], digest)
             cache[local_last] = entry
         compiled = entry[1]
+        compiled.coating, compiled.coating_tolerance = self.coating, self.coating_tolerance
         # objects that are read again at trace time (coating stacks) always come from the current list
         compiled.surfaces = surfaces
         compiled.coatings = {k: s.material for k, s in enumerate(surfaces) if hasattr(s.material, "efficiency_device")}
@@ -800,6 +816,8 @@ class SequentialSystem(AbstractSequentialSystem):
                 if pipeline is None:
                     return {k: v.numpy() for k, v in image.to_host(pinned=False).items()}
                 planes = pipeline.finish()
+                for tabled in compiled.__dict__.pop("_tabled_pending", []):
+                    tabled.check()  # rays outside an efficiency table: fail loudly, not with a clamped value
                 return {k: np.array(v) for k, v in planes.items()} if own else planes
             finally:
                 if own and pipeline is not None:

@@ -215,3 +215,98 @@ def test_image_through_two_coated_surfaces(cuda_device):
     got = image.outputs.ndarray
     assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
     assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
+
+
+# ---------------------------------------------------------------------------
+# efficiency tables: coating="table" against the exact per-ray chain
+# ---------------------------------------------------------------------------
+def _intensity(system, **kwargs):
+    out = system.raytrace(accumulate=False, **configs.PHYSICAL, **kwargs).outputs
+    return na.as_named_array(out.intensity), out
+
+
+@pytest.mark.parametrize("num_periods", [6, 30])
+def test_coating_table_matches_the_exact_chain_to_the_stated_tolerance(cuda_device, num_periods):
+    system = coated_grating(mo_si(num_periods), num_wavelength=16)
+    exact, rays_exact = _intensity(system)
+    system.coating = "table"
+    table, rays_table = _intensity(system)
+    scale = float(np.nanmax(np.abs(exact.ndarray)))
+    assert scale > 0.05  # the stack reflects near 13.5 nm
+    assert np.nanmax(np.abs(table.ndarray - exact.ndarray)) <= 1e-6 * scale  # the contract of coating_tolerance
+    # one exact node per wavelength of the grid: only the cosine is interpolated, and the walk itself is the same
+    for name in ("x", "y", "z"):
+        a, b = getattr(rays_table.position, name), getattr(rays_exact.position, name)
+        assert np.array_equal(na.as_named_array(a).ndarray, na.as_named_array(b).ndarray, equal_nan=True)
+    assert np.array_equal(rays_table.unvignetted.ndarray, rays_exact.unvignetted.ndarray)
+    tabled = next(iter(system._compiled.__dict__["_tabled"].values()))
+    (error_cos, error_wavelength), = set(tabled.errors.values())
+    assert error_cos <= 0.5e-6 and error_wavelength == 0.0
+    assert all(t.exact_in_wavelength for t in tabled.tables.values())
+    # a tighter tolerance is honoured (more cosine nodes), and the tables are rebuilt for it
+    system.coating_tolerance = 1e-9
+    tight, _ = _intensity(system)
+    assert np.nanmax(np.abs(tight.ndarray - exact.ndarray)) <= 1e-9 * scale
+
+
+def test_coating_table_in_the_fused_image_and_in_the_pupil_reductions(cuda_device):
+    system = coated_grating(mo_si(10), num_wavelength=8)
+    edges = na.ScalarArray(np.array([12 * u.nm, 15 * u.nm]), "wavelength")
+    exact = system.image_rays(edges, counts=True, **configs.PHYSICAL)
+    moments_exact = system.pupil_moments(**configs.PHYSICAL)
+    system.coating = "table"
+    table = system.image_rays(edges, counts=True, **configs.PHYSICAL)
+    moments_table = system.pupil_moments(**configs.PHYSICAL)
+    assert np.array_equal(table.counts.cpu().numpy(), exact.counts.cpu().numpy())
+    a, b = table.flux.cpu().numpy(), exact.flux.cpu().numpy()
+    assert b.max() > 0 and np.abs(a - b).max() <= 2e-6 * b.max()
+    ia, ib = moments_table["intensity"].ndarray, moments_exact["intensity"].ndarray
+    assert np.abs(ia - ib).max() <= 2e-6 * ib.max()
+    assert np.array_equal(moments_table["where"].ndarray, moments_exact["where"].ndarray)
+
+
+def test_coating_table_over_a_continuous_wavelength_range(cuda_device):
+    """Dense device rays carry arbitrary wavelengths: nodes on every kink of the optical constants, linear in between."""
+    import torch
+    from optika_b200 import _engine
+
+    system = coated_grating(mo_si(10), num_wavelength=5)
+    system.coating_tolerance = 2e-5  # what a 2-D table of this band reaches within the default size limit
+    _, rays = system._input(None, None, None, None, False, False)
+    start = _engine.trace(system._compiled, rays, surf_count=0, ray_axes_order=system._ray_axes_order)  # dense copies
+    n = start.size
+    rng = torch.Generator(device="cuda").manual_seed(3)
+    start.fields["wavelength"] = (12.6e-6 + 1.8e-6 * torch.rand(n, generator=rng, device="cuda", dtype=torch.float64))
+    exact = _engine.trace(system._compiled, start)
+    compiled = system._compiled
+    compiled.coating = "table"
+    table = _engine.trace(compiled, start)
+    a, b = table.fields["intensity"].cpu().numpy(), exact.fields["intensity"].cpu().numpy()
+    assert np.nanmax(b) > 0.05
+    assert np.nanmax(np.abs(a - b)) <= 2e-5 * np.nanmax(b)
+    tabled = [t for t in compiled.__dict__["_tabled"].values() if t != "exact"]
+    assert tabled and not any(t.exact_in_wavelength for t in tabled[0].tables.values())
+
+
+def test_rays_outside_the_tabulated_cosines_fail_loudly(cuda_device):
+    system = coated_grating(mo_si(6), num_wavelength=4)
+    system.coating = "table"
+    compiled = system._compiled
+    compiled.coating_cos_range = (0.2, 0.5)  # the rays arrive at near-normal incidence: cos ~ 1
+    with pytest.raises(ValueError, match="outside its efficiency table"):
+        system.raytrace(accumulate=False, **configs.PHYSICAL)
+
+
+def test_glass_before_the_coating_takes_the_exact_chain(cuda_device):
+    """A ray that reaches the coating inside a medium has a complex ambient index: not a function of two numbers."""
+    system = coated_grating(mo_si(6), num_wavelength=4)
+    window = optika.surfaces.Surface(
+        name="window", material=M.Glass.n_bk7(),
+        transformation=optika.transformations.Cartesian3dTranslation(z=10 * u.mm),
+    )
+    system.surfaces = [window] + list(system.surfaces)
+    exact, _ = _intensity(system)
+    system.coating = "table"
+    table, _ = _intensity(system)
+    assert np.array_equal(table.ndarray, exact.ndarray, equal_nan=True)  # the same (exact) route ran
+    assert "_tabled" not in system._compiled.__dict__
