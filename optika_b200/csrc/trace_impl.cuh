@@ -1674,7 +1674,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         valid[k] = i0 + k < limit;
-        r[k] = Ray{1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, false};  // dummy ray for idle lanes
+        // dummy ray for idle lanes; its NaN wavelength keeps it out of every table statistic (table2d_lookup)
+        r[k] = Ray{OPTK_NAN, 0.0, 0.0, -1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, false};
     }
     unsigned newton_iterations = 0;
     double cos_incidence = 0.0;  // generic path only: captured at the last traced surface
