@@ -666,9 +666,20 @@ def _tabled_for_rays(system, rays, coated, surf_begin, surf_count, device, ray_a
         wavelengths = [w[0], w[-1]] if continuous else w
         pilot = _subsample_rays(rays)
         order = ray_axes_order
-    log = {}
-    trace(system, pilot, False, None, surf_begin, surf_count, 1, None, None, True, device, False, None, order,
-          _cos_log=log, _exact=True)
+    # the pilot depends on the rays only: remembered per ray grid (a digest of its small named arrays)
+    key = None
+    if not isinstance(rays, DeviceRays):
+        key = (_lowering.fingerprint(rays), surf_begin, surf_count, str(device))
+    cache = system.__dict__.setdefault("_pilot_ranges", {})
+    log = cache.get(key) if key is not None else None
+    if log is None:
+        log = {}
+        trace(system, pilot, False, None, surf_begin, surf_count, 1, None, None, True, device, False, None, order,
+              _cos_log=log, _exact=True)
+        if key is not None:
+            if len(cache) >= 16:
+                cache.pop(next(iter(cache)))
+            cache[key] = log
     ranges = coating_cos_ranges(log, coated, getattr(system, "coating_cos_range", None))
     if ranges is None:
         return None

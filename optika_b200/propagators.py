@@ -30,10 +30,22 @@ def _chain(surfaces: list, rays, accumulate: bool, axis: str | None, device):
             system = _engine.CompiledSystem(surfaces[k : k + L.MAX_SURFACES])
             rays = _engine.trace(system, rays, device=device)
         return rays
-    if len(surfaces) > L.MAX_SURFACES:
-        raise ValueError(f"accumulate_rays supports at most {L.MAX_SURFACES} surfaces")
-    system = _engine.CompiledSystem(surfaces)
-    return _engine.trace(system, rays, accumulate=True, axis=axis, device=device)
+    if len(surfaces) <= L.MAX_SURFACES:
+        system = _engine.CompiledSystem(surfaces)
+        return _engine.trace(system, rays, accumulate=True, axis=axis, device=device)
+    # longer lists: every link is lowered over the configuration shape of the WHOLE list (so all links
+    # produce the same axes), traced with accumulate, and fed the last state of the link before it
+    from . import _lowering
+
+    shape_ = _lowering.config_shape(surfaces)
+    parts = []
+    for k in range(0, len(surfaces), L.MAX_SURFACES):
+        link = surfaces[k : k + L.MAX_SURFACES]
+        system = _engine.CompiledSystem(link, lowered=_lowering.lower_system(link, shape_=dict(shape_)))
+        out = _engine.trace(system, rays, accumulate=True, axis=axis, device=device)
+        parts.append(out)
+        rays = out.last_state()
+    return _engine.DeviceRays.concatenate(parts, axis if axis is not None else "surface")
 
 
 def propagate_rays(propagators, rays, device=None):

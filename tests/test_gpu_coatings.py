@@ -234,10 +234,11 @@ def test_coating_table_matches_the_exact_chain_to_the_stated_tolerance(cuda_devi
     scale = float(np.nanmax(np.abs(exact.ndarray)))
     assert scale > 0.05  # the stack reflects near 13.5 nm
     assert np.nanmax(np.abs(table.ndarray - exact.ndarray)) <= 1e-6 * scale  # the contract of coating_tolerance
-    # one exact node per wavelength of the grid: only the cosine is interpolated, and the walk itself is the same
+    # one exact node per wavelength of the grid: only the cosine is interpolated; the walk is the same up to
+    # rounding (one fused launch here, chained launches of other kernel instantiations there)
     for name in ("x", "y", "z"):
         a, b = getattr(rays_table.position, name), getattr(rays_exact.position, name)
-        assert np.array_equal(na.as_named_array(a).ndarray, na.as_named_array(b).ndarray, equal_nan=True)
+        assert np.allclose(na.as_named_array(a).ndarray, na.as_named_array(b).ndarray, rtol=1e-12, atol=1e-12, equal_nan=True)
     assert np.array_equal(rays_table.unvignetted.ndarray, rays_exact.unvignetted.ndarray)
     tabled = next(iter(system._compiled.__dict__["_tabled"].values()))
     (error_cos, error_wavelength), = set(tabled.errors.values())
