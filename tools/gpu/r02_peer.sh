@@ -1,11 +1,24 @@
 #!/bin/bash
-# peer-memory reduction at N ranks: parity test, strong-scaling simulations with the peer and the NCCL transport
+# reduction transports at N ranks: parity test, strong-scaling simulations with NCCL (high-priority group, the default)
+# and with the peer-memory transport
 N=$1
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -12 > gpurun_out/pytest_multi_peer_n$N.txt
-cat gpurun_out/pytest_multi_peer_n$N.txt
+python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -12 > gpurun_out/pytest_multi_n$N.txt
+cat gpurun_out/pytest_multi_n$N.txt
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-$RUN bench.py --gpus $N --only-strong --strong cfg3,cfg5 --strong-steps 3 > gpurun_out/strong_peer_n$N.json 2> gpurun_out/strong_peer_n$N.err
-tail -c 2500 gpurun_out/strong_peer_n$N.json; tail -5 gpurun_out/strong_peer_n$N.err
-OPTK_REDUCE_TRANSPORT=nccl TORCH_NCCL_HIGH_PRIORITY=1 $RUN bench.py --gpus $N --only-strong --strong cfg5 --strong-steps 3 > gpurun_out/strong_nccl_hp_n$N.json 2> gpurun_out/strong_nccl_hp_n$N.err
-tail -c 1200 gpurun_out/strong_nccl_hp_n$N.json
+$RUN bench.py --gpus $N --only-strong --strong cfg3,cfg5 --strong-steps 3 > gpurun_out/strong_nccl_n$N.json 2> gpurun_out/strong_nccl_n$N.err
+tail -5 gpurun_out/strong_nccl_n$N.err | cut -c 1-400
+OPTK_REDUCE_TRANSPORT=peer $RUN bench.py --gpus $N --only-strong --strong cfg3,cfg5 --strong-steps 3 > gpurun_out/strong_peer_n$N.json 2> gpurun_out/strong_peer_n$N.err
+tail -5 gpurun_out/strong_peer_n$N.err | cut -c 1-400
+OPTK_REDUCE_TRANSPORT=peer python -m pytest tests/test_gpu_multi.py -q -x -k "2" 2>&1 | tail -3
+python - <<'PY'
+import json
+for name in ("strong_nccl_n%s" % "$N", "strong_peer_n%s" % "$N"):
+    try:
+        for line in open("gpurun_out/%s.json" % name):
+            if line.strip().startswith("{"):
+                for k, v in json.loads(line)["config"].items():
+                    print(name, k, {a: v.get(a) for a in ("transport","ms_total","ms_trace","ms_reduce","ms_d2h","efficiency_vs_n1","counts_equal_n1")})
+    except Exception as e:
+        print(name, e)
+PY
