@@ -697,6 +697,23 @@ def run_b200(args):
     # sanity: the traced rays are physical (most of them reach the sensor)
     unv_frac = float(mask_out.float().mean().item())
 
+    # parity of the TIMED kernel's own output, in the run: 1e5 rays spread over the last slab it wrote, against
+    # the oracle on the same inputs (positions / directions 1e-9, masks exact up to enumerated edge rays)
+    parity_in_run = None
+    if rank == 0:
+        import parity
+        from oracle import raytrace as ora
+
+        idx = torch.linspace(0, n_slab - 1, min(n_slab, 100_000), device=device).long()
+        sample = {name: (w_dense[-1] if name == "wavelength" else fields_in[name])[idx].cpu().numpy() for name in _lib.FIELDS}
+        sample["unvignetted"] = np.ones(len(idx), dtype=bool)
+        want = ora.propagate_rays(system.surfaces_all, sample, extended=True)
+        got = {name: out[name][idx].cpu().numpy() for name in _lib.FIELDS}
+        got["unvignetted"] = mask_out[idx].cpu().numpy().astype(bool)
+        report = parity.compare_states(got, want, system.surfaces_all)  # raises on a failure
+        parity_in_run = True
+        parity_report = dict(rays=int(len(idx)), **{k: v for k, v in report.items() if k != "edge_rays"})
+
     # ---- e2e: public API, host buffers in, detector planes out (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -918,6 +935,8 @@ def run_b200(args):
             e2e=dict(e2e, rays_to_host=host_rays) if e2e is not None else None,
             gpu_launches=timed_launches,
             clocks=clocks,
+            parity_in_run=parity_in_run,
+            parity=parity_report,
         )
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -11,14 +11,4 @@ tail -5 gpurun_out/strong_nccl_n$N.err | cut -c 1-400
 OPTK_REDUCE_TRANSPORT=peer $RUN bench.py --gpus $N --only-strong --strong cfg3,cfg5 --strong-steps 3 > gpurun_out/strong_peer_n$N.json 2> gpurun_out/strong_peer_n$N.err
 tail -5 gpurun_out/strong_peer_n$N.err | cut -c 1-400
 OPTK_REDUCE_TRANSPORT=peer python -m pytest tests/test_gpu_multi.py -q -x -k "2" 2>&1 | tail -3
-python - <<'PY'
-import json
-for name in ("strong_nccl_n%s" % "$N", "strong_peer_n%s" % "$N"):
-    try:
-        for line in open("gpurun_out/%s.json" % name):
-            if line.strip().startswith("{"):
-                for k, v in json.loads(line)["config"].items():
-                    print(name, k, {a: v.get(a) for a in ("transport","ms_total","ms_trace","ms_reduce","ms_d2h","efficiency_vs_n1","counts_equal_n1")})
-    except Exception as e:
-        print(name, e)
-PY
+python tools/gpu/summarize_strong.py gpurun_out/strong_nccl_n$N.json gpurun_out/strong_peer_n$N.json

@@ -110,6 +110,9 @@ extern "C" __global__ void __launch_bounds__(256, {minb}) optk_jit_kernel(const 
             import collections
             c = collections.Counter(o.split(".")[0] for o in ops)
             print("SASS instructions:", len(ops), dict(c.most_common(14)))
+            if "--sass" in sys.argv:
+                print("=== SASS ===")
+                print(sass)
 
 
 if __name__ == "__main__":
