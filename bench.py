@@ -361,7 +361,7 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
         image = _engine.DeviceImage.zeros(
             w_edges, ex, ey, device, leading=leading, moments=True, counts=True, fused=True, pad_to=1 if local else world
         )
-        return distributed.ImagePipeline(image, device, local=local)
+        return distributed.ImagePipeline(image, device, local=local, rezero=True)
 
     def barrier():
         if world > 1:
@@ -389,7 +389,7 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
             t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            pipeline.image.zero_()
+            # (the planes are zero: allocated so, and handed back zeroed by the pipeline after every exposure)
             planes = system.collect_grids(
                 grids, w_edges, device=device, pipeline=pipeline, shard=shard, on_launch=on_launch if timed else None
             )
@@ -704,7 +704,8 @@ def run_b200(args):
         import parity
         from oracle import raytrace as ora
 
-        idx = torch.linspace(0, n_slab - 1, min(n_slab, 100_000), device=device).long()
+        m_sample = min(n_slab, 100_000)
+        idx = (torch.arange(m_sample, device=device, dtype=torch.int64) * (n_slab - 1)) // max(m_sample - 1, 1)
         sample = {name: (w_dense[-1] if name == "wavelength" else fields_in[name])[idx].cpu().numpy() for name in _lib.FIELDS}
         sample["unvignetted"] = np.ones(len(idx), dtype=bool)
         want = ora.propagate_rays(system.surfaces_all, sample, extended=True)

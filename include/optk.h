@@ -602,6 +602,50 @@ OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream);
  * ten fp64 arrays + a byte mask in, the same out.  Allocates 162 * n_rays bytes. */
 OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, void* stream);
 
+/* ---- detector physics after binning (kernel 4) ----------------------------------
+ * Replaces the numba kernel optika/sensors/materials/_ramanathan_2020/_ramanathan_2020.py:762-876
+ * (_electrons_measured_numba, called by electrons_measured :468-690): a Monte-Carlo model of a
+ * back-illuminated CCD.  For every photon absorbed in a pixel: the number of electron-hole pairs
+ * (below 50 eV from the tabulated pair-number distribution `cmf` / `n_values`, above from a rounded
+ * normal of mean energy / energy_pair_inf and variance fano_inf * mean), the absorption depth
+ * (exponential of rate `absorption`, truncated to the substrate), the charge-collection efficiency at
+ * that depth (cce_backsurface at the back surface rising linearly to 1 across thickness_implant) applied
+ * as a binomial thinning, and for every surviving electron a Gaussian lateral step of standard deviation
+ * z_ff sqrt(1 - z / z_ff) (z_ff = thickness_substrate - thickness_depletion; none beyond z_ff) from the
+ * photon's uniformly random position in the pixel, rounded to whole pixels; electrons leaving the grid
+ * wrap around (wrap != 0) or are lost.
+ * One record per image plane (everything but the photon counts is per plane: the wavelength axis);
+ * lengths in mm, energies in eV.  `cmf` (cumulative pair-number distribution) and `n_values` are DEVICE
+ * arrays of n_pmf entries (ignored above 50 eV).
+ * Random numbers: Philox4x32-10, key = seed, counter = {pixel index in the whole [n_plane][n_x][n_y]
+ * array (64 bit), photon index, draw}: draw 0 = pair number (words 0-1 -> a 53-bit uniform; above 50 eV
+ * words 2-3 -> the second uniform of a Box-Muller pair, first normal used), draw 1 = depth (words 0-1),
+ * position in the pixel (word 2, word 3: (w + 1/2) 2^-32 - 1/2), draw 2 + e = the lateral step of
+ * electron e (two 53-bit uniforms -> Box-Muller -> x, y), draw 2^31 + 2 + e = its survival.  The result
+ * is independent of the launch geometry; oracle/detector.py reproduces it count for count. */
+typedef struct optk_ccd_plane {
+    double energy;              /* photon energy, eV                                  */
+    double absorption;          /* absorption coefficient of the substrate, 1 / mm    */
+    double thickness_implant;   /* mm                                                 */
+    double thickness_depletion; /* mm                                                 */
+    double thickness_substrate; /* mm                                                 */
+    double width_pixel_x;       /* mm                                                 */
+    double width_pixel_y;       /* mm                                                 */
+    double cce_backsurface;     /* charge-collection efficiency at the back surface   */
+    double energy_pair_inf;     /* asymptotic pair-creation energy, eV                */
+    double fano_inf;            /* asymptotic Fano factor                             */
+    int32_t n_pmf;
+    int32_t reserved;
+    const double* cmf;          /* device, n_pmf: cumulative probability of n_values  */
+    const double* n_values;     /* device, n_pmf: numbers of pairs                    */
+} optk_ccd_plane_t;
+
+/* photons: device int64 [n_plane][n_x][n_y] (absorbed photons per pixel); electrons: device uint64, same
+ * shape, caller-zeroed, counts are ADDED.  `planes` is a HOST array of n_plane records. */
+OPTK_API int optk_electrons_measured(int32_t n_plane, int32_t n_x, int32_t n_y, const optk_ccd_plane_t* planes,
+                                     const int64_t* photons, uint64_t* electrons, int32_t wrap, uint64_t seed,
+                                     void* stream);
+
 /* ---- host memory ---------------------------------------------------------------
  * Page-lock (cudaHostRegister, portable) / release a host range the caller owns, e.g. a POSIX
  * shared-memory mapping that several single-GPU processes read detector planes back into

@@ -180,7 +180,7 @@ def build_table(material, wavelengths, cos_range, config_shape, cindex, device, 
             values = _grid_values(material, nodes, cosines, config_shape, cindex, device)
             table = CoatingTable(nodes, c_lo - step, step, values, float("nan"), 0.0, not continuous)
             # error of the cubic in the cosine, measured at the cell midpoints of (a subset of) the node rows
-            rows = torch.linspace(0, len(nodes_host) - 1, min(len(nodes_host), 257), device=device).round().long().unique()
+            rows = torch.linspace(0, len(nodes_host) - 1, min(len(nodes_host), 257), device=device, dtype=torch.float64).round().long().unique()
             mid = up(c_lo + step * (np.arange(n_cells) + 0.5))
             exact = _grid_values(material, nodes[rows], mid, config_shape, cindex, device)
             w_rows = nodes[rows][:, None].expand_as(exact)
@@ -196,7 +196,7 @@ def build_table(material, wavelengths, cos_range, config_shape, cindex, device, 
             return table
         # error of the linear interpolation between wavelength nodes, at the interval midpoints
         mid_w = 0.5 * (nodes[1:] + nodes[:-1])
-        pick = torch.linspace(0, len(mid_w) - 1, min(len(mid_w), 4097), device=device).round().long().unique()
+        pick = torch.linspace(0, len(mid_w) - 1, min(len(mid_w), 4097), device=device, dtype=torch.float64).round().long().unique()
         cos_probe = up(np.linspace(c_lo, c_hi, 9))
         exact = _grid_values(material, mid_w[pick], cos_probe, config_shape, cindex, device)
         approx = table.lookup(

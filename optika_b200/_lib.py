@@ -244,6 +244,25 @@ class MlInput(C.Structure):
     ]
 
 
+class CcdPlane(C.Structure):
+    _fields_ = [
+        ("energy", C.c_double),
+        ("absorption", C.c_double),
+        ("thickness_implant", C.c_double),
+        ("thickness_depletion", C.c_double),
+        ("thickness_substrate", C.c_double),
+        ("width_pixel_x", C.c_double),
+        ("width_pixel_y", C.c_double),
+        ("cce_backsurface", C.c_double),
+        ("energy_pair_inf", C.c_double),
+        ("fano_inf", C.c_double),
+        ("n_pmf", C.c_int32),
+        ("reserved", C.c_int32),
+        ("cmf", C.c_void_p),
+        ("n_values", C.c_void_p),
+    ]
+
+
 ABI_VERSION = 7
 
 
@@ -279,6 +298,7 @@ SYMBOLS = (
     "optk_host_unregister",
     "optk_memcpy_async",
     "optk_enable_peer_access",
+    "optk_electrons_measured",
 )
 
 _lib = None
@@ -329,6 +349,7 @@ def lib() -> C.CDLL:
     L.optk_host_unregister.argtypes = [vp]
     L.optk_memcpy_async.argtypes = [vp, vp, i64, vp]
     L.optk_enable_peer_access.argtypes = [i32]
+    L.optk_electrons_measured.argtypes = [i32, i32, i32, C.POINTER(CcdPlane), vp, vp, i32, C.c_uint64, vp]
     for name in SYMBOLS:
         if name not in ("optk_last_error",):
             getattr(L, name).restype = C.c_int

@@ -1022,6 +1022,39 @@ OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, vo
     return measure_soa_copy(n_rays, gbytes_per_second, (cudaStream_t)stream);
 }
 
+OPTK_API int optk_electrons_measured(int32_t n_plane, int32_t n_x, int32_t n_y, const optk_ccd_plane_t* planes,
+                                     const int64_t* photons, uint64_t* electrons, int32_t wrap, uint64_t seed,
+                                     void* stream) {
+    DeviceScope device_scope(stream);
+    if (n_plane < 0 || n_x < 0 || n_y < 0 || (!planes && n_plane) || !photons || !electrons) {
+        set_error("optk_electrons_measured: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    if ((long long)n_plane * n_x * n_y == 0) return OPTK_OK;
+    for (int i = 0; i < n_plane; ++i) {
+        const optk_ccd_plane_t& P = planes[i];
+        if (P.energy <= 50.0 && (P.n_pmf < 1 || !P.cmf || !P.n_values)) {
+            set_error("optk_electrons_measured: plane %d (%.3g eV) needs the pair-number distribution", i, P.energy);
+            return OPTK_ERR_INVALID;
+        }
+        if (!(P.thickness_substrate >= 0) || !(P.absorption >= 0) || !(P.energy_pair_inf > 0)) {
+            set_error("optk_electrons_measured: plane %d has a negative thickness / absorption or no pair energy", i);
+            return OPTK_ERR_INVALID;
+        }
+    }
+    optk_ccd_plane_t* device_planes = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    OPTK_CUDA(cudaMallocAsync((void**)&device_planes, sizeof(optk_ccd_plane_t) * n_plane, s));
+    cudaError_t e = cudaMemcpyAsync(device_planes, planes, sizeof(optk_ccd_plane_t) * n_plane, cudaMemcpyHostToDevice, s);
+    int rc = e == cudaSuccess ? OPTK_OK : cuda_fail(e, "cudaMemcpyAsync (planes)");
+    // the record array is pageable host memory: the copy above has consumed it when it returns
+    if (rc == OPTK_OK)
+        rc = launch_electrons(n_plane, n_x, n_y, device_planes, (const long long*)photons, (unsigned long long*)electrons,
+                              wrap ? 1 : 0, seed, s);
+    cudaFreeAsync(device_planes, s);
+    return rc;
+}
+
 OPTK_API int optk_host_register(void* data, int64_t n_bytes) {
     if (!data || n_bytes <= 0) {
         set_error("optk_host_register: bad arguments");

@@ -111,6 +111,8 @@ int launch_apply_efficiency(long long n, double* intensity, const double* e_s, c
 int launch_reduce_groups(long long n_groups, long long n_inner, const double* x, const double* y, const double* intensity,
                          const uint8_t* unvignetted, double* sum_intensity, double* sum_x, double* sum_y,
                          unsigned long long* count, double* sum_x_all, double* sum_y_all, cudaStream_t stream);
+int launch_electrons(int n_plane, int n_x, int n_y, const optk_ccd_plane_t* planes_device, const long long* photons,
+                     unsigned long long* electrons, int wrap, unsigned long long seed, cudaStream_t stream);
 int measure_fp64_peak(double* flops, cudaStream_t stream);
 int measure_soa_copy(long long n_rays, double* gbytes_per_second, cudaStream_t stream);
 

@@ -236,7 +236,7 @@ class ImagePipeline:
     """
 
     def __init__(self, image, device=None, group=None, to_host: bool = True, local: bool = False,
-                 transport: str | None = None):
+                 transport: str | None = None, rezero: bool = False):
         import os
         import torch
 
@@ -272,6 +272,10 @@ class ImagePipeline:
                 if row_i else None
         self.events = []  # (config, start, reduced, copied) CUDA events of the side stream
         self.timing = False
+        # `rezero`: hand the planes of a configuration back ZEROED as soon as they have been summed and
+        # copied (on the side stream, under the trace of the next configuration), so that a series of
+        # exposures does not start each one with a multi-gigabyte memset on the critical path
+        self.rezero = rezero
         self._pending = []
         self._host_group = None
         if self.transport == "peer":
@@ -377,14 +381,17 @@ class ImagePipeline:
         self._pending = []
 
     def _read_back(self, c: int, sources: dict):
-        if not self.to_host:
-            return
-        for kind, host in (("f", self.host_f), ("i", self.host_i if self.row_i else None)):
-            if host is None or sources.get(kind) is None:
-                continue
-            src = sources[kind]
-            n = src.numel()
-            host[c, self.rank * n:(self.rank + 1) * n].copy_(src, non_blocking=True)
+        if self.to_host:
+            for kind, host in (("f", self.host_f), ("i", self.host_i if self.row_i else None)):
+                if host is None or sources.get(kind) is None:
+                    continue
+                src = sources[kind]
+                n = src.numel()
+                host[c, self.rank * n:(self.rank + 1) * n].copy_(src, non_blocking=True)
+        if self.rezero and self.transport != "peer":  # (peer: other ranks may still be reading these planes)
+            self.image.buffer_f64[c].zero_()
+            if self.row_i:
+                self.image.buffer_i64[c].zero_()
 
     def _side(self):
         import contextlib

@@ -24,7 +24,16 @@ from .surfaces import AbstractSurface
 from .transformations import AbstractTransformation
 from .vectors import SpectralPositionalVectorArray
 
-__all__ = ["IdealSensorMaterial", "AbstractImagingSensor", "ImagingSensor"]
+from ._detector_physics import (  # noqa: E402,F401  (optika.sensors.charge_diffusion, electrons_measured, ...)
+    charge_diffusion, mean_charge_capture, kernel_diffusion, energy_bandgap, energy_pair, energy_pair_inf,
+    quantum_yield_ideal, fano_factor, fano_factor_inf, probability_of_n_pairs, electrons_measured,
+)
+
+__all__ = [
+    "IdealSensorMaterial", "AbstractImagingSensor", "ImagingSensor",
+    "charge_diffusion", "mean_charge_capture", "kernel_diffusion", "energy_bandgap", "energy_pair", "energy_pair_inf",
+    "quantum_yield_ideal", "fano_factor", "fano_factor_inf", "probability_of_n_pairs", "electrons_measured",
+]
 
 
 @dataclasses.dataclass(eq=False)
