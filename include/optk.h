@@ -433,6 +433,14 @@ typedef struct optk_grid {
      * series in the offset (truncation < 3e-21) instead of a full-range sincos per ray and angle; the
      * vertex arrays of those two axes are not read.  Both NULL: sincos of the sampled angle. */
     const double* angular_cells[2];
+    /* Chromatic axes: bit a (a = 1 .. 4) set -- vertices[a] is a 2-D array [n[0] + 1][n[a] + 1], one row of
+     * vertices per WAVELENGTH vertex (field / pupil extents from a stop solution per wavelength,
+     * optika/systems/_sequential.py:748-789); the sample of cell (i_0, i_a) is bilinear in (t_0, t_a), along
+     * the wavelength first.  Not combinable with field_2d / pupil_2d for the same pair, nor with
+     * angular_cells.  weight_pupil_chromatic != 0: weight_pupil is [n0][n3][n4] (cell areas per wavelength
+     * cell). */
+    int32_t chromatic;
+    int32_t weight_pupil_chromatic;
 } optk_grid_t;
 
 /* As optk_trace, with the rays of `grid` as input.  surf_count = 0 returns the

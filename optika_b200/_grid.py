@@ -36,6 +36,8 @@ class RayGrid:
     """
 
     vertices: tuple
+    chromatic: tuple = ()
+    """Axes (1 .. 4) whose vertex array is 2-D ``[n_wavelength + 1][n + 1]``: one row per wavelength vertex."""
     at_infinity: bool = True
     weight_scene: np.ndarray | None = None
     weight_pupil: np.ndarray | None = None
@@ -52,8 +54,19 @@ class RayGrid:
             raise ValueError("a ray grid has five axes: wavelength, field x/y, pupil x/y")
         if self.vertices[0].ndim != 1:
             raise ValueError("the wavelength vertices must be one-dimensional")
+        self.chromatic = tuple(sorted(int(a) for a in self.chromatic))
+        n_w = len(self.vertices[0])
+        for a in self.chromatic:
+            if a not in (1, 2, 3, 4) or self.vertices[a].ndim != 2 or self.vertices[a].shape[0] != n_w:
+                raise ValueError(
+                    f"chromatic axis {a} needs a vertex array [n_wavelength + 1 = {n_w}][n + 1], got {self.vertices[a].shape}"
+                )
         for name, (a, b) in (("field", (1, 2)), ("pupil", (3, 4))):
             va, vb = self.vertices[a], self.vertices[b]
+            if a in self.chromatic or b in self.chromatic:
+                if any(self.vertices[c].ndim != 1 for c in (a, b) if c not in self.chromatic):
+                    raise ValueError(f"the {name} axis paired with a chromatic one must be 1-D (separable)")
+                continue
             if not ((va.ndim == 1 and vb.ndim == 1) or (va.ndim == 2 and va.shape == vb.shape)):
                 raise ValueError(
                     f"the {name} vertices are two 1-D arrays (separable grid) or two 2-D arrays of one shape "
@@ -65,7 +78,9 @@ class RayGrid:
         if self.weight_scene is not None:
             self.weight_scene = np.ascontiguousarray(np.broadcast_to(self.weight_scene, n[:3]), dtype=np.float64)
         if self.weight_pupil is not None:
-            self.weight_pupil = np.ascontiguousarray(np.broadcast_to(self.weight_pupil, n[3:]), dtype=np.float64)
+            wp = np.asarray(self.weight_pupil, dtype=np.float64)
+            target = (n[0],) + tuple(n[3:]) if wp.ndim == 3 else tuple(n[3:])  # 3-D: one set of areas per wavelength cell
+            self.weight_pupil = np.ascontiguousarray(np.broadcast_to(wp, target), dtype=np.float64)
         if self.begin is None:
             self.begin = (0,) * 5
         if self.count is None:
@@ -74,18 +89,22 @@ class RayGrid:
 
     @property
     def field_2d(self) -> bool:
-        return self.vertices[1].ndim == 2
+        return self.vertices[1].ndim == 2 and not ({1, 2} & set(self.chromatic))
 
     @property
     def pupil_2d(self) -> bool:
-        return self.vertices[3].ndim == 2
+        return self.vertices[3].ndim == 2 and not ({3, 4} & set(self.chromatic))
 
     @property
     def n(self) -> tuple:
         v = self.vertices
-        nf = (v[1].shape[0] - 1, v[1].shape[1] - 1) if self.field_2d else (len(v[1]) - 1, len(v[2]) - 1)
-        npup = (v[3].shape[0] - 1, v[3].shape[1] - 1) if self.pupil_2d else (len(v[3]) - 1, len(v[4]) - 1)
-        return (len(v[0]) - 1,) + nf + npup
+
+        def cells(a, b, curvilinear):
+            if curvilinear:
+                return (v[a].shape[0] - 1, v[a].shape[1] - 1)
+            return tuple(v[c].shape[-1] - 1 for c in (a, b))
+
+        return (len(v[0]) - 1,) + cells(1, 2, self.field_2d) + cells(3, 4, self.pupil_2d)
 
     @property
     def shape(self) -> dict[str, int]:
@@ -132,7 +151,7 @@ class RayGrid:
         """
         a, b = (1, 2) if self.at_infinity else (3, 4)
         va, vb = self.vertices[a], self.vertices[b]
-        if va.ndim != 1 or vb.ndim != 1:
+        if va.ndim != 1 or vb.ndim != 1 or self.chromatic:
             return [None, None]
         if max(np.max(np.abs(np.diff(va))), np.max(np.abs(np.diff(vb)))) > 0.01:
             return [None, None]
@@ -161,6 +180,8 @@ class RayGrid:
         g.weight_pupil = None if dev["weight_pupil"] is None else dev["weight_pupil"].data_ptr()
         g.field_2d = 1 if self.field_2d else 0
         g.pupil_2d = 1 if self.pupil_2d else 0
+        g.chromatic = sum(1 << a for a in self.chromatic)
+        g.weight_pupil_chromatic = 1 if (self.weight_pupil is not None and self.weight_pupil.ndim == 3) else 0
         for k in range(2):
             cells = dev["angular_cells"][k]
             g.angular_cells[k] = None if cells is None else cells.data_ptr()

@@ -178,6 +178,8 @@ class Grid(C.Structure):
         ("field_2d", C.c_int32),
         ("pupil_2d", C.c_int32),
         ("angular_cells", C.c_void_p * 2),
+        ("chromatic", C.c_int32),
+        ("weight_pupil_chromatic", C.c_int32),
     ]
 
 

@@ -37,7 +37,7 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         efficiency = efficiency || P.surf[s].material_efficiency != OPTK_EFF_UNIT ||
                      P.surf[s].ruling_profile != OPTK_PROFILE_IDEAL;
     // curvilinear grids with non-unit efficiencies are rare enough to share the generic kernels
-    const bool curvilinear = from_grid && (P.grid.field_2d || P.grid.pupil_2d);
+    const bool curvilinear = from_grid && (P.grid.field_2d || P.grid.pupil_2d || P.grid.chromatic);
     if (curvilinear && efficiency) full = false;
     const bool dense = P.dense_in != 0 && !from_grid, acc = P.accumulate != 0, image = P.has_image != 0;
     // 128-bit path: dense inputs, every array 16-byte aligned, even accumulate stride
@@ -204,8 +204,8 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         }
     }
     // a kernel compiled for exactly this surface list, when the launch is long enough to pay for it
-    if (full && !acc && !curvilinear) {
-        JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? 1 : 0,
+    if (full && !acc) {
+        JitVariant variant = {dense ? 1 : 0, vec ? 1 : 0, image ? 1 : 0, from_grid ? (curvilinear ? 2 : 1) : 0,
                               jit_minb > 0 ? jit_minb : (use_heavy ? 2 : 3)};
         variant.groups = (image && P.image.group) ? 1 : 0;
         if (image && !P.image.group)
@@ -219,7 +219,7 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
                                   (P.image.moment_imag ? 1 << OPTK_IMAGE_MOMENT_IMAG : 0);
         if (from_grid)
             variant.grid_flags = 0x100 | (P.grid.at_infinity ? 1 << OPTK_GRID_AT_INFINITY : 0) |
-                                 (P.grid.angular_cells[0] ? 1 << OPTK_GRID_PACKED : 0) |
+                                 ((P.grid.angular_cells[0] && !curvilinear) ? 1 << OPTK_GRID_PACKED : 0) |
                                  (P.grid.jitter ? 1 << OPTK_GRID_JITTER : 0) |
                                  (P.grid.has_frame ? 1 << OPTK_GRID_FRAME : 0) |
                                  (P.grid.weight_scene ? 1 << OPTK_GRID_WEIGHT_SCENE : 0) |

@@ -1476,6 +1476,20 @@ static __device__ __noinline__ Vec3 grid_sample_2d(const double* vx, const doubl
 #define OPTK_GRID_FLAG(bit, runtime) (runtime)
 #endif
 
+// Chromatic axes (optk_grid_t::chromatic): the vertices of axis a form one row per WAVELENGTH vertex,
+// [n_0 + 1][n_a + 1] -- field / pupil extents that come from a stop solution per wavelength
+// (optika/systems/_sequential.py:748-789).  The sample is bilinear in (wavelength, a), along the
+// wavelength first.  Out of line, in the curvilinear instantiations only.
+static __device__ __noinline__ double grid_sample_chromatic(const double* v, int iw, int i, int row, double tw, bool jitter,
+                                                            uint32_t bits25) {
+    const double t = jitter ? ((double)bits25 + 0.5) * 2.98023223876953125e-08 : 0.5;
+    const long long o = (long long)iw * row + i;
+    const double v00 = __ldg(v + o), v01 = __ldg(v + o + 1), v10 = __ldg(v + o + row), v11 = __ldg(v + o + row + 1);
+    if (!jitter) return 0.5 * (0.5 * (v00 + v10) + 0.5 * (v01 + v11));
+    const double lo = fma(tw, v10 - v00, v00), hi = fma(tw, v11 - v01, v01);
+    return fma(t, hi - lo, lo);
+}
+
 // SequentialSystem._rayfunction_from_vertices + _calc_rayfunction_input
 // (optika/systems/_sequential.py:1055-1086, 791-828) for the R consecutive rays of a thread.
 // `j0` is the C-order index of the first ray in the sub-box of this launch (< 2^31).
@@ -1532,9 +1546,15 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         const bool packed = !CURVILINEAR && OPTK_GRID_FLAG(OPTK_GRID_PACKED, G.angular_cells[0] != nullptr);
         const bool field_angular = at_infinity;
         double sx, cx, sy, cy;
+        const double tw = jitter ? ((double)(x[0] >> 7) + 0.5) * 2.98023223876953125e-08 : 0.5;
         if (packed && field_angular) {
             cell_sincos(G.angular_cells[0], g[1], jitter, x[1] >> 7, sx, cx);
             cell_sincos(G.angular_cells[1], g[2], jitter, x[2] >> 7, sy, cy);
+        } else if (CURVILINEAR && (G.chromatic & 6)) {
+            fx = (G.chromatic & 2) ? grid_sample_chromatic(G.vertices[1], g[0], g[1], G.n[1] + 1, tw, jitter, x[1] >> 7)
+                                   : grid_sample(G.vertices[1], g[1], jitter, x[1] >> 7);
+            fy = (G.chromatic & 4) ? grid_sample_chromatic(G.vertices[2], g[0], g[2], G.n[2] + 1, tw, jitter, x[2] >> 7)
+                                   : grid_sample(G.vertices[2], g[2], jitter, x[2] >> 7);
         } else if (CURVILINEAR && G.field_2d) {
             const Vec3 f = grid_sample_2d(G.vertices[1], G.vertices[2], g[1], g[2], G.n[2] + 1, jitter, x[1] >> 7, x[2] >> 7);
             fx = f.x;
@@ -1546,6 +1566,11 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         if (packed && !field_angular) {
             cell_sincos(G.angular_cells[0], g[3], jitter, x[3] >> 7, sx, cx);
             cell_sincos(G.angular_cells[1], g[4], jitter, low, sy, cy);
+        } else if (CURVILINEAR && (G.chromatic & 24)) {
+            px = (G.chromatic & 8) ? grid_sample_chromatic(G.vertices[3], g[0], g[3], G.n[3] + 1, tw, jitter, x[3] >> 7)
+                                   : grid_sample(G.vertices[3], g[3], jitter, x[3] >> 7);
+            py = (G.chromatic & 16) ? grid_sample_chromatic(G.vertices[4], g[0], g[4], G.n[4] + 1, tw, jitter, low)
+                                    : grid_sample(G.vertices[4], g[4], jitter, low);
         } else if (CURVILINEAR && G.pupil_2d) {
             const Vec3 p = grid_sample_2d(G.vertices[3], G.vertices[4], g[3], g[4], G.n[4] + 1, jitter, x[3] >> 7, low);
             px = p.x;
@@ -1570,8 +1595,11 @@ __device__ __forceinline__ void generate_rays(const TraceParams& P, uint32_t j0,
         double weight = 1.0;
         if (OPTK_GRID_FLAG(OPTK_GRID_WEIGHT_SCENE, G.weight_scene != nullptr))
             weight = __ldg(G.weight_scene + (g[0] * G.n[1] + g[1]) * (long long)G.n[2] + g[2]);
-        if (OPTK_GRID_FLAG(OPTK_GRID_WEIGHT_PUPIL, G.weight_pupil != nullptr))
-            weight *= __ldg(G.weight_pupil + g[3] * (long long)G.n[4] + g[4]);
+        if (OPTK_GRID_FLAG(OPTK_GRID_WEIGHT_PUPIL, G.weight_pupil != nullptr)) {
+            long long at = g[3] * (long long)G.n[4] + g[4];
+            if (CURVILINEAR && G.weight_pupil_chromatic) at += (long long)g[0] * G.n[3] * G.n[4];
+            weight *= __ldg(G.weight_pupil + at);
+        }
         r[k].intensity = weight;
         r[k].att = 0.0;
         r[k].n = 1.0;

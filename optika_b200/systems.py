@@ -602,12 +602,15 @@ class SequentialSystem(AbstractSequentialSystem):
         return image
 
     # -- forward model: scene -> detector image ------------------------------
-    def _separable(self, value, axis: str, config_shape: dict, cindex: tuple, what: str) -> np.ndarray:
+    def _separable(self, value, axis: str, config_shape: dict, cindex: tuple, what: str,
+                   axis_wavelength: None | str = None) -> np.ndarray:
         """
         The 1-D vertex array of a grid component that varies along `axis` (and possibly the
         configuration axes).  Other axes (e.g. the wavelength axis the stop solution is
         broadcast over, ``_sequential.py:760-789``) are accepted when the values are constant
-        along them to 1e-9 of the extent of the grid.
+        along them to 1e-9 of the extent of the grid.  Vertices that DO depend on the wavelength
+        (chromatic stop solutions: the field of view of a spectrograph) come back as a 2-D array
+        ``[n_wavelength + 1][n + 1]``, one row per wavelength vertex (``optk_grid_t.chromatic``).
         """
         v = na.as_named_array(value)
         if axis not in v.axes:
@@ -618,9 +621,16 @@ class SequentialSystem(AbstractSequentialSystem):
                 shape_[ax] = n
         nd = np.broadcast_to(na.aligned(v, shape_), tuple(shape_.values()))[cindex]
         axes = [ax for ax in shape_ if ax not in config_shape]
+        full = nd
         nd = np.moveaxis(nd, axes.index(axis), -1).reshape(-1, v.shape[axis])
         extent = float(np.ptp(nd)) or 1.0
         if float(np.ptp(nd, axis=0).max()) > 1e-9 * extent:
+            if axis_wavelength is not None and axis_wavelength in axes and axis_wavelength != axis:
+                # constant along everything but the wavelength axis?
+                rows = np.moveaxis(full, [axes.index(axis_wavelength), axes.index(axis)], [-2, -1])
+                rows = rows.reshape((-1,) + rows.shape[-2:])
+                if float(np.ptp(rows, axis=0).max()) <= 1e-9 * extent:
+                    return np.ascontiguousarray(rows.mean(axis=0), dtype=np.float64)
             raise NotImplementedError(
                 f"the {what} vertices vary along axes other than {axis!r}: only separable grids run on the "
                 "device generator; trace explicit rays with `image_rays` instead"
@@ -655,13 +665,15 @@ class SequentialSystem(AbstractSequentialSystem):
             out.append(np.ascontiguousarray(nd.mean(axis=0), dtype=np.float64))
         return tuple(out)
 
-    def _grid_vertices(self, vector, axes: tuple, config_shape: dict, cindex: tuple, convert, what: str):
-        """1-D (separable) vertex arrays of a field / pupil grid when possible, else 2-D (curvilinear) ones."""
+    def _grid_vertices(self, vector, axes: tuple, config_shape: dict, cindex: tuple, convert, what: str,
+                       axis_wavelength: None | str = None):
+        """1-D (separable) vertex arrays of a field / pupil grid when possible -- 2-D per wavelength vertex
+        when they depend on the wavelength -- else 2-D (curvilinear) ones."""
         x, y = na.as_named_array(convert(vector.x)), na.as_named_array(convert(vector.y))
         if axes[1] not in x.axes and axes[0] not in y.axes:
             return (
-                self._separable(x, axes[0], config_shape, cindex, what + " x"),
-                self._separable(y, axes[1], config_shape, cindex, what + " y"),
+                self._separable(x, axes[0], config_shape, cindex, what + " x", axis_wavelength),
+                self._separable(y, axes[1], config_shape, cindex, what + " y", axis_wavelength),
             )
         return self._curvilinear(vector, axes, config_shape, cindex, convert, what)
 
@@ -724,11 +736,23 @@ class SequentialSystem(AbstractSequentialSystem):
             shape_c, index_c = ({}, ()) if shared else (config_shape, cindex)
             vertices = (
                 self._separable(u.length(grid.wavelength), axis_wavelength, shape_c, index_c, "wavelength"),
-                *self._grid_vertices(grid.field, axis_field, shape_c, index_c, conv_field, "field"),
-                *self._grid_vertices(grid.pupil, axis_pupil, shape_c, index_c, conv_pupil, "pupil"),
+                *self._grid_vertices(grid.field, axis_field, shape_c, index_c, conv_field, "field", axis_wavelength),
+                *self._grid_vertices(grid.pupil, axis_pupil, shape_c, index_c, conv_pupil, "pupil", axis_wavelength),
+            )
+            # axes whose vertices depend on the wavelength: separable in their pair (each component varies
+            # along its own axis only), one row per wavelength vertex
+            def separable(vector, pair):
+                return pair[1] not in na.shape(vector.x) and pair[0] not in na.shape(vector.y)
+
+            chromatic = tuple(
+                a for a in (1, 2, 3, 4)
+                if vertices[a].ndim == 2 and separable(grid.field if a < 3 else grid.pupil, axis_field if a < 3 else axis_pupil)
             )
 
             def named(a, b, axes2):
+                if a in chromatic or b in chromatic:
+                    one = lambda c, ax: na.ScalarArray(vertices[c], (axis_wavelength, ax) if c in chromatic else ax)  # noqa: E731
+                    return na.Cartesian2dVectorArray(one(a, axes2[0]), one(b, axes2[1]))
                 if vertices[a].ndim == 2:
                     return na.Cartesian2dVectorArray(na.ScalarArray(vertices[a], axes2), na.ScalarArray(vertices[b], axes2))
                 return na.Cartesian2dVectorArray(
@@ -744,7 +768,10 @@ class SequentialSystem(AbstractSequentialSystem):
                 axis_wavelength, axis_field, axis_pupil,
                 field_is_angular=at_infinity, pupil_is_angular=not at_infinity, factors=True,
             )
-            n_field = [s_ - 1 for s_ in vertices[1].shape] if vertices[1].ndim == 2 else [len(vertices[1]) - 1, len(vertices[2]) - 1]
+            if 1 in chromatic or 2 in chromatic:
+                n_field = [vertices[c].shape[-1] - 1 for c in (1, 2)]
+            else:
+                n_field = [s_ - 1 for s_ in vertices[1].shape] if vertices[1].ndim == 2 else [len(vertices[1]) - 1, len(vertices[2]) - 1]
             n = [len(vertices[0]) - 1] + n_field
             scene_shape = dict(zip(axes[:3], n[:3]))
             rad = na.as_named_array(radiance)
@@ -753,12 +780,17 @@ class SequentialSystem(AbstractSequentialSystem):
                 raise ValueError(f"the radiance has axes {sorted(extra)} that are not scene or configuration axes")
             full = dict(shape_c, **scene_shape)
             rad = np.broadcast_to(na.aligned(rad, full), tuple(full.values()))[index_c]
-            weight_scene = rad * area_w.numpy(axes[:1])[:, None, None] * area_f.numpy(axes[1:3])[None]
+            # (with chromatic vertices the cell areas carry the wavelength axis: one value per wavelength cell)
+            weight_scene = rad * area_w.numpy(axes[:1])[:, None, None] * na.as_named_array(area_f).numpy(axes[:3])
+            weight_pupil = na.as_named_array(area_p).numpy((axes[0],) + tuple(axes[3:]))
+            if weight_pupil.shape[0] == 1:
+                weight_pupil = weight_pupil[0]
             base = RayGrid(
                 vertices=vertices,
+                chromatic=chromatic,
                 at_infinity=at_infinity,
                 weight_scene=weight_scene,
-                weight_pupil=area_p.numpy(axes[3:]),
+                weight_pupil=weight_pupil,
                 jitter=random,
                 seed=seed,
                 frame=self._frame_input(config_shape, cindex),

@@ -82,15 +82,25 @@ def jitter(cell: np.ndarray, seed: int) -> np.ndarray:
     return np.stack([(w.astype(np.float64) + 0.5) * 2.0**-25 for w in words])
 
 
-def _cells(vertices):
-    """Cells per axis of a grid whose field / pupil vertices are 1-D (separable) or 2-D (curvilinear)."""
+def _cells(vertices, chromatic=()):
+    """
+    Cells per axis of a grid whose field / pupil vertices are 1-D (separable), 2-D (curvilinear), or --
+    for the axes listed in `chromatic` -- 2-D ``[n_wavelength + 1][n_a + 1]``: one row of vertices per
+    WAVELENGTH vertex (stop solutions that depend on the wavelength, ``_sequential.py:748-789``).
+    """
     v = [np.asarray(a, dtype=np.float64) for a in vertices]
-    nf = (v[1].shape[0] - 1, v[1].shape[1] - 1) if v[1].ndim == 2 else (len(v[1]) - 1, len(v[2]) - 1)
-    npup = (v[3].shape[0] - 1, v[3].shape[1] - 1) if v[3].ndim == 2 else (len(v[3]) - 1, len(v[4]) - 1)
-    return v, [len(v[0]) - 1, *nf, *npup]
+
+    def cells(a, b):
+        if a in chromatic or b in chromatic:
+            return [(v[c].shape[1] if c in chromatic else len(v[c])) - 1 for c in (a, b)]
+        if v[a].ndim == 2:
+            return [v[a].shape[0] - 1, v[a].shape[1] - 1]
+        return [len(v[a]) - 1, len(v[b]) - 1]
+
+    return v, [len(v[0]) - 1, *cells(1, 2), *cells(3, 4)]
 
 
-def cell_samples(vertices, begin=None, count=None, random: bool = True, seed: int = 0):
+def cell_samples(vertices, begin=None, count=None, random: bool = True, seed: int = 0, chromatic=()):
     """
     One sample per cell of the sub-box ``[begin, begin + count)`` of a 5-axis vertex grid
     (wavelength, field_x, field_y, pupil_x, pupil_y).  Field and pupil vertices are either
@@ -98,7 +108,7 @@ def cell_samples(vertices, begin=None, count=None, random: bool = True, seed: in
     bilinearly: ``cell_centers`` applied along one axis after the other).  Returns 5 arrays
     of the sub-box shape and the whole-grid cell indices.
     """
-    v, n = _cells(vertices)
+    v, n = _cells(vertices, chromatic)
     begin = [0] * 5 if begin is None else list(begin)
     count = [n[a] - begin[a] for a in range(5)] if count is None else list(count)
     idx = np.meshgrid(*[np.arange(begin[a], begin[a] + count[a], dtype=np.int64) for a in range(5)], indexing="ij")
@@ -113,8 +123,18 @@ def cell_samples(vertices, begin=None, count=None, random: bool = True, seed: in
         return lo + ta * (hi - lo) if random else 0.5 * (lo + hi)
 
     out = [lerp(v[0][idx[0]], v[0][idx[0] + 1], t[0])]
+    def sample_1d(a):
+        if a in chromatic:  # bilinear in (wavelength, axis a): along the wavelength first, as the kernel does
+            lo = lerp(v[a][idx[0], idx[a]], v[a][idx[0] + 1, idx[a]], t[0])
+            hi = lerp(v[a][idx[0], idx[a] + 1], v[a][idx[0] + 1, idx[a] + 1], t[0])
+            return lerp(lo, hi, t[a])
+        return lerp(v[a][idx[a]], v[a][idx[a] + 1], t[a])
+
     for a, b in ((1, 2), (3, 4)):
-        if v[a].ndim == 2:
+        if a in chromatic or b in chromatic:
+            out.append(sample_1d(a))
+            out.append(sample_1d(b))
+        elif v[a].ndim == 2:
             for comp in (v[a], v[b]):
                 lo = lerp(comp[idx[a], idx[b]], comp[idx[a] + 1, idx[b]], t[a])
                 hi = lerp(comp[idx[a], idx[b] + 1], comp[idx[a] + 1, idx[b] + 1], t[a])
@@ -140,13 +160,14 @@ def input_rays(
     random: bool = True,
     seed: int = 0,
     frame=None,
+    chromatic=(),
 ):
     """
     Flat ray state (dict of 1-D arrays, C order over the sub-box) in the layout of
     ``oracle.raytrace`` (``_sequential.py:791-828, 1078-1086``).  ``frame = (R[3, 3], t[3])``
     maps the object-local rays to the coordinates of the first surface.
     """
-    (w, fx, fy, px, py), idx = cell_samples(vertices, begin, count, random, seed)
+    (w, fx, fy, px, py), idx = cell_samples(vertices, begin, count, random, seed, chromatic)
     if at_infinity:
         x, y, (dx, dy, dz) = px, py, direction(fx, fy)
     else:
@@ -156,7 +177,8 @@ def input_rays(
     if weight_scene is not None:
         intensity = intensity * np.asarray(weight_scene, dtype=np.float64)[idx[0], idx[1], idx[2]]
     if weight_pupil is not None:
-        intensity = intensity * np.asarray(weight_pupil, dtype=np.float64)[idx[3], idx[4]]
+        wp = np.asarray(weight_pupil, dtype=np.float64)
+        intensity = intensity * (wp[idx[0], idx[3], idx[4]] if wp.ndim == 3 else wp[idx[3], idx[4]])
     if frame is not None:
         r, t = np.asarray(frame[0], dtype=np.float64), np.asarray(frame[1], dtype=np.float64)
         x, y, z = (r[i, 0] * x + r[i, 1] * y + r[i, 2] * z + t[i] for i in range(3))

@@ -347,3 +347,86 @@ def test_image_with_a_polar_pupil_grid(cuda_device, newtonian):
     got = image.outputs.ndarray
     assert want.sum() > 0 and np.isclose(got.sum(), want.sum(), rtol=1e-9)
     assert (~np.isclose(got, want, rtol=1e-9, atol=1e-9 * want.max())).sum() <= 8
+
+
+# ---------------------------------------------------------------------------
+# chromatic grids: field / pupil vertices that depend on the wavelength (optk_grid_t.chromatic)
+# ---------------------------------------------------------------------------
+def chromatic_vertices(n=(3, 4, 5, 6, 7), axes=(1, 4)):
+    v = vertices(n)
+    stretch = np.linspace(1.0, 1.3, n[0] + 1)
+    for a in axes:
+        v[a] = stretch[:, None] * v[a][None, :] + (0.02 * stretch[:, None] if a > 2 else 0.0)
+    return v
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("axes", [(1,), (1, 2), (3, 4), (1, 4), (1, 2, 3, 4)])
+def test_chromatic_generated_rays_match_oracle(cuda_device, newtonian, jitter, axes):
+    v = chromatic_vertices(axes=axes)
+    rng = np.random.default_rng(0)
+    n = (3, 4, 5, 6, 7)
+    ws = rng.uniform(0.5, 2, n[:3])
+    wp = rng.uniform(0.5, 2, (n[0],) + n[3:]) if set(axes) & {3, 4} else rng.uniform(0.5, 2, n[3:])
+    grid = _grid.RayGrid(v, chromatic=axes, weight_scene=ws, weight_pupil=wp, jitter=jitter, seed=77)
+    assert grid.n == n
+    got = _grid.trace_grid(newtonian._compiled_local, grid, surf_count=0)
+    want = og.input_rays(v, True, ws, wp, random=jitter, seed=77, chromatic=axes)
+    parity.compare_states(device_dict(got), want)
+    # a sub-box and small launches see the same stream
+    sub = grid.sub((1, 0, 2, 3, 0), (2, 4, 2, 2, 7))
+    part = device_dict(_grid.trace_grid(newtonian._compiled_local, sub, surf_count=0, max_launch=50))
+    full = device_dict(got)["dx"].reshape(n)[1:3, :, 2:4, 3:5, :].reshape(-1)
+    assert np.array_equal(part["dx"], full)
+
+
+def test_chromatic_fused_image_matches_oracle_and_the_specialised_kernel(cuda_device, newtonian):
+    from optika_b200 import _lib
+
+    v = chromatic_vertices((2, 6, 6, 32, 32), axes=(1, 2))
+    grid = _grid.RayGrid(v, chromatic=(1, 2), seed=17)
+    ex, ey = newtonian.sensor.pixel_edges()
+    ew = np.array([499e-6, 500e-6, 501e-6])
+    compiled = newtonian._compiled_local
+    rays0 = og.input_rays(v, seed=17, chromatic=(1, 2))
+    want = ora.propagate_rays(newtonian.surfaces_all, rays0, extended=True)
+    local = ora._rays_transform(newtonian.sensor.transformation, want, inverse=True)
+    want_counts = orb.counts(local, ew, ex, ey)
+    images = []
+    for mode in (0, 1):  # table-driven kernels, then a kernel compiled for this walk and this kind of grid
+        _lib.check(_lib.lib().optk_jit_mode(mode))
+        try:
+            image = _engine.DeviceImage.zeros(ew, ex, ey, cuda_device, moments=True, counts=True)
+            _grid.trace_grid(compiled, grid, image=image, write_rays=False)
+            images.append(image.counts.cpu().numpy())
+        finally:
+            _lib.check(_lib.lib().optk_jit_mode(-1))
+    assert images[0].sum() == want_counts.sum() > 0.3 * grid.size
+    assert (images[0] != want_counts).sum() <= 4
+    assert np.array_equal(images[0], images[1])
+
+
+def test_image_with_a_chromatic_stop_solution(cuda_device):
+    """
+    ``image(..., normalized_field=True)`` of a spectrograph: the field of view comes from a stop solution
+    per WAVELENGTH (``_sequential.py:748-789``), so the denormalised field vertices depend on the wavelength.
+    The image must equal the oracle's on the rays of the very grid ``ray_grids`` builds.
+    """
+    system = configs.spherical_grating(num_field=4, num_pupil=8, num_wavelength=3, num_pixel=128)
+    wavelength = na.linspace(38 * u.nm, 42 * u.nm, axis="wavelength", num=4)
+    field = na.Cartesian2dVectorLinearSpace(-0.6, 0.6, axis=na.Cartesian2dVectorArray("field_x", "field_y"), num=7)
+    pupil = na.Cartesian2dVectorLinearSpace(-0.9, 0.9, axis=na.Cartesian2dVectorArray("pupil_x", "pupil_y"), num=17)
+    axes = ("wavelength", ("field_x", "field_y"), ("pupil_x", "pupil_y"))
+    (grid,) = system.ray_grids(1.0, wavelength, field, pupil, *axes, normalized_field=True, normalized_pupil=True, seed=4)
+    assert grid.chromatic and set(grid.chromatic) <= {1, 2, 3, 4}  # the sensor is the field stop: its image moves with wavelength
+    w_edges = np.array([38 * u.nm, 42 * u.nm])
+    planes = system.collect_grids([grid], w_edges, device=cuda_device, counts=True)
+    rays0 = og.input_rays(grid.vertices, True, grid.weight_scene, grid.weight_pupil, seed=4, chromatic=grid.chromatic)
+    want = ora.propagate_rays(system.surfaces_all, rays0, extended=True)
+    local = ora._rays_transform(system.sensor.transformation, want, inverse=True)
+    ex, ey = system.sensor.pixel_edges()
+    want_counts = orb.counts(local, w_edges, ex, ey)
+    assert planes["counts"].sum() == want_counts.sum() > 0.5 * grid.size
+    assert (planes["counts"].reshape(want_counts.shape) != want_counts).sum() <= 4
+    want_flux, _, _ = orb.collect(local, w_edges, ex, ey)
+    assert np.isclose(planes["flux"].sum(), want_flux.sum(), rtol=1e-9)

@@ -169,8 +169,42 @@ def test_ray_grids_carry_radiance_times_area():
     aw, af, ap = og.cell_area(g.vertices, True, False)
     assert np.allclose(g.weight_scene, radiance.ndarray * aw[:, None, None] * af[None], rtol=1e-12)
     assert np.allclose(g.weight_pupil, ap, rtol=1e-12)
+    # field vertices that depend on the wavelength (a chromatic stop solution): one row per wavelength vertex
+    scale = na.linspace(1, 2, "wavelength", 3)
+    chromatic_field = na.Cartesian2dVectorArray(field.x * scale, field.y)
+    (gc,) = system.ray_grids(
+        radiance, w, chromatic_field, pupil, "wavelength", ("field_x", "field_y"), ("pupil_x", "pupil_y"), False, False
+    )
+    assert gc.chromatic == (1,) and gc.n == g.n and gc.vertices[1].shape == (3, 5) and gc.vertices[2].ndim == 1
+    assert np.allclose(gc.vertices[1], scale.ndarray[:, None] * g.vertices[1][None, :], rtol=1e-15)
+    assert gc.angular_cells() == [None, None] and gc.struct is not None
+    # cell areas: the solid angle of every (wavelength vertex, field cell), averaged over the two vertices of the cell
+    per_vertex = np.stack([og.cell_area([g.vertices[0], row, g.vertices[2], g.vertices[3], g.vertices[4]], True, False)[1]
+                           for row in gc.vertices[1]])
+    area_f = 0.5 * (per_vertex[1:] + per_vertex[:-1])
+    assert np.allclose(gc.weight_scene, radiance.ndarray * aw[:, None, None] * area_f, rtol=1e-12)
+    assert np.allclose(gc.weight_pupil, ap, rtol=1e-12)
+    # vertices that vary along anything else are still refused
     with pytest.raises(NotImplementedError):
-        bad = na.Cartesian2dVectorArray(field.x * na.linspace(1, 2, "wavelength", 3), field.y)
+        bad = na.Cartesian2dVectorArray(field.x * na.linspace(1, 2, "other", 3), field.y)
         system.ray_grids(
             radiance, w, bad, pupil, "wavelength", ("field_x", "field_y"), ("pupil_x", "pupil_y"), False, False
         )
+
+
+def test_chromatic_cell_samples_are_bilinear_in_wavelength_and_axis():
+    w = np.array([1.0, 2.0, 4.0])
+    fx = np.array([[0.0, 1.0, 2.0], [0.0, 2.0, 4.0], [0.0, 4.0, 8.0]])  # [wavelength vertex][field_x vertex]
+    other = np.array([0.0, 1.0])
+    vertices = [w, fx, other, other, other]
+    (sw, sfx, sfy, spx, spy), idx = og.cell_samples(vertices, random=False, chromatic=(1,))
+    assert sfx.shape == (2, 2, 1, 1, 1)
+    # cell centres: the mean of the four corners
+    assert np.allclose(sfx[:, :, 0, 0, 0], [[0.75, 2.25], [1.5, 4.5]])
+    (sw, sfx, *_), idx = og.cell_samples(vertices, random=True, seed=3, chromatic=(1,))
+    t = og.jitter(((idx[0] * 2 + idx[1]) * 1 + 0).astype(np.uint64), 3)
+    lo = fx[idx[0], idx[1]] + t[0] * (fx[idx[0] + 1, idx[1]] - fx[idx[0], idx[1]])
+    hi = fx[idx[0], idx[1] + 1] + t[0] * (fx[idx[0] + 1, idx[1] + 1] - fx[idx[0], idx[1] + 1])
+    assert np.allclose(sfx, lo + t[1] * (hi - lo), rtol=1e-15)
+    rays = og.input_rays(vertices, weight_pupil=np.arange(2.0).reshape(2, 1, 1) + 1, chromatic=(1,), seed=3)
+    assert np.allclose(rays["intensity"].reshape(2, 2), [[1, 1], [2, 2]])
