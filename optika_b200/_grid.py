@@ -36,8 +36,6 @@ class RayGrid:
     """
 
     vertices: tuple
-    chromatic: tuple = ()
-    """Axes (1 .. 4) whose vertex array is 2-D ``[n_wavelength + 1][n + 1]``: one row per wavelength vertex."""
     at_infinity: bool = True
     weight_scene: np.ndarray | None = None
     weight_pupil: np.ndarray | None = None
@@ -47,6 +45,8 @@ class RayGrid:
     axes: tuple = AXES
     begin: tuple | None = None
     count: tuple | None = None
+    chromatic: tuple = ()
+    """Axes (1 .. 4) whose vertex array is 2-D ``[n_wavelength + 1][n + 1]``: one row per wavelength vertex."""
 
     def __post_init__(self):
         self.vertices = tuple(np.ascontiguousarray(v, dtype=np.float64) for v in self.vertices)
@@ -398,7 +398,7 @@ def _tabled_for_grid(system, grid: RayGrid, device):
 
         pilot = RayGrid(
             vertices=tuple(pick(v) for v in grid.vertices), at_infinity=grid.at_infinity, jitter=grid.jitter,
-            seed=grid.seed, frame=grid.frame, axes=grid.axes,
+            seed=grid.seed, frame=grid.frame, axes=grid.axes, chromatic=grid.chromatic,
         )
         log = {}
         for c in range(system.n_config):
