@@ -60,6 +60,7 @@ def test_struct_layout_matches_c(tmp_path, lib):
         "optk_ml_segment_t": _lib.MlSegment,
         "optk_ml_input_t": _lib.MlInput,
         "optk_stop_problem_t": _lib.StopProblem,
+        "optk_ccd_plane_t": _lib.CcdPlane,
     }
     probes = [
         ("optk_surface_t", "transform"), ("optk_surface_t", "sag"), ("optk_surface_t", "ruling_power"),
@@ -71,6 +72,9 @@ def test_struct_layout_matches_c(tmp_path, lib):
         ("optk_ml_input_t", "direction_stride"), ("optk_ml_input_t", "n_stride"),
         ("optk_image_t", "group_size"), ("optk_stop_problem_t", "max_iterations"), ("optk_stop_problem_t", "step"),
         ("optk_stop_problem_t", "max_abs_error"),
+        ("optk_image_t", "uniform_edges"), ("optk_grid_t", "angular_cells"), ("optk_grid_t", "chromatic"),
+        ("optk_grid_t", "weight_pupil_chromatic"), ("optk_ccd_plane_t", "fano_inf"), ("optk_ccd_plane_t", "n_pmf"),
+        ("optk_ccd_plane_t", "cmf"), ("optk_ccd_plane_t", "n_values"),
     ]
     src = ["#include <stdio.h>", "#include <stddef.h>", '#include "optk.h"', "int main(void) {"]
     for name in structs:
@@ -195,3 +199,31 @@ def test_no_cpu_fallback():
     code = "import sys, optika_b200, optika_b200.systems, optika_b200.sensors; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT)).stdout.strip()
     assert out == "False"
+
+
+def test_round_two_entry_points_validate_their_arguments_without_a_gpu(lib):
+    """Efficiency tables, the electron kernel and the host-memory helpers check their arguments before any CUDA call."""
+    from optika_b200 import _lib
+
+    table = (_lib.Surface * 1)()
+    table[0].sag_kind = _lib.SAG_FLAT
+    table[0].stages = _lib.STAGE_ALL
+    table[0].material_kind = _lib.MAT_MIRROR
+    table[0].material_efficiency = _lib.EFF_TABLE2D  # no table pointers, no node counts
+    handle = C.c_void_p()
+    with pytest.raises(ValueError, match="2-D efficiency table"):
+        _lib.check(lib.optk_system_create(table, 1, 1, C.byref(handle)))
+    table[0].material_kind = _lib.MAT_GLASS  # a table needs a mirror or a pass-through material
+    with pytest.raises(ValueError, match="mirror or pass-through"):
+        _lib.check(lib.optk_system_create(table, 1, 1, C.byref(handle)))
+    table[0].material_efficiency = 7
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.optk_system_create(table, 1, 1, C.byref(handle)))
+    with pytest.raises(ValueError):
+        _lib.check(lib.optk_electrons_measured(1, 2, 2, None, None, None, 0, 0, None))
+    with pytest.raises(ValueError):
+        _lib.check(lib.optk_host_register(None, 16))
+    with pytest.raises(ValueError):
+        _lib.check(lib.optk_host_unregister(None))
+    with pytest.raises(ValueError):
+        _lib.check(lib.optk_memcpy_async(None, None, 8, None))

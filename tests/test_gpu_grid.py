@@ -373,9 +373,9 @@ def test_chromatic_generated_rays_match_oracle(cuda_device, newtonian, jitter, a
     got = _grid.trace_grid(newtonian._compiled_local, grid, surf_count=0)
     want = og.input_rays(v, True, ws, wp, random=jitter, seed=77, chromatic=axes)
     parity.compare_states(device_dict(got), want)
-    # a sub-box and small launches see the same stream
+    # a sub-box sees the same stream
     sub = grid.sub((1, 0, 2, 3, 0), (2, 4, 2, 2, 7))
-    part = device_dict(_grid.trace_grid(newtonian._compiled_local, sub, surf_count=0, max_launch=50))
+    part = device_dict(_grid.trace_grid(newtonian._compiled_local, sub, surf_count=0))
     full = device_dict(got)["dx"].reshape(n)[1:3, :, 2:4, 3:5, :].reshape(-1)
     assert np.array_equal(part["dx"], full)
 
