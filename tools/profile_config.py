@@ -26,6 +26,7 @@ def main():
         "cfg1": lambda: configs.newtonian(100, 100, 128),
         "cfg2": lambda: configs.spherical_grating(100, 100, 1, 2048),
         "cfg3": lambda: configs.toroidal_vls(100, 100, 1),
+        "cfg5": lambda: configs.telescope_4k(num_tilt=1, num_pixel=4096),  # the round-2 full-detector telescope, one tilt
     }[name]()
     device = torch.device("cuda", 0)
     _, rays = system._input(None, None, None, None, False, False)
@@ -44,6 +45,8 @@ def main():
             "cfg1": [lin(499 * u.nm, 501 * u.nm, 1), lin(-0.1 * deg, 0.1 * deg, 100), lin(-0.1 * deg, 0.1 * deg, 100), lin(-40, 40, 100), lin(-40, 40, 100)],
             "cfg2": [lin(17 * u.nm, 63 * u.nm, 1), lin(-0.05 * deg, 0.05 * deg, 100), lin(-0.05 * deg, 0.05 * deg, 100), lin(-45, 45, 100), lin(-45, 45, 100)],
             "cfg3": [lin(25 * u.nm, 35 * u.nm, 1), lin(-0.2 * deg, 0.2 * deg, 100), lin(-0.2 * deg, 0.2 * deg, 100), lin(-22, 22, 100), lin(-22, 22, 100)],
+            # a quarter of the detector: 1118 x 1118 field cells (one per pixel) x 10 x 8 pupil cells = 1e8 rays
+            "cfg5": [lin(499 * u.nm, 501 * u.nm, 1), lin(-0.0048, 0.0, 1118), lin(-0.0048, 0.0, 1118), lin(-160, 160, 10), lin(-160, 160, 8)],
         }[name]
         compiled = system._compiled_local
         ex, ey = system.sensor.pixel_edges()
