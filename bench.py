@@ -780,7 +780,7 @@ def run_b200(args):
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 2))
+        e2e_steps = max(1, args.steps)
         for _ in range(e2e_steps):
             e2e_step()
         barrier()

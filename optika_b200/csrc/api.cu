@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "bin.cuh"
 #include "params.cuh"
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in Nsight when a tool is attached, cost nothing otherwise
 
 #include <cmath>
 #include <cstdarg>
@@ -48,6 +49,13 @@ struct optk_system {
 struct DeviceScope {
     int previous = -1;
     bool switched = false;
+    bool ranged = false;
+    // an NVTX range per entry point (the C-ABI boundary is where a profile of the reference's Python would
+    // want its markers: SURVEY.md section 5, tracing / profiling)
+    DeviceScope(void* stream, const char* name) : DeviceScope(stream) {
+        nvtxRangePushA(name);
+        ranged = true;
+    }
     explicit DeviceScope(void* stream) {
         int wanted = -1;
         if (!stream) return;
@@ -58,6 +66,7 @@ struct DeviceScope {
         if (wanted != previous && cudaSetDevice(wanted) == cudaSuccess) switched = true;
     }
     ~DeviceScope() {
+        if (ranged) nvtxRangePop();
         if (switched) cudaSetDevice(previous);
     }
     DeviceScope(const DeviceScope&) = delete;
@@ -444,7 +453,7 @@ OPTK_API int optk_trace(const optk_system_t* sys, int32_t config, const optk_ray
                int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
                int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
                optk_trace_stats_t* stats_device, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_trace");
     static thread_local TraceParams P;
     long long n = 0;
     int rc = grid_size(in, &n);
@@ -483,7 +492,7 @@ OPTK_API int optk_trace_grid(const optk_system_t* sys, int32_t config, const opt
                     int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
                     int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,
                     optk_trace_stats_t* stats_device, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_trace_grid");
     static thread_local TraceParams P;
     if (!grid) {
         set_error("optk_trace_grid: grid is NULL");
@@ -550,7 +559,7 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
                      const double* wavelength, const double* fixed_x, const double* fixed_y, const double* fixed_z,
                      const double* target_x, const double* target_y, double* x, double* y, double* z,
                      uint32_t* n_unconverged, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_solve_stops");
     static thread_local TraceParams P;
     if (!problem || n < 0) {
         set_error("optk_solve_stops: problem is NULL or n is negative");
@@ -615,7 +624,7 @@ OPTK_API int optk_solve_stops(const optk_system_t* sys, int32_t config, const op
 OPTK_API int optk_reduce_groups(int64_t n_groups, int64_t n_inner, const double* x, const double* y,
                        const double* intensity, const uint8_t* unvignetted, double* sum_intensity, double* sum_x,
                        double* sum_y, uint64_t* count, double* sum_x_all, double* sum_y_all, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_reduce_groups");
     if (n_groups < 0 || n_inner < 1 || n_groups > 0x7fffffffLL || n_inner > 0x7fffffffLL ||
         n_groups * n_inner > 0x7fffffffLL) {
         set_error("optk_reduce_groups: n_groups >= 0, n_inner >= 1 and n_groups * n_inner <= 2^31 - 1 are required");
@@ -638,7 +647,7 @@ OPTK_API int64_t optk_jit_compiled(void) { return jit_compiled_count(); }
 
 OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp, const double* fp_re, const double* fp_im,
                 double* out_re, double* out_im, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_interp");
     if (n < 0 || m < 1 || !x || !xp || !fp_re || !out_re || (fp_im && !out_im)) {
         set_error("optk_interp: bad arguments");
         return OPTK_ERR_INVALID;
@@ -647,7 +656,7 @@ OPTK_API int optk_interp(int64_t n, const double* x, int32_t m, const double* xp
 }
 
 OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e_s, const double* e_p, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_apply_efficiency");
     if (n < 0 || !intensity || !e_s || !e_p) {
         set_error("optk_apply_efficiency: bad arguments");
         return OPTK_ERR_INVALID;
@@ -657,7 +666,7 @@ OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e
 
 OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
              const double* intensity, const uint8_t* unvignetted, const optk_image_t* image, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_bin");
     if (!wavelength || !x || !y || !image) {
         set_error("optk_bin: NULL argument");
         return OPTK_ERR_INVALID;
@@ -895,7 +904,7 @@ OPTK_API int optk_trace_host(const optk_system_t* sys, int32_t config, const opt
 OPTK_API int optk_multilayer(const optk_ml_input_t* input, int32_t n_layers, const optk_ml_layer_t* layers,
                     int32_t n_segments, const optk_ml_segment_t* segments, double* reflectivity_s,
                     double* reflectivity_p, double* transmissivity_s, double* transmissivity_p, void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_multilayer");
     if (!input || !layers || n_layers < 1 || n_layers > OPTK_ML_MAX_LAYERS) {
         set_error("optk_multilayer: need 1..%d layers (the last one is the substrate)", OPTK_ML_MAX_LAYERS);
         return OPTK_ERR_INVALID;
@@ -1025,7 +1034,7 @@ OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, vo
 OPTK_API int optk_electrons_measured(int32_t n_plane, int32_t n_x, int32_t n_y, const optk_ccd_plane_t* planes,
                                      const int64_t* photons, uint64_t* electrons, int32_t wrap, uint64_t seed,
                                      void* stream) {
-    DeviceScope device_scope(stream);
+    DeviceScope device_scope(stream, "optk_electrons_measured");
     if (n_plane < 0 || n_x < 0 || n_y < 0 || (!planes && n_plane) || !photons || !electrons) {
         set_error("optk_electrons_measured: bad arguments");
         return OPTK_ERR_INVALID;

@@ -252,9 +252,9 @@ void* jit_kernel(const TraceParams& P, const JitVariant& v) {
     if (g_mode == 0) return nullptr;
     // automatic: compile (~1.5 s) only for launches long enough that a production run of them
     // pays for it; a kernel that is already in the disk cache costs a file read and is taken for
-    // mid-sized launches too
+    // launches from 2^17 rays on
     const bool may_compile = g_mode == 1 || P.n_rays >= (1LL << 25) || v.groups;  // group launches have no other kernel
-    if (!may_compile && P.n_rays < (1LL << 20)) return nullptr;
+    if (!may_compile && P.n_rays < (1LL << 17)) return nullptr;  // below ~1e5 rays the launch is latency either way
     std::string key;
     const std::string src = jit_source(P, v, &key);
     // a CUfunction belongs to the context of ONE device: the in-process cache is per device ordinal
