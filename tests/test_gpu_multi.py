@@ -22,8 +22,9 @@ def _free_port() -> int:
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_reduced_image_equals_single_gpu_image(world):
+@pytest.mark.parametrize("world,transport", [(2, "nccl"), (4, "nccl"), (8, "nccl"), (2, "peer")])
+def test_sharded_reduced_image_equals_single_gpu_image(world, transport):
+    import os
     import torch
 
     if torch.cuda.device_count() < world:
@@ -33,7 +34,9 @@ def test_sharded_reduced_image_equals_single_gpu_image(world):
         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
         str(ROOT / "tests" / "workers" / "multi_gpu_image.py"),
     ]
-    done = subprocess.run(command, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    # "nccl": reduce_scatter on a high-priority group (the default); "peer": CUDA IPC + copy engines + interprocess events
+    env = dict(os.environ, OPTK_REDUCE_TRANSPORT=transport)
+    done = subprocess.run(command, capture_output=True, text=True, timeout=900, cwd=str(ROOT), env=env)
     assert done.returncode == 0, done.stdout[-3000:] + done.stderr[-3000:]
     line = [ln for ln in done.stdout.splitlines() if ln.startswith("RESULT ")][-1]
     report = json.loads(line[len("RESULT "):])
