@@ -149,7 +149,11 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
         return e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }();
     // (with calls in the walk the extra registers do not pay: cfg 3 fused 9.8 -> 11.1 ms)
-    const bool use_heavy = full && from_grid && image && (heavy_mode == 1 || (heavy_mode < 0 && heavy && !out_of_line));
+    // Round 2: after the diet of the binning and generator code the 24-warp build wins for long
+    // surface lists too (cfg 5, 1.07e10 rays: 365 ms against 379 with 16 warps and 110 registers), so the 16-warp
+    // build is only taken on request (OPTK_TRACE_HEAVY=1).
+    (void)out_of_line;
+    const bool use_heavy = full && from_grid && image && heavy_mode == 1;
     if (curvilinear)
         kernel = select_grid_kernel(full, acc, image, true);
     else if (full && efficiency)
