@@ -132,6 +132,13 @@ typedef enum optk_aperture_kind {
 #define OPTK_F_HOLO_DIVERGING_1 0x080
 #define OPTK_F_HOLO_DIVERGING_2 0x100
 #define OPTK_F_TRANSLATION_ONLY 0x400 /* set by the library: `transform` has R == identity */
+/* Set by the library per launch (never by callers): the rays arrive in the LOCAL frame of the previous surface
+ * of the walk and `sag_transform` (unused by the full operator) holds the relative map previous-local ->
+ * this-local, applied forwards; _TRANSLATION: its rotation is the identity; _IDENTITY: both surfaces share
+ * one frame, nothing to apply. */
+#define OPTK_F_RELATIVE_IN 0x800
+#define OPTK_F_RELATIVE_TRANSLATION 0x1000
+#define OPTK_F_RELATIVE_IDENTITY 0x2000
 #define OPTK_F_LOCAL_OUT 0x200 /* skip the final local -> global step: the rays leave the
                                   surface in its LOCAL frame (sensor.transformation.inverse,
                                   optika/systems/_sequential.py:983-986)                    */

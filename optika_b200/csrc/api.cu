@@ -338,6 +338,7 @@ int pack_trace(const optk_system_t* sys, int32_t config, int32_t surf_begin, int
     }
     P->n_surf = surf_count;
     P->accumulate = accumulate ? 1 : 0;
+    P->relative_done = 0;  // fresh copies of the surfaces: launch_trace may compose their frames again
     return OPTK_OK;
 }
 

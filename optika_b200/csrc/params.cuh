@@ -43,6 +43,8 @@ struct TraceParams {
     // dims = grid.count (the sub-box), addressed in two levels like a broadcast view
     int32_t from_grid;
     int32_t has_out;  // any output pointer is set (fused image calls usually write no rays)
+    int32_t relative_done;  // launch_trace has composed the frames of consecutive surfaces (once per parameter block)
+    int32_t pad_relative;
     FastDiv div_tiles;  // divisor tiles_per_outer
     optk_grid_t grid;
     unsigned long long cell_stride[5];  // C-order strides of the whole grid n[] (Philox counter)

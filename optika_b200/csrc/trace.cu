@@ -23,6 +23,54 @@ trace_kernel_t select_generic_kernel(bool dense, bool acc, bool image) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------
+// relative frames: one affine per transition of the walk instead of "local -> global" after a surface and
+// "global -> local" before the next (AbstractSurface.propagate_rays, optika/surfaces.py:141-142, 195-196,
+// composed on the host in double precision; results differ from the two-step form by rounding, 1e-16)
+// ---------------------------------------------------------------------------
+static void relative_frames(TraceParams& Q) {
+    auto frame_of = [](const optk_surface_t& S, double (&r)[9], double (&t)[3]) {
+        static const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        const bool has = (S.flags & OPTK_F_TRANSFORM) != 0;
+        for (int i = 0; i < 9; ++i) r[i] = has ? S.transform.r[i] : eye[i];
+        for (int i = 0; i < 3; ++i) t[i] = has ? S.transform.t[i] : 0.0;
+    };
+    for (int k = 1; k < Q.n_surf; ++k) {
+        optk_surface_t& A = Q.surf[k - 1];
+        optk_surface_t& B = Q.surf[k];
+        if (A.flags & OPTK_F_LOCAL_OUT) continue;  // the caller wants A's rays local: leave the pair alone
+        if (!((A.flags | B.flags) & OPTK_F_TRANSFORM)) continue;  // both in the global frame already
+        double ra[9], ta[3], rb[9], tb[3];
+        frame_of(A, ra, ta);
+        frame_of(B, rb, tb);
+        // x_B = R_B^T (R_A x_A + t_A - t_B)
+        bool same = true;
+        for (int i = 0; i < 9; ++i) same = same && ra[i] == rb[i];
+        bool same_t = true;
+        for (int i = 0; i < 3; ++i) same_t = same_t && ta[i] == tb[i];
+        optk_affine_t rel;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) {
+                double v = 0.0;
+                for (int m = 0; m < 3; ++m) v += rb[3 * m + i] * ra[3 * m + j];
+                rel.r[3 * i + j] = same ? (i == j ? 1.0 : 0.0) : v;
+            }
+            double v = 0.0;
+            for (int m = 0; m < 3; ++m) v += rb[3 * m + i] * (ta[m] - tb[m]);
+            rel.t[i] = v;
+        }
+        A.flags |= OPTK_F_LOCAL_OUT;
+        B.flags |= OPTK_F_RELATIVE_IN;
+        if (same && same_t) B.flags |= OPTK_F_RELATIVE_IDENTITY;
+        else if (same) {
+            bool identity = true;  // a shared rotation other than the identity still rotates the offset: general case
+            for (int i = 0; i < 9; ++i) identity = identity && rb[i] == (i % 4 == 0 ? 1.0 : 0.0);
+            if (identity) B.flags |= OPTK_F_RELATIVE_TRANSLATION;
+        }
+        B.sag_transform = rel;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------
 int launch_trace(const TraceParams& P, cudaStream_t stream) {
@@ -49,6 +97,15 @@ int launch_trace(const TraceParams& P, cudaStream_t stream) {
     const int rays_per_thread = full ? 2 : 1;
     const int block = 256;
     TraceParams& Q = const_cast<TraceParams&>(P);
+    static const int relative_mode = [] {
+        const char* e = getenv("OPTK_TRACE_RELATIVE");
+        return e ? atoi(e) : 1;
+    }();
+    // (idempotent: a surface that already arrives relative is skipped, e.g. the tail launch of the pipeline split)
+    if (full && !acc && relative_mode && P.n_surf > 1 && !(P.surf[1].flags & OPTK_F_RELATIVE_IN) && !P.relative_done) {
+        relative_frames(Q);
+        Q.relative_done = 1;
+    }
     // HBM-streaming case (dense in, dense out, nothing else): the persistent bulk-copy pipeline
     // takes the full 512-ray tiles, the ordinary kernel the remainder
     // The pipeline runs 16 warps per SM (114 registers, no spills), the direct-load kernel 24:

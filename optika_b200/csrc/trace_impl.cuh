@@ -562,8 +562,27 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                                              bool& attenuating) {
     const int flags = K::flags(S);
 
-    // 1. global -> surface-local (surfaces.py:141-142)
-    if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
+    // 1. global -> surface-local (surfaces.py:141-142).  Inside a walk the rays come straight from the local
+    // frame of the previous surface (launch_trace composes "previous local -> global -> this local" into one
+    // map per transition: half the affine arithmetic of a system whose surfaces each have a frame).
+    if (flags & OPTK_F_RELATIVE_IN) {
+        if (flags & OPTK_F_RELATIVE_IDENTITY) {
+            // consecutive surfaces in one frame (an obscuration in front of the mirror that casts it)
+        } else if (flags & OPTK_F_RELATIVE_TRANSLATION) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                r[k].px += S.sag_transform.t[0];
+                r[k].py += S.sag_transform.t[1];
+                r[k].pz += S.sag_transform.t[2];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                affine_forward(S.sag_transform, r[k].px, r[k].py, r[k].pz, false);
+                affine_forward(S.sag_transform, r[k].dx, r[k].dy, r[k].dz, true);
+            }
+        }
+    } else if (flags & OPTK_F_TRANSLATION_ONLY) {  // R == identity: R^T (p - t) = p - t exactly
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             r[k].px -= S.transform.t[0];
