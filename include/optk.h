@@ -132,6 +132,12 @@ typedef enum optk_aperture_kind {
 #define OPTK_F_HOLO_DIVERGING_1 0x080
 #define OPTK_F_HOLO_DIVERGING_2 0x100
 #define OPTK_F_TRANSLATION_ONLY 0x400 /* set by the library: `transform` has R == identity */
+/* Set by the library (optk_system_create): the polygon's vertices are in strictly convex position, listed
+ * counter-clockwise (_CONVEX) or clockwise (_CONVEX | _CLOCKWISE).  aperture[0] then holds B = max |vertex
+ * coordinate| and aperture[1] the width 1e-12 B^2 of the band around the edge lines inside which the kernels
+ * decide with the exact even-odd arithmetic; everywhere else eight half-plane tests give the same answer. */
+#define OPTK_F_APERTURE_CONVEX 0x4000
+#define OPTK_F_APERTURE_CLOCKWISE 0x8000
 /* Set by the library per launch (never by callers): the rays arrive in the LOCAL frame of the previous surface
  * of the walk and `sag_transform` (unused by the full operator) holds the relative map previous-local ->
  * this-local, applied forwards; _TRANSLATION: its rotation is the identity; _IDENTITY: both surfaces share

@@ -342,6 +342,36 @@ int pack_trace(const optk_system_t* sys, int32_t config, int32_t surf_begin, int
     return OPTK_OK;
 }
 
+// A polygon whose vertices are in strictly convex position (every vertex clearly on the inner side of every
+// edge it does not belong to, which also rules out star polygons, repeated and collinear vertices) is the
+// intersection of its edges' half-planes: see OPTK_F_APERTURE_CONVEX in optk.h and aperture_test.
+void classify_polygon(optk_surface_t& s) {
+    const int n = s.n_vertices;
+    if (n < 3 || n > OPTK_MAX_VERTICES) return;
+    double bound = 0.0, area2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1) % n;
+        if (!std::isfinite(s.vertices_x[i]) || !std::isfinite(s.vertices_y[i])) return;
+        bound = std::fmax(bound, std::fmax(std::fabs(s.vertices_x[i]), std::fabs(s.vertices_y[i])));
+        area2 += s.vertices_x[i] * s.vertices_y[j] - s.vertices_x[j] * s.vertices_y[i];
+    }
+    if (!(bound > 0.0) || !(bound < 1e150) || area2 == 0.0) return;
+    const double orientation = area2 > 0.0 ? 1.0 : -1.0;
+    const double margin = 1e-9 * bound * bound;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1) % n;
+        const double ex = s.vertices_x[j] - s.vertices_x[i], ey = s.vertices_y[j] - s.vertices_y[i];
+        for (int k = 0; k < n; ++k) {
+            if (k == i || k == j) continue;
+            const double c = ex * (s.vertices_y[k] - s.vertices_y[i]) - ey * (s.vertices_x[k] - s.vertices_x[i]);
+            if (!(orientation * c > margin)) return;
+        }
+    }
+    s.flags |= OPTK_F_APERTURE_CONVEX | (orientation < 0.0 ? OPTK_F_APERTURE_CLOCKWISE : 0);
+    s.aperture[0] = bound;
+    s.aperture[1] = 1e-12 * bound * bound;
+}
+
 }  // namespace
 
 extern "C" {
@@ -380,6 +410,8 @@ OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, 
         const bool identity = r[0] == 1.0 && r[4] == 1.0 && r[8] == 1.0 && r[1] == 0.0 && r[2] == 0.0 &&
                               r[3] == 0.0 && r[5] == 0.0 && r[6] == 0.0 && r[7] == 0.0;
         if ((s.flags & OPTK_F_TRANSFORM) && identity) s.flags |= OPTK_F_TRANSLATION_ONLY;
+        s.flags &= ~(OPTK_F_APERTURE_CONVEX | OPTK_F_APERTURE_CLOCKWISE);
+        if (s.aperture_kind == OPTK_APERTURE_POLYGON) classify_polygon(s);
         if (s.aperture_kind == OPTK_APERTURE_CIRCULAR || s.aperture_kind == OPTK_APERTURE_SECTOR) {
             // T = max{v : sqrt(v) <= radius} (correctly rounded sqrt): "sqrt(x^2 + y^2) <= radius"
             // (optika/apertures/_apertures.py:309) becomes "x^2 + y^2 <= T" with identical results

@@ -78,9 +78,8 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 // B200 has no fp64 divide or sqrt unit: `a / b` and `sqrt(x)` compile to a MUFU seed,
 // Newton steps, a residual correction AND exponent-range fix-ups behind a branch and a
 // call (20-25 instructions, and the branch stops the scheduler from interleaving the
-// two rays a thread carries).  Here: seed (20+ bits) -> two Newton steps -> one residual
-// correction = faithfully rounded (error < 1 ulp, >99.9 % correctly rounded) in 9-12
-// straight-line instructions.  Zero / inf / NaN operands are repaired with selects from the
+// two rays a thread carries).  Here: seed (20 bits) -> one Newton step -> one residual
+// correction (or one third-order step) = error < 1 ulp in 6-9 straight-line instructions.  Zero / inf / NaN operands are repaired with selects from the
 // raw seed, which already has the IEEE special values (rcp(0) = inf, rcp(inf) = 0,
 // rsqrt(0) = inf, rsqrt(<0) = NaN), so NaN / inf propagation matches the plain operators.
 // Subnormal operands are flushed to zero and intermediate overflow beyond 1e300 is not
@@ -108,21 +107,28 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
     return y;
 }
 
+// The seeds carry the leading 20 bits of the mantissa (MUFU.RCP64H / RSQ64H read and write the high word
+// only): relative error e0 <= 2^-19.  One third-order step takes that to e0^3 < 2^-57, below the rounding of
+// the last operation; a second step (round 1) only recomputed digits that were already right.
+// tests/test_gpu_math.py measures all four against correctly rounded results (<= 1 ulp) through
+// optk_debug_math.
+__device__ __forceinline__ double frcp_raw(double x) {
+    const double y0 = rcp_seed(x);
+    const double e = fma(-x, y0, 1.0);
+    return fma(e, fma(y0, e, y0), y0);  // y0 (1 + e + e^2)
+}
+
 __device__ __forceinline__ double frcp(double x) {
     const double y0 = rcp_seed(x);
-    double e = fma(-x, y0, 1.0);
-    double y = fma(y0, e, y0);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
+    const double e = fma(-x, y0, 1.0);
+    const double y = fma(e, fma(y0, e, y0), y0);
     return not_finite(y) ? y0 : y;  // x = 0, inf, NaN: the seed is the answer
 }
 
 __device__ __forceinline__ double fdiv(double a, double b) {
     const double y0 = rcp_seed(b);
-    double e = fma(-b, y0, 1.0);
-    double y = fma(y0, e, y0);
-    e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
+    const double e = fma(-b, y0, 1.0);
+    const double y = fma(y0, e, y0);  // 1 / b to 2^-38: the residual step below squares that
     const double q0 = a * y;
     double q = fma(fma(-b, q0, a), y, q0);
     // b = 0 / inf, a = inf, NaN: the IEEE value comes from the seed.  One predicated multiply
@@ -143,11 +149,8 @@ __device__ __forceinline__ double fdiv(double a, double b) {
 __device__ __forceinline__ double fsqrt(double x) {
     const double y0 = rsqrt_seed(x);
     double g = x * y0, h = 0.5 * y0;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);  // sqrt(x) and 1 / (2 sqrt(x)) to 2^-38
     h = fma(h, r, h);
     g = fma(fma(-g, g, x), h, g);
     // x = 0 (seed inf), +inf (seed 0), negative or NaN (seed NaN) all leave g = NaN.  The
@@ -159,13 +162,19 @@ __device__ __forceinline__ double fsqrt(double x) {
     return (not_finite(g) && (unsigned)__double2hiint(x) <= 0x80000000u) ? x : g;
 }
 
+// 1 / sqrt(x) without the repair of x = 0 / inf (both give NaN here): for radicands that are >= 1 by
+// construction (1 + slopes^2) or whose zero is a NaN of the caller anyway (the toroid's domain boundary).
+__device__ __forceinline__ double frsqrt_raw(double x) {
+    const double y0 = rsqrt_seed(x);
+    const double e = fma(-x * y0, y0, 1.0);  // 1 - x y0^2
+    return fma(y0 * e, fma(0.375, e, 0.5), y0);  // y0 (1 + e / 2 + 3 e^2 / 8)
+}
+
 // 1 / sqrt(x)
 __device__ __forceinline__ double frsqrt(double x) {
     const double y0 = rsqrt_seed(x);
-    double e = fma(-x * y0, y0, 1.0);  // 1 - x y^2
-    double y = fma(0.5 * y0, e, y0);
-    e = fma(-x * y, y, 1.0);
-    y = fma(y * fma(0.375, e, 0.5), e, y);  // second step with the e^2 term
+    const double e = fma(-x * y0, y0, 1.0);
+    const double y = fma(y0 * e, fma(0.375, e, 0.5), y0);
     return not_finite(y) ? y0 : y;
 }
 

@@ -27,6 +27,27 @@ import configs
 POLYGON, POLYNOMIAL = L.APERTURE_POLYGON, L.RULING_POLYNOMIAL
 
 
+def convex_flags(vx, vy):
+    """OPTK_F_APERTURE_CONVEX / _CLOCKWISE as api.cu::classify_polygon sets them"""
+    n = len(vx)
+    if n < 3:
+        return 0
+    bound = max(np.abs(vx).max(), np.abs(vy).max())
+    area2 = sum(vx[i] * vy[(i + 1) % n] - vx[(i + 1) % n] * vy[i] for i in range(n))
+    if not bound > 0 or area2 == 0:
+        return 0
+    o = 1.0 if area2 > 0 else -1.0
+    for i in range(n):
+        j = (i + 1) % n
+        ex, ey = vx[j] - vx[i], vy[j] - vy[i]
+        for k in range(n):
+            if k in (i, j):
+                continue
+            if not o * (ex * (vy[k] - vy[i]) - ey * (vx[k] - vx[i])) > 1e-9 * bound * bound:
+                return 0
+    return 0x4000 | (0x8000 if o < 0 else 0)
+
+
 def walk_source(table, n_surface):
     lines = []
     for k in range(n_surface):
@@ -35,6 +56,8 @@ def walk_source(table, n_surface):
         r = np.array(list(S.transform.r)).reshape(3, 3)
         if (flags & L.F_TRANSFORM) and np.array_equal(r, np.eye(3)):
             flags |= 0x400  # OPTK_F_TRANSLATION_ONLY
+        if S.aperture_kind == POLYGON:
+            flags |= convex_flags(np.array(S.vertices_x[: S.n_vertices]), np.array(S.vertices_y[: S.n_vertices]))
         eff = S.material_efficiency != 0 or S.ruling_profile != 0
         nv = S.n_vertices if S.aperture_kind == POLYGON else 0
         nc = S.n_coeff if S.ruling_kind == POLYNOMIAL else 0
