@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 7
+#define OPTK_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -622,6 +622,12 @@ OPTK_API int optk_measure_fp64_peak(double* flops_per_second, void* stream);
 /* Bandwidth (GB/s, 162 B per ray) of the trace kernel's access pattern with no arithmetic:
  * ten fp64 arrays + a byte mask in, the same out.  Allocates 162 * n_rays bytes. */
 OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, void* stream);
+/* The kernels' own fp64 division / reciprocal / square-root sequences (csrc/common.cuh: MUFU seed, one
+ * third-order step or one Newton step + residual correction, no branches), element by element on device
+ * arrays, so that their error can be measured against correctly rounded results (tests/test_gpu_math.py:
+ * <= 1 ulp; zero / inf / NaN as the IEEE operators).  op: 0 a / b, 1 1 / a, 2 sqrt(a), 3 1 / sqrt(a),
+ * 4 / 5 the variants of 1 / a and 1 / sqrt(a) without the repair of a = 0 and a = inf (b is read for op 0 only). */
+OPTK_API int optk_debug_math(int32_t op, int64_t n, const double* a, const double* b, double* out, void* stream);
 
 /* ---- detector physics after binning (kernel 4) ----------------------------------
  * Replaces the numba kernel optika/sensors/materials/_ramanathan_2020/_ramanathan_2020.py:762-876

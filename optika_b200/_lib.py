@@ -265,7 +265,7 @@ class CcdPlane(C.Structure):
     ]
 
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class OptkError(RuntimeError):
@@ -301,6 +301,7 @@ SYMBOLS = (
     "optk_memcpy_async",
     "optk_enable_peer_access",
     "optk_electrons_measured",
+    "optk_debug_math",
 )
 
 _lib = None
@@ -351,6 +352,7 @@ def lib() -> C.CDLL:
     L.optk_host_unregister.argtypes = [vp]
     L.optk_memcpy_async.argtypes = [vp, vp, i64, vp]
     L.optk_enable_peer_access.argtypes = [i32]
+    L.optk_debug_math.argtypes = [i32, i64, vp, vp, vp, vp]
     L.optk_electrons_measured.argtypes = [i32, i32, i32, C.POINTER(CcdPlane), vp, vp, i32, C.c_uint64, vp]
     for name in SYMBOLS:
         if name not in ("optk_last_error",):

@@ -697,6 +697,15 @@ OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e
     return launch_apply_efficiency(n, intensity, e_s, e_p, (cudaStream_t)stream);
 }
 
+OPTK_API int optk_debug_math(int32_t op, int64_t n, const double* a, const double* b, double* out, void* stream) {
+    DeviceScope device_scope(stream, "optk_debug_math");
+    if (op < 0 || op > 5 || n < 0 || !a || !out || (op == 0 && !b)) {
+        set_error("optk_debug_math: bad arguments");
+        return OPTK_ERR_INVALID;
+    }
+    return launch_debug_math(op, n, a, b, out, (cudaStream_t)stream);
+}
+
 OPTK_API int optk_bin(int64_t n_rays, const double* wavelength, const double* x, const double* y, const double* dz,
              const double* intensity, const uint8_t* unvignetted, const optk_image_t* image, void* stream) {
     DeviceScope device_scope(stream, "optk_bin");

@@ -80,6 +80,34 @@ int launch_apply_efficiency(long long n, double* intensity, const double* e_s, c
     return OPTK_OK;
 }
 
+// optk_debug_math: the fp64 helper sequences of common.cuh on arrays
+__global__ void __launch_bounds__(256)
+math_kernel(int op, long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = a[i];
+    double y;
+    switch (op) {
+        case 0: y = fdiv(x, b[i]); break;
+        case 1: y = frcp(x); break;
+        case 2: y = fsqrt(x); break;
+        case 3: y = frsqrt(x); break;
+        case 4: y = frcp_raw(x); break;
+        default: y = frsqrt_raw(x); break;
+    }
+    out[i] = y;
+}
+
+int launch_debug_math(int op, long long n, const double* a, const double* b, double* out, cudaStream_t stream) {
+    if (n == 0) return OPTK_OK;
+    unsigned grid;
+    int rc = grid_for(n, &grid);
+    if (rc) return rc;
+    math_kernel<<<grid, 256, 0, stream>>>(op, n, a, b, out);
+    OPTK_CUDA(cudaGetLastError());
+    return OPTK_OK;
+}
+
 // ---------------------------------------------------------------------------
 // Reductions over the pupil of traced rays, per field point: what
 // SequentialSystem.distortion / vignetting / area_effective take from the ray arrays

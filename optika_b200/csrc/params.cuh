@@ -110,6 +110,7 @@ int launch_multilayer(const MultilayerParams& P, cudaStream_t stream);
 int launch_interp(long long n, const double* x, int m, const double* xp, const double* fp_re, const double* fp_im,
                   double* out_re, double* out_im, cudaStream_t stream);
 int launch_apply_efficiency(long long n, double* intensity, const double* e_s, const double* e_p, cudaStream_t stream);
+int launch_debug_math(int op, long long n, const double* a, const double* b, double* out, cudaStream_t stream);
 int launch_reduce_groups(long long n_groups, long long n_inner, const double* x, const double* y, const double* intensity,
                          const uint8_t* unvignetted, double* sum_intensity, double* sum_x, double* sum_y,
                          unsigned long long* count, double* sum_x_all, double* sum_y_all, cudaStream_t stream);
