@@ -146,6 +146,15 @@ __device__ __forceinline__ double fdiv(double a, double b) {
     return q;
 }
 
+// a / b to 2^-38 (one Newton step on the seed, no residual correction), NaN instead of inf for b = 0: for the
+// steps of an iteration that corrects itself -- a step of size s lands within 4e-12 s of where the exact
+// quotient would, and the next step (or the convergence test, which looks at s) absorbs that.
+__device__ __forceinline__ double fdiv_newton(double a, double b) {
+    const double y0 = rcp_seed(b);
+    const double e = fma(-b, y0, 1.0);
+    return a * fma(y0, e, y0);
+}
+
 __device__ __forceinline__ double fsqrt(double x) {
     const double y0 = rsqrt_seed(x);
     double g = x * y0, h = 0.5 * y0;

@@ -180,7 +180,7 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
         for (int j = 0; j < nc && j < OPTK_MAX_COEFF; ++j) pw[j] = S.ruling_power[j];
         snprintf(line, sizeof(line),
                  "    surface_full<2, %s, FixedKinds<%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d>>"
-                 "(P.surf[%d], r, newton_iterations, attenuating);\n",
+                 "(P.surf[%d], r, newton_iterations, state);\n",
                  eff ? "true" : "false", S.sag_kind, S.material_kind, S.ruling_kind, S.aperture_kind, S.flags, nv, nc,
                  pw[0], pw[1], pw[2], pw[3], pw[4], pw[5], pw[6], pw[7], k);
         walk += line;
@@ -230,7 +230,7 @@ std::string jit_source(const TraceParams& P, const JitVariant& v, std::string* k
         "#include \"trace_impl.cuh\"\n"
         "namespace optk {\n"
         "__device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,\n"
-        "                                              bool& attenuating) {\n";
+        "                                              WalkState& state) {\n";
     src += walk;
     src += "}\n}  // namespace optk\n";
     snprintf(line, sizeof(line),

@@ -495,7 +495,7 @@ __device__ __forceinline__ void toroid_intercept(const optk_surface_t& S, const 
     bool active[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        t[k] = fdiv(-r[k].pz, r[k].dz);
+        t[k] = fdiv_newton(-r[k].pz, r[k].dz);
         if (!(fabs(t[k]) < OPTK_INF)) t[k] = 0.0;
         active[k] = true;
     }
@@ -507,9 +507,9 @@ __device__ __forceinline__ void toroid_intercept(const optk_surface_t& S, const 
             toroid_eval(c, rr, r[k].px + r[k].dx * t[k], r[k].py + r[k].dy * t[k], z, dzdx, dzdy);
             const double f = (r[k].pz + r[k].dz * t[k]) - z;
             const double df = r[k].dz - (dzdx * r[k].dx + dzdy * r[k].dy);
-            const double step = fdiv(f, df);
+            const double step = fdiv_newton(f, df);
             const double tt = t[k] - step;
-            const double tolerance = 1e-13 * fmax(1.0, fabs(tt));
+            const double tolerance = 1e-13 * (1.0 + fabs(tt));
             const bool done = !(fabs(step) > tolerance) || (step * step * curvature <= tolerance * fabs(df));
             t[k] = active[k] ? tt : t[k];
             iterations += active[k] ? 1u : 0u;
@@ -536,17 +536,17 @@ static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double q
         const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));
         // The reference starts at t = 0, and its first step lands next to the vertex plane.  Start
         // there directly (one division instead of a toroid evaluation); same root.
-        double tt = fdiv(-qz, vz);
+        double tt = fdiv_newton(-qz, vz);
         if (!(fabs(tt) < OPTK_INF)) tt = 0.0;
         for (int it = 0; it < 64; ++it) {
             double z, dzdx, dzdy;
             toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
             const double f = (qz + vz * tt) - z;
             const double df = vz - (dzdx * vx + dzdy * vy);
-            const double step = fdiv(f, df);
+            const double step = fdiv_newton(f, df);
             tt -= step;
             ++hit.iterations;
-            const double tolerance = 1e-13 * fmax(1.0, fabs(tt));
+            const double tolerance = 1e-13 * (1.0 + fabs(tt));
             if (!(fabs(step) > tolerance)) break;
             if (step * step * curvature <= tolerance * fabs(df)) break;
         }
@@ -598,12 +598,22 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
 // parallelism for the long fp64 dependency chains).
 // AbstractSurface.propagate_rays, optika/surfaces.py:123-198.
 // ---------------------------------------------------------------------------
-// `attenuating`: some ray of the thread still carries a non-zero attenuation (set when the rays
-// are loaded, cleared by every non-mirror material, which zeroes the attenuation).
+// What a thread knows about its rays between the surfaces of a walk.
+// `attenuating`: some ray of the thread still carries a non-zero attenuation (set when the rays are loaded,
+// cleared by every non-mirror material, which zeroes the attenuation).
+// `unit`: the directions are unit vectors to rounding -- true behind every surface: either the surface
+// verified it (the "straight" test below) or Snell's law renormalised them.  Only the first surface of a
+// walk has to look.
+struct WalkState {
+    bool attenuating;
+    bool unit;
+};
+
 template <int R, bool EFF = false, class K = TableKinds>
 __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations,
-                                             bool& attenuating) {
+                                             WalkState& state) {
     const int flags = K::flags(S);
+    bool& attenuating = state.attenuating;
 
     // 1. global -> surface-local (surfaces.py:141-142).  Inside a walk the rays come straight from the local
     // frame of the previous surface (launch_trace composes "previous local -> global -> this local" into one
@@ -792,7 +802,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
         // unit to 1e-14 (user input) take the full formula, which renormalises them as the
         // reference does.
         bool straight = same_medium && !mirror && K::ruling(S) == OPTK_RULING_NONE;
-        if (straight) {
+        if (straight && !state.unit) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const double a2 = r[k].dx * r[k].dx + r[k].dy * r[k].dy + r[k].dz * r[k].dz;
@@ -800,6 +810,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             }
         }
         if (!mirror) attenuating = false;  // every non-mirror material zeroes the attenuation below
+        state.unit = true;  // verified just now, or renormalised by the full formula below
         if (straight) {
 #pragma unroll
             for (int k = 0; k < R; ++k) r[k].att = 0.0;  // _materials.py:101-105, 440-444; index unchanged
@@ -1119,17 +1130,17 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
             // stops at |step| < 1e-6 mm; see DESIGN.md "toroid intercept").
             const double c = S.sag[3], rr = S.sag[2];
             const double curvature = 4.0 * fmax(fabs(c), fabs(frcp(rr)));  // see sag_cold
-            t = fdiv(-r.pz, r.dz);
+            t = fdiv_newton(-r.pz, r.dz);
             if (!(fabs(t) < OPTK_INF)) t = 0.0;
             for (int it = 0; it < 64; ++it) {
                 double z, dzdx, dzdy;
                 toroid_eval(c, rr, qx + vx * t, qy + vy * t, z, dzdx, dzdy);
                 const double f = (r.pz + r.dz * t) - z;
                 const double df = r.dz - (dzdx * vx + dzdy * vy);
-                const double step = fdiv(f, df);
+                const double step = fdiv_newton(f, df);
                 t -= step;
                 ++newton_iterations;
-                const double tolerance = 1e-13 * fmax(1.0, fabs(t));
+                const double tolerance = 1e-13 * (1.0 + fabs(t));
                 if (!(fabs(step) > tolerance)) break;
                 if (step * step * curvature <= tolerance * fabs(df)) break;
             }
@@ -1700,7 +1711,7 @@ __device__ __forceinline__ void store_rays_vec(const optk_rays_out_t& out, long 
 
 #ifdef OPTK_JIT_WALK
 __device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,
-                                              bool& attenuating);
+                                              WalkState& state);
 #endif
 
 // SPEC: 0 the surface list is walked from the table; 1 a run-time compiled walk (R = 2, no ACC)
@@ -1812,10 +1823,10 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     }
 
     // generated rays start with zero attenuation: the Beer-Lambert branch is dead code there
-    bool attenuating = false;
+    WalkState state = {false, false};
     if (FULL && !GRID) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) attenuating = attenuating || (r[k].att != 0.0);
+        for (int k = 0; k < R; ++k) state.attenuating = state.attenuating || (r[k].att != 0.0);
     }
 
     // No `if (valid)` around the walk: threads past the end trace a harmless dummy ray, so the
@@ -1826,12 +1837,12 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
             // a kernel compiled at run time for one system (jit.cu): the walk is a straight sequence of
             // surface_full<2, EFF, FixedKinds<...>>(P.surf[k], ...) with compile-time k
 #ifdef OPTK_JIT_WALK
-            optk_jit_walk(P, r, newton_iterations, attenuating);
+            optk_jit_walk(P, r, newton_iterations, state);
 #endif
         } else
         for (int s = 0; s < P.n_surf; ++s) {
             if (FULL)
-                surface_full<R, EFF>(P.surf[s], r, newton_iterations, attenuating);
+                surface_full<R, EFF>(P.surf[s], r, newton_iterations, state);
             else
                 surface_generic(P.surf[s], r[0], newton_iterations, normal_given, gnx, gny, gnz, cos_incidence);
             if (ACC && P.has_out) {

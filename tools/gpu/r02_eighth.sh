@@ -1,7 +1,7 @@
 #!/bin/bash
 # cfg 3 diet (third-order fp64 helpers, convex polygon half-planes): new tests, the kernels' parity tests, instruction counters
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_math.py tests/test_gpu_polygon.py tests/test_gpu_trace.py tests/test_gpu_jit.py tests/test_gpu_grid.py tests/test_gpu_multilayer.py -x -q -m gpu > gpurun_out/r02c_pytest_focus.txt 2>&1
+python -m pytest tests -q -m gpu > gpurun_out/r02c_pytest_focus.txt 2>&1
 tail -15 gpurun_out/r02c_pytest_focus.txt
 M=smsp__inst_executed.sum,gpu__time_duration.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active
 for what in "cfg3 dense" "cfg3 grid" "cfg2 grid" "cfg2 image" "cfg2 dense" "cfg1 grid" "cfg5 grid"; do

@@ -65,7 +65,7 @@ def walk_source(table, n_surface):
         args = [S.sag_kind, S.material_kind, S.ruling_kind, S.aperture_kind, flags, nv, nc, *pw]
         lines.append(
             f"    surface_full<2, {'true' if eff else 'false'}, FixedKinds<{', '.join(map(str, args))}>>"
-            f"(P.surf[{k}], r, newton_iterations, attenuating);"
+            f"(P.surf[{k}], r, newton_iterations, state);"
         )
     return "\n".join(lines)
 
@@ -109,7 +109,7 @@ def main():
 #include "trace_impl.cuh"
 namespace optk {{
 __device__ __forceinline__ void optk_jit_walk(const TraceParams& P, Ray (&r)[2], unsigned& newton_iterations,
-                                              bool& attenuating) {{
+                                              WalkState& state) {{
 {walk_source(table, len(surfaces))}
 }}
 }}  // namespace optk
