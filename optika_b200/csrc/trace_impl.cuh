@@ -431,8 +431,10 @@ __device__ __forceinline__ bool aperture_test(const optk_surface_t& S, double x,
                 const double bound = S.aperture[0], band = S.aperture[1];
                 const bool clockwise = K::flags(S) & OPTK_F_APERTURE_CLOCKWISE;
                 const int nv = K::n_vertices(S);
-                const bool in_box = (fabs(x) <= bound) && (fabs(y) <= bound);  // false for NaN: outside, as there
-                bool all_in = in_box, any_out = !in_box;
+                // a NaN coordinate is neither: it takes the exact arithmetic, whose comparisons decide as the
+                // reference's do (a NaN x with y inside the polygon's range comes out INSIDE there)
+                bool all_in = (fabs(x) <= bound) && (fabs(y) <= bound);
+                bool any_out = (fabs(x) > bound) || (fabs(y) > bound);
                 double x0 = S.vertices_x[nv - 1], y0 = S.vertices_y[nv - 1];
                 auto edge = [&](int i) {
                     const double x1 = S.vertices_x[i], y1 = S.vertices_y[i];
@@ -1823,7 +1825,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
     }
 
     // generated rays start with zero attenuation: the Beer-Lambert branch is dead code there
-    WalkState state = {false, false};
+    // (generated directions are (-cos b sin a, -sin b, cos b cos a): unit to 4e-16 by construction)
+    WalkState state = {false, GRID != 0};
     if (FULL && !GRID) {
 #pragma unroll
         for (int k = 0; k < R; ++k) state.attenuating = state.attenuating || (r[k].att != 0.0);

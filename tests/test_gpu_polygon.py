@@ -13,7 +13,6 @@ import pytest
 
 import optika_b200 as optika
 from optika_b200 import named as na
-from optika_b200 import transformations as tf
 from optika_b200 import units as u
 from optika_b200 import _lib, _lowering
 from oracle import raytrace as ora
@@ -119,7 +118,9 @@ def test_polygon_masks_in_the_specialised_kernel(cuda_device, name):
     aperture = make()
     vx, vy = vertices_of(aperture)
     x, y = probe_points(vx, vy, seed=3)
-    surface = optika.surfaces.Surface(aperture=aperture, transformation=tf.Cartesian3dTranslation(z=2.0))
+    # (no surface transformation: the oracle applies every transformation as a full matrix, which turns a NaN x
+    # into a NaN y as well; a translation in the reference and in the kernels does not)
+    surface = optika.surfaces.Surface(aperture=aperture)
     rays = rays_at(x, y, repeat=8)
     r0, _ = configs.flatten_rays(rays)
     want = ora.surface_propagate(surface, r0)["unvignetted"]
