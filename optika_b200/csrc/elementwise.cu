@@ -93,6 +93,8 @@ math_kernel(int op, long long n, const double* __restrict__ a, const double* __r
         case 2: y = fsqrt(x); break;
         case 3: y = frsqrt(x); break;
         case 4: y = frcp_raw(x); break;
+        case 6: y = fdiv_finite(x, b[i]); break;
+        case 7: y = fdiv_newton(x, b[i]); break;
         default: y = frsqrt_raw(x); break;
     }
     out[i] = y;

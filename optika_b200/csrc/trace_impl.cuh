@@ -85,7 +85,7 @@ __device__ __forceinline__ double parabola_intercept(double f, double ox, double
     const bool stable = -h * fuz >= 0.0;  // -h and root have the same sign (or one of them is zero)
     const double num = (general && !stable) ? (-h - root) : c;
     const double den = general ? (stable ? (-h + root) : a) : 4.0 * fuz;
-    return fdiv(num, den);
+    return fdiv_finite(num, den);
 }
 
 // Path length t to the surface for a ray o + t u (closed forms), or NaN/inf on a miss.
@@ -95,7 +95,7 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
     switch (K::sag(S)) {
         case OPTK_SAG_FLAT:
             // optika/sags/_flat.py:58: d = -o.z / u.z
-            return fdiv(-oz, uz);
+            return fdiv_finite(-oz, uz);
         case OPTK_SAG_SPHERICAL: {
             // optika/sags/_spherical.py:176-184
             const double r = S.sag[0];
@@ -152,7 +152,7 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
             const double dot = bx * ncx + bz * ncz;
             const double disc = nca2 * (r * r) - dot * dot;
             if (disc > 0) return fdiv(negative_b - sign0(r * uz) * fsqrt(disc), nca2);
-            return fdiv(-oz, uz);
+            return fdiv_finite(-oz, uz);
         }
     }
     return NAN;
@@ -606,10 +606,18 @@ static __device__ __noinline__ double surface_efficiency(const optk_surface_t& S
 // `unit`: the directions are unit vectors to rounding -- true behind every surface: either the surface
 // verified it (the "straight" test below) or Snell's law renormalised them.  Only the first surface of a
 // walk has to look.
+// `deferred`: the walk started from finite positions (generated rays) and only its last state is reported.  The
+// reference turns the intensity into NaN at the surface whose displacement is not finite (sags/_abc.py:116-120
+// with attenuation 0); a position that is not finite stays so through every later surface, so looking once, at
+// the end of the walk, marks the same rays (trace_body does; 3 instructions per ray instead of per surface).
 struct WalkState {
     bool attenuating;
     bool unit;
+    bool deferred;
 };
+
+// 0 * (finite) = 0, 0 * (inf or NaN) = NaN: adds the reference's NaN without a select
+__device__ __forceinline__ void poison_intensity(Ray& r) { r.intensity = fma(0.0, r.px + r.py + r.pz, r.intensity); }
 
 template <int R, bool EFF = false, class K = TableKinds>
 __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R], unsigned& newton_iterations,
@@ -658,7 +666,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
         case OPTK_SAG_FLAT:
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                t[k] = fdiv(-r[k].pz, r[k].dz);  // optika/sags/_flat.py:58
+                t[k] = fdiv_finite(-r[k].pz, r[k].dz);  // optika/sags/_flat.py:58
                 nx[k] = 0.0; ny[k] = 0.0; nz[k] = -1.0;  // :43-47
             }
             break;
@@ -732,9 +740,8 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const double hx = r[k].px + r[k].dx * t[k], hy = r[k].py + r[k].dy * t[k], hz = r[k].pz + r[k].dz * t[k];
-            // 0 * (finite) = 0, 0 * (inf or NaN) = NaN: adds the reference's NaN without a select
-            r[k].intensity = fma(0.0, hx + hy + hz, r[k].intensity);
             r[k].px = hx; r[k].py = hy; r[k].pz = hz;
+            if (!state.deferred) poison_intensity(r[k]);
         }
     }
 
@@ -761,7 +768,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             const double k2 = kx * kx + ky * ky + kz * kz;
             const double an = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
             const double sg = (an == 0.0) ? an : copysign(1.0, an);  // numpy.sign
-            const double f = fdiv(sg * S.ruling_order * r[k].w, r[k].n * k2);
+            const double f = fdiv_finite(sg * S.ruling_order * r[k].w, r[k].n * k2);
             r[k].dx += f * kx;
             r[k].dy += f * ky;
             r[k].dz += f * kz;
@@ -1199,7 +1206,7 @@ static __device__ __noinline__ void surface_generic(const optk_surface_t& S, Ray
             // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
             const double k2 = kx * kx + ky * ky + kz * kz;
             const double s = sign0(r.dx * nx + r.dy * ny + r.dz * nz);
-            const double f = fdiv(s * S.ruling_order * r.w, r.n * k2);
+            const double f = fdiv_finite(s * S.ruling_order * r.w, r.n * k2);
             r.dx += f * kx;
             r.dy += f * ky;
             r.dz += f * kz;
@@ -1826,7 +1833,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
 
     // generated rays start with zero attenuation: the Beer-Lambert branch is dead code there
     // (generated directions are (-cos b sin a, -sin b, cos b cos a): unit to 4e-16 by construction)
-    WalkState state = {false, GRID != 0};
+    WalkState state = {false, GRID != 0, GRID != 0 && !ACC && FULL};
     if (FULL && !GRID) {
 #pragma unroll
         for (int k = 0; k < R; ++k) state.attenuating = state.attenuating || (r[k].att != 0.0);
@@ -1863,6 +1870,10 @@ __device__ __forceinline__ void trace_body(const TraceParams& P) {
                         if (valid[k]) store_ray(P.out, o + k, r[k]);
                 }
             }
+        }
+        if (state.deferred) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) poison_intensity(r[k]);
         }
         if (!ACC && P.has_out) {  // one uniform test instead of eleven null checks per ray
             bool done = false;

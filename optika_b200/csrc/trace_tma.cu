@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, MINB) trace_kernel_tma(const __grid_c
             if (next < n_tiles) issue_tile(P, &stages[s], &full[s], next, has_mask);
         }
 
-        WalkState state = {(r[0].att != 0.0) || (r[1].att != 0.0), false};
+        WalkState state = {(r[0].att != 0.0) || (r[1].att != 0.0), false, false};
         for (int k = 0; k < P.n_surf; ++k) surface_full<2>(P.surf[k], r, newton_iterations, state);
         store_rays_vec(P.out, tile * TILE + j, r);
         if (P.stats) n_unvignetted += (r[0].unv ? 1 : 0) + (r[1].unv ? 1 : 0);

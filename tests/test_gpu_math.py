@@ -47,6 +47,27 @@ def test_division_within_one_ulp(cuda_device):
     assert np.mean(err <= 0.5) > 0.95  # almost always the correctly rounded quotient
 
 
+def test_division_by_a_finite_divisor(cuda_device):
+    """fdiv_finite: no residual step (<= 1.5 ulp); b = 0, a = inf, NaN and 0 / 0 as IEEE without a repair."""
+    a, b = operands(6), operands(7)
+    err = ulps(run(6, a, b), a.astype(np.longdouble) / b.astype(np.longdouble))
+    assert err.max() <= 1.5, err.max()
+    inf, nan = np.inf, np.nan
+    a = np.array([1.0, -1.0, 1.0, -1.0, 0.0, inf, -inf, nan, 1.0, 0.0, 5.0])
+    b = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 2.0, 3.0, 1.0, nan, 4.0, -2.5])
+    with np.errstate(all="ignore"):
+        want = a / b
+    got = run(6, a, b)
+    assert np.array_equal(got, want, equal_nan=True), (got, want)
+
+
+def test_division_for_newton_steps(cuda_device):
+    """fdiv_newton: one Newton step on the seed, relative error below 2^-36."""
+    a, b = operands(8), operands(9)
+    got = run(7, a, b)
+    assert np.max(np.abs(got / (a / b) - 1)) < 2.0 ** -36
+
+
 @pytest.mark.parametrize("op", [1, 4], ids=["repaired", "raw"])
 def test_reciprocal_within_one_ulp(cuda_device, op):
     a = operands(3)
