@@ -39,8 +39,8 @@ extern "C" {
 #define OPTK_API
 #endif
 
-#define OPTK_MAX_SURFACES 24 /* surfaces per launch; longer systems are chained   */
-#define OPTK_MAX_VERTICES 16 /* polygon aperture vertices                          */
+#define OPTK_MAX_SURFACES 22 /* surfaces per launch; longer systems are chained   */
+#define OPTK_MAX_VERTICES 32 /* polygon aperture vertices                          */
 #define OPTK_MAX_COEFF 8     /* terms of a Polynomial1dRulingSpacing               */
 #define OPTK_MAX_AXES 8      /* named axes of a ray grid                           */
 #define OPTK_NUM_FIELDS 10   /* fp64 fields of a ray                               */

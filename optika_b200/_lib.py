@@ -27,8 +27,8 @@ __all__ = [
     "MlInput",
 ]
 
-MAX_SURFACES = 24
-MAX_VERTICES = 16
+MAX_SURFACES = 22
+MAX_VERTICES = 32
 MAX_COEFF = 8
 MAX_AXES = 8
 NUM_FIELDS = 10

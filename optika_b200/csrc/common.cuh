@@ -295,10 +295,12 @@ __device__ __forceinline__ void fsincos(double x, double* s, double* c) {
 __device__ __forceinline__ void affine_forward(const optk_affine_t& a, double& x, double& y, double& z,
                                                bool is_direction) {
     double rx, ry, rz;
+    // (explicit multiply-adds: nvcc and NVRTC then round the same way, and the table-driven and the run-time
+    // compiled kernels stay bit-identical)
     if (is_direction) {
-        rx = a.r[0] * x + a.r[1] * y + a.r[2] * z;
-        ry = a.r[3] * x + a.r[4] * y + a.r[5] * z;
-        rz = a.r[6] * x + a.r[7] * y + a.r[8] * z;
+        rx = fma(a.r[0], x, fma(a.r[1], y, a.r[2] * z));
+        ry = fma(a.r[3], x, fma(a.r[4], y, a.r[5] * z));
+        rz = fma(a.r[6], x, fma(a.r[7], y, a.r[8] * z));
     } else {  // the offset rides in the innermost multiply-add: three instructions per component, not four
         rx = fma(a.r[0], x, fma(a.r[1], y, fma(a.r[2], z, a.t[0])));
         ry = fma(a.r[3], x, fma(a.r[4], y, fma(a.r[5], z, a.t[1])));
@@ -315,9 +317,9 @@ __device__ __forceinline__ void affine_inverse(const optk_affine_t& a, double& x
         y -= a.t[1];
         z -= a.t[2];
     }
-    double rx = a.r[0] * x + a.r[3] * y + a.r[6] * z;
-    double ry = a.r[1] * x + a.r[4] * y + a.r[7] * z;
-    double rz = a.r[2] * x + a.r[5] * y + a.r[8] * z;
+    double rx = fma(a.r[0], x, fma(a.r[3], y, a.r[6] * z));
+    double ry = fma(a.r[1], x, fma(a.r[4], y, a.r[7] * z));
+    double rz = fma(a.r[2], x, fma(a.r[5], y, a.r[8] * z));
     x = rx; y = ry; z = rz;
 }
 

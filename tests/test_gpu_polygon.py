@@ -47,6 +47,8 @@ POLYGONS = {
     "hexagon_inverted": (lambda: optika.apertures.RegularPolygonalAperture(14.0, 6, inverted=True), True),
     "trapezoid": (lambda: optika.apertures.IsoscelesTrapezoidalAperture(x_left=3.0, x_right=16.0, angle=50 * u.deg), True),
     "sixteen": (lambda: polygon(*regular(16, 15.0)), True),
+    "thirty_two": (lambda: polygon(*regular(32, 15.0, phase=0.03)), True),  # OPTK_MAX_VERTICES
+    "star_of_twenty": (lambda: polygon(*(np.array(regular(20, 1.0)) * np.where(np.arange(20) % 2, 6.0, 14.0))), False),
     "triangle_far_from_origin": (lambda: polygon([100.0, 130.0, 110.0], [200.0, 205.0, 240.0]), True),
     "arrow_not_convex": (lambda: polygon([-10.0, 12.0, 4.0, 9.0, -6.0], [-8.0, -9.0, 0.0, 11.0, 7.0]), False),
     "pentagram": (lambda: polygon(*PENTAGRAM), False),
@@ -110,7 +112,7 @@ def test_polygon_masks_equal_the_oracle_everywhere(cuda_device, name):
     assert 0.05 < want[:20000].mean() < 0.95  # the random part samples both sides
 
 
-@pytest.mark.parametrize("name", ["octagon", "heptagon_clockwise", "arrow_not_convex", "triangle_far_from_origin"])
+@pytest.mark.parametrize("name", ["octagon", "heptagon_clockwise", "arrow_not_convex", "triangle_far_from_origin", "thirty_two", "star_of_twenty"])
 def test_polygon_masks_in_the_specialised_kernel(cuda_device, name):
     """The same points through the kernel NVRTC compiles for the surface (long launch, OPTK_JIT forced on)."""
     lib = _lib.lib()
@@ -145,3 +147,9 @@ def test_convexity_is_classified_by_the_library(cuda_device):
     rays = rays_at(np.array([0.0, 11.0 * np.cos(0.1), 30.0]), np.array([0.0, 11.0 * np.sin(0.1), 0.0]))
     got = host_states(surface.propagate_rays(rays))["unvignetted"]
     assert got.tolist() == [False, True, False]
+
+
+def test_more_vertices_than_the_table_holds_are_refused():
+    with pytest.raises(ValueError, match="at most"):
+        surface = optika.surfaces.Surface(aperture=polygon(*regular(_lib.MAX_VERTICES + 1, 10.0)))
+        _lowering.lower_system([surface], stages=_lib.STAGE_ALL)

@@ -364,6 +364,35 @@ def test_glass_lens_wavelength_rescale_and_attenuation(cuda_device):
     assert not np.allclose(want["wavelength"][0], want["wavelength"][1])
 
 
+def test_systems_longer_than_one_launch_are_chained(cuda_device):
+    """
+    A periscope of flat mirrors with more surfaces than one launch carries (OPTK_MAX_SURFACES): propagate_rays
+    and accumulate_rays chain launches, every state of every surface equals the oracle's.
+    """
+    n = _lib.MAX_SURFACES + 7
+    surfaces = []
+    for k in range(n):
+        surfaces.append(optika.surfaces.Surface(
+            name=f"fold_{k}",
+            material=optika.materials.Mirror() if k % 3 else optika.materials.Vacuum(),
+            aperture=optika.apertures.CircularAperture(24.0 + k),
+            transformation=tf.TransformationList([
+                tf.Cartesian3dRotationY((3.0 if k % 2 else -3.0) * u.deg),
+                tf.Cartesian3dTranslation(x=0.3 * k, z=(40.0 if (k // 1) % 2 == 0 else -40.0) + 0.5 * k),
+            ]),
+        ))
+    rays = random_rays(n=3000)
+    r0, _ = configs.flatten_rays(rays)
+    got = host_states(optika.propagators.accumulate_rays(surfaces, rays, axis="surface"), axis="surface")
+    want = ora.accumulate_rays(surfaces, r0, converge=True, extended=True)
+    assert got["px"].shape[0] == n
+    parity.compare_states(got, want, surfaces)
+    last = host_states(optika.propagators.propagate_rays(surfaces, rays))
+    for name in ("px", "py", "pz", "dx", "dy", "dz"):
+        assert np.allclose(last[name], want[name][-1], rtol=0, atol=1e-9 * 100, equal_nan=True), name
+    assert np.array_equal(last["unvignetted"], want["unvignetted"][-1])
+
+
 def test_missed_surfaces_propagate_nan_and_inf(cuda_device):
     """Rays that miss a sphere give NaN, a conic gives inf (optika/sags/_conic.py:154), as in the reference."""
     rays = random_rays(n=2000, spread=400.0)
