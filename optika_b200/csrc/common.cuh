@@ -73,6 +73,16 @@ __device__ __forceinline__ double sign0(double x) {
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
+// Dot products and sums of squares with the multiply-adds written out.  `a * b + c * d + e * f` leaves the
+// choice of which products are fused to the compiler, and the choice can differ between two copies of the same
+// expression (nvcc / NVRTC, a tail the optimiser duplicated for a rare branch): the table-driven and the
+// run-time compiled kernels are held to bit-identical results, so the hot paths say what they mean.
+__device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+    return fma(ax, bx, fma(ay, by, az * bz));
+}
+__device__ __forceinline__ double norm2_3(double x, double y, double z) { return fma(x, x, fma(y, y, z * z)); }
+__device__ __forceinline__ double norm2_2(double x, double y) { return fma(x, x, y * y); }
+
 // ---------------------------------------------------------------------------
 // fp64 reciprocal / division / square root, branch-free.
 // B200 has no fp64 divide or sqrt unit: `a / b` and `sqrt(x)` compile to a MUFU seed,

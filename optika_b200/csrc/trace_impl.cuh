@@ -76,11 +76,11 @@ __device__ __forceinline__ double signed_root(double v, double root) {
 // cancellation-free form c / (-h + s sqrt()).  One division, no branch.
 __device__ __forceinline__ double parabola_intercept(double f, double ox, double oy, double oz, double ux, double uy,
                                                      double uz) {
-    const double a = ux * ux + uy * uy;
-    const double h = ox * ux + oy * uy - 2.0 * f * uz;
-    const double c = ox * ox + oy * oy - 4.0 * f * oz;
+    const double a = norm2_2(ux, uy);
     const double fuz = f * uz;
-    const double root = signed_root(fuz, fsqrt(h * h - a * c));
+    const double h = fma(ox, ux, fma(oy, uy, -2.0 * fuz));
+    const double c = fma(ox, ox, fma(oy, oy, -4.0 * (f * oz)));
+    const double root = signed_root(fuz, fsqrt(fma(h, h, -(a * c))));
     const bool general = a > 1e-10;
     const bool stable = -h * fuz >= 0.0;  // -h and root have the same sign (or one of them is zero)
     const double num = (general && !stable) ? (-h - root) : c;
@@ -100,8 +100,8 @@ __device__ __forceinline__ double sag_intercept_closed(const optk_surface_t& S, 
             // optika/sags/_spherical.py:176-184
             const double r = S.sag[0];
             const double pz = oz - r;
-            const double up = ux * ox + uy * oy + uz * pz;
-            const double disc = up * up - (ox * ox + oy * oy + pz * pz - r * r);
+            const double up = dot3(ux, uy, uz, ox, oy, pz);
+            const double disc = fma(up, up, -(norm2_3(ox, oy, pz) - r * r));
             return -up - sign0(r * uz) * fsqrt(disc);
         }
         case OPTK_SAG_PARABOLIC:
@@ -167,16 +167,16 @@ __device__ __forceinline__ void toroid_eval(double c, double r, double x, double
     // the reference; exactly on its boundary (a = 0 or b = 0, a set of measure zero) the reference's
     // infinite slope becomes NaN (so the unrepaired reciprocal roots do: 0 * inf either way).
     const double y2 = y * y;
-    const double a = 1.0 - c * c * y2;
+    const double a = fma(-(c * c), y2, 1.0);
     const double inv_g = frsqrt_raw(a);
     const double g = a * inv_g;
-    const double zy = c * y2 * frcp_raw(1.0 + g);  // 1 + g >= 1, or NaN
+    const double zy = (c * y2) * frcp_raw(1.0 + g);  // 1 + g >= 1, or NaN
     const double rz = r - zy;
-    const double b = rz * rz - x * x;
+    const double b = fma(rz, rz, -(x * x));
     const double inv_f = frsqrt_raw(b);
-    z = r - b * inv_f;
+    z = fma(-b, inv_f, r);
     dzdx = x * inv_f;
-    dzdy = rz * (c * y * inv_g) * inv_f;
+    dzdy = (rz * ((c * y) * inv_g)) * inv_f;
 }
 
 // Unit normal at a point of the sag frame (not rotated back, as in the reference).
@@ -206,7 +206,7 @@ __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, do
             // optika/sags/_parabolic.py:56-63: (x, y, -R) / sqrt((x/R)^2 + (y/R)^2 + 1) / R
             const double ir = 0.5 * S.sag[3];  // 1 / (2 f)
             const double xr = x * ir, yr = y * ir;
-            const double inv = frsqrt_raw(xr * xr + yr * yr + 1.0);
+            const double inv = frsqrt_raw(fma(xr, xr, fma(yr, yr, 1.0)));
             nx = xr * inv;
             ny = yr * inv;
             nz = -inv;
@@ -217,7 +217,7 @@ __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, do
             const double c = S.sag[3];
             const double ig = frsqrt_raw(1.0 - (1.0 + S.sag[1]) * c * c * (x * x + y * y));
             const double dzdx = c * x * ig, dzdy = c * y * ig;
-            const double inv = frsqrt_raw(dzdx * dzdx + dzdy * dzdy + 1.0);
+            const double inv = frsqrt_raw(fma(dzdx, dzdx, fma(dzdy, dzdy, 1.0)));
             nx = dzdx * inv;
             ny = dzdy * inv;
             nz = -inv;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void sag_normal(const optk_surface_t& S, double x, do
             // optika/sags/_toroidal.py:71-88
             double z, dzdx, dzdy;
             toroid_eval(S.sag[3], S.sag[2], x, y, z, dzdx, dzdy);
-            const double inv = frsqrt_raw(dzdx * dzdx + dzdy * dzdy + 1.0);
+            const double inv = frsqrt_raw(fma(dzdx, dzdx, fma(dzdy, dzdy, 1.0)));
             nx = dzdx * inv;
             ny = dzdy * inv;
             nz = -inv;
@@ -299,13 +299,13 @@ __device__ __forceinline__ void ruling_vector(const optk_surface_t& S, double px
         case OPTK_RULING_POLYNOMIAL: {
             // optika/rulings/_spacing.py:109-128
             if (K::flags(S) & OPTK_F_RULING_TRANSFORM) affine_forward(S.ruling_transform, px, py, pz, false);
-            const double x = px * S.ruling_normal[0] + py * S.ruling_normal[1] + pz * S.ruling_normal[2];
+            const double x = dot3(px, py, pz, S.ruling_normal[0], S.ruling_normal[1], S.ruling_normal[2]);
             double d = 0.0;
             if (K::fixed) {
 #pragma unroll
-                for (int k = 0; k < K::n_coeff(S); ++k) d += S.ruling_coeff[k] * ipow(x, K::power(S, k));
+                for (int k = 0; k < K::n_coeff(S); ++k) d = fma(S.ruling_coeff[k], ipow(x, K::power(S, k)), d);
             } else {
-                for (int k = 0; k < K::n_coeff(S); ++k) d += S.ruling_coeff[k] * ipow(x, K::power(S, k));
+                for (int k = 0; k < K::n_coeff(S); ++k) d = fma(S.ruling_coeff[k], ipow(x, K::power(S, k)), d);
             }
             kx = d * S.ruling_normal[0];
             ky = d * S.ruling_normal[1];
@@ -506,9 +506,9 @@ __device__ __forceinline__ void toroid_intercept(const optk_surface_t& S, const 
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             double z, dzdx, dzdy;
-            toroid_eval(c, rr, r[k].px + r[k].dx * t[k], r[k].py + r[k].dy * t[k], z, dzdx, dzdy);
-            const double f = (r[k].pz + r[k].dz * t[k]) - z;
-            const double df = r[k].dz - (dzdx * r[k].dx + dzdy * r[k].dy);
+            toroid_eval(c, rr, fma(r[k].dx, t[k], r[k].px), fma(r[k].dy, t[k], r[k].py), z, dzdx, dzdy);
+            const double f = fma(r[k].dz, t[k], r[k].pz) - z;
+            const double df = r[k].dz - fma(dzdx, r[k].dx, dzdy * r[k].dy);
             const double step = fdiv_newton(f, df);
             const double tt = t[k] - step;
             const double tolerance = 1e-13 * (1.0 + fabs(tt));
@@ -542,9 +542,9 @@ static __device__ __noinline__ SagHit sag_cold(const optk_surface_t& S, double q
         if (!(fabs(tt) < OPTK_INF)) tt = 0.0;
         for (int it = 0; it < 64; ++it) {
             double z, dzdx, dzdy;
-            toroid_eval(c, rr, qx + vx * tt, qy + vy * tt, z, dzdx, dzdy);
-            const double f = (qz + vz * tt) - z;
-            const double df = vz - (dzdx * vx + dzdy * vy);
+            toroid_eval(c, rr, fma(vx, tt, qx), fma(vy, tt, qy), z, dzdx, dzdy);
+            const double f = fma(vz, tt, qz) - z;
+            const double df = vz - fma(dzdx, vx, dzdy * vy);
             const double step = fdiv_newton(f, df);
             tt -= step;
             ++hit.iterations;
@@ -677,12 +677,12 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             for (int k = 0; k < R; ++k) {
                 const double qx = r[k].px, qy = r[k].py, pz = r[k].pz - rad;
                 const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
-                const double up = vx * qx + vy * qy + vz * pz;
-                const double disc = up * up - (qx * qx + qy * qy + pz * pz - rad * rad);
+                const double up = dot3(vx, vy, vz, qx, qy, pz);
+                const double disc = fma(up, up, -(norm2_3(qx, qy, pz) - rad * rad));
                 t[k] = -up - signed_root(rad * vz, fsqrt(disc));
-                nx[k] = c * (qx + vx * t[k]);
-                ny[k] = c * (qy + vy * t[k]);
-                nz[k] = -fsqrt(1.0 - nx[k] * nx[k] - ny[k] * ny[k]);
+                nx[k] = c * fma(vx, t[k], qx);
+                ny[k] = c * fma(vy, t[k], qy);
+                nz[k] = -fsqrt(fma(-ny[k], ny[k], fma(-nx[k], nx[k], 1.0)));
             }
             break;
         }
@@ -692,8 +692,8 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 t[k] = parabola_intercept(f, r[k].px, r[k].py, r[k].pz, r[k].dx, r[k].dy, r[k].dz);
-                const double xr = (r[k].px + r[k].dx * t[k]) * ir, yr = (r[k].py + r[k].dy * t[k]) * ir;
-                const double inv = frsqrt_raw(xr * xr + yr * yr + 1.0);
+                const double xr = fma(r[k].dx, t[k], r[k].px) * ir, yr = fma(r[k].dy, t[k], r[k].py) * ir;
+                const double inv = frsqrt_raw(fma(xr, xr, fma(yr, yr, 1.0)));
                 nx[k] = xr * inv;
                 ny[k] = yr * inv;
                 nz[k] = -inv;
@@ -739,7 +739,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
         }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const double hx = r[k].px + r[k].dx * t[k], hy = r[k].py + r[k].dy * t[k], hz = r[k].pz + r[k].dz * t[k];
+            const double hx = fma(r[k].dx, t[k], r[k].px), hy = fma(r[k].dy, t[k], r[k].py), hz = fma(r[k].dz, t[k], r[k].pz);
             r[k].px = hx; r[k].py = hy; r[k].pz = hz;
             if (!state.deferred) poison_intensity(r[k]);
         }
@@ -765,13 +765,13 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                 kz = kappa.z;
             }
             // a + sign(a.n) m w g / (n d), g = kappa / d, d = |kappa|  ==  a + sign(a.n) m w kappa / (n d^2)
-            const double k2 = kx * kx + ky * ky + kz * kz;
-            const double an = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
+            const double k2 = norm2_3(kx, ky, kz);
+            const double an = dot3(r[k].dx, r[k].dy, r[k].dz, nx[k], ny[k], nz[k]);
             const double sg = (an == 0.0) ? an : copysign(1.0, an);  // numpy.sign
             const double f = fdiv_finite(sg * S.ruling_order * r[k].w, r[k].n * k2);
-            r[k].dx += f * kx;
-            r[k].dy += f * ky;
-            r[k].dz += f * kz;
+            r[k].dx = fma(f, kx, r[k].dx);
+            r[k].dy = fma(f, ky, r[k].dy);
+            r[k].dz = fma(f, kz, r[k].dz);
         }
     }
 
@@ -814,7 +814,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
         if (straight && !state.unit) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const double a2 = r[k].dx * r[k].dx + r[k].dy * r[k].dy + r[k].dz * r[k].dz;
+                const double a2 = norm2_3(r[k].dx, r[k].dy, r[k].dz);
                 straight = straight && (fabs(a2 - 1.0) <= 1e-14);
             }
         }
@@ -839,14 +839,14 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             // optika/materials/_snells_law.py:341-366
-            const double a2 = r[k].dx * r[k].dx + r[k].dy * r[k].dy + r[k].dz * r[k].dz;
-            const double au = r[k].dx * nx[k] + r[k].dy * ny[k] + r[k].dz * nz[k];
-            const double root = fsqrt(inv_r2[k] + au * au - a2);
+            const double a2 = norm2_3(r[k].dx, r[k].dy, r[k].dz);
+            const double au = dot3(r[k].dx, r[k].dy, r[k].dz, nx[k], ny[k], nz[k]);
+            const double root = fsqrt(fma(au, au, inv_r2[k] - a2));
             // d = -au + sgn (2 mirror - 1) root with sgn = -copysign(1, au)
             const double d = -au + copysign(root, mirror ? -au : au);
-            r[k].dx = ratio[k] * (r[k].dx + d * nx[k]);
-            r[k].dy = ratio[k] * (r[k].dy + d * ny[k]);
-            r[k].dz = ratio[k] * (r[k].dz + d * nz[k]);
+            r[k].dx = ratio[k] * fma(d, nx[k], r[k].dx);
+            r[k].dy = ratio[k] * fma(d, ny[k], r[k].dy);
+            r[k].dz = ratio[k] * fma(d, nz[k], r[k].dz);
             if (!mirror) r[k].att = 0.0;  // _materials.py:101-105, 141-145, 440-444
             r[k].n = n2[k];
         }
