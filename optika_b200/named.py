@@ -432,6 +432,51 @@ class _VectorArray:
         return dataclasses.replace(self, **kwargs)
 
 
+def _solid_angle_cells(components) -> np.ndarray:
+    """
+    Solid angles of the cells of a vertex grid of directions, given as three arrays broadcastable to
+    ``[..., n_x + 1, n_y + 1]`` (not necessarily unit): ``[..., n_x, n_y]``.  Every cell is two spherical
+    triangles (00, 10, 11) + (00, 11, 01), each ``2 atan2(a . (b x c), 1 + a.b + b.c + c.a)`` on the normalised
+    corners.  The image of a 4096 x 4096 detector has 1.7e7 field cells: blocks of rows are normalised and worked on
+    by a few threads (NumPy releases the GIL) instead of through two hundred 134 MB temporaries on one.
+    """
+    import concurrent.futures
+    import os
+
+    components = np.broadcast_arrays(*[np.asarray(c, dtype=np.float64) for c in components])
+    shape_ = components[0].shape
+    n_x, n_y = shape_[-2] - 1, shape_[-1] - 1
+    out = np.empty(shape_[:-2] + (n_x, n_y))
+
+    def dot(p, q):
+        return p[0] * q[0] + p[1] * q[1] + p[2] * q[2]
+
+    def triple(p, q, r):  # p . (q x r)
+        return (p[0] * (q[1] * r[2] - q[2] * r[1]) + p[1] * (q[2] * r[0] - q[0] * r[2]) + p[2] * (q[0] * r[1] - q[1] * r[0]))
+
+    def block(rows):
+        i0, i1 = rows
+        v = np.stack([c[..., i0:i1 + 1, :] for c in components])
+        v /= np.sqrt(dot(v, v))
+        a, b, c, d = v[..., :-1, :-1], v[..., 1:, :-1], v[..., 1:, 1:], v[..., :-1, 1:]
+        ca = dot(c, a)
+        first = np.arctan2(triple(a, b, c), 1 + dot(a, b) + dot(b, c) + ca)
+        second = np.arctan2(triple(a, c, d), 1 + ca + dot(c, d) + dot(d, a))
+        out[..., i0:i1, :] = 2 * first + 2 * second
+
+    per_row = max(1, n_y * int(np.prod(shape_[:-2], dtype=np.int64)))
+    rows = max(1, min(n_x, (1 << 20) // per_row))
+    blocks = [(i, min(i + rows, n_x)) for i in range(0, n_x, rows)]
+    workers = min(len(blocks), os.cpu_count() or 1, 16)
+    if workers > 1:
+        with concurrent.futures.ThreadPoolExecutor(workers) as pool:
+            list(pool.map(block, blocks))
+    else:
+        for r in blocks:
+            block(r)
+    return out
+
+
 def _corners(v: "_VectorArray", axis: tuple[str, str]):
     """The four corner vertices (00, 10, 11, 01) of every cell of a 2-D vertex grid."""
     ax, ay = axis
@@ -472,14 +517,15 @@ class Cartesian3dVectorArray(_VectorArray):
         Signed solid angle [sr] of the spherical quadrilateral spanned by the four direction
         vertices of every cell: two spherical triangles, each by Van Oosterom & Strackee (1983).
         """
-        v00, v10, v11, v01 = (v.normalized for v in _corners(self, axis))
-
-        def triangle(a, b, c):
-            num = a @ b.cross(c)
-            den = 1 + a @ b + b @ c + c @ a
-            return 2 * np.arctan2(num, den)
-
-        return triangle(v00, v10, v11) + triangle(v00, v11, v01)
+        ax, ay = axis
+        shape_ = self.shape
+        if ax not in shape_ or ay not in shape_:
+            raise ValueError(f"axes {axis} must both be present in {shape_}")
+        other = tuple(a for a in shape_ if a not in axis)
+        order = other + (ax, ay)
+        full = {a: shape_[a] for a in order}
+        out = _solid_angle_cells([aligned(as_named_array(getattr(self, c)), full) for c in self._names])
+        return ScalarArray(out, order)
 
     def cross(self, o: "Cartesian3dVectorArray") -> "Cartesian3dVectorArray":
         return Cartesian3dVectorArray(

@@ -228,3 +228,35 @@ def test_reductions_have_no_cpu_fallback():
     system = configs.newtonian(num_field=2, num_pupil=4)
     with pytest.raises(RuntimeError):
         system.pupil_moments(**configs.PHYSICAL)
+
+
+def test_solid_angles_of_direction_grids_blocked_and_threaded():
+    """
+    ``Cartesian3dVectorArray.solid_angle_cell`` works on blocks of rows with a few threads (a 4096 x 4096 field grid
+    has 1.7e7 cells): same values as the oracle's plain formula, with leading axes, either axis order, vertices that
+    are not unit vectors, and a grid large enough to be split.  (The triple product carries an absolute rounding
+    error of ~1e-16 sr in either evaluation.)
+    """
+    from optika_b200 import _util
+    from oracle import grid as og
+
+    rng = np.random.default_rng(5)
+    ax = np.sort(rng.uniform(-0.3, 0.3, 1501))
+    ay = np.sort(rng.uniform(-0.2, 0.4, 1203))
+    field = na.Cartesian2dVectorArray(na.ScalarArray(ax, "fx"), na.ScalarArray(ay, "fy"))
+    got = _util.direction(field).solid_angle_cell(("fx", "fy"))
+    want = og.solid_angle_cell(*np.meshgrid(ax, ay, indexing="ij"))
+    assert got.shape == {"fx": 1500, "fy": 1202}
+    assert np.allclose(got.numpy(("fx", "fy")), want, rtol=1e-12, atol=2e-15)
+    swapped = _util.direction(field).solid_angle_cell(("fy", "fx"))  # orientation flips the sign
+    assert np.allclose(swapped.numpy(("fx", "fy")), -want, rtol=1e-12, atol=2e-15)
+    # a leading (wavelength) axis: one grid per row
+    rows = np.stack([ax[:40] * s for s in (1.0, 1.1, 1.3)])
+    chromatic = na.Cartesian2dVectorArray(na.ScalarArray(rows, ("w", "fx")), na.ScalarArray(ay[:33], "fy"))
+    got = _util.direction(chromatic).solid_angle_cell(("fx", "fy")).numpy(("w", "fx", "fy"))
+    for k in range(3):
+        assert np.allclose(got[k], og.solid_angle_cell(*np.meshgrid(rows[k], ay[:33], indexing="ij")), rtol=1e-12, atol=2e-15)
+    # directions that are not normalised give the same solid angles
+    d = _util.direction(field)
+    scaled = na.Cartesian3dVectorArray(d.x * 3.0, d.y * 3.0, d.z * 3.0)
+    assert np.allclose(scaled.solid_angle_cell(("fx", "fy")).numpy(("fx", "fy")), want, rtol=1e-12, atol=2e-15)
