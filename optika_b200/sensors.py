@@ -36,6 +36,53 @@ __all__ = [
 ]
 
 
+_NOISE_BLOCK = 1 << 20
+
+
+def _noise_blocks(draw, out: np.ndarray, seed, stream: int) -> np.ndarray:
+    """
+    Fill the flat array `out` with ``draw(rng, slice)`` block by block on a few threads.  Every block of 2^20 pixels
+    has its own generator, spawned from (seed, stream, block index): the result depends on the seed and on nothing
+    else (not on the number of threads), and a 4096 x 4096 x 8 exposure takes 0.5 s instead of 4.5 s.
+    """
+    import concurrent.futures
+    import os
+
+    n = out.size
+    blocks = [(k, slice(i, min(i + _NOISE_BLOCK, n))) for k, i in enumerate(range(0, n, _NOISE_BLOCK))]
+    entropy = 0 if seed is None else int(seed)
+    if seed is None:
+        entropy = int(np.random.SeedSequence().entropy)
+
+    def work(block):
+        k, where = block
+        rng = np.random.default_rng(np.random.SeedSequence(entropy, spawn_key=(stream, k)))
+        out[where] = draw(rng, where)
+
+    workers = min(len(blocks), os.cpu_count() or 1, 16)
+    if workers > 1:
+        with concurrent.futures.ThreadPoolExecutor(workers) as pool:
+            list(pool.map(work, blocks))
+    else:
+        for b in blocks:
+            work(b)
+    return out
+
+
+def shot_noise(photons: np.ndarray, seed) -> np.ndarray:
+    """Poisson-distributed counts with the given expectations (negative expectations count as zero)."""
+    lam = np.maximum(np.ascontiguousarray(photons, dtype=np.float64), 0).reshape(-1)
+    out = np.empty(lam.size, dtype=np.int64)
+    return _noise_blocks(lambda rng, where: rng.poisson(lam[where]), out, seed, 0).reshape(np.shape(photons))
+
+
+def read_noise(electrons: np.ndarray, sigma: float, seed) -> np.ndarray:
+    """`electrons` plus zero-mean Gaussian noise of `sigma` electrons."""
+    loc = np.ascontiguousarray(electrons, dtype=np.float64).reshape(-1)
+    out = np.empty(loc.size, dtype=np.float64)
+    return _noise_blocks(lambda rng, where: rng.normal(loc=loc[where], scale=sigma), out, seed, 1).reshape(np.shape(electrons))
+
+
 @dataclasses.dataclass(eq=False)
 class IdealSensorMaterial(_materials.Vacuum):
     """
@@ -44,13 +91,16 @@ class IdealSensorMaterial(_materials.Vacuum):
     ``direction_refracted = -direction . normal`` and photons map 1:1 to electrons.
     """
 
+    uses_direction = False  # nothing below depends on the angle of incidence: callers need not form it
+
     def signal(self, photons, wavelength=None, direction=1, noise: bool = False, rng=None, **kwargs):
-        # optika/sensors/materials/_materials.py:1576-1601; shot noise is drawn on the host
-        # (per pixel, tiny) from a seeded NumPy generator
+        # optika/sensors/materials/_materials.py:1576-1601; shot noise is drawn on the host from seeded NumPy
+        # generators, one per block of pixels (`shot_noise`); `rng` is the seed (or a Generator to take one from)
         if noise:
-            rng = np.random.default_rng(rng)
+            if isinstance(rng, np.random.Generator):
+                rng = int(rng.integers(0, 2**63 - 1))
             p = na.as_named_array(photons)
-            photons = na.ScalarArray(rng.poisson(np.maximum(p.ndarray, 0)).astype(np.int64), p.axes)
+            photons = na.ScalarArray(shot_noise(p.ndarray, rng), p.axes)
         return photons
 
 
@@ -193,16 +243,20 @@ class AbstractImagingSensor(AbstractSurface):
         """
         Photons -> electrons (``_sensors.py:173-252``).  `noise` adds Poisson shot noise
         (in the material) and zero-mean Gaussian read noise of ``read_noise`` electrons
-        (``:243-248``), drawn on the host from ``numpy.random.default_rng(seed)``.
+        (``:243-248``), drawn on the host from NumPy generators spawned from `seed`, one per block of 2^20 pixels
+        (`shot_noise`, `read_noise`).  `direction` may be a callable that forms it on demand.
         """
         if timedelta is None:
             timedelta = self.timedelta_exposure
         photons = image.outputs * timedelta
-        rng = np.random.default_rng(seed) if noise else None
-        electrons = self.material.signal(photons=photons, direction=direction, noise=noise, rng=rng)
+        if noise and seed is None:
+            seed = int(np.random.SeedSequence().entropy % (2**63))
+        if callable(direction):  # formed only for materials that look at it (a full-size complex array otherwise)
+            direction = direction() if getattr(self.material, "uses_direction", True) else 1
+        electrons = self.material.signal(photons=photons, direction=direction, noise=noise, rng=seed if noise else None)
         if noise:
             e = na.as_named_array(electrons)
-            electrons = na.ScalarArray(rng.normal(loc=e.ndarray, scale=float(self.read_noise)), e.axes)
+            electrons = na.ScalarArray(read_noise(e.ndarray, float(self.read_noise), seed), e.axes)
         return dataclasses.replace(image, outputs=electrons)
 
     def measure(

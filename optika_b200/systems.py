@@ -929,8 +929,6 @@ class SequentialSystem(AbstractSequentialSystem):
         ex, ey = self.sensor.pixel_edges()
         planes = self.collect_grids(grids, w_edges, device=device, reduce=reduce)
         flux, moment = planes["flux"], planes["moment_real"]
-        with np.errstate(invalid="ignore", divide="ignore"):
-            direction = np.where(flux > 0, moment / flux, 1) + 0j  # sensors/_sensors.py:163-169
         sensor = self.sensor
         axes_out = tuple(compiled.shape) + (axis_wavelength, sensor.axis_pixel.x, sensor.axis_pixel.y)
         from .vectors import SpectralPositionalVectorArray
@@ -942,6 +940,9 @@ class SequentialSystem(AbstractSequentialSystem):
             ),
         )
         collected = na.FunctionArray(inputs=inputs, outputs=na.ScalarArray(flux, axes_out))
-        return sensor.expose(
-            collected, na.ScalarArray(direction, axes_out), axis_wavelength=axis_wavelength, noise=noise, seed=seed
-        )
+
+        def direction():  # sensors/_sensors.py:163-169; only materials that depend on the angle of incidence ask
+            with np.errstate(invalid="ignore", divide="ignore"):
+                return na.ScalarArray(np.where(flux > 0, moment / flux, 1) + 0j, axes_out)
+
+        return sensor.expose(collected, direction, axis_wavelength=axis_wavelength, noise=noise, seed=seed)

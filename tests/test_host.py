@@ -260,3 +260,26 @@ def test_solid_angles_of_direction_grids_blocked_and_threaded():
     d = _util.direction(field)
     scaled = na.Cartesian3dVectorArray(d.x * 3.0, d.y * 3.0, d.z * 3.0)
     assert np.allclose(scaled.solid_angle_cell(("fx", "fy")).numpy(("fx", "fy")), want, rtol=1e-12, atol=2e-15)
+
+
+def test_detector_noise_is_seeded_per_block_of_pixels():
+    """
+    Shot and read noise (``ImagingSensor.expose``) come from one NumPy generator per block of 2^20 pixels, spawned from
+    the seed: reproducible, independent of how many threads drew them, and with the right moments.
+    """
+    from optika_b200 import sensors
+
+    lam = np.random.default_rng(0).uniform(0, 300, 3 * sensors._NOISE_BLOCK + 12345)
+    a, b = sensors.shot_noise(lam, 11), sensors.shot_noise(lam, 11)
+    assert a.dtype == np.int64 and np.array_equal(a, b) and not np.array_equal(a, sensors.shot_noise(lam, 12))
+    # the first block does not depend on what follows it
+    assert np.array_equal(sensors.shot_noise(lam[: sensors._NOISE_BLOCK], 11), a[: sensors._NOISE_BLOCK])
+    z = (a - lam)[lam > 30] / np.sqrt(lam[lam > 30])
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+    assert sensors.shot_noise(np.array([-3.0, 0.0]), 1).tolist() == [0, 0]
+    r = sensors.read_noise(a, 2.5, 11) - a
+    assert abs(r.mean()) < 1e-2 and abs(r.std() - 2.5) < 1e-2
+    assert np.array_equal(sensors.read_noise(a.reshape(3, -1)[:, :7], 0.0, 4), a.reshape(3, -1)[:, :7])
+    # blocks are independent streams: no block repeats another
+    assert not np.array_equal((sensors.read_noise(np.zeros(2 * sensors._NOISE_BLOCK), 1.0, 3)[: sensors._NOISE_BLOCK]),
+                              (sensors.read_noise(np.zeros(2 * sensors._NOISE_BLOCK), 1.0, 3)[sensors._NOISE_BLOCK:]))
