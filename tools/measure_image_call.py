@@ -32,7 +32,7 @@ field = na.Cartesian2dVectorArray(
 pupil = na.Cartesian2dVectorArray(na.ScalarArray(np.linspace(-160, 160, 11), axes[3]), na.ScalarArray(np.linspace(-160, 160, 9), axes[4]))
 from optika_b200.vectors import SpectralPositionalVectorArray
 
-scene = na.FunctionArray(inputs=SpectralPositionalVectorArray(wavelength=wavelength, position=field), outputs=1e3)
+scene = na.FunctionArray(inputs=SpectralPositionalVectorArray(wavelength=wavelength, position=field), outputs=1e15)
 out = {}
 for label, noise in (("first call (compiles / loads kernels)", False), ("noise=False", False), ("noise=True", True)):
     torch.cuda.synchronize()
