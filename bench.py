@@ -357,9 +357,9 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
     n_rays = sum(g.size for g in grids)
     stream = torch.cuda.current_stream(device)
 
-    def make(local, counts=True):
+    def make(local, counts=True, moments=True):
         image = _engine.DeviceImage.zeros(
-            w_edges, ex, ey, device, leading=leading, moments=True, counts=counts, fused=True, pad_to=1 if local else world
+            w_edges, ex, ey, device, leading=leading, moments=moments, counts=counts, fused=True, pad_to=1 if local else world
         )
         return distributed.ImagePipeline(image, device, local=local, rezero=True)
 
@@ -482,35 +482,41 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
     del pipeline
     torch.cuda.empty_cache()
 
-    # the same exposure with the planes `SequentialSystem.image` returns by default: flux and flux x cos, no
-    # counts plane (the hit counts above exist for the exact comparison between N ranks and one)
-    lean = make(local=(world == 1), counts=False)
-    ms2, st2, planes2, _ = run(lean, shard=True, n_steps=steps, n_warm=warmup)
-    d2h2 = sum(int(v.nbytes) for v in planes2.values())
-    t2 = torch.tensor([ms2, st2["ms_trace"], st2["ms_reduce"], st2["ms_d2h"]], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    two = dict(zip(("ms_total", "ms_trace", "ms_reduce", "ms_d2h"), [float(v) for v in t2.tolist()]))
-    two.update(d2h_bytes=d2h2, planes="flux / flux cos (the default of SequentialSystem.image)",
-               intercepts_per_s=n_rays * n_surfaces / (two["ms_total"] * 1e-3))
-    del planes2
-    lean.close()
-    del lean
-    torch.cuda.empty_cache()
-    if world > 1:
-        n1 = None
-        if rank == 0:
-            single = make(local=True, counts=False)
-            ms1, st1, planes1, _ = run(single, shard=False, n_steps=max(1, min(steps, 2)), n_warm=1, collective=False)
-            n1 = dict(ms_total=ms1, **st1)
-            del planes1
-            single.close()
-            del single
-        dist.barrier()
-        if rank == 0:
-            two["n1_same_run"] = n1
-            two["efficiency_vs_n1"] = n1["ms_total"] / (world * two["ms_total"])
+    # The same exposure with fewer planes read back (the hit counts above exist for the exact comparison between N
+    # ranks and one).  `two_planes`: flux and flux x cos(incidence), what `SequentialSystem.image` needs for a sensor
+    # material that depends on the angle of incidence; `one_plane`: flux only, what it reads back for the default
+    # IdealSensorMaterial (optika/sensors/materials/_materials.py:1566-1643 ignores the direction).
+    def variant(moments, planes_text):
+        lean = make(local=(world == 1), counts=False, moments=moments)
+        ms2, st2, planes2, _ = run(lean, shard=True, n_steps=steps, n_warm=warmup)
+        d2h2 = sum(int(v.nbytes) for v in planes2.values())
+        t2 = torch.tensor([ms2, st2["ms_trace"], st2["ms_reduce"], st2["ms_d2h"]], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        res = dict(zip(("ms_total", "ms_trace", "ms_reduce", "ms_d2h"), [float(v) for v in t2.tolist()]))
+        res.update(d2h_bytes=d2h2, planes=planes_text, intercepts_per_s=n_rays * n_surfaces / (res["ms_total"] * 1e-3))
+        del planes2
+        lean.close()
+        del lean
         torch.cuda.empty_cache()
+        if world > 1:
+            n1 = None
+            if rank == 0:
+                single = make(local=True, counts=False, moments=moments)
+                ms1, st1, planes1, _ = run(single, shard=False, n_steps=max(1, min(steps, 2)), n_warm=1, collective=False)
+                n1 = dict(ms_total=ms1, **st1)
+                del planes1
+                single.close()
+                del single
+            dist.barrier()
+            if rank == 0:
+                res["n1_same_run"] = n1
+                res["efficiency_vs_n1"] = n1["ms_total"] / (world * res["ms_total"])
+            torch.cuda.empty_cache()
+        return res
+
+    two = variant(True, "flux / flux cos (SequentialSystem.image with a sensor material that uses the angle of incidence)")
+    out["one_plane"] = variant(False, "flux (SequentialSystem.image with the default IdealSensorMaterial)")
     out["two_planes"] = two
     return out
 

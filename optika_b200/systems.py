@@ -800,12 +800,13 @@ class SequentialSystem(AbstractSequentialSystem):
         return grids
 
     def collect_grids(self, grids: list, wavelength_edges, device=None, reduce: bool = True, counts: bool = False,
-                      pipeline=None, image=None, shard: bool = True, on_launch=None) -> dict:
+                      pipeline=None, image=None, shard: bool = True, on_launch=None, moments: bool = True) -> dict:
         """
         The device part of :meth:`image`: every ray of `grids` (one :class:`~optika_b200._grid.RayGrid`
         per configuration, from :meth:`ray_grids`) is drawn, traced and binned on the device
         (``optk_trace_grid``: fused, no ray touches HBM) and the detector planes come back as host
-        arrays ``{"flux", "moment_real"[, "counts"]}`` of shape ``[config axes..., n_w, n_x, n_y]``.
+        arrays ``{"flux"[, "moment_real"][, "counts"]}`` of shape ``[config axes..., n_w, n_x, n_y]``
+        (`moments`: the flux x cos(incidence) plane behind ``sensor.collect``'s direction, ``sensors/_sensors.py:163-169``).
 
         Under ``torch.distributed`` every rank traces a slab of the grid (the axis that balances best,
         :func:`optika_b200.distributed.best_shard_axis`); while configuration k + 1 is traced, the planes
@@ -827,7 +828,7 @@ class SequentialSystem(AbstractSequentialSystem):
             if image is None:
                 image = _engine.DeviceImage.zeros(
                     np.asarray(wavelength_edges, dtype=float), ex, ey, device, leading=tuple(compiled.shape.values()),
-                    moments=True, counts=counts, fused=True, pad_to=world if reduce else 1,
+                    moments=moments, counts=counts, fused=True, pad_to=world if reduce else 1,
                 ) if pipeline is None else pipeline.image
             if pipeline is None:
                 pipeline = distributed.ImagePipeline(image, device, local=(world == 1)) if (reduce or world == 1) else None
@@ -927,9 +928,12 @@ class SequentialSystem(AbstractSequentialSystem):
             w_edges = np.array([w_edges.min(), w_edges.max()])  # :1189-1196
         compiled = self._compiled_local
         ex, ey = self.sensor.pixel_edges()
-        planes = self.collect_grids(grids, w_edges, device=device, reduce=reduce)
-        flux, moment = planes["flux"], planes["moment_real"]
         sensor = self.sensor
+        # the angle of incidence on the detector is binned (and reduced, and read back) only for sensor materials
+        # that look at it; the default IdealSensorMaterial does not (sensors/materials/_materials.py:1576-1601)
+        uses_direction = bool(getattr(sensor.material, "uses_direction", True))
+        planes = self.collect_grids(grids, w_edges, device=device, reduce=reduce, moments=uses_direction)
+        flux, moment = planes["flux"], planes.get("moment_real")
         axes_out = tuple(compiled.shape) + (axis_wavelength, sensor.axis_pixel.x, sensor.axis_pixel.y)
         from .vectors import SpectralPositionalVectorArray
 

@@ -15,9 +15,10 @@ for path in sys.argv[1:]:
                         row = {k: (round(v[k], 3) if isinstance(v.get(k), float) else v.get(k)) for k in KEYS}
                         n1 = v.get("n1_same_run")
                         print(path, name, row, "n1 ms", round(n1["ms_total"], 2) if n1 else None)
-                        two = v.get("two_planes")
-                        if two:
-                            print("    two planes:", {k: (round(two[k], 3) if isinstance(two.get(k), float) else two.get(k))
-                                                    for k in ("ms_total", "ms_trace", "ms_reduce", "ms_d2h", "efficiency_vs_n1")})
+                        for key, label in (("two_planes", "two planes"), ("one_plane", "one plane")):
+                            two = v.get(key)
+                            if two:
+                                print(f"    {label}:", {k: (round(two[k], 3) if isinstance(two.get(k), float) else two.get(k))
+                                                        for k in ("ms_total", "ms_trace", "ms_reduce", "ms_d2h", "efficiency_vs_n1")})
     except Exception as e:  # noqa: BLE001
         print(path, e)
