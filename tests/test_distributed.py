@@ -205,6 +205,18 @@ def test_image_pipeline_single_process_is_a_plain_read_back():
     assert planes["flux"].shape == (1, 3, 2) and np.all(planes["flux"] == 2.0) and np.all(planes["moment_real"] == 3.0)
     assert "counts" not in planes
     pipeline.close()
+    # one plane: what `SequentialSystem.image` asks for when the sensor material ignores the angle of incidence
+    lean = _engine.DeviceImage.zeros(np.array([0.0, 1.0]), np.linspace(0, 1, 4), np.linspace(0, 1, 3), "cpu",
+                                     leading=(2,), moments=False, counts=False, fused=True, pad_to=4)
+    assert lean.moment_real is None and lean.buffer_f64.shape == (2, 8) and lean.buffer_i64 is None
+    lean.flux[1] += 5.0
+    pipeline = distributed.ImagePipeline(lean, "cpu")
+    for c in range(2):
+        pipeline.submit(c)
+    planes = pipeline.finish()
+    assert set(planes) == {"flux"} and planes["flux"].shape == (2, 1, 3, 2)
+    assert np.all(planes["flux"][0] == 0.0) and np.all(planes["flux"][1] == 5.0)
+    pipeline.close()
 
 
 def test_fused_image_planes_are_addressed_through_their_strides():
