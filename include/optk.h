@@ -627,8 +627,7 @@ OPTK_API int optk_measure_soa_copy(int64_t n_rays, double* gbytes_per_second, vo
  * arrays, so that their error can be measured against correctly rounded results (tests/test_gpu_math.py:
  * <= 1 ulp; zero / inf / NaN as the IEEE operators).  op: 0 a / b, 1 1 / a, 2 sqrt(a), 3 1 / sqrt(a),
  * 4 / 5 the variants of 1 / a and 1 / sqrt(a) without the repair of a = 0 and a = inf, 6 a / b for a divisor
- * that is never infinite (<= 1.5 ulp), 7 a / b to 2^-38 for self-correcting iterations (b is read for op 0, 6, 7),
- * 8 sqrt(a) for radicands that are never +inf (no repair: +-0 -> 0 through a clamped seed). */
+ * that is never infinite (<= 1.5 ulp), 7 a / b to 2^-38 for self-correcting iterations (b is read for op 0, 6, 7). */
 OPTK_API int optk_debug_math(int32_t op, int64_t n, const double* a, const double* b, double* out, void* stream);
 
 /* ---- detector physics after binning (kernel 4) ----------------------------------

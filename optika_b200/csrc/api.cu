@@ -699,7 +699,7 @@ OPTK_API int optk_apply_efficiency(int64_t n, double* intensity, const double* e
 
 OPTK_API int optk_debug_math(int32_t op, int64_t n, const double* a, const double* b, double* out, void* stream) {
     DeviceScope device_scope(stream, "optk_debug_math");
-    if (op < 0 || op > 8 || n < 0 || !a || !out || ((op == 0 || op == 6 || op == 7) && !b)) {
+    if (op < 0 || op > 7 || n < 0 || !a || !out || ((op == 0 || op >= 6) && !b)) {
         set_error("optk_debug_math: bad arguments");
         return OPTK_ERR_INVALID;
     }

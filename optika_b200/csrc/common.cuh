@@ -203,31 +203,6 @@ __device__ __forceinline__ double fsqrt(double x) {
     return (not_finite(g) && (unsigned)__double2hiint(x) <= 0x80000000u) ? x : g;
 }
 
-// sqrt(x) for radicands that are differences of squares (discriminants, 1 - n_x^2 - n_y^2, Snell's root): +-0
-// gives 0, negative and NaN give NaN as the plain operator does, but WITHOUT a repair: the seed of +-0 is +-inf,
-// clamped to +-2^1023 with two integer min, after which g = x y0 = 0, the Newton step keeps it there and the
-// residual step adds 0.  (x = +inf would give NaN instead of inf: an infinite radicand of this kind comes with an
-// inf - inf, i.e. a NaN, anyway.)  9 FP64 + 3 integer instructions, no compare, no select.
-__device__ __forceinline__ double fsqrt_fast(double x) {
-    double y0;
-    asm("{\n"
-        ".reg .b32 lo, hi;\n"
-        ".reg .f64 s;\n"
-        "rsqrt.approx.ftz.f64 s, %1;\n"
-        "mov.b64 {lo, hi}, s;\n"
-        "min.s32 hi, hi, 0x7fe00000;\n"
-        "min.u32 hi, hi, 0xffe00000;\n"
-        "mov.b64 %0, {lo, hi};\n"
-        "}"
-        : "=d"(y0)
-        : "d"(x));
-    double g = x * y0, h = 0.5 * y0;
-    const double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    return fma(fma(-g, g, x), h, g);
-}
-
 // 1 / sqrt(x) without the repair of x = 0 / inf (both give NaN here): for radicands that are >= 1 by
 // construction (1 + slopes^2) or whose zero is a NaN of the caller anyway (the toroid's domain boundary).
 __device__ __forceinline__ double frsqrt_raw(double x) {

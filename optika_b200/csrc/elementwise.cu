@@ -95,7 +95,6 @@ math_kernel(int op, long long n, const double* __restrict__ a, const double* __r
         case 4: y = frcp_raw(x); break;
         case 6: y = fdiv_finite(x, b[i]); break;
         case 7: y = fdiv_newton(x, b[i]); break;
-        case 8: y = fsqrt_fast(x); break;
         default: y = frsqrt_raw(x); break;
     }
     out[i] = y;

@@ -80,7 +80,7 @@ __device__ __forceinline__ double parabola_intercept(double f, double ox, double
     const double fuz = f * uz;
     const double h = fma(ox, ux, fma(oy, uy, -2.0 * fuz));
     const double c = fma(ox, ox, fma(oy, oy, -4.0 * (f * oz)));
-    const double root = signed_root(fuz, fsqrt_fast(fma(h, h, -(a * c))));
+    const double root = signed_root(fuz, fsqrt(fma(h, h, -(a * c))));
     const bool general = a > 1e-10;
     const bool stable = -h * fuz >= 0.0;  // -h and root have the same sign (or one of them is zero)
     const double num = (general && !stable) ? (-h - root) : c;
@@ -679,10 +679,10 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
                 const double vx = r[k].dx, vy = r[k].dy, vz = r[k].dz;
                 const double up = dot3(vx, vy, vz, qx, qy, pz);
                 const double disc = fma(up, up, -(norm2_3(qx, qy, pz) - rad * rad));
-                t[k] = -up - signed_root(rad * vz, fsqrt_fast(disc));
+                t[k] = -up - signed_root(rad * vz, fsqrt(disc));
                 nx[k] = c * fma(vx, t[k], qx);
                 ny[k] = c * fma(vy, t[k], qy);
-                nz[k] = -fsqrt_fast(fma(-ny[k], ny[k], fma(-nx[k], nx[k], 1.0)));
+                nz[k] = -fsqrt(fma(-ny[k], ny[k], fma(-nx[k], nx[k], 1.0)));
             }
             break;
         }
@@ -841,7 +841,7 @@ __device__ __forceinline__ void surface_full(const optk_surface_t& S, Ray (&r)[R
             // optika/materials/_snells_law.py:341-366
             const double a2 = norm2_3(r[k].dx, r[k].dy, r[k].dz);
             const double au = dot3(r[k].dx, r[k].dy, r[k].dz, nx[k], ny[k], nz[k]);
-            const double root = fsqrt_fast(fma(au, au, inv_r2[k] - a2));
+            const double root = fsqrt(fma(au, au, inv_r2[k] - a2));
             // d = -au + sgn (2 mirror - 1) root with sgn = -copysign(1, au)
             const double d = -au + copysign(root, mirror ? -au : au);
             r[k].dx = ratio[k] * fma(d, nx[k], r[k].dx);

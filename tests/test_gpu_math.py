@@ -81,15 +81,6 @@ def test_square_root_within_one_ulp(cuda_device):
     assert err.max() <= 1.0, err.max()
 
 
-def test_square_root_of_discriminants(cuda_device):
-    """fsqrt_fast: the same digits as fsqrt, zero and negative radicands right without a repair."""
-    a = operands(10, signed=False)
-    assert np.array_equal(run(8, a), run(2, a))
-    got = run(8, np.array([0.0, -0.0, -1.0, np.nan, 4.0, 1e-300, 1e300]))
-    assert got[0] == 0.0 and got[1] == 0.0 and np.isnan(got[2]) and np.isnan(got[3]) and got[4] == 2.0
-    assert np.isclose(got[5], 1e-150, rtol=1e-15) and np.isclose(got[6], 1e150, rtol=1e-15)
-
-
 @pytest.mark.parametrize("op", [3, 5], ids=["repaired", "raw"])
 def test_reciprocal_square_root_within_one_ulp(cuda_device, op):
     a = operands(5, signed=False)
