@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OPTK_ABI_VERSION 8
+#define OPTK_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define OPTK_API __attribute__((visibility("default")))
@@ -356,6 +356,11 @@ OPTK_API int optk_system_create(const optk_surface_t* table, int32_t n_surface, 
                        optk_system_t** out);
 OPTK_API int optk_system_destroy(optk_system_t* sys);
 OPTK_API int optk_system_size(const optk_system_t* sys, int32_t* n_surface, int32_t* n_config);
+/* One surface of one configuration AS THE LIBRARY KEEPS IT: the caller's values plus what optk_system_create
+ * derives once per surface -- sag[3] = 1 / sag[0], aperture[3] = the squared-radius threshold of circular and sector
+ * apertures, OPTK_F_TRANSLATION_ONLY, OPTK_F_APERTURE_CONVEX / _CLOCKWISE with aperture[0..1] for convex polygons.
+ * Efficiency-table pointers are the device copies.  Needs no GPU (inspection, tests). */
+OPTK_API int optk_system_surface(const optk_system_t* sys, int32_t config, int32_t index, optk_surface_t* out);
 
 /* ---- fused sequential trace (kernel 1) --------------------------------------
  * Replaces optika.propagators.propagate_rays (optika/propagators.py:19-41) and,

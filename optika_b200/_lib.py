@@ -67,6 +67,9 @@ F_APERTURE_ANGULAR = 0x040
 F_HOLO_DIVERGING_1 = 0x080
 F_HOLO_DIVERGING_2 = 0x100
 F_LOCAL_OUT = 0x200
+F_TRANSLATION_ONLY = 0x400  # set by the library
+F_APERTURE_CONVEX = 0x4000  # set by the library (optk_system_create)
+F_APERTURE_CLOCKWISE = 0x8000
 
 STAGE_INTERCEPT = 0x01
 STAGE_ATTENUATE = 0x02
@@ -265,7 +268,7 @@ class CcdPlane(C.Structure):
     ]
 
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class OptkError(RuntimeError):
@@ -283,6 +286,7 @@ SYMBOLS = (
     "optk_system_create",
     "optk_system_destroy",
     "optk_system_size",
+    "optk_system_surface",
     "optk_trace",
     "optk_trace_host",
     "optk_trace_grid",
@@ -325,6 +329,7 @@ def lib() -> C.CDLL:
     L.optk_system_create.argtypes = [C.POINTER(Surface), i32, i32, C.POINTER(vp)]
     L.optk_system_destroy.argtypes = [vp]
     L.optk_system_size.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.optk_system_surface.argtypes = [vp, i32, i32, C.POINTER(Surface)]
     L.optk_trace.argtypes = [
         vp, i32, C.POINTER(RaysIn), C.POINTER(RaysOut), i32, i32, i32, i32, i64,
         C.POINTER(Image), C.POINTER(Affine), vp, vp,

@@ -482,6 +482,20 @@ OPTK_API int optk_system_size(const optk_system_t* sys, int32_t* n_surface, int3
     return OPTK_OK;
 }
 
+OPTK_API int optk_system_surface(const optk_system_t* sys, int32_t config, int32_t index, optk_surface_t* out) {
+    if (!sys || !out) {
+        set_error("optk_system_surface: NULL argument");
+        return OPTK_ERR_INVALID;
+    }
+    if (config < 0 || config >= sys->n_config || index < 0 || index >= sys->n_surface) {
+        set_error("optk_system_surface: configuration %d / surface %d out of range [0, %d) x [0, %d)", config, index,
+                  sys->n_config, sys->n_surface);
+        return OPTK_ERR_INVALID;
+    }
+    *out = sys->table[(size_t)config * sys->n_surface + index];
+    return OPTK_OK;
+}
+
 OPTK_API int optk_trace(const optk_system_t* sys, int32_t config, const optk_rays_in_t* in, const optk_rays_out_t* out,
                int32_t surf_begin, int32_t surf_count, int32_t surf_step, int32_t accumulate,
                int64_t accumulate_stride, const optk_image_t* image, const optk_affine_t* image_frame,

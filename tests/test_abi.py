@@ -110,6 +110,9 @@ def test_constants_match_header():
     assert define("OPTK_ML_MAX_AXES") == _lib.ML_MAX_AXES
     assert define("OPTK_STAGE_ALL") == _lib.STAGE_ALL
     assert define("OPTK_F_LOCAL_OUT") == _lib.F_LOCAL_OUT
+    assert define("OPTK_F_TRANSLATION_ONLY") == _lib.F_TRANSLATION_ONLY
+    assert define("OPTK_F_APERTURE_CONVEX") == _lib.F_APERTURE_CONVEX
+    assert define("OPTK_F_APERTURE_CLOCKWISE") == _lib.F_APERTURE_CLOCKWISE
     assert define("OPTK_STAGE_KAPPA_OUT") == _lib.STAGE_KAPPA_OUT
 
 
@@ -132,6 +135,77 @@ def test_system_create_validates_without_a_gpu(lib):
     _lib.check(lib.optk_system_size(handle, C.byref(n_s), C.byref(n_c)))
     assert (n_s.value, n_c.value) == (1, 1)
     _lib.check(lib.optk_system_destroy(handle))
+
+
+def test_what_the_library_derives_per_surface(lib):
+    """
+    optk_system_create adds per-surface constants and flags (read back with optk_system_surface, no GPU): which
+    polygons are strictly convex and how they are oriented -- the half-plane test of the kernels relies on it --,
+    the squared-radius threshold of circles, rotation-free frames.
+    """
+    import numpy as np
+
+    from optika_b200 import _lib
+
+    def regular(n, radius=10.0, phase=0.1):
+        a = phase + 2 * np.pi * np.arange(n) / n
+        return radius * np.cos(a), radius * np.sin(a)
+
+    pentagram = tuple(np.array(regular(5))[:, [0, 2, 4, 1, 3]])
+    cases = {
+        "octagon": (regular(8), _lib.F_APERTURE_CONVEX),
+        "clockwise": (tuple(v[::-1] for v in regular(7)), _lib.F_APERTURE_CONVEX | _lib.F_APERTURE_CLOCKWISE),
+        "thirty_two": (regular(_lib.MAX_VERTICES), _lib.F_APERTURE_CONVEX),
+        "far_from_origin": (([100.0, 130.0, 110.0], [200.0, 205.0, 240.0]), _lib.F_APERTURE_CONVEX),
+        "arrow": (([-10.0, 12.0, 4.0, 9.0, -6.0], [-8.0, -9.0, 0.0, 11.0, 7.0]), 0),
+        "pentagram": (pentagram, 0),  # every turn has the same sign, but it winds twice
+        "collinear": (([-10.0, 0.0, 10.0, 10.0, -10.0], [-5.0, -5.0, -5.0, 5.0, 5.0]), 0),
+        "repeated": (([-10.0, 10.0, 10.0, 10.0, -10.0], [-5.0, -5.0, -5.0, 5.0, 5.0]), 0),
+        "degenerate": (([0.0, 1.0, 2.0], [0.0, 1.0, 2.0]), 0),
+    }
+    table = (_lib.Surface * (len(cases) + 2))()
+    for k, ((vx, vy), _) in enumerate(cases.values()):
+        S = table[k]
+        S.sag_kind, S.aperture_kind, S.stages = _lib.SAG_FLAT, _lib.APERTURE_POLYGON, _lib.STAGE_ALL
+        S.flags = _lib.F_APERTURE_ACTIVE | _lib.F_APERTURE_CONVEX  # a caller cannot claim convexity
+        S.n_vertices = len(vx)
+        for i in range(len(vx)):
+            S.vertices_x[i], S.vertices_y[i] = float(vx[i]), float(vy[i])
+    circle, shifted = table[len(cases)], table[len(cases) + 1]
+    circle.sag_kind, circle.aperture_kind, circle.stages = _lib.SAG_SPHERICAL, _lib.APERTURE_CIRCULAR, _lib.STAGE_ALL
+    circle.sag[0], circle.aperture[0] = 250.0, 12.3
+    shifted.sag_kind, shifted.stages, shifted.flags = _lib.SAG_FLAT, _lib.STAGE_ALL, _lib.F_TRANSFORM
+    for i in (0, 4, 8):
+        shifted.transform.r[i] = 1.0
+    shifted.transform.t[2] = 40.0
+    for S in table:
+        for i in (0, 4, 8):
+            S.sag_transform.r[i] = S.aperture_transform.r[i] = S.ruling_transform.r[i] = 1.0
+            if not S.flags & _lib.F_TRANSFORM:
+                S.transform.r[i] = 1.0
+    handle = C.c_void_p()
+    _lib.check(lib.optk_system_create(table, len(table), 1, C.byref(handle)))
+    try:
+        got = _lib.Surface()
+        for k, (name, ((vx, vy), want)) in enumerate(cases.items()):
+            _lib.check(lib.optk_system_surface(handle, 0, k, C.byref(got)))
+            mask = _lib.F_APERTURE_CONVEX | _lib.F_APERTURE_CLOCKWISE
+            assert got.flags & mask == want, name
+            if want:
+                bound = max(np.abs(vx).max(), np.abs(vy).max())
+                assert got.aperture[0] == bound and np.isclose(got.aperture[1], 1e-12 * bound**2, rtol=1e-12), name
+            assert list(got.vertices_x[: len(vx)]) == [float(v) for v in vx]  # the vertices themselves are untouched
+        _lib.check(lib.optk_system_surface(handle, 0, len(cases), C.byref(got)))
+        threshold = got.aperture[3]
+        assert np.sqrt(threshold) <= 12.3 < np.sqrt(np.nextafter(threshold, np.inf)) and got.sag[3] == 1 / 250.0
+        _lib.check(lib.optk_system_surface(handle, 0, len(cases) + 1, C.byref(got)))
+        assert got.flags & _lib.F_TRANSLATION_ONLY and got.transform.t[2] == 40.0
+        with pytest.raises(ValueError):
+            _lib.check(lib.optk_system_surface(handle, 1, 0, C.byref(got)))
+        with pytest.raises(ValueError):
+            _lib.check(lib.optk_system_surface(handle, 0, len(table), C.byref(got)))
+    finally:
+        _lib.check(lib.optk_system_destroy(handle))
 
 
 def test_stop_solver_and_reductions_validate_their_arguments_without_a_gpu(lib):
