@@ -440,6 +440,11 @@ def strong_scaling(name, system, grid_spec, n_surfaces, flop_per_ray, device, ra
         images=f"{int(np.prod(leading)) if leading else 1} x {len(ex) - 1} x {len(ey) - 1} pixels, planes flux / flux cos / counts",
         d2h_bytes=d2h_total,
         d2h_bytes_per_rank=d2h_total // world,
+        note="this object times THREE planes per image (flux, flux x cos(incidence), hit counts): the counts exist so that "
+             "the sharded + reduced image can be compared with the one-GPU image count for count; at N = 8 their read-back "
+             "(3.2 GB for cfg 5) is bound by what the host can ingest, not by the trace. `two_planes` / `one_plane` time "
+             "the same exposure with the planes SequentialSystem.image needs: flux x cos only for sensor materials that "
+             "use the angle of incidence, flux alone for the default IdealSensorMaterial",
         collective=({
             "peer": "every rank pulls its 1/N slice of every other rank's planes over NVLink with the copy engines "
                     "(CUDA IPC peer memory, interprocess events), adds the N pieces, and copies the sum to a shared "
