@@ -208,6 +208,80 @@ def test_what_the_library_derives_per_surface(lib):
         _lib.check(lib.optk_system_destroy(handle))
 
 
+def test_polygon_classification_on_random_polygons(lib):
+    """
+    The library's convexity test against an independent criterion on 300 random vertex lists: points on a circle in
+    angular order (convex, either orientation), the same with one vertex pulled inside (not convex), and random
+    permutations (edges cross).  Independent criterion: every vertex strictly inside every non-adjacent edge's
+    half-plane, by exact rational arithmetic.
+    """
+    import fractions
+    import numpy as np
+
+    from optika_b200 import _lib
+
+    def convex_exact(vx, vy):
+        fx, fy = [fractions.Fraction(float(v)) for v in vx], [fractions.Fraction(float(v)) for v in vy]
+        n = len(fx)
+        area2 = sum(fx[i] * fy[(i + 1) % n] - fx[(i + 1) % n] * fy[i] for i in range(n))
+        if area2 == 0:
+            return 0, 0
+        o = 1 if area2 > 0 else -1
+        margin = min(
+            o * ((fx[(i + 1) % n] - fx[i]) * (fy[k] - fy[i]) - (fy[(i + 1) % n] - fy[i]) * (fx[k] - fx[i]))
+            for i in range(n) for k in range(n) if k not in (i, (i + 1) % n)
+        )
+        return (o if margin > 0 else 0), float(margin)
+
+    rng = np.random.default_rng(11)
+    polygons = []
+    for trial in range(300):
+        n = int(rng.integers(3, _lib.MAX_VERTICES + 1))
+        angles = np.sort(rng.uniform(0, 2 * np.pi, n))
+        if np.min(np.diff(np.concatenate([angles, [angles[0] + 2 * np.pi]]))) < 1e-3:
+            continue
+        radius = rng.uniform(0.1, 50.0)
+        vx, vy = radius * np.cos(angles) + rng.normal(0, 5), radius * np.sin(angles) + rng.normal(0, 5)
+        kind = trial % 4
+        if kind == 1:
+            vx, vy = vx[::-1].copy(), vy[::-1].copy()
+        elif kind == 2 and n > 3:
+            k = int(rng.integers(n))
+            vx[k], vy[k] = 0.5 * (vx[k - 1] + vx[(k + 1) % n]) * 0.9 + 0.1 * vx.mean(), 0.5 * (vy[k - 1] + vy[(k + 1) % n]) * 0.9 + 0.1 * vy.mean()
+        elif kind == 3 and n > 4:
+            order = rng.permutation(n)
+            vx, vy = vx[order], vy[order]
+        polygons.append((vx, vy))
+    table = (_lib.Surface * len(polygons))()
+    for S, (vx, vy) in zip(table, polygons):
+        S.sag_kind, S.aperture_kind, S.stages, S.flags = _lib.SAG_FLAT, _lib.APERTURE_POLYGON, _lib.STAGE_ALL, _lib.F_APERTURE_ACTIVE
+        S.n_vertices = len(vx)
+        for i in range(len(vx)):
+            S.vertices_x[i], S.vertices_y[i] = float(vx[i]), float(vy[i])
+        for i in (0, 4, 8):
+            S.transform.r[i] = S.sag_transform.r[i] = S.aperture_transform.r[i] = S.ruling_transform.r[i] = 1.0
+    handle = C.c_void_p()
+    _lib.check(lib.optk_system_create(table, len(table), 1, C.byref(handle)))
+    try:
+        got = _lib.Surface()
+        seen = {0: 0, 1: 0, -1: 0}
+        for k, (vx, vy) in enumerate(polygons):
+            _lib.check(lib.optk_system_surface(handle, 0, k, C.byref(got)))
+            orientation, margin = convex_exact(vx, vy)
+            bound = max(np.abs(vx).max(), np.abs(vy).max())
+            convex = bool(got.flags & _lib.F_APERTURE_CONVEX)
+            if abs(margin) > 2e-9 * bound**2:  # the library wants a clear margin (1e-9 B^2); right at it either answer is fine
+                assert convex == (orientation != 0), (k, margin, bound)
+            if convex:
+                assert orientation != 0 and bool(got.flags & _lib.F_APERTURE_CLOCKWISE) == (orientation < 0), k
+                seen[orientation] += 1
+            else:
+                seen[0] += 1
+        assert min(seen.values()) > 20  # all three outcomes occur
+    finally:
+        _lib.check(lib.optk_system_destroy(handle))
+
+
 def test_stop_solver_and_reductions_validate_their_arguments_without_a_gpu(lib):
     """Argument checks of optk_solve_stops / optk_reduce_groups come before any CUDA call."""
     from optika_b200 import _lib

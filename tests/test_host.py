@@ -283,3 +283,20 @@ def test_detector_noise_is_seeded_per_block_of_pixels():
     # blocks are independent streams: no block repeats another
     assert not np.array_equal((sensors.read_noise(np.zeros(2 * sensors._NOISE_BLOCK), 1.0, 3)[: sensors._NOISE_BLOCK]),
                               (sensors.read_noise(np.zeros(2 * sensors._NOISE_BLOCK), 1.0, 3)[sensors._NOISE_BLOCK:]))
+
+
+def test_solid_angles_add_up():
+    """Properties of the cell solid angles: a grid over the whole sphere sums to 4 pi, and refining a grid conserves the total."""
+    from optika_b200 import _util
+
+    def total(ax, ay):
+        f = na.Cartesian2dVectorArray(na.ScalarArray(ax, "a"), na.ScalarArray(ay, "b"))
+        return np.abs(_util.direction(f).solid_angle_cell(("a", "b")).numpy(("a", "b"))).sum()
+
+    assert np.isclose(total(np.linspace(-np.pi, np.pi, 721), np.linspace(-np.pi / 2, np.pi / 2, 361)), 4 * np.pi, rtol=1e-12)
+    # great-circle quadrilaterals are not the curvilinear cells: the total over a patch changes at second order in the
+    # cell size only, and converges to the patch's d(azimuth) d(sin elevation)
+    coarse = total(np.linspace(0.1, 0.3, 11), np.linspace(-0.2, 0.25, 12))
+    fine = total(np.linspace(0.1, 0.3, 401), np.linspace(-0.2, 0.25, 441))
+    exact = 0.2 * (np.sin(0.25) + np.sin(0.2))
+    assert abs(fine - exact) < 1e-8 and abs(coarse - exact) < 2e-5 and abs(fine - exact) < abs(coarse - exact)
